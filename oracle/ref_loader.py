@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py) — import the UNMODIFIED reference.
+
+The reference's model files import third-party packages that are absent from this image
+(``lightning``, ``ml_collections``, ``torchmetrics``). This loader places
+minimal stub modules in ``sys.modules`` and imports ``model_cross`` / ``modelv3`` straight
+from the reference tree, which must be present (build container only; the GPU box has no
+/root/reference and must never call this).
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import torch.nn as nn
+
+REFERENCE_DIRS = [os.environ.get("CAVIT_REFERENCE_DIR", ""), "/root/reference"]
+
+
+def reference_dir():
+    for d in REFERENCE_DIRS:
+        if d and os.path.isfile(os.path.join(d, "model_cross.py")):
+            return d
+    return None
+
+
+class ConfigDict(dict):
+    """Stand-in for ml_collections.ConfigDict: attribute access, nested dict wrapping."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = ConfigDict(v) if isinstance(v, dict) and not isinstance(v, ConfigDict) else v
+
+
+def _install_stubs():
+    if "lightning" not in sys.modules:
+        L = types.ModuleType("lightning")
+
+        class LightningModule(nn.Module):
+            def log(self, *a, **k):
+                return None
+
+        L.LightningModule = LightningModule
+        sys.modules["lightning"] = L
+    if "ml_collections" not in sys.modules:
+        mc = types.ModuleType("ml_collections")
+        mc.ConfigDict = ConfigDict
+        sys.modules["ml_collections"] = mc
+    if "torchmetrics" not in sys.modules:
+        tm = types.ModuleType("torchmetrics")
+        tmf = types.ModuleType("torchmetrics.functional")
+        tmc = types.ModuleType("torchmetrics.classification")
+        for nm in ("BinaryAccuracy", "BinaryPrecision", "BinaryRecall", "BinarySpecificity",
+                   "BinaryF1Score", "BinaryConfusionMatrix"):
+            setattr(tmc, nm, type(nm, (), {}))
+        tm.functional = tmf
+        tm.classification = tmc
+        sys.modules["torchmetrics"] = tm
+        sys.modules["torchmetrics.functional"] = tmf
+        sys.modules["torchmetrics.classification"] = tmc
+
+
+def load(module_name: str):
+    """Import `module_name` (e.g. 'model_cross', 'modelv3') from the reference tree."""
+    d = reference_dir()
+    if d is None:
+        raise FileNotFoundError("reference tree not found (set CAVIT_REFERENCE_DIR)")
+    _install_stubs()
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    return importlib.import_module(module_name)
+
+
+def to_config_dict(cfg) -> ConfigDict:
+    """Attribute bag -> ConfigDict stub (what the reference constructors expect)."""
+    out = ConfigDict()
+    for k, v in vars(cfg).items():
+        setattr(out, k, v)
+    return out
