@@ -1,0 +1,109 @@
+"""ctypes binding of libcavit_sm100a.so (include/cavit.h). There is NO fallback: if the shared
+library is missing or the device is not a B200 (sm_100), importing/using the ops raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcavit_sm100a.so")
+
+c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_GELU_BWD, EPI_EMBED = range(6)
+
+
+class CavitError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", c_i32), ("N", c_i32), ("K", c_i32), ("groups", c_i32),
+        ("a_mn", c_i32), ("b_mn", c_i32), ("epi", c_i32), ("out_fp32", c_i32),
+        ("A", c_vp), ("lda", c_i64), ("a_gs", c_i64),
+        ("B", c_vp), ("ldb", c_i64), ("b_gs", c_i64),
+        ("out", c_vp), ("ldo", c_i64), ("out_gs", c_i64),
+        ("bias", c_vp), ("bias_gs", c_i64),
+        ("resid", c_vp), ("ldr", c_i64), ("resid_gs", c_i64),
+        ("aux", c_vp), ("ldaux", c_i64), ("aux_gs", c_i64),
+        ("accumulate", c_i32), ("embed_np", c_i32),
+    ]
+
+
+_SIGS = {
+    "cavit_abi_version": (c_i32, []),
+    "cavit_last_error": (C.c_char_p, []),
+    "cavit_device_ok": (c_i32, [c_i32]),
+    "cavit_device_status": (c_i32, [c_i32]),
+    "cavit_launch_count": (C.c_longlong, []),
+    "cavit_gemm": (c_i32, [C.POINTER(GemmArgs), c_vp]),
+    "cavit_ln_fwd": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_ln_bwd_workspace_floats": (C.c_size_t, [c_i32, c_i32]),
+    "cavit_ln_bwd": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64,
+                             c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_ln_fusion_fwd": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32),
+                                    c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_ln_fusion_bwd": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
+                                    C.POINTER(c_i32), C.POINTER(c_i32), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_attn_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_attn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_xattn_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_xattn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_patchify": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_cls_rows": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_embed_param_grads": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_cast_bf16": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "cavit_colsum_bf16": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "cavit_gather_rows_f32": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_head_loss_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_head_loss_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
+                                    c_f32, c_vp]),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+
+
+def lib():
+    """Load the shared library (once). Raises CavitError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CavitError(
+                f"{LIB_PATH} not found: build it with `python cross-attention-vit_b200/build.py` "
+                "(cavit has no CPU / PyTorch fallback path)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.cavit_abi_version() != 1:
+            raise CavitError("libcavit_sm100a.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().cavit_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "cavit"):
+    if rc != 0:
+        raise CavitError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def require_device(index: int = 0):
+    import torch
+    if not torch.cuda.is_available():
+        raise CavitError("cavit needs a CUDA device (B200, sm_100a); none is visible and there is no fallback")
+    if not lib().cavit_device_ok(index):
+        raise CavitError(f"cuda:{index} is not compute capability 10.x; cavit is built for sm_100a only")
+
+
+def device_status(reset: bool = True) -> int:
+    return int(lib().cavit_device_status(1 if reset else 0))
+
+
+def launch_count() -> int:
+    return int(lib().cavit_launch_count())

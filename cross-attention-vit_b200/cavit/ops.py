@@ -1,0 +1,179 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, kernels enqueued on torch's current
+stream. These are what the engine (cavit/engine.py) and the GPU parity tests call. No op here
+has a PyTorch implementation behind it — if the library or a B200 is missing they raise."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._abi import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_EMBED, EPI_GELU_BWD, EPI_NONE, GemmArgs,
+                   check, lib)
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, groups: int = 1,
+         a_mn: bool = False, b_mn: bool = False, lda: int, ldb: int, ldo: int, a_gs: int = 0, b_gs: int = 0,
+         out_gs: int = 0, epi: int = EPI_NONE, bias: Optional[torch.Tensor] = None, bias_gs: int = 0,
+         resid: Optional[torch.Tensor] = None, ldr: int = 0, resid_gs: int = 0,
+         aux: Optional[torch.Tensor] = None, ldaux: int = 0, aux_gs: int = 0, accumulate: bool = False,
+         embed_np: int = 0) -> GemmArgs:
+    """D[g][m][n] = sum_k A_g(m,k) B_g(n,k) (see include/cavit.h: cavit_gemm)."""
+    assert A.dtype == BF16 and B.dtype == BF16 and out.dtype in (BF16, F32)
+    a = GemmArgs()
+    a.M, a.N, a.K, a.groups = M, N, K, groups
+    a.a_mn, a.b_mn, a.epi, a.out_fp32 = int(a_mn), int(b_mn), epi, int(out.dtype == F32)
+    a.A, a.lda, a.a_gs = A.data_ptr(), lda, a_gs
+    a.B, a.ldb, a.b_gs = B.data_ptr(), ldb, b_gs
+    a.out, a.ldo, a.out_gs = out.data_ptr(), ldo, out_gs
+    a.bias, a.bias_gs = _p(bias), bias_gs
+    a.resid, a.ldr, a.resid_gs = _p(resid), ldr, resid_gs
+    a.aux, a.ldaux, a.aux_gs = _p(aux), ldaux, aux_gs
+    a.accumulate, a.embed_np = int(accumulate), embed_np
+    check(lib().cavit_gemm(C.byref(a), _stream()), "cavit_gemm")
+    return a
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, epi=EPI_NONE, bias=None, resid=None,
+               aux=None):
+    """x [G,T,K] bf16, w [G,N,K] bf16 -> out [G,T,N]: Y = X W^T (+ epilogue)."""
+    G, T, K = x.shape
+    N = w.shape[1]
+    return gemm(x, w, out, M=T, N=N, K=K, groups=G, lda=K, ldb=K, ldo=N, a_gs=T * K, b_gs=N * K, out_gs=T * N,
+                epi=epi, bias=bias, bias_gs=N, resid=resid, ldr=N, resid_gs=T * N, aux=aux, ldaux=N, aux_gs=T * N)
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, epi=EPI_NONE, aux=None):
+    """dy [G,T,N] bf16, w [G,N,K] bf16 -> dX [G,T,K] = dY W."""
+    G, T, N = dy.shape
+    K = w.shape[2]
+    return gemm(dy, w, out, M=T, N=K, K=N, groups=G, a_mn=False, b_mn=True, lda=N, ldb=K, ldo=K, a_gs=T * N,
+                b_gs=N * K, out_gs=T * K, epi=epi, aux=aux, ldaux=K, aux_gs=T * K)
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulate: bool = False):
+    """dy [G,T,N] bf16, x [G,T,K] bf16 -> dW [G,N,K] fp32 = dY^T X."""
+    G, T, N = dy.shape
+    K = x.shape[2]
+    return gemm(dy, x, out, M=N, N=K, K=T, groups=G, a_mn=True, b_mn=True, lda=N, ldb=K, ldo=K, a_gs=T * N,
+                b_gs=T * K, out_gs=N * K, accumulate=accumulate)
+
+
+def ln_fwd(x, gamma, beta, y, mean, rstd, *, rows_per_group, groups, C, x_row_stride=None, x_gs=None, eps=1e-5):
+    x_row_stride = C if x_row_stride is None else x_row_stride
+    x_gs = rows_per_group * x_row_stride if x_gs is None else x_gs
+    check(lib().cavit_ln_fwd(x.data_ptr(), x_row_stride, x_gs, rows_per_group, groups, C, gamma.data_ptr(),
+                             beta.data_ptr(), eps, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _stream()),
+          "cavit_ln_fwd")
+
+
+def ln_bwd_workspace(groups: int, C: int, device) -> torch.Tensor:
+    return torch.empty(lib().cavit_ln_bwd_workspace_floats(groups, C), dtype=F32, device=device)
+
+
+def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, partials, *, rows_per_group, groups, C, dresid=None,
+           dx_bf16=None, x_row_stride=None, x_gs=None, dx_row_stride=None, dx_gs=None):
+    x_row_stride = C if x_row_stride is None else x_row_stride
+    x_gs = rows_per_group * x_row_stride if x_gs is None else x_gs
+    dx_row_stride = C if dx_row_stride is None else dx_row_stride
+    dx_gs = rows_per_group * dx_row_stride if dx_gs is None else dx_gs
+    check(lib().cavit_ln_bwd(dy.data_ptr(), x.data_ptr(), x_row_stride, x_gs, mean.data_ptr(), rstd.data_ptr(),
+                             gamma.data_ptr(), rows_per_group, groups, C, _p(dresid), dx.data_ptr(), dx_row_stride,
+                             dx_gs, _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(), partials.data_ptr(),
+                             _stream()), "cavit_ln_bwd")
+
+
+def _i32arr(v):
+    return (C.c_int32 * len(v))(*v)
+
+
+def ln_fusion_fwd(streams, gamma, beta, y, mean, rstd, *, B, N, C_, cls_src, tok_src, eps=1e-5):
+    K = len(cls_src)
+    check(lib().cavit_ln_fusion_fwd(streams.data_ptr(), B * N * C_, B, N, C_, K, _i32arr(cls_src), _i32arr(tok_src),
+                                    gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), mean.data_ptr(),
+                                    rstd.data_ptr(), _stream()), "cavit_ln_fusion_fwd")
+
+
+def ln_fusion_bwd(dy, streams, mean, rstd, gamma, dstreams, dgamma, dbeta, partials, *, B, N, C_, cls_src, tok_src):
+    K = len(cls_src)
+    check(lib().cavit_ln_fusion_bwd(dy.data_ptr(), streams.data_ptr(), B * N * C_, mean.data_ptr(), rstd.data_ptr(),
+                                    gamma.data_ptr(), B, N, C_, K, _i32arr(cls_src), _i32arr(tok_src),
+                                    dstreams.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), partials.data_ptr(),
+                                    _stream()), "cavit_ln_fusion_bwd")
+
+
+def attn_fwd(qkv, out, lse, *, G, B, N, H, scale):
+    check(lib().cavit_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), G, B, N, H, scale, _stream()),
+          "cavit_attn_fwd")
+
+
+def attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, *, G, B, N, H, scale):
+    check(lib().cavit_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                               delta.data_ptr(), dq_acc.data_ptr(), G, B, N, H, scale, _stream()), "cavit_attn_bwd")
+
+
+def xattn_fwd(q, kv, out, probs, *, K, B, N, H, scale):
+    check(lib().cavit_xattn_fwd(q.data_ptr(), kv.data_ptr(), out.data_ptr(), probs.data_ptr(), K, B, N, H, scale,
+                                _stream()), "cavit_xattn_fwd")
+
+
+def xattn_bwd(q, kv, probs, dout, dq, dkv, *, K, B, N, H, scale):
+    check(lib().cavit_xattn_bwd(q.data_ptr(), kv.data_ptr(), probs.data_ptr(), dout.data_ptr(), dq.data_ptr(),
+                                dkv.data_ptr(), K, B, N, H, scale, _stream()), "cavit_xattn_bwd")
+
+
+def patchify(img, patches, *, patch_size):
+    B, M, _, D, H, W = img.shape
+    dp, hp, wp = patch_size
+    check(lib().cavit_patchify(img.data_ptr(), patches.data_ptr(), B, M, D, H, W, dp, hp, wp, _stream()),
+          "cavit_patchify")
+
+
+def cls_rows(cls, pos, tokens, *, M, B, N, C_):
+    check(lib().cavit_cls_rows(cls.data_ptr(), pos.data_ptr(), tokens.data_ptr(), M, B, N, C_, _stream()),
+          "cavit_cls_rows")
+
+
+def embed_param_grads(dtokens, dpos, dcls, *, M, B, N, C_):
+    check(lib().cavit_embed_param_grads(dtokens.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), M, B, N, C_, _stream()),
+          "cavit_embed_param_grads")
+
+
+def cast_bf16(src, dst):
+    check(lib().cavit_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cavit_cast_bf16")
+
+
+def colsum_bf16(x, out, *, rows, C_, groups, ldx=None, x_gs=None, out_gs=None):
+    ldx = C_ if ldx is None else ldx
+    x_gs = rows * ldx if x_gs is None else x_gs
+    out_gs = C_ if out_gs is None else out_gs
+    check(lib().cavit_colsum_bf16(x.data_ptr(), ldx, x_gs, rows, C_, groups, out.data_ptr(), out_gs, _stream()),
+          "cavit_colsum_bf16")
+
+
+def gather_rows_f32(src, dst, *, rows, C_, groups, src_row_stride, src_gs, dst_row_stride, dst_gs, accumulate=False):
+    check(lib().cavit_gather_rows_f32(src.data_ptr(), src_row_stride, src_gs, dst.data_ptr(), dst_row_stride, dst_gs,
+                                      rows, C_, groups, int(accumulate), _stream()), "cavit_gather_rows_f32")
+
+
+def head_loss_fwd(h, W2, b2, labels, logits, loss, *, M, B, F, classes, smoothing):
+    check(lib().cavit_head_loss_fwd(h.data_ptr(), W2.data_ptr(), b2.data_ptr(), labels.data_ptr(), logits.data_ptr(),
+                                    loss.data_ptr(), M, B, F, classes, smoothing, _stream()), "cavit_head_loss_fwd")
+
+
+def head_loss_bwd(h, W2, labels, logits, dh, dW2, db2, *, M, B, F, classes, smoothing, loss_scale=1.0):
+    check(lib().cavit_head_loss_bwd(h.data_ptr(), W2.data_ptr(), labels.data_ptr(), logits.data_ptr(), loss_scale,
+                                    dh.data_ptr(), dW2.data_ptr(), db2.data_ptr(), M, B, F, classes, smoothing,
+                                    _stream()), "cavit_head_loss_bwd")

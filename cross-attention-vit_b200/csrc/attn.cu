@@ -1,0 +1,565 @@
+// cavit-sm100 — K-ATTN: fused self-attention softmax(Q K^T * scale) V for head_dim 64 on tcgen05.
+//
+// Forward (one CTA per 128 query rows of one (stream, sample, head)):
+//   S = Q K_j^T            tcgen05.mma 128x128x64 into TMEM          (K-major A and B)
+//   online softmax         one thread per query row reads its S row with tcgen05.ld, keeps the
+//                          running max / sum in registers, writes P (bf16) into a 128B-swizzled
+//                          shared tile
+//   O_j = P V_j            tcgen05.mma 128x64x128 (A = P from smem, B = V as MN-major operand)
+//   O = O*alpha + O_j      accumulated in registers, normalised and stored as merged heads.
+// The N x N score matrix exists only in TMEM / shared memory. K/V tiles are double-buffered TMA
+// loads straight out of the packed QKV activation ([T][3C], exactly what the QKV GEMM wrote), so
+// no head-split permute is ever materialised ('b n (h d) -> b h n d', model_cross.py:53).
+//
+// Backward (one CTA per 128 key/value rows; loops over query tiles), SURVEY.md §A.9:
+//   S^T = K Q_i^T, dP^T = V dO_i^T          (TMEM)
+//   P^T = exp(S^T*scale - LSE), dS^T = P^T o (dP^T - D)    (registers -> swizzled smem, bf16)
+//   dV += P^T dO_i, dK += dS^T Q_i          (TMEM accumulators, B operands MN-major)
+//   dQ_i = dS K                             (A = dS^T tile viewed MN-major) -> fp32 red.global.add
+//
+// Ragged tails (N = tile + 1): out-of-range keys get P = 0; out-of-range query rows are not stored.
+#include "common.cuh"
+#include "internal.h"
+
+namespace cavit {
+
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_TILE = 128;
+constexpr int ATT_D = 64;
+constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_D * 2;  // 16 KB: [128 rows][64 bf16]
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Store 32 consecutive bf16 values (cols c0..c0+31 of row r) into a [128][128] bf16 tile kept as two
+// K-major SWIZZLE_128B chunks of 64 columns (chunk pitch 16 KB, row pitch 128 B).
+__device__ __forceinline__ void store_row_chunk_sw128(uint8_t* tile, int r, int c0, const float (&v)[32]) {
+  const int half = c0 >> 6;
+  const int c16_0 = (c0 & 63) >> 3;  // first 16-byte chunk inside the 128-byte row
+  uint8_t* row = tile + half * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 q;
+    q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+    q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(row + (((c16_0 + i) ^ (r & 7)) << 4)) = q;
+  }
+}
+
+struct AttnFwdParams {
+  bf16* out;
+  float* lse;
+  int N, H, C, B;
+  long long out_gs;  // elements between groups in out
+  float scale_log2;  // scale * log2(e)
+  int* status;
+};
+
+// smem: Q | K0 | K1 | V0 | V1 | P(2 chunks) | barriers
+constexpr int ATT_FWD_SMEM = 7 * ATT_TILE_BYTES + 1024 + 128;
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = base + ATT_TILE_BYTES, sV = base + 3 * ATT_TILE_BYTES;
+  const uint32_t sP = base + 5 * ATT_TILE_BYTES;
+  uint8_t* genP = gen + 5 * ATT_TILE_BYTES;
+  const uint32_t bar0 = base + 7 * ATT_TILE_BYTES;
+  const uint32_t bar_q = bar0, bar_kv0 = bar0 + 8, bar_s = bar0 + 24, bar_o = bar0 + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 7 * ATT_TILE_BYTES + 40);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = blockIdx.z, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int q0 = blockIdx.x * ATT_TILE;
+  const int row_base = b * p.N;
+  const int nkv = (p.N + ATT_TILE - 1) / ATT_TILE;
+
+  if (tid == 0) {
+    *abort_flag = 0;
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv0, 1);
+    mbar_init(bar_kv0 + 8, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmQKV);
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + 128;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, ATT_TILE_BYTES);
+    tma_load_3d(&tmQKV, bar_q, sQ, h * ATT_D, row_base + q0, g);
+    mbar_arrive_expect_tx(bar_kv0, 2 * ATT_TILE_BYTES);
+    tma_load_3d(&tmQKV, bar_kv0, sK, p.C + h * ATT_D, row_base, g);
+    tma_load_3d(&tmQKV, bar_kv0, sV, 2 * p.C + h * ATT_D, row_base, g);
+  }
+
+  const uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);
+  const uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);
+  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+
+  float o[ATT_D];
+#pragma unroll
+  for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int j = 0; j < nkv; ++j) {
+    const int buf = j & 1;
+    if (tid == 0) {
+      if (j + 1 < nkv) {  // prefetch next K/V tile into the other buffer (its readers finished at j-1)
+        const uint32_t bar = bar_kv0 + 8 * ((j + 1) & 1);
+        mbar_arrive_expect_tx(bar, 2 * ATT_TILE_BYTES);
+        tma_load_3d(&tmQKV, bar, sK + ((j + 1) & 1) * ATT_TILE_BYTES, p.C + h * ATT_D, row_base + (j + 1) * ATT_TILE, g);
+        tma_load_3d(&tmQKV, bar, sV + ((j + 1) & 1) * ATT_TILE_BYTES, 2 * p.C + h * ATT_D, row_base + (j + 1) * ATT_TILE, g);
+      }
+      if (j == 0) mbar_wait(bar_q, 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+      mbar_wait(bar_kv0 + 8 * buf, (j >> 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k) {
+        const uint64_t ad = umma_desc_sw128(sQ + k * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(sK + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
+        umma_bf16_ss(tS, ad, bd, idesc_s, k != 0);
+      }
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, j & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+
+    const int kv_valid = min(ATT_TILE, p.N - j * ATT_TILE);  // columns < kv_valid are real keys
+    // pass 1: row maximum (log2 domain)
+    float m_tile = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tS + t_lane + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i < kv_valid) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+    }
+    const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
+    const float alpha = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
+    float l_tile = 0.f;
+    // pass 2: probabilities -> bf16 -> swizzled smem
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tS + t_lane + c * 32, r);
+      tmem_ld_wait();
+      float pv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e = ex2_approx(__uint_as_float(r[i]) * p.scale_log2 - m_new);
+        pv[i] = (c * 32 + i < kv_valid) ? e : 0.f;
+        // sum what the MMA will actually see (bf16-rounded probabilities)
+        l_tile += __bfloat162float(__float2bfloat16(pv[i]));
+      }
+      store_row_chunk_sw128(genP, tid, c * 32, pv);
+    }
+    l_run = l_run * alpha + l_tile;
+    m_run = m_new;
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < ATT_TILE / 16; ++k) {
+        const uint64_t ad = umma_desc_sw128(sP + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(sV + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
+        umma_bf16_ss(tO, ad, bd, idesc_o, k != 0);
+      }
+      umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, j & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tO + t_lane + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+    __syncthreads();  // everyone is done with S / O / P of this tile before thread 0 reuses them
+  }
+
+  const int q = q0 + tid;
+  if (q < p.N) {
+    const float inv_l = 1.0f / l_run;
+    bf16* orow = p.out + (long long)g * p.out_gs + (long long)(row_base + q) * p.C + h * ATT_D;
+#pragma unroll
+    for (int i = 0; i < ATT_D; i += 8) {
+      uint4 w;
+      w.x = pack_bf16(o[i] * inv_l, o[i + 1] * inv_l);
+      w.y = pack_bf16(o[i + 2] * inv_l, o[i + 3] * inv_l);
+      w.z = pack_bf16(o[i + 4] * inv_l, o[i + 5] * inv_l);
+      w.w = pack_bf16(o[i + 6] * inv_l, o[i + 7] * inv_l);
+      *reinterpret_cast<uint4*>(orow + i) = w;
+    }
+    p.lse[(((long long)g * p.B + b) * p.H + h) * p.N + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// delta[g][b][h][q] = sum_d dO[row][h*64+d] * O[row][h*64+d]; one warp per (row, head).
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                  long long rows_total /*G*B*N*/, int N, int H, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = wid; w < rows_total * H; w += nw) {
+    const long long row = w / H;
+    const int h = (int)(w % H);
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(o + row * C + h * ATT_D + lane * 2);
+    const uint32_t d = *reinterpret_cast<const uint32_t*>(dout + row * C + h * ATT_D + lane * 2);
+    const float2 af = unpack_bf16(a), df = unpack_bf16(d);
+    const float s = warp_sum(af.x * df.x + af.y * df.y);
+    if (lane == 0) {
+      const long long gb = row / N;
+      const int q = (int)(row % N);
+      delta[(gb * H + h) * N + q] = s;
+    }
+  }
+}
+
+struct AttnBwdParams {
+  const float* lse;
+  const float* delta;
+  bf16* dqkv;
+  float* dq_acc;
+  int N, H, C, B;
+  long long qkv_gs, acc_gs;
+  float scale, scale_log2;
+  int* status;
+};
+
+// smem: K | V | Q0 | Q1 | dO0 | dO1 | PT(2 chunks) | dST(2 chunks) | lse[128] delta[128] | barriers
+constexpr int ATT_BWD_SMEM = 10 * ATT_TILE_BYTES + 1024 + 1024 + 128;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sK = base, sV = base + ATT_TILE_BYTES, sQ = base + 2 * ATT_TILE_BYTES, sDO = base + 4 * ATT_TILE_BYTES;
+  const uint32_t sPT = base + 6 * ATT_TILE_BYTES, sDST = base + 8 * ATT_TILE_BYTES;
+  uint8_t* genPT = gen + 6 * ATT_TILE_BYTES;
+  uint8_t* genDST = gen + 8 * ATT_TILE_BYTES;
+  float* s_lse = reinterpret_cast<float*>(gen + 10 * ATT_TILE_BYTES);
+  float* s_delta = s_lse + ATT_TILE;
+  const uint32_t bar0 = base + 10 * ATT_TILE_BYTES + 1024;
+  const uint32_t bar_kv = bar0, bar_q0 = bar0 + 8, bar_s = bar0 + 24, bar_d = bar0 + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 10 * ATT_TILE_BYTES + 1024 + 40);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = blockIdx.z, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int kv0 = blockIdx.x * ATT_TILE;
+  const int row_base = b * p.N;
+  const int nq = (p.N + ATT_TILE - 1) / ATT_TILE;
+
+  if (tid == 0) {
+    *abort_flag = 0;
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_q0, 1);
+    mbar_init(bar_q0 + 8, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_d, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmQKV);
+    prefetch_tmap(&tmDO);
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_kv, 2 * ATT_TILE_BYTES);
+    tma_load_3d(&tmQKV, bar_kv, sK, p.C + h * ATT_D, row_base + kv0, g);
+    tma_load_3d(&tmQKV, bar_kv, sV, 2 * p.C + h * ATT_D, row_base + kv0, g);
+    mbar_arrive_expect_tx(bar_q0, 2 * ATT_TILE_BYTES);
+    tma_load_3d(&tmQKV, bar_q0, sQ, h * ATT_D, row_base, g);
+    tma_load_3d(&tmDO, bar_q0, sDO, h * ATT_D, row_base, g);
+  }
+
+  const uint32_t idesc_kk = umma_idesc_bf16(128, 0, 0);   // S^T, dP^T : both operands K-major, N = 128
+  const uint32_t idesc_kmn = umma_idesc_bf16(64, 0, 1);   // dV, dK    : A K-major (smem P^T/dS^T), B MN-major, N = 64
+  const uint32_t idesc_mnmn = umma_idesc_bf16(64, 1, 1);  // dQ        : A = dS^T viewed MN-major, B = K MN-major
+  const long long lse_base = (((long long)g * p.B + b) * p.H + h) * p.N;
+  const bool kv_ok = (kv0 + tid) < p.N;
+
+  for (int i = 0; i < nq; ++i) {
+    const int buf = i & 1;
+    const int q0 = i * ATT_TILE;
+    // stage LSE / delta of this query tile (log2 domain for LSE)
+    {
+      const int q = q0 + tid;
+      s_lse[tid] = (q < p.N) ? p.lse[lse_base + q] * 1.4426950408889634f : 0.f;
+      s_delta[tid] = (q < p.N) ? p.delta[lse_base + q] : 0.f;
+    }
+    if (tid == 0) {
+      if (i + 1 < nq) {
+        const uint32_t bar = bar_q0 + 8 * ((i + 1) & 1);
+        mbar_arrive_expect_tx(bar, 2 * ATT_TILE_BYTES);
+        tma_load_3d(&tmQKV, bar, sQ + ((i + 1) & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + q0 + ATT_TILE, g);
+        tma_load_3d(&tmDO, bar, sDO + ((i + 1) & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + q0 + ATT_TILE, g);
+      }
+      if (i == 0) mbar_wait(bar_kv, 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+      mbar_wait(bar_q0 + 8 * buf, (i >> 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k) {
+        const uint64_t kd = umma_desc_sw128(sK + k * 32, 16, 1024);
+        const uint64_t qd = umma_desc_sw128(sQ + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
+        umma_bf16_ss(tST, kd, qd, idesc_kk, k != 0);
+      }
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k) {
+        const uint64_t vd = umma_desc_sw128(sV + k * 32, 16, 1024);
+        const uint64_t dd = umma_desc_sw128(sDO + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
+        umma_bf16_ss(tDPT, vd, dd, idesc_kk, k != 0);
+      }
+      umma_commit(bar_s);
+    }
+    __syncthreads();  // s_lse / s_delta visible
+    mbar_wait(bar_s, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+    const int q_valid = min(ATT_TILE, p.N - q0);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tST + t_lane + c * 32, rs);
+      tmem_ld32(tDPT + t_lane + c * 32, rp);
+      tmem_ld_wait();
+      float pt[32], dst[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        const bool ok = kv_ok && (col < q_valid);
+        const float pr = ok ? ex2_approx(__uint_as_float(rs[j]) * p.scale_log2 - s_lse[col]) : 0.f;
+        pt[j] = pr;
+        dst[j] = pr * (__uint_as_float(rp[j]) - s_delta[col]);
+      }
+      store_row_chunk_sw128(genPT, tid, c * 32, pt);
+      store_row_chunk_sw128(genDST, tid, c * 32, dst);
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // dV[kv][d] += P^T[kv][q] dO[q][d]      A: sPT (K-major over q), B: sDO tile as MN-major (N = d)
+#pragma unroll
+      for (int k = 0; k < ATT_TILE / 16; ++k) {
+        const uint64_t ad = umma_desc_sw128(sPT + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(sDO + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
+        umma_bf16_ss(tDV, ad, bd, idesc_kmn, (i | k) != 0);
+      }
+      // dK[kv][d] += dS^T[kv][q] Q[q][d]
+#pragma unroll
+      for (int k = 0; k < ATT_TILE / 16; ++k) {
+        const uint64_t ad = umma_desc_sw128(sDST + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(sQ + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
+        umma_bf16_ss(tDK, ad, bd, idesc_kmn, (i | k) != 0);
+      }
+      // dQ[q][d] = dS[q][kv] K[kv][d]         A: sDST viewed MN-major (M = q contiguous, K = kv rows)
+#pragma unroll
+      for (int k = 0; k < ATT_TILE / 16; ++k) {
+        const uint64_t ad = umma_desc_sw128(sDST + k * 2048, ATT_TILE_BYTES, 1024);
+        const uint64_t bd = umma_desc_sw128(sK + k * 2048, ATT_TILE_BYTES, 1024);
+        umma_bf16_ss(tDQ, ad, bd, idesc_mnmn, k != 0);
+      }
+      umma_commit(bar_d);
+    }
+    mbar_wait(bar_d, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+    {
+      const int q = q0 + tid;
+      float* acc = p.dq_acc + (long long)g * p.acc_gs + (long long)(row_base + q) * p.C + h * ATT_D;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tDQ + t_lane + c * 32, r);
+        tmem_ld_wait();
+        if (q < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(acc + c * 32 + j, __uint_as_float(r[j]) * p.scale);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // write dK (scaled) and dV for this key/value tile
+  {
+    const int kv = kv0 + tid;
+    bf16* drow = p.dqkv + (long long)g * p.qkv_gs + (long long)(row_base + kv) * (3 * p.C) + h * ATT_D;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t t = which == 0 ? tDK : tDV;
+      const float sc = which == 0 ? p.scale : 1.0f;
+      bf16* dst = drow + (which == 0 ? p.C : 2 * p.C);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t + t_lane + c * 32, r);
+        tmem_ld_wait();
+        if (kv < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc);
+            w.y = pack_bf16(__uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
+            w.z = pack_bf16(__uint_as_float(r[j + 4]) * sc, __uint_as_float(r[j + 5]) * sc);
+            w.w = pack_bf16(__uint_as_float(r[j + 6]) * sc, __uint_as_float(r[j + 7]) * sc);
+            *reinterpret_cast<uint4*>(dst + c * 32 + j) = w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// dqkv[row][0:C] = bf16(dq_acc[row][0:C])
+__global__ void attn_dq_store_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, long long rows, int C) {
+  const int C4 = C >> 2;
+  const long long total = rows * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / C4;
+    const int c4 = (int)(i % C4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(acc) + i);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *(reinterpret_cast<uint2*>(dqkv + row * 3 * C) + c4) = o;
+  }
+}
+
+}  // namespace cavit
+
+using namespace cavit;
+
+extern "C" {
+
+int cavit_attn_fwd(const void* qkv, void* out, float* lse, int32_t G, int32_t B, int32_t N, int32_t H, float scale,
+                   void* stream) {
+  if (!qkv || !out || !lse) return fail(CAVIT_E_BADARG, "cavit_attn_fwd: null pointer");
+  if (G <= 0 || B <= 0 || N <= 0 || H <= 0) return fail(CAVIT_E_BADARG, "cavit_attn_fwd: bad extents");
+  const int C = H * ATT_D;
+  const long long T = (long long)B * N;
+  const CUtensorMap* tm = tensor_map_bf16_3d(qkv, 3 * C, T, G, 3 * C, T * 3 * C, 64, ATT_TILE);
+  if (!tm) return CAVIT_E_BADARG;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM);
+    if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "attn fwd smem attribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  AttnFwdParams p;
+  p.out = reinterpret_cast<bf16*>(out);
+  p.lse = lse;
+  p.N = N; p.H = H; p.C = C; p.B = B;
+  p.out_gs = T * C;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.status = status_word();
+  if (!p.status) return fail(CAVIT_E_DEVICE, "no status word");
+  dim3 grid((N + ATT_TILE - 1) / ATT_TILE, B * H, G);
+  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_FWD_SMEM, as_stream(stream)>>>(*tm, p);
+  count_launch();
+  return check_launch("cavit_attn_fwd");
+}
+
+int cavit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                   float* dq_acc, int32_t G, int32_t B, int32_t N, int32_t H, float scale, void* stream) {
+  if (!qkv || !out || !dout || !lse || !dqkv || !delta || !dq_acc) return fail(CAVIT_E_BADARG, "cavit_attn_bwd: null pointer");
+  if (G <= 0 || B <= 0 || N <= 0 || H <= 0) return fail(CAVIT_E_BADARG, "cavit_attn_bwd: bad extents");
+  const int C = H * ATT_D;
+  const long long T = (long long)B * N;
+  cudaStream_t st = as_stream(stream);
+  const CUtensorMap* tq = tensor_map_bf16_3d(qkv, 3 * C, T, G, 3 * C, T * 3 * C, 64, ATT_TILE);
+  const CUtensorMap* td = tensor_map_bf16_3d(dout, C, T, G, C, T * C, 64, ATT_TILE);
+  if (!tq || !td) return CAVIT_E_BADARG;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
+    if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "attn bwd smem attribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  {
+    const long long warps = (long long)G * T * H;
+    long long blocks = (warps + 7) / 8;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    attn_delta_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(out), reinterpret_cast<const bf16*>(dout),
+                                                   delta, (long long)G * T, N, H, C);
+    count_launch();
+  }
+  cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)G * T * C, st);
+  AttnBwdParams p;
+  p.lse = lse; p.delta = delta;
+  p.dqkv = reinterpret_cast<bf16*>(dqkv);
+  p.dq_acc = dq_acc;
+  p.N = N; p.H = H; p.C = C; p.B = B;
+  p.qkv_gs = T * 3 * C;
+  p.acc_gs = T * C;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.status = status_word();
+  if (!p.status) return fail(CAVIT_E_DEVICE, "no status word");
+  dim3 grid((N + ATT_TILE - 1) / ATT_TILE, B * H, G);
+  attn_bwd_kernel<<<grid, ATT_THREADS, ATT_BWD_SMEM, st>>>(*tq, *td, p);
+  count_launch();
+  int rc = check_launch("cavit_attn_bwd");
+  if (rc) return rc;
+  {
+    const long long total = (long long)G * T * C / 4;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    attn_dq_store_kernel<<<(int)blocks, 256, 0, st>>>(dq_acc, reinterpret_cast<bf16*>(dqkv), (long long)G * T, C);
+    count_launch();
+  }
+  return check_launch("cavit_attn_bwd(dq)");
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// Host-side internals shared by the translation units of libcavit_sm100a.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cavit.h"
+
+namespace cavit {
+
+// thread-local last-error message; returns `code` so callers can `return fail(...)`.
+int fail(int code, const char* fmt, ...);
+// device status word (kernel-side time-outs). One per process (single device per process).
+int* status_word();
+void count_launch(int n = 1);
+// Checks cudaGetLastError() after a launch.
+int check_launch(const char* what);
+
+// 3-D bf16 tensor map {inner, rows, groups} with 128-byte swizzle. Cached by value.
+// Returns nullptr on failure (fail() already called).
+const CUtensorMap* tensor_map_bf16_3d(const void* base, uint64_t inner, uint64_t rows, uint64_t groups,
+                                      uint64_t row_stride_elems, uint64_t group_stride_elems,
+                                      uint32_t box_inner, uint32_t box_rows);
+// 4-D bf16 tensor map {d0, d1, d2, d3} (strides in elements for dims 1..3), 128-byte swizzle.
+const CUtensorMap* tensor_map_bf16_4d(const void* base, const uint64_t dims[4], const uint64_t strides_elems[3],
+                                      const uint32_t box[4]);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+int sm_count();
+
+}  // namespace cavit

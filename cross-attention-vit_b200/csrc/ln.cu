@@ -1,0 +1,333 @@
+// cavit-sm100 — K-LN: LayerNorm forward / backward, warp-per-row, HBM-bound.
+//
+// Each warp owns one row: every lane issues up to NV independent 16-byte loads (coalesced 512 B
+// per warp instruction), statistics are reduced with warp shuffles in fp32 (two-pass: mean, then
+// centred variance, like ATen), and the normalised row is written as bf16 (the GEMM operand
+// format) with 8-byte stores. Backward fuses the residual-gradient add and the bf16 copy of dx
+// that the next dgrad/wgrad GEMM consumes; d(gamma)/d(beta) are reduced deterministically in two
+// stages (per-warp partial rows, then a column reduction).
+//
+// The "fusion" row map implements `cat(cls_i, patches_j)` (model_cross.py:140) without the copy:
+// row 0 of every sample is read from the CLS-donor stream, rows 1.. from the patch-donor stream.
+//
+// Algorithmic bytes per row (C columns): fwd 4C (x) + 2C (y) + 8; bwd 2C (dy) + 4C (x) + 4C (dresid)
+// + 4C (dx) + 2C (dx bf16).
+#include "common.cuh"
+#include "internal.h"
+
+namespace cavit {
+
+constexpr int LN_THREADS = 256;
+constexpr int LN_WARPS = LN_THREADS / 32;
+constexpr int LN_MAX_BLOCKS_PER_GROUP = 64;
+constexpr int LN_MAX_FUSIONS = 16;
+
+struct RowMap {
+  int fusion;  // 0: plain rows; 1: fusion gather
+  int N;       // tokens per sample (fusion mode)
+  int cls_src[LN_MAX_FUSIONS];
+  int tok_src[LN_MAX_FUSIONS];
+};
+
+__device__ __forceinline__ long long src_offset(const RowMap& rm, int g, long long r, long long row_stride,
+                                                long long gs) {
+  if (!rm.fusion) return (long long)g * gs + r * row_stride;
+  const int n = (int)(r % rm.N);
+  const int s = (n == 0) ? rm.cls_src[g] : rm.tok_src[g];
+  return (long long)s * gs + r * row_stride;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(LN_THREADS)
+ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, int rows_per_group, int groups, int C,
+              const float* __restrict__ gamma, const float* __restrict__ beta, float eps, bf16* __restrict__ y,
+              float* __restrict__ mean, float* __restrict__ rstd, const RowMap rm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = (long long)rows_per_group * groups;
+  const int C4 = C >> 2;
+  const float inv_c = 1.0f / (float)C;
+  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < total; row += (long long)gridDim.x * LN_WARPS) {
+    const int g = (int)(row / rows_per_group);
+    const long long r = row - (long long)g * rows_per_group;
+    const float4* xr = reinterpret_cast<const float4*>(x + src_offset(rm, g, r, row_stride, gs));
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < C4) {
+        v[i] = __ldg(xr + c4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      } else {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float mu = warp_sum(s) * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < C4) {
+        const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+        ss += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rs = rsqrtf(warp_sum(ss) * inv_c + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma + (long long)g * C);
+    const float4* b4 = reinterpret_cast<const float4*>(beta + (long long)g * C);
+    uint2* yr = reinterpret_cast<uint2*>(y + row * C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < C4) {
+        const float4 gm = __ldg(g4 + c4), bt = __ldg(b4 + c4);
+        uint2 o;
+        o.x = pack_bf16((v[i].x - mu) * rs * gm.x + bt.x, (v[i].y - mu) * rs * gm.y + bt.y);
+        o.y = pack_bf16((v[i].z - mu) * rs * gm.z + bt.z, (v[i].w - mu) * rs * gm.w + bt.w);
+        yr[c4] = o;
+      }
+    }
+    if (lane == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+  }
+}
+
+// grid = (blocks_per_group, groups). partials: [groups][blocks_per_group*LN_WARPS][2][C]
+template <int NV>
+__global__ void __launch_bounds__(LN_THREADS)
+ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long long row_stride, long long gs,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+              int rows_per_group, int C, const float* dresid, float* dx, long long dx_row_stride, long long dx_gs,
+              bf16* __restrict__ dx_bf16, float* __restrict__ partials, const RowMap rm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.y;
+  const int C4 = C >> 2;
+  const float inv_c = 1.0f / (float)C;
+  float4 gm[NV], dg[NV], db[NV];
+  const float4* g4 = reinterpret_cast<const float4*>(gamma + (long long)g * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    gm[i] = (c4 < C4) ? __ldg(g4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows_per_group; r += (long long)gridDim.x * LN_WARPS) {
+    const long long row = (long long)g * rows_per_group + r;
+    const long long soff = src_offset(rm, g, r, row_stride, gs);
+    const float4* xr = reinterpret_cast<const float4*>(x + soff);
+    const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * C);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], gy[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < C4) {
+        const float4 xv = __ldg(xr + c4);
+        const uint2 d2 = __ldg(dyr + c4);
+        const float2 d01 = unpack_bf16(d2.x), d23 = unpack_bf16(d2.y);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        dg[i].x += d01.x * xh[i].x; dg[i].y += d01.y * xh[i].y; dg[i].z += d23.x * xh[i].z; dg[i].w += d23.y * xh[i].w;
+        db[i].x += d01.x; db[i].y += d01.y; db[i].z += d23.x; db[i].w += d23.y;
+        gy[i] = make_float4(d01.x * gm[i].x, d01.y * gm[i].y, d23.x * gm[i].z, d23.y * gm[i].w);
+        s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+        s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+      }
+    }
+    const float m1 = warp_sum(s1) * inv_c, m2 = warp_sum(s2) * inv_c;
+    long long doff;
+    if (rm.fusion) doff = soff;  // scatter back to where the row was gathered from
+    else doff = (long long)g * dx_gs + r * dx_row_stride;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < C4) {
+        float4 o;
+        o.x = rs * (gy[i].x - m1 - xh[i].x * m2);
+        o.y = rs * (gy[i].y - m1 - xh[i].y * m2);
+        o.z = rs * (gy[i].z - m1 - xh[i].z * m2);
+        o.w = rs * (gy[i].w - m1 - xh[i].w * m2);
+        if (rm.fusion) {
+          float* d = dx + doff + c4 * 4;
+          atomicAdd(d + 0, o.x); atomicAdd(d + 1, o.y); atomicAdd(d + 2, o.z); atomicAdd(d + 3, o.w);
+        } else {
+          if (dresid) {
+            const float4 dr = *(reinterpret_cast<const float4*>(dresid + doff) + c4);
+            o.x += dr.x; o.y += dr.y; o.z += dr.z; o.w += dr.w;
+          }
+          *(reinterpret_cast<float4*>(dx + doff) + c4) = o;
+          if (dx_bf16) {
+            uint2 q;
+            q.x = pack_bf16(o.x, o.y);
+            q.y = pack_bf16(o.z, o.w);
+            *(reinterpret_cast<uint2*>(dx_bf16 + row * C) + c4) = q;
+          }
+        }
+      }
+    }
+  }
+  // per-warp partial rows of d(gamma), d(beta)
+  const long long prow = ((long long)g * gridDim.x + blockIdx.x) * LN_WARPS + warp;
+  float4* pg = reinterpret_cast<float4*>(partials + prow * 2 * C);
+  float4* pb = reinterpret_cast<float4*>(partials + prow * 2 * C + C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    if (c4 < C4) {
+      pg[c4] = dg[i];
+      pb[c4] = db[i];
+    }
+  }
+}
+
+// grid = (ceil(C/32), groups); block = (32, 8)
+__global__ void ln_param_grad_finalize(const float* __restrict__ partials, int prow_per_group, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sg[8][33], sb[8][33];
+  const int g = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float ag = 0.f, ab = 0.f;
+  if (c < C) {
+    for (int r = threadIdx.y; r < prow_per_group; r += 8) {
+      const float* p = partials + ((long long)g * prow_per_group + r) * 2 * C;
+      ag += p[c];
+      ab += p[C + c];
+    }
+  }
+  sg[threadIdx.y][threadIdx.x] = ag;
+  sb[threadIdx.y][threadIdx.x] = ab;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int r = 1; r < 8; ++r) {
+      ag += sg[r][threadIdx.x];
+      ab += sb[r][threadIdx.x];
+    }
+    dgamma[(long long)g * C + c] = ag;
+    dbeta[(long long)g * C + c] = ab;
+  }
+}
+
+static int blocks_per_group(long long rows) {
+  long long b = (rows + LN_WARPS - 1) / LN_WARPS;
+  if (b > LN_MAX_BLOCKS_PER_GROUP) b = LN_MAX_BLOCKS_PER_GROUP;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+static int ln_fwd_launch(const float* x, long long row_stride, long long gs, int rpg, int groups, int C,
+                         const float* gamma, const float* beta, float eps, void* y, float* mean, float* rstd,
+                         const RowMap& rm, cudaStream_t st) {
+  if (C % 4 || C <= 0 || C > 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm: C=%d (need C %% 4 == 0, C <= 1024)", C);
+  if ((row_stride % 4) || (gs % 4)) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm: strides must be multiples of 4");
+  const long long total = (long long)rpg * groups;
+  if (total <= 0) return fail(CAVIT_E_BADARG, "layernorm: no rows");
+  long long blocks = (total + LN_WARPS - 1) / LN_WARPS;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  const int nv = (C / 4 + 31) / 32;
+#define LN_FWD_CASE(NVV)                                                                                      \
+  case NVV:                                                                                                   \
+    ln_fwd_kernel<NVV><<<(int)blocks, LN_THREADS, 0, st>>>(x, row_stride, gs, rpg, groups, C, gamma, beta, eps, \
+                                                           reinterpret_cast<bf16*>(y), mean, rstd, rm);       \
+    break;
+  switch (nv) {
+    LN_FWD_CASE(1) LN_FWD_CASE(2) LN_FWD_CASE(3) LN_FWD_CASE(4) LN_FWD_CASE(5) LN_FWD_CASE(6) LN_FWD_CASE(7) LN_FWD_CASE(8)
+    default: return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm: C=%d", C);
+  }
+#undef LN_FWD_CASE
+  count_launch();
+  return check_launch("cavit_ln_fwd");
+}
+
+static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, long long gs, const float* mean,
+                         const float* rstd, const float* gamma, int rpg, int groups, int C, const float* dresid,
+                         float* dx, long long dx_rs, long long dx_gs, void* dx_bf16, float* dgamma, float* dbeta,
+                         float* partials, const RowMap& rm, cudaStream_t st) {
+  if (C % 4 || C <= 0 || C > 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: C=%d", C);
+  if ((row_stride % 4) || (gs % 4) || (dx_rs % 4) || (dx_gs % 4))
+    return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: strides must be multiples of 4");
+  if (!partials || !dgamma || !dbeta) return fail(CAVIT_E_BADARG, "layernorm bwd: null workspace / outputs");
+  const int bpg = blocks_per_group(rpg);
+  dim3 grid(bpg, groups);
+  const int nv = (C / 4 + 31) / 32;
+#define LN_BWD_CASE(NVV)                                                                                       \
+  case NVV:                                                                                                    \
+    ln_bwd_kernel<NVV><<<grid, LN_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dy), x, row_stride, gs, mean, \
+                                                    rstd, gamma, rpg, C, dresid, dx, dx_rs, dx_gs,             \
+                                                    reinterpret_cast<bf16*>(dx_bf16), partials, rm);           \
+    break;
+  switch (nv) {
+    LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4) LN_BWD_CASE(5) LN_BWD_CASE(6) LN_BWD_CASE(7) LN_BWD_CASE(8)
+    default: return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: C=%d", C);
+  }
+#undef LN_BWD_CASE
+  count_launch();
+  int rc = check_launch("cavit_ln_bwd");
+  if (rc) return rc;
+  dim3 fgrid((C + 31) / 32, groups), fblock(32, 8);
+  ln_param_grad_finalize<<<fgrid, fblock, 0, st>>>(partials, bpg * LN_WARPS, C, dgamma, dbeta);
+  count_launch();
+  return check_launch("cavit_ln_bwd(finalize)");
+}
+
+}  // namespace cavit
+
+using namespace cavit;
+
+extern "C" {
+
+int cavit_ln_fwd(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t rows_per_group, int32_t groups,
+                 int32_t C, const float* gamma, const float* beta, float eps, void* y, float* mean, float* rstd,
+                 void* stream) {
+  if (!x || !gamma || !beta || !y || !mean || !rstd) return fail(CAVIT_E_BADARG, "cavit_ln_fwd: null pointer");
+  RowMap rm{};
+  rm.fusion = 0;
+  return ln_fwd_launch(x, x_row_stride, x_gs, rows_per_group, groups, C, gamma, beta, eps, y, mean, rstd, rm,
+                       as_stream(stream));
+}
+
+size_t cavit_ln_bwd_workspace_floats(int32_t groups, int32_t C) {
+  return (size_t)groups * LN_MAX_BLOCKS_PER_GROUP * LN_WARPS * 2 * (size_t)C;
+}
+
+int cavit_ln_bwd(const void* dy, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,
+                 const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
+                 const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_bf16, float* dgamma,
+                 float* dbeta, float* partials, void* stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || !dx) return fail(CAVIT_E_BADARG, "cavit_ln_bwd: null pointer");
+  RowMap rm{};
+  rm.fusion = 0;
+  return ln_bwd_launch(dy, x, x_row_stride, x_gs, mean, rstd, gamma, rows_per_group, groups, C, dresid, dx,
+                       dx_row_stride, dx_gs, dx_bf16, dgamma, dbeta, partials, rm, as_stream(stream));
+}
+
+int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, int32_t B, int32_t N, int32_t C, int32_t K,
+                        const int32_t* cls_src, const int32_t* tok_src, const float* gamma, const float* beta,
+                        float eps, void* y, float* mean, float* rstd, void* stream) {
+  if (!streams || !cls_src || !tok_src || !gamma || !beta || !y) return fail(CAVIT_E_BADARG, "cavit_ln_fusion_fwd: null pointer");
+  if (K <= 0 || K > LN_MAX_FUSIONS) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_ln_fusion_fwd: K=%d (max %d)", K, LN_MAX_FUSIONS);
+  RowMap rm{};
+  rm.fusion = 1;
+  rm.N = N;
+  for (int k = 0; k < K; ++k) { rm.cls_src[k] = cls_src[k]; rm.tok_src[k] = tok_src[k]; }
+  return ln_fwd_launch(streams, C, stream_gs, B * N, K, C, gamma, beta, eps, y, mean, rstd, rm, as_stream(stream));
+}
+
+int cavit_ln_fusion_bwd(const void* dy, const float* streams, int64_t stream_gs, const float* mean, const float* rstd,
+                        const float* gamma, int32_t B, int32_t N, int32_t C, int32_t K, const int32_t* cls_src,
+                        const int32_t* tok_src, float* dstreams, float* dgamma, float* dbeta, float* partials,
+                        void* stream) {
+  if (!dy || !streams || !cls_src || !tok_src || !dstreams) return fail(CAVIT_E_BADARG, "cavit_ln_fusion_bwd: null pointer");
+  if (K <= 0 || K > LN_MAX_FUSIONS) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_ln_fusion_bwd: K=%d", K);
+  RowMap rm{};
+  rm.fusion = 1;
+  rm.N = N;
+  for (int k = 0; k < K; ++k) { rm.cls_src[k] = cls_src[k]; rm.tok_src[k] = tok_src[k]; }
+  return ln_bwd_launch(dy, streams, C, stream_gs, mean, rstd, gamma, B * N, K, C, nullptr, dstreams, C, stream_gs,
+                       nullptr, dgamma, dbeta, partials, rm, as_stream(stream));
+}
+
+}  // extern "C"

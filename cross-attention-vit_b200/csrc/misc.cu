@@ -1,0 +1,356 @@
+// cavit-sm100 — small memory-bound kernels around the GEMM / attention cores: patch gather,
+// CLS row, embedding parameter gradients, casts, bias-gradient column sums, row gathers and the
+// classification tail (last head Linear + mean over streams + cross-entropy, fwd and bwd).
+#include "common.cuh"
+#include "internal.h"
+
+namespace cavit {
+
+// ------------------------------------------------------------------------------------------ cast
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = __float2bfloat16(src[(n4 << 2) + threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------ patchify
+// out[m][b*Np + t][f] = img[b][m][0][di*dp + a][hi*hp + bb][wi*wp + c]
+//   t = (hi*Wn + wi)*Dn + di   (d fastest),   f = (a*hp + bb)*wp + c      
+// One thread produces two consecutive features (one 4-byte bf16x2 store).
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int M, int D, int H,
+                                int W, int dp, int hp, int wp) {
+  const int Dn = D / dp, Hn = H / hp, Wn = W / wp;
+  const long long Np = (long long)Dn * Hn * Wn;
+  const int P = dp * hp * wp;
+  const long long pairs = (long long)M * B * Np * P / 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+    long long e = i * 2;
+    const int f = (int)(e % P);
+    e /= P;
+    const long long t = e % Np;
+    e /= Np;
+    const int b = (int)(e % B);
+    const int m = (int)(e / B);
+    const int di = (int)(t % Dn), wi = (int)((t / Dn) % Wn), hi = (int)(t / ((long long)Dn * Wn));
+    const float* vol = img + ((long long)b * M + m) * ((long long)D * H * W);
+    float v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ff = f + j;
+      const int c = ff % wp, bb = (ff / wp) % hp, a = ff / (wp * hp);
+      v[j] = __ldg(vol + ((long long)(di * dp + a) * H + (hi * hp + bb)) * W + (wi * wp + c));
+    }
+    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16(v[0], v[1]);
+  }
+}
+
+// tokens[m][b*N][c] = cls[c] + pos[0][c]
+__global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ tokens,
+                                int MB, int N, int C) {
+  const long long total = (long long)MB * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long mb = i / C;
+    tokens[mb * (long long)N * C + c] = cls[c] + pos[c];
+  }
+}
+
+// dpos[n][c] = sum over (m,b) of dtokens[(m*B+b)*N + n][c]; dcls = dpos[0] (cls and pos[0] feed the same row).
+__global__ void embed_param_grads_kernel(const float* __restrict__ dtok, float* __restrict__ dpos, float* __restrict__ dcls,
+                                         int MB, int N, int C) {
+  const int C4 = C >> 2;
+  const long long total = (long long)N * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* p = reinterpret_cast<const float4*>(dtok) + i;
+    for (int mb = 0; mb < MB; ++mb) {
+      const float4 v = __ldg(p + (long long)mb * total);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dpos)[i] = acc;
+    if (i < C4) reinterpret_cast<float4*>(dcls)[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ colsum
+// out[g][c] = sum_r x[g][r][c]. grid = (ceil(C/64), groups, row_slices); block = (32, 8); each
+// thread owns 2 columns. Row slices are combined with atomics into a zero-initialised out.
+__global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, long long gs, int rows, int C,
+                                   float* __restrict__ out, long long out_gs) {
+  __shared__ float2 sm[8][33];
+  const int g = blockIdx.y;
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  const int slices = gridDim.z;
+  const int rows_per = (rows + slices - 1) / slices;
+  const int r0 = blockIdx.z * rows_per, r1 = min(rows, r0 + rows_per);
+  float2 acc = make_float2(0.f, 0.f);
+  if (c < C) {
+    const bf16* p = x + (long long)g * gs + c;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(p + (long long)r * ldx));
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int r = 1; r < 8; ++r) {
+      acc.x += sm[r][threadIdx.x].x;
+      acc.y += sm[r][threadIdx.x].y;
+    }
+    float* o = out + (long long)g * out_gs + c;
+    atomicAdd(o, acc.x);
+    if (c + 1 < C) atomicAdd(o + 1, acc.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ gather rows
+__global__ void gather_rows_f32_kernel(const float* __restrict__ src, long long srs, long long sgs, float* __restrict__ dst,
+                                       long long drs, long long dgs, int rows, int C, int groups, int accumulate) {
+  const int C4 = C >> 2;
+  const long long total = (long long)groups * rows * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long e = i / C4;
+    const int r = (int)(e % rows);
+    const int g = (int)(e / rows);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)g * sgs + (long long)r * srs) + c4);
+    float4* d = reinterpret_cast<float4*>(dst + (long long)g * dgs + (long long)r * drs) + c4;
+    if (accumulate) {
+      float4 o = *d;
+      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      *d = o;
+    } else {
+      *d = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ classification tail
+constexpr int HEAD_MAX_CLASSES = 8;
+
+// grid = B, block = 256. logits[b][k] = (1/M) sum_m ( b2[m][k] + sum_f h[m][b][f] W2[m][k][f] )
+__global__ void head_logits_kernel(const bf16* __restrict__ h, const float* __restrict__ W2, const float* __restrict__ b2,
+                                   float* __restrict__ logits, int M, int B, int F, int classes) {
+  __shared__ float red[HEAD_MAX_CLASSES][8];
+  const int b = blockIdx.x;
+  float acc[HEAD_MAX_CLASSES];
+#pragma unroll
+  for (int k = 0; k < HEAD_MAX_CLASSES; ++k) acc[k] = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const bf16* hr = h + ((long long)m * B + b) * F;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      const float hv = __bfloat162float(hr[f]);
+#pragma unroll
+      for (int k = 0; k < HEAD_MAX_CLASSES; ++k)
+        if (k < classes) acc[k] += hv * __ldg(W2 + ((long long)m * classes + k) * F + f);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < HEAD_MAX_CLASSES; ++k) {
+    const float s = warp_sum(acc[k]);
+    if (lane == 0) red[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < classes) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+    for (int m = 0; m < M; ++m) s += b2[m * classes + threadIdx.x];
+    logits[b * classes + threadIdx.x] = s / (float)M;
+  }
+}
+
+// single block: loss = mean_b CE(logits[b], label[b]) with label smoothing
+__global__ void ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, float* __restrict__ loss,
+                               int B, int classes, float smoothing) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* z = logits + b * classes;
+    float mx = z[0];
+    for (int k = 1; k < classes; ++k) mx = fmaxf(mx, z[k]);
+    float se = 0.f, sz = 0.f;
+    for (int k = 0; k < classes; ++k) {
+      se += expf(z[k] - mx);
+      sz += z[k];
+    }
+    const float lse = mx + logf(se);
+    const float nll = lse - z[labels[b]];
+    const float smooth = lse - sz / (float)classes;
+    acc += (1.f - smoothing) * nll + smoothing * smooth;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    loss[0] = s / (float)B;
+  }
+}
+
+__device__ __forceinline__ void dlogits_row(const float* z, long long label, int classes, float smoothing, float scale,
+                                            float* dz) {
+  float mx = z[0];
+  for (int k = 1; k < classes; ++k) mx = fmaxf(mx, z[k]);
+  float se = 0.f;
+  for (int k = 0; k < classes; ++k) se += expf(z[k] - mx);
+  for (int k = 0; k < classes; ++k) {
+    const float p = expf(z[k] - mx) / se;
+    const float tgt = (1.f - smoothing) * (k == label ? 1.f : 0.f) + smoothing / (float)classes;
+    dz[k] = (p - tgt) * scale;
+  }
+}
+
+// grid = (B, M): dh[m][b][f] = sum_k dz[b][k] W2[m][k][f],  dz = dlogits / M
+__global__ void head_dh_kernel(const float* __restrict__ W2, const long long* __restrict__ labels,
+                               const float* __restrict__ logits, float scale, bf16* __restrict__ dh, int M, int B, int F,
+                               int classes, float smoothing) {
+  const int b = blockIdx.x, m = blockIdx.y;
+  float dz[HEAD_MAX_CLASSES];
+  dlogits_row(logits + b * classes, labels[b], classes, smoothing, scale / ((float)B * (float)M), dz);
+  bf16* o = dh + ((long long)m * B + b) * F;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < classes; ++k) s += dz[k] * __ldg(W2 + ((long long)m * classes + k) * F + f);
+    o[f] = __float2bfloat16(s);
+  }
+}
+
+// grid = (ceil(F/256), M): dW2[m][k][f] = sum_b dz[b][k] h[m][b][f];  block (0, m) also writes db2.
+__global__ void head_dw_kernel(const bf16* __restrict__ h, const long long* __restrict__ labels,
+                               const float* __restrict__ logits, float scale, float* __restrict__ dW2,
+                               float* __restrict__ db2, int M, int B, int F, int classes, float smoothing) {
+  const int m = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[HEAD_MAX_CLASSES], accb[HEAD_MAX_CLASSES];
+#pragma unroll
+  for (int k = 0; k < HEAD_MAX_CLASSES; ++k) acc[k] = accb[k] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float dz[HEAD_MAX_CLASSES];
+    dlogits_row(logits + b * classes, labels[b], classes, smoothing, scale / ((float)B * (float)M), dz);
+    const float hv = (f < F) ? __bfloat162float(h[((long long)m * B + b) * F + f]) : 0.f;
+#pragma unroll
+    for (int k = 0; k < HEAD_MAX_CLASSES; ++k)
+      if (k < classes) {
+        acc[k] += dz[k] * hv;
+        accb[k] += dz[k];
+      }
+  }
+  if (f < F)
+    for (int k = 0; k < classes; ++k) dW2[((long long)m * classes + k) * F + f] = acc[k];
+  if (blockIdx.x == 0 && threadIdx.x < classes) db2[m * classes + threadIdx.x] = accb[threadIdx.x];
+}
+
+static int grid_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace cavit
+
+using namespace cavit;
+
+extern "C" {
+
+int cavit_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0) return fail(CAVIT_E_BADARG, "cavit_cast_bf16: bad args");
+  if (n == 0) return CAVIT_OK;
+  cast_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+  count_launch();
+  return check_launch("cavit_cast_bf16");
+}
+
+int cavit_patchify(const float* img, void* patches, int32_t B, int32_t M, int32_t D, int32_t H, int32_t W, int32_t dp,
+                   int32_t hp, int32_t wp, void* stream) {
+  if (!img || !patches) return fail(CAVIT_E_BADARG, "cavit_patchify: null pointer");
+  if (dp <= 0 || hp <= 0 || wp <= 0 || D % dp || H % hp || W % wp)
+    return fail(CAVIT_E_BADARG, "image dimensions must be divisible by the patch size");
+  const long long P = (long long)dp * hp * wp;
+  if (P % 2) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_patchify: patch_dim must be even");
+  const long long pairs = (long long)M * B * (D / dp) * (H / hp) * (W / wp) * P / 2;
+  patchify_kernel<<<grid_for(pairs, 256), 256, 0, as_stream(stream)>>>(img, reinterpret_cast<bf16*>(patches), B, M, D, H, W,
+                                                                        dp, hp, wp);
+  count_launch();
+  return check_launch("cavit_patchify");
+}
+
+int cavit_cls_rows(const float* cls, const float* pos, float* tokens, int32_t M, int32_t B, int32_t N, int32_t C,
+                   void* stream) {
+  if (!cls || !pos || !tokens) return fail(CAVIT_E_BADARG, "cavit_cls_rows: null pointer");
+  cls_rows_kernel<<<grid_for((long long)M * B * C, 256), 256, 0, as_stream(stream)>>>(cls, pos, tokens, M * B, N, C);
+  count_launch();
+  return check_launch("cavit_cls_rows");
+}
+
+int cavit_embed_param_grads(const float* dtokens, float* dpos, float* dcls, int32_t M, int32_t B, int32_t N, int32_t C,
+                            void* stream) {
+  if (!dtokens || !dpos || !dcls || (C % 4)) return fail(CAVIT_E_BADARG, "cavit_embed_param_grads: bad args");
+  embed_param_grads_kernel<<<grid_for((long long)N * C / 4, 128), 128, 0, as_stream(stream)>>>(dtokens, dpos, dcls, M * B, N, C);
+  count_launch();
+  return check_launch("cavit_embed_param_grads");
+}
+
+int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C, int32_t groups, float* out,
+                      int64_t out_gs, void* stream) {
+  if (!x || !out || rows <= 0 || C <= 0 || (C % 2) || (ldx % 2)) return fail(CAVIT_E_BADARG, "cavit_colsum_bf16: bad args");
+  cudaStream_t st = as_stream(stream);
+  for (int g = 0; g < groups; ++g) cudaMemsetAsync(out + (long long)g * out_gs, 0, sizeof(float) * C, st);
+  int slices = rows / 512;
+  if (slices < 1) slices = 1;
+  if (slices > 64) slices = 64;
+  dim3 grid((C + 63) / 64, groups, slices), block(32, 8);
+  colsum_bf16_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, x_gs, rows, C, out, out_gs);
+  count_launch();
+  return check_launch("cavit_colsum_bf16");
+}
+
+int cavit_gather_rows_f32(const float* src, int64_t srs, int64_t sgs, float* dst, int64_t drs, int64_t dgs, int32_t rows,
+                          int32_t C, int32_t groups, int32_t accumulate, void* stream) {
+  if (!src || !dst || (C % 4) || (srs % 4) || (sgs % 4) || (drs % 4) || (dgs % 4))
+    return fail(CAVIT_E_BADARG, "cavit_gather_rows_f32: bad args");
+  gather_rows_f32_kernel<<<grid_for((long long)groups * rows * C / 4, 256), 256, 0, as_stream(stream)>>>(
+      src, srs, sgs, dst, drs, dgs, rows, C, groups, accumulate);
+  count_launch();
+  return check_launch("cavit_gather_rows_f32");
+}
+
+int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const int64_t* labels, float* logits, float* loss,
+                        int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing, void* stream) {
+  if (!h || !W2 || !b2 || !labels || !logits || !loss) return fail(CAVIT_E_BADARG, "cavit_head_loss_fwd: null pointer");
+  if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d (max %d)", classes, HEAD_MAX_CLASSES);
+  cudaStream_t st = as_stream(stream);
+  head_logits_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const bf16*>(h), W2, b2, logits, M, B, F, classes);
+  ce_loss_kernel<<<1, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), loss, B, classes, smoothing);
+  count_launch(2);
+  return check_launch("cavit_head_loss_fwd");
+}
+
+int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, const float* logits, float loss_scale,
+                        void* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing,
+                        void* stream) {
+  if (!h || !W2 || !labels || !logits || !dh || !dW2 || !db2) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: null pointer");
+  if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d", classes);
+  cudaStream_t st = as_stream(stream);
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+  head_dh_kernel<<<dim3(B, M), 256, 0, st>>>(W2, lab, logits, loss_scale, reinterpret_cast<bf16*>(dh), M, B, F, classes, smoothing);
+  head_dw_kernel<<<dim3((F + 255) / 256, M), 256, 0, st>>>(reinterpret_cast<const bf16*>(h), lab, logits, loss_scale, dW2, db2,
+                                                           M, B, F, classes, smoothing);
+  count_launch(2);
+  return check_launch("cavit_head_loss_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+/* cavit.h — C ABI of libcavit_sm100a.so, the B200 (sm_100a) cross-attention ViT hot path.
+ *
+ * The reference (vsahni3/cross-attention-ViT) has no FFI: its boundary is the Python module API
+ * (`ModelCross.forward`, /root/reference/model_cross.py:186-212; `ModelVIT.forward`,
+ * /root/reference/modelv3.py:123-147), every op of which is a torch/ATen call. Each entry point
+ * below replaces the ATen call sites named in its comment; `INTEGRATION.md` shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers owned by the caller unless marked host;
+ *   - enqueue-only on `stream` (a cudaStream_t passed as void*), no host synchronisation, safe
+ *     under CUDA-graph capture; the library keeps no pointers past a call except a cache of TMA
+ *     descriptors keyed by value;
+ *   - return 0 on success, <0 on error (CAVIT_E_*); `cavit_last_error()` gives a thread-local
+ *     message. Unsupported shapes / devices are hard errors: there is NO fallback path;
+ *   - bf16 = 2-byte bfloat16, row-major, "ld" = leading dimension in ELEMENTS, "gs" = stride
+ *     between groups (token streams / fusions) in ELEMENTS.
+ */
+#ifndef CAVIT_H_
+#define CAVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAVIT_ABI_VERSION 1
+
+enum {
+  CAVIT_OK = 0,
+  CAVIT_E_BADARG = -1,
+  CAVIT_E_UNSUPPORTED_SHAPE = -2,
+  CAVIT_E_ARCH = -3,
+  CAVIT_E_LAUNCH = -4,
+  CAVIT_E_DEVICE = -5
+};
+
+/* GEMM epilogues (fused into the tcgen05 kernel's TMEM read-out). */
+enum {
+  CAVIT_EPI_NONE = 0,          /* out = acc                                             */
+  CAVIT_EPI_BIAS = 1,          /* out = acc + bias[n]                                   */
+  CAVIT_EPI_BIAS_GELU = 2,     /* aux = u = acc + bias (bf16, pre-activation); out = GELU_erf(u) */
+  CAVIT_EPI_BIAS_RESID = 3,    /* out = acc + bias[n] + resid[m][n]   (fp32 residual stream) */
+  CAVIT_EPI_GELU_BWD = 4,      /* out = acc * GELU'(aux[m][n])        (fc2 dgrad)        */
+  CAVIT_EPI_EMBED = 5          /* out[row_map(m)][n] = acc + bias[n] + pos[1 + m % Np][n] (patch embedding) */
+};
+
+int cavit_abi_version(void);
+const char* cavit_last_error(void);
+/* 1 if device `dev` is compute capability 10.x (B200), else 0. */
+int cavit_device_ok(int dev);
+/* Synchronises the device and returns the kernel-side status word (0 = OK; 1xx = a bounded
+ * mbarrier wait timed out inside a tcgen05 kernel). `reset` != 0 clears it. */
+int cavit_device_status(int reset);
+/* Number of kernel launches issued through this library since load (bench.py's gpu_launches). */
+long long cavit_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * cavit_gemm — D[g][m][n] = sum_k A_g(m,k) * B_g(n,k), bf16 operands, fp32 accumulation in TMEM.
+ * Replaces: every nn.Linear on the path — to_qkv / to_out / FeedForward / wk,wv / patch_to_embedding
+ *   forward `addmm`s (/root/reference/model_cross.py:23-26,43-47,81-85,168) and their autograd
+ *   dgrad / wgrad `mm`s.
+ * Operand storage:  *_mn = 0  stored [rows = M or N][K], K contiguous, ld = row stride;
+ *                   *_mn = 1  stored [K][M or N],  M/N contiguous, ld = stride between k-rows.
+ *   forward  Y = X W^T      : A = X (mn 0), B = W[N][K]        (mn 0)
+ *   dgrad    dX = dY W      : A = dY (mn 0), B = W[Nout][Kin]   (mn 1, reduction over Nout)
+ *   wgrad    dW = dY^T X    : A = dY[T][Nout] (mn 1), B = X[T][Kin] (mn 1), reduction over T
+ * Requirements: K % 8 == 0, ld % 8 == 0, 16-byte aligned bases. `groups` independent problems with
+ * identical shapes are batched in one launch via the *_gs strides.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cavit_gemm_args {
+  int32_t M, N, K, groups;
+  int32_t a_mn, b_mn;
+  int32_t epi;        /* CAVIT_EPI_*                      */
+  int32_t out_fp32;   /* 0: out is bf16, 1: out is fp32   */
+  const void* A; int64_t lda, a_gs;
+  const void* B; int64_t ldb, b_gs;
+  void* out; int64_t ldo, out_gs;
+  const float* bias; int64_t bias_gs;               /* [groups][N] fp32 (NULL allowed for EPI_NONE) */
+  const float* resid; int64_t ldr, resid_gs;        /* EPI_BIAS_RESID: fp32 [M][N]; EPI_EMBED: pos [1+Np][N] */
+  void* aux; int64_t ldaux, aux_gs;                 /* EPI_BIAS_GELU: bf16 out u; EPI_GELU_BWD: bf16 in u */
+  int32_t accumulate;  /* 1: out (fp32 only) += result (used by split wgrad accumulation) */
+  int32_t embed_np;    /* EPI_EMBED: patches per sample (row m -> out row (m / Np) * (Np + 1) + 1 + m % Np) */
+} cavit_gemm_args;
+int cavit_gemm(const cavit_gemm_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over the last axis (biased variance, affine), fp32 statistics.
+ * Replaces: nn.LayerNorm inside PreNorm and the per-stream final norm
+ *   (/root/reference/model_cross.py:14-17,174,203; modelv3.py:21,115) and
+ *   `native_layer_norm_backward`.
+ * x is fp32 with arbitrary row stride; rows are split into `groups` of `rows_per_group`, group g
+ * uses gamma/beta[g][C]. y is bf16 [groups*rows_per_group][C] dense.
+ * ------------------------------------------------------------------------------------------- */
+int cavit_ln_fwd(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t rows_per_group, int32_t groups,
+                 int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16, float* mean,
+                 float* rstd, void* stream);
+/* dx[row] = (dresid ? dresid[row] : 0) + LN'(dy)[row]; optionally also written as bf16 (dx_bf16).
+ * dgamma/dbeta [groups][C] are fully reduced (two-stage, deterministic) using `partials`, a fp32
+ * workspace of cavit_ln_bwd_workspace_floats(groups, C) elements. dx may alias dresid.            */
+size_t cavit_ln_bwd_workspace_floats(int32_t groups, int32_t C);
+int cavit_ln_bwd(const void* dy_bf16, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,
+                 const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
+                 const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_bf16,
+                 float* dgamma, float* dbeta, float* partials, void* stream);
+
+/* Fused gather + LayerNorm for the cross-modal fusion input `cat(cls_i, patches_j)`
+ * (/root/reference/model_cross.py:140, 109): row 0 of every sample comes from stream cls_src[k],
+ * rows 1.. from stream tok_src[k]; fusion k uses gamma/beta[k]. streams: fp32 [M][B*N][C].
+ * y: bf16 [K][B*N][C]. cls_src/tok_src are HOST int arrays of length K (K <= 16). */
+int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, int32_t B, int32_t N, int32_t C,
+                        int32_t K, const int32_t* cls_src, const int32_t* tok_src, const float* gamma,
+                        const float* beta, float eps, void* y_bf16, float* mean, float* rstd, void* stream);
+/* Backward of the above: scatters LN'(dy) into the fp32 stream gradients (+=): row 0 into stream
+ * cls_src[k], rows 1.. into stream tok_src[k]. Rows of one destination stream never collide
+ * between fusions (a stream is CLS donor of at most one fusion; patch rows of a stream that feed
+ * several fusions are accumulated with atomics). */
+int cavit_ln_fusion_bwd(const void* dy_bf16, const float* streams, int64_t stream_gs, const float* mean,
+                        const float* rstd, const float* gamma, int32_t B, int32_t N, int32_t C, int32_t K,
+                        const int32_t* cls_src, const int32_t* tok_src, float* dstreams, float* dgamma,
+                        float* dbeta, float* partials, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-attention core softmax(Q K^T * scale) V, head_dim 64, fused online softmax on tcgen05;
+ * the N x N score matrix never leaves the SM.
+ * Replaces: Attention.forward's permute / bmm / softmax / bmm / permute chain
+ *   (/root/reference/model_cross.py:53-60, modelv3.py:59-66) and its autograd.
+ * qkv: bf16 [G][B*N][3*C] packed exactly as to_qkv writes it (q | k | v thirds, each (h d));
+ * out: bf16 [G][B*N][C] merged heads ('b h n d -> b n (h d)'); lse: fp32 [G][B][H][N].
+ * ------------------------------------------------------------------------------------------- */
+int cavit_attn_fwd(const void* qkv, void* out, float* lse, int32_t G, int32_t B, int32_t N, int32_t H,
+                   float scale, void* stream);
+/* dqkv: bf16 [G][B*N][3*C]. `delta` fp32 [G][B][H][N] workspace (rowsum(dO*O)).
+ * `dq_acc` fp32 [G][B*N][C] workspace (zero-initialised by the call). */
+int cavit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                   float* delta, float* dq_acc, int32_t G, int32_t B, int32_t N, int32_t H, float scale,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Single-query cross attention (L_q = 1): one CLS query per (sample, head) against N keys/values.
+ * Replaces: CrossAttention.forward's matmul / softmax / matmul (/root/reference/model_cross.py:95-99).
+ * q: fp32 [K][B][C]; kv: bf16 [K][B*N][2*C] (k | v halves); out: fp32 [K][B][C];
+ * probs: fp32 [K][B][H][N] saved for backward.
+ * ------------------------------------------------------------------------------------------- */
+int cavit_xattn_fwd(const float* q, const void* kv, float* out, float* probs, int32_t K, int32_t B, int32_t N,
+                    int32_t H, float scale, void* stream);
+/* dq: fp32 [K][B][C]; dkv: bf16 [K][B*N][2*C]. */
+int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const float* dout, float* dq,
+                    void* dkv, int32_t K, int32_t B, int32_t N, int32_t H, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch extraction: 'b c (d p1)(h p2)(w p3) -> b (h w d)(p1 p2 p3 c)' gather of one [B, M, 1, D, H, W]
+ * fp32 batch into bf16 patch rows [M][B*Np][P] (bit-exact index map).
+ * Replaces: einops.rearrange at /root/reference/model_cross.py:193, modelv3.py:129.
+ * ------------------------------------------------------------------------------------------- */
+int cavit_patchify(const float* img, void* patches_bf16, int32_t B, int32_t M, int32_t D, int32_t H, int32_t W,
+                   int32_t dp, int32_t hp, int32_t wp, void* stream);
+/* tokens[m][b*N + 0][:] = cls + pos[0]  for all streams/samples (/root/reference/model_cross.py:195-197). */
+int cavit_cls_rows(const float* cls, const float* pos, float* tokens, int32_t M, int32_t B, int32_t N,
+                   int32_t C, void* stream);
+/* d(pos)[n][c] = sum_{m,b} dtokens[m][b*N+n][c];  d(cls)[c] = sum_{m,b} dtokens[m][b*N][c]. */
+int cavit_embed_param_grads(const float* dtokens, float* dpos, float* dcls, int32_t M, int32_t B, int32_t N,
+                            int32_t C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small utilities.
+ * ------------------------------------------------------------------------------------------- */
+/* dst_bf16[i] = (bf16) src[i] */
+int cavit_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* out[g][c] (+)= sum_r x[g][r][c];  x bf16 [groups][rows][C] (bias gradients). */
+int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C, int32_t groups,
+                      float* out, int64_t out_gs, void* stream);
+/* Strided row copy / gather: dst[g][r][:] = src[g][r * src_row_stride ...][:C] (fp32). */
+int cavit_gather_rows_f32(const float* src, int64_t src_row_stride, int64_t src_gs, float* dst,
+                          int64_t dst_row_stride, int64_t dst_gs, int32_t rows, int32_t C, int32_t groups,
+                          int32_t accumulate, void* stream);
+
+/* Classification tail: logits = mean_m(h_m W2_m^T + b2_m); loss = CE(logits, labels, smoothing).
+ * Replaces: mlp_head[*][3], torch.mean, F.cross_entropy (/root/reference/model_cross.py:181,205-211).
+ * h: bf16 [M][B][F]; W2: fp32 [M][classes][F]; b2: fp32 [M][classes]; labels: int64 [B].
+ * logits fp32 [B][classes]; loss fp32 [1]. Backward: dh bf16 [M][B][F], dW2, db2 (overwritten). */
+int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const int64_t* labels, float* logits,
+                        float* loss, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing,
+                        void* stream);
+int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, const float* logits,
+                        float loss_scale, void* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F,
+                        int32_t classes, float smoothing, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAVIT_H_ */

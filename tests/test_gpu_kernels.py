@@ -1,0 +1,377 @@
+"""GPU parity tests of the individual CUDA kernels, called through the C ABI (cavit.ops), against
+plain PyTorch fp32/fp64 references of the same op on identical (bf16-rounded) inputs.
+
+Tolerances: GEMM / attention outputs in bf16 mode: <= 2e-2 relative (north_star); measured values
+are ~3e-3 (bf16 output rounding). fp32 outputs: <= 1e-4 relative. Index work is bit-exact."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    from cavit import _abi
+    _abi.require_device(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    assert _abi.device_status() == 0
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def status_ok():
+    from cavit import _abi
+    st = _abi.device_status()
+    assert st == 0, f"kernel-side status {st}"
+
+
+GEMM_SHAPES = [
+    # G, T(M), N, K
+    (1, 128, 128, 64),
+    (1, 256, 256, 128),
+    (2, 200, 384, 192),     # ragged M, K multiple of 64
+    (3, 197 * 3, 1152, 384),
+    (1, 77, 136, 72),       # ragged everything (K % 64 != 0, N % 32 != 0)
+    (4, 1026, 1536, 384),
+    (1, 2, 256, 128),       # skinny
+]
+
+
+@pytest.mark.parametrize("G,T,N,K", GEMM_SHAPES)
+def test_gemm_forward_layout(G, T, N, K):
+    from cavit import ops
+    torch.manual_seed(0)
+    x = bf(torch.randn(G, T, K, device=DEV))
+    w = bf(torch.randn(G, N, K, device=DEV) / math.sqrt(K))
+    want = torch.einsum("gtk,gnk->gtn", x.float(), w.float())
+    out = torch.full((G, T, N), float("nan"), device=DEV, dtype=torch.float32)
+    ops.linear_fwd(x, w, out)
+    status_ok()
+    assert rel(out, want) < 1e-5
+    outb = torch.empty((G, T, N), device=DEV, dtype=torch.bfloat16)
+    ops.linear_fwd(x, w, outb)
+    status_ok()
+    assert rel(outb, want) < 5e-3
+
+
+@pytest.mark.parametrize("G,T,N,K", GEMM_SHAPES)
+def test_gemm_dgrad_layout(G, T, N, K):
+    from cavit import ops
+    torch.manual_seed(1)
+    dy = bf(torch.randn(G, T, N, device=DEV))
+    w = bf(torch.randn(G, N, K, device=DEV) / math.sqrt(N))
+    want = torch.einsum("gtn,gnk->gtk", dy.float(), w.float())
+    out = torch.full((G, T, K), float("nan"), device=DEV, dtype=torch.float32)
+    ops.linear_dgrad(dy, w, out)
+    status_ok()
+    assert rel(out, want) < 1e-5
+
+
+@pytest.mark.parametrize("G,T,N,K", GEMM_SHAPES)
+def test_gemm_wgrad_layout(G, T, N, K):
+    from cavit import ops
+    torch.manual_seed(2)
+    dy = bf(torch.randn(G, T, N, device=DEV))
+    x = bf(torch.randn(G, T, K, device=DEV) / math.sqrt(T))
+    want = torch.einsum("gtn,gtk->gnk", dy.float(), x.float())
+    out = torch.full((G, N, K), float("nan"), device=DEV, dtype=torch.float32)
+    ops.linear_wgrad(dy, x, out)
+    status_ok()
+    assert rel(out, want) < 1e-5
+    ops.linear_wgrad(dy, x, out, accumulate=True)
+    status_ok()
+    assert rel(out, 2 * want) < 1e-5
+
+
+def test_gemm_epilogues():
+    from cavit import ops
+    from cavit._abi import EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_GELU_BWD
+    torch.manual_seed(3)
+    G, T, N, K = 2, 300, 384, 128
+    x = bf(torch.randn(G, T, K, device=DEV))
+    w = bf(torch.randn(G, N, K, device=DEV) / math.sqrt(K))
+    bias = torch.randn(G, N, device=DEV)
+    resid = torch.randn(G, T, N, device=DEV)
+    base = torch.einsum("gtk,gnk->gtn", x.float(), w.float())
+    out = torch.empty(G, T, N, device=DEV)
+    ops.linear_fwd(x, w, out, epi=EPI_BIAS, bias=bias)
+    assert rel(out, base + bias[:, None]) < 1e-5
+    ops.linear_fwd(x, w, out, epi=EPI_BIAS_RESID, bias=bias, resid=resid)
+    assert rel(out, base + bias[:, None] + resid) < 1e-5
+    # in-place residual (out aliases resid) is what the engine does
+    r2 = resid.clone()
+    ops.linear_fwd(x, w, r2, epi=EPI_BIAS_RESID, bias=bias, resid=r2)
+    assert rel(r2, base + bias[:, None] + resid) < 1e-5
+    h = torch.empty(G, T, N, device=DEV, dtype=torch.bfloat16)
+    u = torch.empty(G, T, N, device=DEV, dtype=torch.bfloat16)
+    ops.linear_fwd(x, w, h, epi=EPI_BIAS_GELU, bias=bias, aux=u)
+    u_want = base + bias[:, None]
+    assert rel(u, u_want) < 5e-3
+    assert rel(h, torch.nn.functional.gelu(u.float())) < 5e-3
+    # GELU backward epilogue on the dgrad layout: dU = (dY W) * gelu'(u)
+    dy = bf(torch.randn(G, T, K, device=DEV))   # pretend fc2: dY [T, K] -> dH [T, N] with W2 [K, N]
+    w2 = bf(torch.randn(G, K, N, device=DEV) / math.sqrt(K))
+    du = torch.empty(G, T, N, device=DEV, dtype=torch.bfloat16)
+    ops.linear_dgrad(dy, w2, du, epi=EPI_GELU_BWD, aux=u)
+    uu = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uu).backward(torch.einsum("gtk,gkn->gtn", dy.float(), w2.float()))
+    assert rel(du, uu.grad) < 5e-3
+    status_ok()
+
+
+@pytest.mark.parametrize("C", [128, 192, 384, 768, 1024])
+def test_layernorm_fwd_bwd(C):
+    from cavit import ops
+    torch.manual_seed(4)
+    G, R = 3, 173
+    x = torch.randn(G, R, C, device=DEV) * 3 + 1
+    gamma = 1 + 0.1 * torch.randn(G, C, device=DEV)
+    beta = 0.1 * torch.randn(G, C, device=DEV)
+    y = torch.empty(G, R, C, device=DEV, dtype=torch.bfloat16)
+    mean = torch.empty(G, R, device=DEV)
+    rstd = torch.empty(G, R, device=DEV)
+    ops.ln_fwd(x, gamma, beta, y, mean, rstd, rows_per_group=R, groups=G, C=C)
+    xd = x.double().requires_grad_(True)
+    gd = gamma.double().requires_grad_(True)
+    bd = beta.double().requires_grad_(True)
+    mu = xd.mean(-1, keepdim=True)
+    var = ((xd - mu) ** 2).mean(-1, keepdim=True)
+    want = (xd - mu) / torch.sqrt(var + 1e-5) * gd[:, None] + bd[:, None]
+    assert rel(y, want) < 4e-3
+    assert rel(mean, mu.squeeze(-1)) < 1e-5
+    assert rel(rstd, 1 / torch.sqrt(var.squeeze(-1) + 1e-5)) < 1e-5
+    dy = bf(torch.randn(G, R, C, device=DEV))
+    dres = torch.randn(G, R, C, device=DEV)
+    want.backward(dy.double())
+    dx = torch.empty_like(x)
+    dxb = torch.empty(G, R, C, device=DEV, dtype=torch.bfloat16)
+    dg = torch.empty(G, C, device=DEV)
+    db = torch.empty(G, C, device=DEV)
+    ws = ops.ln_bwd_workspace(G, C, DEV)
+    ops.ln_bwd(dy, x, mean, rstd, gamma, dx, dg, db, ws, rows_per_group=R, groups=G, C=C, dresid=dres, dx_bf16=dxb)
+    assert rel(dx, xd.grad + dres.double()) < 1e-4
+    assert rel(dxb, xd.grad + dres.double()) < 4e-3
+    assert rel(dg, gd.grad) < 1e-4
+    assert rel(db, bd.grad) < 1e-4
+    status_ok()
+
+
+def test_layernorm_fusion_gather_and_scatter():
+    from cavit import ops
+    torch.manual_seed(5)
+    M, B, N, C = 3, 2, 9, 128
+    cls_src, tok_src = [0, 1, 2], [1, 2, 1]   # stream 1 donates patches to two fusions
+    K = 3
+    streams = torch.randn(M, B * N, C, device=DEV)
+    gamma = 1 + 0.1 * torch.randn(K, C, device=DEV)
+    beta = 0.1 * torch.randn(K, C, device=DEV)
+    y = torch.empty(K, B * N, C, device=DEV, dtype=torch.bfloat16)
+    mean = torch.empty(K, B * N, device=DEV)
+    rstd = torch.empty(K, B * N, device=DEV)
+    ops.ln_fusion_fwd(streams, gamma, beta, y, mean, rstd, B=B, N=N, C_=C, cls_src=cls_src, tok_src=tok_src)
+    sd = streams.double().requires_grad_(True)
+    s4 = sd.view(M, B, N, C)
+    outs = []
+    for k in range(K):
+        tmp = torch.cat((s4[cls_src[k]][:, 0:1], s4[tok_src[k]][:, 1:]), dim=1)
+        outs.append(torch.nn.functional.layer_norm(tmp, (C,), gamma[k].double(), beta[k].double(), 1e-5))
+    want = torch.stack(outs).view(K, B * N, C)
+    assert rel(y, want) < 4e-3
+    dy = bf(torch.randn(K, B * N, C, device=DEV))
+    want.backward(dy.double())
+    dstreams = torch.randn(M, B * N, C, device=DEV)
+    base = dstreams.clone()
+    dg = torch.empty(K, C, device=DEV)
+    db = torch.empty(K, C, device=DEV)
+    ws = ops.ln_bwd_workspace(K, C, DEV)
+    ops.ln_fusion_bwd(dy, streams, mean, rstd, gamma, dstreams, dg, db, ws, B=B, N=N, C_=C, cls_src=cls_src,
+                      tok_src=tok_src)
+    assert rel(dstreams - base, sd.grad) < 1e-4
+    status_ok()
+
+
+@pytest.mark.parametrize("img_size,patch", [((16, 24, 8), (8, 8, 4)), ((32, 32, 1), (16, 16, 1)), ((16, 16, 16), (16, 8, 2))])
+def test_patchify_bit_exact(img_size, patch):
+    from cavit import ops
+    from oracle.functional import patchify
+    torch.manual_seed(6)
+    B, M = 2, 3
+    D, H, W = img_size
+    img = torch.randn(B, M, 1, D, H, W, device=DEV)
+    Np = (D // patch[0]) * (H // patch[1]) * (W // patch[2])
+    P = patch[0] * patch[1] * patch[2]
+    out = torch.empty(M, B * Np, P, device=DEV, dtype=torch.bfloat16)
+    ops.patchify(img, out, patch_size=patch)
+    for m in range(M):
+        want = patchify(img[:, m].cpu(), patch).to(torch.bfloat16).reshape(B * Np, P)
+        assert torch.equal(out[m].cpu(), want)   # bit-exact indexing (values are the same RNE cast)
+    status_ok()
+
+
+def test_embed_gemm_epilogue_and_cls_rows():
+    from cavit import ops
+    from cavit._abi import EPI_EMBED
+    torch.manual_seed(7)
+    M, B, Np, P, C = 2, 3, 8, 128, 128
+    N = Np + 1
+    patches = bf(torch.randn(1, M * B * Np, P, device=DEV))
+    w = bf(torch.randn(1, C, P, device=DEV) / math.sqrt(P))
+    bias = torch.randn(C, device=DEV)
+    pos = torch.randn(N, C, device=DEV)
+    cls = torch.randn(C, device=DEV)
+    tokens = torch.full((M, B * N, C), float("nan"), device=DEV)
+    ops.gemm(patches, w, tokens, M=M * B * Np, N=C, K=P, lda=P, ldb=P, ldo=C, epi=EPI_EMBED, bias=bias, resid=pos,
+             ldr=C, embed_np=Np)
+    ops.cls_rows(cls, pos, tokens, M=M, B=B, N=N, C_=C)
+    emb = (patches[0].float() @ w[0].float().T + bias).view(M, B, Np, C) + pos[1:]
+    want = torch.cat((cls.expand(M, B, 1, C) + pos[0], emb), dim=2).reshape(M, B * N, C)
+    assert rel(tokens, want) < 1e-5
+    dtok = torch.randn(M, B * N, C, device=DEV)
+    dpos = torch.empty(N, C, device=DEV)
+    dcls = torch.empty(C, device=DEV)
+    ops.embed_param_grads(dtok, dpos, dcls, M=M, B=B, N=N, C_=C)
+    assert rel(dpos, dtok.view(M * B, N, C).sum(0)) < 1e-5
+    assert rel(dcls, dtok.view(M * B, N, C)[:, 0].sum(0)) < 1e-5
+    status_ok()
+
+
+def test_colsum_cast_gather():
+    from cavit import ops
+    torch.manual_seed(8)
+    G, R, C = 3, 1500, 384
+    x = bf(torch.randn(G, R, C, device=DEV))
+    out = torch.empty(G, C, device=DEV)
+    ops.colsum_bf16(x, out, rows=R, C_=C, groups=G)
+    assert rel(out, x.float().sum(1)) < 1e-4
+    src = torch.randn(1001, device=DEV)
+    dst = torch.empty(1001, device=DEV, dtype=torch.bfloat16)
+    ops.cast_bf16(src, dst)
+    assert torch.equal(dst, src.to(torch.bfloat16))
+    s = torch.randn(G, 5 * 9, 128, device=DEV)
+    d = torch.zeros(G, 5, 128, device=DEV)
+    ops.gather_rows_f32(s, d, rows=5, C_=128, groups=G, src_row_stride=9 * 128, src_gs=45 * 128, dst_row_stride=128,
+                        dst_gs=5 * 128)
+    assert torch.equal(d, s.view(G, 5, 9, 128)[:, :, 0])
+    status_ok()
+
+
+def test_head_loss_fwd_bwd():
+    from cavit import ops
+    torch.manual_seed(9)
+    M, B, F, K = 4, 5, 256, 2
+    h = bf(torch.randn(M, B, F, device=DEV))
+    W2 = torch.randn(M, K, F, device=DEV) / math.sqrt(F)
+    b2 = torch.randn(M, K, device=DEV) * 0.1
+    labels = torch.randint(0, K, (B,), device=DEV)
+    for smoothing in (0.0, 0.1):
+        logits = torch.empty(B, K, device=DEV)
+        loss = torch.empty(1, device=DEV)
+        ops.head_loss_fwd(h, W2, b2, labels, logits, loss, M=M, B=B, F=F, classes=K, smoothing=smoothing)
+        hd = h.double().requires_grad_(True)
+        Wd = W2.double().requires_grad_(True)
+        bd = b2.double().requires_grad_(True)
+        lg = (torch.einsum("mbf,mkf->mbk", hd, Wd) + bd[:, None]).mean(0)
+        ls = torch.nn.functional.cross_entropy(lg, labels, label_smoothing=smoothing)
+        assert rel(logits, lg) < 1e-5
+        assert abs(float(loss) - float(ls)) < 1e-5
+        ls.backward()
+        dh = torch.empty(M, B, F, device=DEV, dtype=torch.bfloat16)
+        dW2 = torch.empty_like(W2)
+        db2 = torch.empty_like(b2)
+        ops.head_loss_bwd(h, W2, labels, logits, dh, dW2, db2, M=M, B=B, F=F, classes=K, smoothing=smoothing)
+        assert rel(dh, hd.grad) < 5e-3
+        assert rel(dW2, Wd.grad) < 1e-4
+        assert rel(db2, bd.grad) < 1e-4
+    status_ok()
+
+
+def _attn_ref(qkv, B, N, H):
+    """fp64 reference on the bf16-rounded packed QKV: returns O [G, B*N, C], LSE [G,B,H,N], and a
+    differentiable handle."""
+    G = qkv.shape[0]
+    C = H * 64
+    x = qkv.double().view(G, B, N, 3, H, 64).requires_grad_(True)
+    q, k, v = x[:, :, :, 0], x[:, :, :, 1], x[:, :, :, 2]            # [G,B,N,H,64]
+    s = torch.einsum("gbqhd,gbkhd->gbhqk", q, k) * 64 ** -0.5
+    lse = torch.logsumexp(s, dim=-1)
+    o = torch.einsum("gbhqk,gbkhd->gbqhd", torch.softmax(s, dim=-1), v).reshape(G, B * N, C)
+    return x, o, lse
+
+
+@pytest.mark.parametrize("G,B,N,H", [(1, 1, 128, 1), (1, 2, 64, 2), (2, 2, 197, 3), (1, 1, 513, 2), (1, 3, 9, 2),
+                                     (1, 1, 257, 1)])
+def test_attention_fwd(G, B, N, H):
+    from cavit import ops
+    torch.manual_seed(10)
+    C = H * 64
+    qkv = bf(torch.randn(G, B * N, 3 * C, device=DEV))
+    out = torch.full((G, B * N, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = torch.full((G, B, H, N), float("nan"), device=DEV)
+    ops.attn_fwd(qkv, out, lse, G=G, B=B, N=N, H=H, scale=64 ** -0.5)
+    status_ok()
+    _, o, l = _attn_ref(qkv, B, N, H)
+    assert rel(out, o) < 1e-2
+    assert rel(lse, l) < 1e-3
+
+
+@pytest.mark.parametrize("G,B,N,H", [(1, 1, 128, 1), (1, 2, 64, 2), (2, 2, 197, 3), (1, 1, 513, 2), (1, 3, 9, 2)])
+def test_attention_bwd(G, B, N, H):
+    from cavit import ops
+    torch.manual_seed(11)
+    C = H * 64
+    qkv = bf(torch.randn(G, B * N, 3 * C, device=DEV))
+    x, o, l = _attn_ref(qkv, B, N, H)
+    dout = bf(torch.randn(G, B * N, C, device=DEV))
+    o.backward(dout.double())
+    want = x.grad.reshape(G, B * N, 3 * C)
+    # feed the kernel the reference O / LSE so this test is independent of the forward kernel
+    dqkv = torch.full((G, B * N, 3 * C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    delta = torch.empty(G, B, H, N, device=DEV)
+    dq_acc = torch.empty(G, B * N, C, device=DEV)
+    ops.attn_bwd(qkv, bf(o.detach().float()), dout, l.detach().float().contiguous(), dqkv, delta, dq_acc, G=G, B=B, N=N,
+                 H=H, scale=64 ** -0.5)
+    status_ok()
+    for i, nm in enumerate("qkv"):
+        got = dqkv.view(G, B * N, 3, C)[:, :, i]
+        ref = want.view(G, B * N, 3, C)[:, :, i]
+        assert rel(got, ref) < 2e-2, nm
+
+
+@pytest.mark.parametrize("K,B,N,H", [(1, 1, 9, 1), (4, 3, 197, 2), (2, 2, 513, 3)])
+def test_single_query_cross_attention(K, B, N, H):
+    from cavit import ops
+    torch.manual_seed(12)
+    C = H * 64
+    q = torch.randn(K, B, C, device=DEV)
+    kv = bf(torch.randn(K, B * N, 2 * C, device=DEV))
+    out = torch.empty(K, B, C, device=DEV)
+    probs = torch.empty(K, B, H, N, device=DEV)
+    ops.xattn_fwd(q, kv, out, probs, K=K, B=B, N=N, H=H, scale=64 ** -0.5)
+    qd = q.double().requires_grad_(True)
+    kvd = kv.double().requires_grad_(True)
+    kk = kvd.view(K, B, N, 2, H, 64)
+    s = torch.einsum("kbhd,kbnhd->kbhn", qd.view(K, B, H, 64), kk[:, :, :, 0]) * 64 ** -0.5
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("kbhn,kbnhd->kbhd", p, kk[:, :, :, 1]).reshape(K, B, C)
+    assert rel(out, o) < 1e-4
+    assert rel(probs, p) < 1e-4
+    dout = torch.randn(K, B, C, device=DEV)
+    o.backward(dout.double())
+    dq = torch.empty(K, B, C, device=DEV)
+    dkv = torch.empty(K, B * N, 2 * C, device=DEV, dtype=torch.bfloat16)
+    ops.xattn_bwd(q, kv, probs, dout, dq, dkv, K=K, B=B, N=N, H=H, scale=64 ** -0.5)
+    assert rel(dq, qd.grad) < 1e-4
+    assert rel(dkv, kvd.grad) < 5e-3
+    status_ok()
