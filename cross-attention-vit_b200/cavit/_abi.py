@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
         ("bias", c_vp), ("bias_gs", c_i64),
         ("resid", c_vp), ("ldr", c_i64), ("resid_gs", c_i64),
         ("aux", c_vp), ("ldaux", c_i64), ("aux_gs", c_i64),
-        ("accumulate", c_i32), ("embed_np", c_i32),
+        ("accumulate", c_i32), ("split_k", c_i32), ("embed_np", c_i32),
     ]
 
 
@@ -42,22 +42,25 @@ _SIGS = {
     "cavit_ln_bwd_workspace_floats": (C.c_size_t, [c_i32, c_i32]),
     "cavit_ln_bwd": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64,
                              c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "cavit_ln_fusion_fwd": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32),
+    "cavit_ln_fusion_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32),
                                     c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
-    "cavit_ln_fusion_bwd": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
+    "cavit_ln_fusion_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
                                     C.POINTER(c_i32), C.POINTER(c_i32), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cavit_attn_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
     "cavit_attn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
     "cavit_xattn_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
     "cavit_xattn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
-    "cavit_patchify": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_patchify": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cavit_cls_rows": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cavit_embed_param_grads": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cavit_cast_bf16": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "cavit_colsum_bf16": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
-    "cavit_gather_rows_f32": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_gather_rows_f32": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_add_bf16_f32": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "cavit_gelu_bwd_bf16": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "cavit_compact_patch_rows_bf16": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cavit_head_loss_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
-    "cavit_head_loss_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
+    "cavit_head_loss_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
                                     c_f32, c_vp]),
 }
 

@@ -1,0 +1,570 @@
+"""Whole-model execution engine: runs ModelCross / ModelVIT forward and backward as a static
+sequence of C-ABI kernel launches over pre-allocated, stream-major buffers.
+
+Layout decisions (B200-first):
+  * token streams are stored stream-major, fp32 residual stream  X[g][b*N + n][c]  (g = MRI
+    sequence for ModelCross, one group for ModelVIT); every per-stream op (LayerNorm, GEMM,
+    attention) is ONE grouped launch over all streams (blockIdx / TMA coordinate = stream);
+  * all parameters live in one flat fp32 master buffer, ordered so that the per-stream copies of
+    the same weight are adjacent ([stream][out][in]); the nn.Parameters of the drop-in module are
+    views into it (state_dict keys unchanged). One cast kernel per step refreshes the flat bf16
+    operand copy; wgrad kernels write straight into a flat fp32 gradient buffer with the same
+    layout (param.grad are views; the DP all-reduce works on contiguous slabs);
+  * GEMM operands are bf16 (fp32 accumulate in TMEM); the residual stream, LayerNorm / softmax
+    statistics, LSE, logits and loss stay fp32.
+
+Reference semantics followed: /root/reference/model_cross.py:186-212 (ModelCross.forward),
+:128-148 (MultiScaleBlock), :111-114 (CrossAttentionBlock), :69-72 (SelfAttentionBlock);
+/root/reference/modelv3.py:123-147 (ModelVIT.forward).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _abi, ops
+from ._abi import EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_EMBED, EPI_GELU_BWD, EPI_NONE
+
+BF16, F32 = torch.bfloat16, torch.float32
+_ALIGN = 64  # elements; keeps every segment 16-byte aligned in bf16 and 256-byte aligned in fp32
+
+
+def _num_patches(cfg) -> int:
+    D, H, W = cfg.img_size
+    dp, hp, wp = cfg.patch_size
+    return (D // dp) * (H // hp) * (W // wp)
+
+
+class ParamLayout:
+    """Flat packing of the model parameters. `segments[name] = (offset, shape)`; `slots` maps every
+    state_dict key to (segment, element offset inside the flat buffer, shape)."""
+
+    def __init__(self):
+        self.segments: "OrderedDict[str, Tuple[int, Tuple[int, ...]]]" = OrderedDict()
+        self.slots: "OrderedDict[str, Tuple[int, Tuple[int, ...]]]" = OrderedDict()
+        self.total = 0
+        self.layer_ranges: List[Tuple[str, int, int]] = []  # (tag, start, end) in backward-completion order
+
+    def add(self, name: str, shape: Tuple[int, ...], keys: List[Tuple[str, int, Tuple[int, ...]]]):
+        """Add a packed segment; keys = [(state_dict key, element offset within the segment, shape)]."""
+        n = 1
+        for s in shape:
+            n *= s
+        off = self.total
+        self.segments[name] = (off, tuple(shape))
+        for key, rel, shp in keys:
+            self.slots[key] = (off + rel, tuple(shp))
+        self.total = off + ((n + _ALIGN - 1) // _ALIGN) * _ALIGN
+        return off
+
+
+def build_layout(kind: str, cfg) -> ParamLayout:
+    C, F, H = cfg.hidden_dim, cfg.mlp_dim, cfg.num_heads
+    M = cfg.num_modalities
+    Np = _num_patches(cfg)
+    P = cfg.patch_size[0] * cfg.patch_size[1] * cfg.patch_size[2]
+    lay = ParamLayout()
+    N = (Np + 1) if kind == "cross" else (Np * M + 1)
+    start = lay.total
+    lay.add("pos", (N, C), [("pos_embedding", 0, (1, N, C))])
+    lay.add("cls", (C,), [("cls_token", 0, (1, 1, C))])
+    lay.add("embed.w", (C, P), [("patch_to_embedding.weight", 0, (C, P))])
+    lay.add("embed.b", (C,), [("patch_to_embedding.bias", 0, (C,))])
+    lay.layer_ranges.append(("embed", start, lay.total))
+
+    def grouped(seg, shape_one, keys):
+        n = 1
+        for s in shape_one:
+            n *= s
+        lay.add(seg, (len(keys),) + tuple(shape_one), [(k, i * n, shape_one) for i, k in enumerate(keys)])
+
+    def self_block(tag, prefixes):
+        start = lay.total
+        grouped(f"{tag}.ln1.w", (C,), [p + "0.norm.weight" if kind == "vit" else p + "attn.norm.weight" for p in prefixes])
+        grouped(f"{tag}.ln1.b", (C,), [p + "0.norm.bias" if kind == "vit" else p + "attn.norm.bias" for p in prefixes])
+        a = "0.fn." if kind == "vit" else "attn.fn."
+        f = "2." if kind == "vit" else "ffn."
+        grouped(f"{tag}.wqkv", (3 * C, C), [p + a + "to_qkv.weight" for p in prefixes])
+        if H != 1:
+            grouped(f"{tag}.wo", (C, C), [p + a + "to_out.0.weight" for p in prefixes])
+            grouped(f"{tag}.bo", (C,), [p + a + "to_out.0.bias" for p in prefixes])
+        grouped(f"{tag}.ln2.w", (C,), [p + f + "norm.weight" for p in prefixes])
+        grouped(f"{tag}.ln2.b", (C,), [p + f + "norm.bias" for p in prefixes])
+        grouped(f"{tag}.w1", (F, C), [p + f + "fn.net.0.weight" for p in prefixes])
+        grouped(f"{tag}.b1", (F,), [p + f + "fn.net.0.bias" for p in prefixes])
+        grouped(f"{tag}.w2", (C, F), [p + f + "fn.net.3.weight" for p in prefixes])
+        grouped(f"{tag}.b2", (C,), [p + f + "fn.net.3.bias" for p in prefixes])
+        lay.layer_ranges.append((tag, start, lay.total))
+
+    if kind == "cross":
+        K = len(cfg.attn_order)
+        l = 0
+        for mb in range(cfg.num_multi_blocks):
+            for sb in range(cfg.num_self_blocks):
+                self_block(f"L{l}", [f"transformer.{mb}.blocks.{m}.{sb}." for m in range(M)])
+                l += 1
+            if K:
+                start = lay.total
+                pre = [f"transformer.{mb}.fusion.{k}." for k in range(K)]
+                tag = f"X{mb}"
+                grouped(f"{tag}.lnA.w", (C,), [p + "attn.norm.weight" for p in pre])
+                grouped(f"{tag}.lnA.b", (C,), [p + "attn.norm.bias" for p in pre])
+                grouped(f"{tag}.wq", (C, C), [p + "attn.fn.wq.weight" for p in pre])
+                grouped(f"{tag}.bq", (C,), [p + "attn.fn.wq.bias" for p in pre])
+                # wk | wv of one fusion adjacent: one [2C, C] operand per fusion
+                keys = []
+                for k, p in enumerate(pre):
+                    keys.append((p + "attn.fn.wk.weight", (2 * k) * C * C, (C, C)))
+                    keys.append((p + "attn.fn.wv.weight", (2 * k + 1) * C * C, (C, C)))
+                lay.add(f"{tag}.wkv", (K, 2 * C, C), keys)
+                keys = []
+                for k, p in enumerate(pre):
+                    keys.append((p + "attn.fn.wk.bias", (2 * k) * C, (C,)))
+                    keys.append((p + "attn.fn.wv.bias", (2 * k + 1) * C, (C,)))
+                lay.add(f"{tag}.bkv", (K, 2 * C), keys)
+                grouped(f"{tag}.wp", (C, C), [p + "attn.fn.proj.weight" for p in pre])
+                grouped(f"{tag}.bp", (C,), [p + "attn.fn.proj.bias" for p in pre])
+                grouped(f"{tag}.lnF.w", (C,), [p + "ffn.norm.weight" for p in pre])
+                grouped(f"{tag}.lnF.b", (C,), [p + "ffn.norm.bias" for p in pre])
+                grouped(f"{tag}.w1", (F, C), [p + "ffn.fn.net.0.weight" for p in pre])
+                grouped(f"{tag}.b1", (F,), [p + "ffn.fn.net.0.bias" for p in pre])
+                grouped(f"{tag}.w2", (C, F), [p + "ffn.fn.net.3.weight" for p in pre])
+                grouped(f"{tag}.b2", (C,), [p + "ffn.fn.net.3.bias" for p in pre])
+                lay.layer_ranges.append((tag, start, lay.total))
+        start = lay.total
+        grouped("fin.ln.w", (C,), [f"norm.{m}.weight" for m in range(M)])
+        grouped("fin.ln.b", (C,), [f"norm.{m}.bias" for m in range(M)])
+        grouped("head.w1", (F, C), [f"mlp_head.{m}.0.weight" for m in range(M)])
+        grouped("head.b1", (F,), [f"mlp_head.{m}.0.bias" for m in range(M)])
+        grouped("head.w2", (cfg.num_classes, F), [f"mlp_head.{m}.3.weight" for m in range(M)])
+        grouped("head.b2", (cfg.num_classes,), [f"mlp_head.{m}.3.bias" for m in range(M)])
+        lay.layer_ranges.append(("head", start, lay.total))
+    else:
+        for l in range(cfg.num_layers):
+            self_block(f"L{l}", [f"transformer.layers.{l}."])
+        start = lay.total
+        grouped("fin.ln.w", (C,), ["mlp_head.0.weight"])
+        grouped("fin.ln.b", (C,), ["mlp_head.0.bias"])
+        grouped("head.w1", (F, C), ["mlp_head.1.weight"])
+        grouped("head.b1", (F,), ["mlp_head.1.bias"])
+        grouped("head.w2", (cfg.num_classes, F), ["mlp_head.4.weight"])
+        grouped("head.b2", (cfg.num_classes,), ["mlp_head.4.bias"])
+        lay.layer_ranges.append(("head", start, lay.total))
+    return lay
+
+
+class Engine:
+    """Executes one model (kind = 'cross' | 'vit') on one device. Not thread-safe."""
+
+    def __init__(self, kind: str, cfg, named_params: "OrderedDict[str, torch.nn.Parameter]", device):
+        assert kind in ("cross", "vit")
+        _abi.require_device(torch.device(device).index or 0)
+        self.kind, self.cfg, self.device = kind, cfg, torch.device(device)
+        self.C, self.F, self.H = cfg.hidden_dim, cfg.mlp_dim, cfg.num_heads
+        if self.C != self.H * 64:
+            raise _abi.CavitError(f"cavit attention kernels are specialised for head_dim 64 (hidden_dim {self.C}, heads {self.H})")
+        if self.C % 64 or self.F % 8:
+            raise _abi.CavitError("hidden_dim must be a multiple of 64 and mlp_dim a multiple of 8")
+        self.Mimg = cfg.num_modalities
+        self.Np = _num_patches(cfg)
+        self.P = cfg.patch_size[0] * cfg.patch_size[1] * cfg.patch_size[2]
+        if self.P % 8:
+            raise _abi.CavitError("patch_dim must be a multiple of 8")
+        self.classes = cfg.num_classes
+        if kind == "cross":
+            self.G, self.N = self.Mimg, self.Np + 1
+            self.L = cfg.num_multi_blocks * cfg.num_self_blocks
+            order = sorted((int(i), int(j)) for i, j in dict(cfg.attn_order).items() if int(i) < self.Mimg)
+            self.cls_src = [i for i, _ in order]   # fusion k: CLS of stream cls_src[k] ...
+            self.tok_src = [j for _, j in order]   # ... attends patch tokens of stream tok_src[k]
+            self.smoothing = float(cfg.label_smoothing)
+        else:
+            self.G, self.N = 1, self.Np * self.Mimg + 1
+            self.L = cfg.num_layers
+            self.cls_src, self.tok_src = [], []
+            self.smoothing = 0.0
+        self.K = len(self.cls_src)
+        self.scale = 64 ** -0.5
+        self.layout = build_layout(kind, cfg)
+        missing = [k for k in named_params if k not in self.layout.slots]
+        extra = [k for k in self.layout.slots if k not in named_params]
+        if missing or extra:
+            raise _abi.CavitError(f"parameter schema mismatch: missing {missing[:3]} extra {extra[:3]}")
+        self.params = named_params
+        self.flat = torch.zeros(self.layout.total, dtype=F32, device=self.device)
+        self.flat_bf16 = torch.zeros(self.layout.total, dtype=BF16, device=self.device)
+        self.grad_bufs = [torch.zeros(self.layout.total, dtype=F32, device=self.device)]
+        self._grad_idx = 0
+        self._bf16_version = -1
+        self.adopt_parameters()
+        self._plan_key = None
+        self.saved_valid = False
+
+    # ------------------------------------------------------------------ parameters
+    def adopt_parameters(self):
+        """Copy current parameter values into the flat master buffer and re-point every
+        nn.Parameter at its slice (idempotent; called again if a param was re-allocated)."""
+        with torch.no_grad():
+            for key, p in self.params.items():
+                off, shp = self.layout.slots[key]
+                view = self.flat[off:off + p.numel()].view(shp)
+                if p.data_ptr() != view.data_ptr():
+                    view.copy_(p.detach().to(device=self.device, dtype=F32))
+                    p.data = view
+        self._bf16_version = -1
+
+    def _params_in_place(self) -> bool:
+        for key, p in self.params.items():
+            off, _ = self.layout.slots[key]
+            if p.data_ptr() != self.flat.data_ptr() + 4 * off:
+                return False
+        return True
+
+    def refresh_operands(self):
+        if not self._params_in_place():
+            self.adopt_parameters()
+        v = self.flat._version
+        if v != self._bf16_version:
+            ops.cast_bf16(self.flat, self.flat_bf16)
+            self._bf16_version = v
+
+    def _seg(self, buf, name):
+        off, shp = self.layout.segments[name]
+        n = 1
+        for s in shp:
+            n *= s
+        return buf[off:off + n].view(shp)
+
+    def w(self, name):
+        return self._seg(self.flat, name)
+
+    def wb(self, name):
+        return self._seg(self.flat_bf16, name)
+
+    def g(self, name):
+        return self._seg(self.grad, name)
+
+    def has(self, name):
+        return name in self.layout.segments
+
+    # ------------------------------------------------------------------ planning
+    def _plan(self, B: int, train: bool):
+        key = (B, train)
+        if self._plan_key == key:
+            return
+        dev = self.device
+        G, N, C, F, H, K = self.G, self.N, self.C, self.F, self.H, self.K
+        T = B * N
+
+        def e(shape, dt=F32):
+            return torch.empty(shape, dtype=dt, device=dev)
+
+        a: Dict[str, torch.Tensor] = {}
+        a["patches"] = e((self.Mimg * B * self.Np, self.P), BF16)
+        nL = self.L if train else 1
+        nX = 2 * self.L + 1 if train else 3
+        a["X"] = [e((G, T, C)) for _ in range(nX)]
+        for nm, shp, dt in [("xn1", (G, T, C), BF16), ("mean1", (G, T), F32), ("rstd1", (G, T), F32),
+                            ("qkv", (G, T, 3 * C), BF16), ("ao", (G, T, C), BF16), ("lse", (G, B, H, N), F32),
+                            ("xn2", (G, T, C), BF16), ("mean2", (G, T), F32), ("rstd2", (G, T), F32),
+                            ("u", (G, T, F), BF16), ("h", (G, T, F), BF16)]:
+            a[nm] = [e(shp, dt) for _ in range(nL)]
+        if K:
+            nF = self.cfg.num_multi_blocks if train else 1
+            for nm, shp, dt in [("f_cls", (K, B, C), F32), ("f_xn", (K, T, C), BF16), ("f_mean", (K, T), F32),
+                                ("f_rstd", (K, T), F32), ("f_kv", (K, T, 2 * C), BF16), ("f_q", (K, B, C), F32),
+                                ("f_probs", (K, B, H, N), F32), ("f_xo", (K, B, C), F32), ("f_xob", (K, B, C), BF16),
+                                ("f_y", (K, B, C), F32), ("f_yn", (K, B, C), BF16), ("f_meany", (K, B), F32),
+                                ("f_rstdy", (K, B), F32), ("f_u", (K, B, F), BF16), ("f_h", (K, B, F), BF16),
+                                ("f_z", (K, B, C), F32)]:
+                a[nm] = [e(shp, dt) for _ in range(nF)]
+        a["clsn"] = e((G, B, C), BF16)
+        a["meanc"], a["rstdc"] = e((G, B)), e((G, B))
+        a["uh"], a["hh"] = e((G, B, F), BF16), e((G, B, F), BF16)
+        a["logits"], a["loss"] = e((B, self.classes)), e((1,))
+        if train:
+            a["dX"], a["dXb"] = e((G, T, C)), e((G, T, C), BF16)
+            a["dbig"] = e((G, T, F), BF16)
+            a["dmid"] = e((G, T, C), BF16)
+            a["dqkv"] = e((G, T, 3 * C), BF16)
+            a["delta"] = e((G, B, H, N))
+            a["dq_acc"] = e((G, T, C))
+            a["ln_ws"] = ops.ln_bwd_workspace(max(G, K, 1), C, dev)
+            a["dhh"], a["duh"], a["dclsn"] = e((G, B, F), BF16), e((G, B, F), BF16), e((G, B, C), BF16)
+            a["dcomp"] = e((self.Mimg * B * self.Np, C), BF16)
+            if K:
+                a["d_z"], a["d_zb"] = e((K, B, C)), e((K, B, C), BF16)
+                a["d_u"], a["d_yn"] = e((K, B, F), BF16), e((K, B, C), BF16)
+                a["d_y"], a["d_yb"] = e((K, B, C)), e((K, B, C), BF16)
+                a["d_xo"], a["d_q"], a["d_qb"] = e((K, B, C)), e((K, B, C)), e((K, B, C), BF16)
+                a["d_kv"], a["d_xn"] = e((K, T, 2 * C), BF16), e((K, T, C), BF16)
+                a["d_xncls"] = e((K, B, C))
+        self.a = a
+        self._plan_key = key
+        self.B, self.T = B, T
+        self.saved_valid = False
+
+    # ------------------------------------------------------------------ GEMM helpers
+    def _split_for(self, G, N_out, K_in, T):
+        tiles = G * ((N_out + 127) // 128) * ((K_in + 127) // 128)
+        want = (2 * 148 + tiles - 1) // tiles
+        kb = (T + 63) // 64
+        return max(1, min(want, kb // 4 if kb >= 8 else 1, 64))
+
+    def _fwd(self, x, w, out, *, G, T, N, K, epi=EPI_NONE, bias=None, resid=None, aux=None, lda=None, a_gs=None):
+        lda = K if lda is None else lda
+        a_gs = T * lda if a_gs is None else a_gs
+        ops.gemm(x, w, out, M=T, N=N, K=K, groups=G, lda=lda, ldb=K, ldo=N, a_gs=a_gs, b_gs=N * K, out_gs=T * N,
+                 epi=epi, bias=bias, bias_gs=N, resid=resid, ldr=N, resid_gs=T * N, aux=aux, ldaux=N, aux_gs=T * N)
+
+    def _dgrad(self, dy, w, out, *, G, T, N, K, epi=EPI_NONE, aux=None):
+        """dX[T,K] = dY[T,N] W[N,K]."""
+        ops.gemm(dy, w, out, M=T, N=K, K=N, groups=G, a_mn=False, b_mn=True, lda=N, ldb=K, ldo=K, a_gs=T * N,
+                 b_gs=N * K, out_gs=T * K, epi=epi, aux=aux, ldaux=K, aux_gs=T * K)
+
+    def _wgrad(self, dy, x, dw, *, G, T, N, K, ldx=None, x_gs=None):
+        """dW[N,K] = dY[T,N]^T X[T,K] (fp32, written into the flat gradient buffer)."""
+        ldx = K if ldx is None else ldx
+        x_gs = T * ldx if x_gs is None else x_gs
+        ops.gemm(dy, x, dw, M=N, N=K, K=T, groups=G, a_mn=True, b_mn=True, lda=N, ldb=ldx, ldo=K, a_gs=T * N,
+                 b_gs=x_gs, out_gs=N * K, split_k=self._split_for(G, N, K, T))
+
+    def _colsum(self, x, out, *, G, T, N):
+        ops.colsum_bf16(x, out, rows=T, C_=N, groups=G)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, img: torch.Tensor, labels: torch.Tensor, train: bool):
+        cfg = self.cfg
+        if img.dim() != 6 or img.shape[1] != self.Mimg or tuple(img.shape[3:]) != tuple(cfg.img_size) or img.shape[2] != 1:
+            raise _abi.CavitError(f"img must be [B, {self.Mimg}, 1, {tuple(cfg.img_size)}], got {tuple(img.shape)}")
+        if img.dtype != F32 or not img.is_cuda:
+            raise _abi.CavitError("img must be a float32 CUDA tensor")
+        img = img.contiguous()
+        labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
+        B = img.shape[0]
+        self._plan(B, train)
+        self.refresh_operands()
+        a, G, N, C, F, H, T, K = self.a, self.G, self.N, self.C, self.F, self.H, self.T, self.K
+        # ---- tokenisation: unfold -> embedding GEMM (+bias +pos, CLS-skipping row map) -> CLS rows
+        ops.patchify(img, a["patches"], patch_size=cfg.patch_size, sample_major=(self.kind == "vit"))
+        np_seq = self.N - 1
+        X0 = a["X"][0]
+        ops.gemm(a["patches"], self.wb("embed.w"), X0, M=self.Mimg * B * self.Np, N=C, K=self.P, lda=self.P,
+                 ldb=self.P, ldo=C, epi=EPI_EMBED, bias=self.w("embed.b"), resid=self.w("pos"), ldr=C, embed_np=np_seq)
+        ops.cls_rows(self.w("cls"), self.w("pos"), X0, M=G, B=B, N=N, C_=C)
+        xi = 0
+        for l in range(self.L):
+            s = l if train else 0
+            if train:
+                x_in, x_mid, x_out = a["X"][2 * l], a["X"][2 * l + 1], a["X"][2 * l + 2]
+            else:
+                x_in, x_mid, x_out = a["X"][xi], a["X"][(xi + 1) % 3], a["X"][(xi + 2) % 3]
+                xi = (xi + 2) % 3
+            tag = f"L{l}"
+            ops.ln_fwd(x_in, self.w(f"{tag}.ln1.w"), self.w(f"{tag}.ln1.b"), a["xn1"][s], a["mean1"][s], a["rstd1"][s],
+                       rows_per_group=T, groups=G, C=C)
+            self._fwd(a["xn1"][s], self.wb(f"{tag}.wqkv"), a["qkv"][s], G=G, T=T, N=3 * C, K=C)
+            ops.attn_fwd(a["qkv"][s], a["ao"][s], a["lse"][s], G=G, B=B, N=N, H=H, scale=self.scale)
+            if H != 1:
+                self._fwd(a["ao"][s], self.wb(f"{tag}.wo"), x_mid, G=G, T=T, N=C, K=C, epi=EPI_BIAS_RESID,
+                          bias=self.w(f"{tag}.bo"), resid=x_in)
+            else:  # to_out = nn.Identity() when heads == 1 (model_cross.py:37,44-48)
+                ops.add_bf16_f32(x_in, a["ao"][s], x_mid)
+            ops.ln_fwd(x_mid, self.w(f"{tag}.ln2.w"), self.w(f"{tag}.ln2.b"), a["xn2"][s], a["mean2"][s], a["rstd2"][s],
+                       rows_per_group=T, groups=G, C=C)
+            self._fwd(a["xn2"][s], self.wb(f"{tag}.w1"), a["h"][s], G=G, T=T, N=F, K=C, epi=EPI_BIAS_GELU,
+                      bias=self.w(f"{tag}.b1"), aux=a["u"][s])
+            self._fwd(a["h"][s], self.wb(f"{tag}.w2"), x_out, G=G, T=T, N=C, K=F, epi=EPI_BIAS_RESID,
+                      bias=self.w(f"{tag}.b2"), resid=x_mid)
+            if self.kind == "cross" and K and (l + 1) % cfg.num_self_blocks == 0:
+                self._fusion_fwd(l // cfg.num_self_blocks, x_out, train)
+        x_fin = a["X"][2 * self.L] if train else a["X"][xi]
+        self._x_fin = x_fin
+        # ---- final norm on the CLS rows only (row 0 is all the reference consumes), heads, loss
+        ops.ln_fwd(x_fin, self.w("fin.ln.w"), self.w("fin.ln.b"), a["clsn"], a["meanc"], a["rstdc"], rows_per_group=B,
+                   groups=G, C=C, x_row_stride=N * C, x_gs=T * C)
+        self._fwd(a["clsn"], self.wb("head.w1"), a["hh"], G=G, T=B, N=F, K=C, epi=EPI_BIAS_GELU, bias=self.w("head.b1"),
+                  aux=a["uh"])
+        ops.head_loss_fwd(a["hh"], self.w("head.w2"), self.w("head.b2"), labels, a["logits"], a["loss"], M=G, B=B, F=F,
+                          classes=self.classes, smoothing=self.smoothing)
+        self._labels = labels
+        self.saved_valid = train
+        return a["logits"], a["loss"]
+
+    def _fusion_fwd(self, mb: int, X: torch.Tensor, train: bool):
+        """CrossAttentionBlock over all K fusions of multi-block `mb`; rewrites the CLS rows of the
+        receiving streams in place (outs[i] = cat(new_cls, attn[i][:, 1:]), model_cross.py:142)."""
+        a, N, C, F, H, T, K, B = self.a, self.N, self.C, self.F, self.H, self.T, self.K, self.B
+        s = mb if train else 0
+        tag = f"X{mb}"
+        f_cls = a["f_cls"][s]
+        for k in range(K):  # save the CLS rows the fusions read (they are overwritten below)
+            ops.gather_rows_f32(X[self.cls_src[k]], f_cls[k], rows=B, C_=C, groups=1, src_row_stride=N * C, src_gs=0,
+                                dst_row_stride=C, dst_gs=0)
+        ops.ln_fusion_fwd(X, f_cls, self.w(f"{tag}.lnA.w"), self.w(f"{tag}.lnA.b"), a["f_xn"][s], a["f_mean"][s],
+                          a["f_rstd"][s], B=B, N=N, C_=C, cls_src=self.cls_src, tok_src=self.tok_src)
+        # K | V projection of every token, one [T, 2C] GEMM per fusion (grouped)
+        self._fwd(a["f_xn"][s], self.wb(f"{tag}.wkv"), a["f_kv"][s], G=K, T=T, N=2 * C, K=C, epi=EPI_BIAS,
+                  bias=self.w(f"{tag}.bkv"))
+        # query from the CLS row only: rows b*N of xn (row stride N*C)
+        self._fwd(a["f_xn"][s], self.wb(f"{tag}.wq"), a["f_q"][s], G=K, T=B, N=C, K=C, epi=EPI_BIAS,
+                  bias=self.w(f"{tag}.bq"), lda=N * C, a_gs=T * C)
+        ops.xattn_fwd(a["f_q"][s], a["f_kv"][s], a["f_xo"][s], a["f_probs"][s], K=K, B=B, N=N, H=H, scale=self.scale)
+        ops.cast_bf16(a["f_xo"][s], a["f_xob"][s])
+        self._fwd(a["f_xob"][s], self.wb(f"{tag}.wp"), a["f_y"][s], G=K, T=B, N=C, K=C, epi=EPI_BIAS_RESID,
+                  bias=self.w(f"{tag}.bp"), resid=f_cls)
+        ops.ln_fwd(a["f_y"][s], self.w(f"{tag}.lnF.w"), self.w(f"{tag}.lnF.b"), a["f_yn"][s], a["f_meany"][s],
+                   a["f_rstdy"][s], rows_per_group=B, groups=K, C=C)
+        self._fwd(a["f_yn"][s], self.wb(f"{tag}.w1"), a["f_h"][s], G=K, T=B, N=F, K=C, epi=EPI_BIAS_GELU,
+                  bias=self.w(f"{tag}.b1"), aux=a["f_u"][s])
+        self._fwd(a["f_h"][s], self.wb(f"{tag}.w2"), a["f_z"][s], G=K, T=B, N=C, K=F, epi=EPI_BIAS_RESID,
+                  bias=self.w(f"{tag}.b2"), resid=a["f_y"][s])
+        for k in range(K):
+            ops.gather_rows_f32(a["f_z"][s][k], X[self.cls_src[k]], rows=B, C_=C, groups=1, src_row_stride=C, src_gs=0,
+                                dst_row_stride=N * C, dst_gs=0)
+
+    # ------------------------------------------------------------------ backward
+    def _next_grad_buffer(self):
+        """Gradient buffer for this backward. If a parameter's .grad still aliases the candidate
+        (gradient accumulation without zero_grad), switch to another buffer so nothing is clobbered."""
+        def aliased(buf):
+            lo, hi = buf.data_ptr(), buf.data_ptr() + 4 * buf.numel()
+            for p in self.params.values():
+                if p.grad is not None and lo <= p.grad.data_ptr() < hi:
+                    return True
+            return False
+        for i, buf in enumerate(self.grad_bufs):
+            if not aliased(buf):
+                self._grad_idx = i
+                return buf
+        self.grad_bufs.append(torch.zeros(self.layout.total, dtype=F32, device=self.device))
+        self._grad_idx = len(self.grad_bufs) - 1
+        return self.grad_bufs[-1]
+
+    def backward(self, loss_scale: float = 1.0, on_range_done=None, loss_scale_dev: Optional[torch.Tensor] = None):
+        """Backward of the last training forward. Fills the flat gradient buffer and returns it.
+        `on_range_done(tag, start, end)` is called right after the kernels producing the gradients
+        of flat range [start, end) have been enqueued (used to overlap the DP all-reduce)."""
+        if not self.saved_valid:
+            raise _abi.CavitError("backward() without a preceding training forward()")
+        self.saved_valid = False
+        cfg = self.cfg
+        a, G, N, C, F, H, T, K, B = self.a, self.G, self.N, self.C, self.F, self.H, self.T, self.K, self.B
+        self.grad = self._next_grad_buffer()
+        ranges = {t: (s, e_) for t, s, e_ in self.layout.layer_ranges}
+
+        def done(tag):
+            if on_range_done is not None:
+                s, e_ = ranges[tag]
+                on_range_done(tag, s, e_)
+
+        ws = a["ln_ws"]
+        # ---- loss, heads, final norm
+        ops.head_loss_bwd(a["hh"], self.w("head.w2"), self._labels, a["logits"], a["dhh"], self.g("head.w2"),
+                          self.g("head.b2"), M=G, B=B, F=F, classes=self.classes, smoothing=self.smoothing,
+                          loss_scale=loss_scale, loss_scale_dev=loss_scale_dev)
+        ops.gelu_bwd_bf16(a["dhh"], a["uh"], a["duh"])
+        self._dgrad(a["duh"], self.wb("head.w1"), a["dclsn"], G=G, T=B, N=F, K=C)
+        self._wgrad(a["duh"], a["clsn"], self.g("head.w1"), G=G, T=B, N=F, K=C)
+        self._colsum(a["duh"], self.g("head.b1"), G=G, T=B, N=F)
+        dX, dXb = a["dX"], a["dXb"]
+        dX.zero_()
+        ops.ln_bwd(a["dclsn"], self._x_fin, a["meanc"], a["rstdc"], self.w("fin.ln.w"), dX, self.g("fin.ln.w"),
+                   self.g("fin.ln.b"), ws, rows_per_group=B, groups=G, C=C, x_row_stride=N * C, x_gs=T * C,
+                   dx_row_stride=N * C, dx_gs=T * C)
+        done("head")
+        need_cast = True  # dXb must mirror dX before the first layer's GEMMs
+        for l in reversed(range(self.L)):
+            tag = f"L{l}"
+            if self.kind == "cross" and K and (l + 1) % cfg.num_self_blocks == 0:
+                self._fusion_bwd(l // cfg.num_self_blocks, dX)
+                done(f"X{l // cfg.num_self_blocks}")
+                need_cast = True
+            if need_cast:
+                ops.cast_bf16(dX, dXb)
+                need_cast = False
+            x_in, x_mid = a["X"][2 * l], a["X"][2 * l + 1]
+            # FFN: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
+            self._dgrad(dXb, self.wb(f"{tag}.w2"), a["dbig"], G=G, T=T, N=C, K=F, epi=EPI_GELU_BWD, aux=a["u"][l])
+            self._wgrad(dXb, a["h"][l], self.g(f"{tag}.w2"), G=G, T=T, N=C, K=F)
+            self._colsum(dXb, self.g(f"{tag}.b2"), G=G, T=T, N=C)
+            self._dgrad(a["dbig"], self.wb(f"{tag}.w1"), a["dmid"], G=G, T=T, N=F, K=C)
+            self._wgrad(a["dbig"], a["xn2"][l], self.g(f"{tag}.w1"), G=G, T=T, N=F, K=C)
+            self._colsum(a["dbig"], self.g(f"{tag}.b1"), G=G, T=T, N=F)
+            ops.ln_bwd(a["dmid"], x_mid, a["mean2"][l], a["rstd2"][l], self.w(f"{tag}.ln2.w"), dX, self.g(f"{tag}.ln2.w"),
+                       self.g(f"{tag}.ln2.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX, dx_bf16=dXb)
+            # attention: x_mid = x_in + Wo attn(LN1(x_in)) + bo
+            if H != 1:
+                self._dgrad(dXb, self.wb(f"{tag}.wo"), a["dmid"], G=G, T=T, N=C, K=C)
+                self._wgrad(dXb, a["ao"][l], self.g(f"{tag}.wo"), G=G, T=T, N=C, K=C)
+                self._colsum(dXb, self.g(f"{tag}.bo"), G=G, T=T, N=C)
+                dao = a["dmid"]
+            else:
+                dao = dXb
+            ops.attn_bwd(a["qkv"][l], a["ao"][l], dao, a["lse"][l], a["dqkv"], a["delta"], a["dq_acc"], G=G, B=B, N=N,
+                         H=H, scale=self.scale)
+            self._dgrad(a["dqkv"], self.wb(f"{tag}.wqkv"), a["dmid"], G=G, T=T, N=3 * C, K=C)
+            self._wgrad(a["dqkv"], a["xn1"][l], self.g(f"{tag}.wqkv"), G=G, T=T, N=3 * C, K=C)
+            ops.ln_bwd(a["dmid"], x_in, a["mean1"][l], a["rstd1"][l], self.w(f"{tag}.ln1.w"), dX, self.g(f"{tag}.ln1.w"),
+                       self.g(f"{tag}.ln1.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX, dx_bf16=dXb)
+            done(tag)
+        # ---- embedding: d(pos), d(cls), dW = dY^T unfold(x), db
+        ops.embed_param_grads(dX, self.g("pos"), self.g("cls"), M=G, B=B, N=N, C_=C)
+        np_seq = self.N - 1
+        ops.compact_patch_rows_bf16(dXb, a["dcomp"], S=G * B, Np=np_seq, C_=C)
+        R = self.Mimg * B * self.Np
+        self._wgrad(a["dcomp"], a["patches"], self.g("embed.w"), G=1, T=R, N=C, K=self.P)
+        self._colsum(a["dcomp"], self.g("embed.b"), G=1, T=R, N=C)
+        done("embed")
+        return self.grad
+
+    def _fusion_bwd(self, mb: int, dX: torch.Tensor):
+        a, N, C, F, H, T, K, B = self.a, self.N, self.C, self.F, self.H, self.T, self.K, self.B
+        tag = f"X{mb}"
+        ws = a["ln_ws"]
+        s = mb
+        d_z = a["d_z"]
+        # gradient of the new CLS rows; the old CLS rows of receiving streams get no pass-through gradient
+        for k in range(K):
+            ops.gather_rows_f32(dX[self.cls_src[k]], d_z[k], rows=B, C_=C, groups=1, src_row_stride=N * C, src_gs=0,
+                                dst_row_stride=C, dst_gs=0, zero_src=True)
+        ops.cast_bf16(d_z, a["d_zb"])
+        # FFN on the single CLS token
+        self._dgrad(a["d_zb"], self.wb(f"{tag}.w2"), a["d_u"], G=K, T=B, N=C, K=F, epi=EPI_GELU_BWD, aux=a["f_u"][s])
+        self._wgrad(a["d_zb"], a["f_h"][s], self.g(f"{tag}.w2"), G=K, T=B, N=C, K=F)
+        self._colsum(a["d_zb"], self.g(f"{tag}.b2"), G=K, T=B, N=C)
+        self._dgrad(a["d_u"], self.wb(f"{tag}.w1"), a["d_yn"], G=K, T=B, N=F, K=C)
+        self._wgrad(a["d_u"], a["f_yn"][s], self.g(f"{tag}.w1"), G=K, T=B, N=F, K=C)
+        self._colsum(a["d_u"], self.g(f"{tag}.b1"), G=K, T=B, N=F)
+        ops.ln_bwd(a["d_yn"], a["f_y"][s], a["f_meany"][s], a["f_rstdy"][s], self.w(f"{tag}.lnF.w"), a["d_y"],
+                   self.g(f"{tag}.lnF.w"), self.g(f"{tag}.lnF.b"), ws, rows_per_group=B, groups=K, C=C, dresid=d_z,
+                   dx_bf16=a["d_yb"])
+        # y = proj(xattn) + cls_in
+        self._dgrad(a["d_yb"], self.wb(f"{tag}.wp"), a["d_xo"], G=K, T=B, N=C, K=C)
+        self._wgrad(a["d_yb"], a["f_xob"][s], self.g(f"{tag}.wp"), G=K, T=B, N=C, K=C)
+        self._colsum(a["d_yb"], self.g(f"{tag}.bp"), G=K, T=B, N=C)
+        ops.xattn_bwd(a["f_q"][s], a["f_kv"][s], a["f_probs"][s], a["d_xo"], a["d_q"], a["d_kv"], K=K, B=B, N=N, H=H,
+                      scale=self.scale)
+        # query path (CLS row of xn only)
+        ops.cast_bf16(a["d_q"], a["d_qb"])
+        self._dgrad(a["d_qb"], self.wb(f"{tag}.wq"), a["d_xncls"], G=K, T=B, N=C, K=C)
+        self._wgrad(a["d_qb"], a["f_xn"][s], self.g(f"{tag}.wq"), G=K, T=B, N=C, K=C, ldx=N * C, x_gs=T * C)
+        self._colsum(a["d_qb"], self.g(f"{tag}.bq"), G=K, T=B, N=C)
+        # key / value path (all tokens)
+        self._dgrad(a["d_kv"], self.wb(f"{tag}.wkv"), a["d_xn"], G=K, T=T, N=2 * C, K=C)
+        self._wgrad(a["d_kv"], a["f_xn"][s], self.g(f"{tag}.wkv"), G=K, T=T, N=2 * C, K=C)
+        self._colsum(a["d_kv"], self.g(f"{tag}.bkv"), G=K, T=T, N=2 * C)
+        # LayerNorm of cat(cls_i, patches_j): scatter-add into the stream gradients
+        ops.ln_fusion_bwd(a["d_xn"], self._x_for_fusion(mb), a["f_cls"][s], a["f_mean"][s], a["f_rstd"][s],
+                          self.w(f"{tag}.lnA.w"), dX, self.g(f"{tag}.lnA.w"), self.g(f"{tag}.lnA.b"), ws, B=B, N=N, C_=C,
+                          cls_src=self.cls_src, tok_src=self.tok_src, dy_cls=a["d_xncls"])
+        # residual path of the CLS token: y = ... + cls_in
+        for k in range(K):
+            ops.gather_rows_f32(a["d_y"][k], dX[self.cls_src[k]], rows=B, C_=C, groups=1, src_row_stride=C, src_gs=0,
+                                dst_row_stride=N * C, dst_gs=0, accumulate=True)
+
+    def _x_for_fusion(self, mb: int) -> torch.Tensor:
+        # streams as the fusion saw them (patch rows are untouched by the in-place CLS rewrite)
+        return self.a["X"][2 * (mb + 1) * self.cfg.num_self_blocks]

@@ -1,0 +1,289 @@
+"""Drop-in module classes: same constructor argument (one config attribute bag), same module tree /
+``state_dict`` keys / initialisation order, same ``forward(img, labels) -> (logits, loss)`` as the
+reference's ``ModelCross`` (/root/reference/model_cross.py:152-212) and ``ModelVIT``
+(/root/reference/modelv3.py:90-147) — but ``forward`` runs the sm_100a kernel path of
+``cavit.engine`` instead of ATen ops.
+
+The sub-modules below exist to own the parameters under the reference's names (so reference
+checkpoints load and `torch.manual_seed(s)` reproduces the reference's random init); the compute
+is done by the whole-model engine, which fuses across them.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+from .engine import Engine
+
+try:  # the reference derives from lightning.LightningModule; keep that when lightning exists
+    import lightning as _L
+    _Base = _L.LightningModule
+except Exception:  # pragma: no cover - lightning is not installed in the build image
+    class _Base(nn.Module):
+        def log(self, *args, **kwargs):
+            return None
+
+
+def _engine_only(name):
+    def forward(self, *a, **k):
+        raise _abi.CavitError(
+            f"{name} is a parameter container in cavit; call the top-level model's forward(img, labels), "
+            "which runs the fused sm_100a path")
+    return forward
+
+
+class PreNorm(nn.Module):
+    def __init__(self, config, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(config.hidden_dim)
+        self.fn = fn
+    forward = _engine_only("PreNorm")
+
+
+class FeedForward(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(config.hidden_dim, config.mlp_dim), nn.GELU(), nn.Dropout(config.dropout),
+                                 nn.Linear(config.mlp_dim, config.hidden_dim), nn.Dropout(config.dropout))
+    forward = _engine_only("FeedForward")
+
+
+class Attention(nn.Module):
+    def __init__(self, config, dim_head):
+        super().__init__()
+        inner = dim_head * config.num_heads
+        assert inner == config.hidden_dim
+        self.heads = config.num_heads
+        self.scale = dim_head ** -0.5
+        self.attend = nn.Softmax(dim=-1)
+        self.to_qkv = nn.Linear(config.hidden_dim, inner * 3, bias=False)
+        # the reference drops the output projection when there is a single head spanning hidden_dim
+        single = config.num_heads == 1 and dim_head == config.hidden_dim
+        self.to_out = nn.Identity() if single else nn.Sequential(nn.Linear(inner, config.hidden_dim),
+                                                                 nn.Dropout(config.dropout))
+    forward = _engine_only("Attention")
+
+
+class SelfAttentionBlock(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.attn = PreNorm(config, Attention(config, dim_head=config.hidden_dim // config.num_heads))
+        self.ffn = PreNorm(config, FeedForward(config))
+    forward = _engine_only("SelfAttentionBlock")
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.num_heads = config.num_heads
+        self.scale = (config.hidden_dim // config.num_heads) ** -0.5
+        self.wq = nn.Linear(config.hidden_dim, config.hidden_dim)
+        self.wk = nn.Linear(config.hidden_dim, config.hidden_dim)
+        self.wv = nn.Linear(config.hidden_dim, config.hidden_dim)
+        self.attn_drop = nn.Dropout(config.dropout)
+        self.proj = nn.Linear(config.hidden_dim, config.hidden_dim)
+        self.proj_drop = nn.Dropout(config.dropout)
+    forward = _engine_only("CrossAttention")
+
+
+class CrossAttentionBlock(nn.Module):
+    def __init__(self, config, act_layer=nn.GELU):
+        super().__init__()
+        self.attn = PreNorm(config, CrossAttention(config))
+        self.ffn = PreNorm(config, FeedForward(config))
+    forward = _engine_only("CrossAttentionBlock")
+
+
+class MultiScaleBlock(nn.Module):
+    def __init__(self, config, act_layer=nn.GELU):
+        super().__init__()
+        self.attn_order = config.attn_order
+        self.blocks = nn.ModuleList([
+            nn.Sequential(*[SelfAttentionBlock(config) for _ in range(config.num_self_blocks)])
+            for _ in range(config.num_modalities)])
+        self.fusion = nn.ModuleList([CrossAttentionBlock(config) for _ in range(len(self.attn_order))])
+    forward = _engine_only("MultiScaleBlock")
+
+
+class Transformer(nn.Module):
+    """ModelVIT's encoder stack (/root/reference/modelv3.py:69-88): per layer
+    [PreNorm(Attention), StochasticDepth(0), PreNorm(FeedForward), StochasticDepth(0)]."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(config.num_layers):
+            self.layers.append(nn.ModuleList([
+                PreNorm(config, Attention(config, dim_head=config.hidden_dim // config.num_heads)),
+                nn.Identity(),  # StochasticDepth(p=0, mode="row") is the identity and owns no parameters
+                PreNorm(config, FeedForward(config)),
+                nn.Identity(),
+            ]))
+    forward = _engine_only("Transformer")
+
+
+class _CavitFn(torch.autograd.Function):
+    """One autograd node for the whole model: forward and backward are static kernel sequences."""
+
+    @staticmethod
+    def forward(ctx, engine, img, labels, *params):
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        logits, loss = engine.forward(img, labels, train=train)
+        ctx.engine = engine
+        ctx.train = train
+        ctx.mark_non_differentiable(logits_out := logits.clone())
+        return logits_out, loss.reshape(()).clone()
+
+    @staticmethod
+    def backward(ctx, _dlogits, dloss):
+        eng = ctx.engine
+        hook = getattr(eng, "on_range_done", None)
+        scale_dev = None
+        if dloss is not None:  # consumed on the device: no host synchronisation between fwd and bwd
+            scale_dev = dloss.detach().to(device=eng.device, dtype=torch.float32).reshape(1).contiguous()
+        flat = eng.backward(loss_scale=1.0, on_range_done=hook, loss_scale_dev=scale_dev)
+        grads = []
+        for key, p in eng.params.items():
+            if p.requires_grad:
+                off, shp = eng.layout.slots[key]
+                grads.append(flat[off:off + p.numel()].view(shp))
+            else:
+                grads.append(None)
+        return (None, None, None, *grads)
+
+
+class _CavitModel(_Base):
+    _kind = "cross"
+
+    def _post_init(self, config):
+        self.config = config
+        self.patch_size = config.patch_size
+        self.lr = config.lr
+        self.weight_decay = config.weight_decay
+        self.optim_params = config.optim_params
+        self._dropout_p = float(config.dropout)
+        self._engine_obj = None
+        self.initialize_model()
+
+    @staticmethod
+    def init_weights(module):
+        if isinstance(module, nn.Linear):
+            nn.init.xavier_uniform_(module.weight)
+            if module.bias is not None:
+                nn.init.zeros_(module.bias)
+        elif isinstance(module, nn.LayerNorm):
+            nn.init.ones_(module.weight)
+            nn.init.zeros_(module.bias)
+
+    def initialize_model(self):
+        self.apply(type(self).init_weights)
+        nn.init.normal_(self.pos_embedding, mean=0.0, std=0.02)
+        nn.init.normal_(self.cls_token, mean=0.0, std=0.02)
+
+    # ---------------------------------------------------------------- engine plumbing
+    def engine(self) -> Engine:
+        dev = self.pos_embedding.device
+        if dev.type != "cuda":
+            raise _abi.CavitError("cavit models run on a CUDA B200 only: move the model with .cuda() first "
+                                  "(there is no CPU / eager fallback)")
+        eng = self._engine_obj
+        if eng is None or eng.device != dev:
+            named = OrderedDict(self.named_parameters())
+            eng = Engine(self._kind, self.config, named, dev)
+            object.__setattr__(self, "_engine_obj", eng)
+        return eng
+
+    def forward(self, img, labels):
+        if self.training and self._dropout_p > 0.0:
+            raise _abi.CavitError("dropout > 0 in training mode is not implemented in the cavit kernel path yet; "
+                                  "use dropout=0.0 or eval()")
+        eng = self.engine()
+        params = list(eng.params.values())
+        return _CavitFn.apply(eng, img, labels, *params)
+
+    # ---------------------------------------------------------------- Lightning-style hooks
+    def training_step(self, batch, batch_idx):
+        x, labels = batch
+        logits, loss = self(x, labels)
+        self.log("train_loss", loss, on_epoch=True, on_step=False, sync_dist=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        x, labels = batch
+        logits, loss = self(x, labels)
+        self.log("val_loss", loss, on_epoch=True, on_step=False, sync_dist=True)
+
+    def configure_optimizers(self):
+        opt = torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)
+        sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=self.optim_params["T_max"],
+                                                           eta_min=self.optim_params["eta_min"])
+        return {"optimizer": opt, "lr_scheduler": {"scheduler": sched, "interval": "epoch"}}
+
+    def on_test_epoch_start(self):
+        self.test_logits, self.test_targets = [], []
+
+    def test_step(self, batch, batch_idx):
+        x, labels = batch
+        logits, _ = self(x, labels)
+        self.test_logits.append(logits.cpu())
+        self.test_targets.append(labels.cpu())
+
+    def on_test_epoch_end(self):
+        self.test_logits = torch.cat(self.test_logits)
+        self.test_targets = torch.cat(self.test_targets)
+
+
+def _check_divisible(config):
+    assert all(config.img_size[i] % config.patch_size[i] == 0 for i in range(len(config.img_size))), \
+        'image dimensions must be divisible by the patch size'
+
+
+class ModelCross(_CavitModel):
+    """CrossViT-style multi-sequence MRI classifier (drop-in for the reference's ModelCross)."""
+    _kind = "cross"
+
+    def __init__(self, config):
+        super().__init__()
+        _check_divisible(config)
+        D, H, W = config.img_size
+        dp, hp, wp = config.patch_size
+        num_patches = (D // dp) * (H // hp) * (W // wp)
+        self.label_smoothing = config.label_smoothing
+        self.num_modalities = config.num_modalities
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, config.hidden_dim))
+        self.patch_to_embedding = nn.Linear(dp * hp * wp, config.hidden_dim)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, config.hidden_dim))
+        self.dropout = nn.Dropout(config.dropout)
+        self.transformer = nn.Sequential(*[MultiScaleBlock(config) for _ in range(config.num_multi_blocks)])
+        self.norm = nn.ModuleList([nn.LayerNorm(config.hidden_dim) for _ in range(config.num_modalities)])
+        self.mlp_head = nn.ModuleList([
+            nn.Sequential(nn.Linear(config.hidden_dim, config.mlp_dim), nn.GELU(), nn.Dropout(config.dropout),
+                          nn.Linear(config.mlp_dim, config.num_classes), nn.Dropout(config.dropout))
+            for _ in range(config.num_modalities)])
+        self._post_init(config)
+
+
+class ModelVIT(_CavitModel):
+    """Plain pre-norm ViT over the concatenation of all sequences' patch tokens (drop-in for the
+    reference's ModelVIT)."""
+    _kind = "vit"
+
+    def __init__(self, config):
+        super().__init__()
+        _check_divisible(config)
+        D, H, W = config.img_size
+        dp, hp, wp = config.patch_size
+        num_patches = (D // dp) * (H // hp) * (W // wp) * config.num_modalities
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, config.hidden_dim))
+        self.patch_to_embedding = nn.Linear(dp * hp * wp, config.hidden_dim)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, config.hidden_dim))
+        self.dropout = nn.Dropout(config.dropout)
+        self.transformer = Transformer(config)
+        self.to_cls_token = nn.Identity()
+        self.mlp_head = nn.Sequential(nn.LayerNorm(config.hidden_dim), nn.Linear(config.hidden_dim, config.mlp_dim),
+                                      nn.GELU(), nn.Dropout(config.dropout),
+                                      nn.Linear(config.mlp_dim, config.num_classes), nn.Dropout(config.dropout))
+        self._post_init(config)

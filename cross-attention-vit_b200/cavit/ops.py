@@ -29,7 +29,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          out_gs: int = 0, epi: int = EPI_NONE, bias: Optional[torch.Tensor] = None, bias_gs: int = 0,
          resid: Optional[torch.Tensor] = None, ldr: int = 0, resid_gs: int = 0,
          aux: Optional[torch.Tensor] = None, ldaux: int = 0, aux_gs: int = 0, accumulate: bool = False,
-         embed_np: int = 0) -> GemmArgs:
+         embed_np: int = 0, split_k: int = 1) -> GemmArgs:
     """D[g][m][n] = sum_k A_g(m,k) B_g(n,k) (see include/cavit.h: cavit_gemm)."""
     assert A.dtype == BF16 and B.dtype == BF16 and out.dtype in (BF16, F32)
     a = GemmArgs()
@@ -41,7 +41,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     a.bias, a.bias_gs = _p(bias), bias_gs
     a.resid, a.ldr, a.resid_gs = _p(resid), ldr, resid_gs
     a.aux, a.ldaux, a.aux_gs = _p(aux), ldaux, aux_gs
-    a.accumulate, a.embed_np = int(accumulate), embed_np
+    a.accumulate, a.embed_np, a.split_k = int(accumulate), embed_np, split_k
     check(lib().cavit_gemm(C.byref(a), _stream()), "cavit_gemm")
     return a
 
@@ -63,12 +63,12 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, epi=EP
                 b_gs=N * K, out_gs=T * K, epi=epi, aux=aux, ldaux=K, aux_gs=T * K)
 
 
-def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulate: bool = False):
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulate: bool = False, split_k: int = 1):
     """dy [G,T,N] bf16, x [G,T,K] bf16 -> dW [G,N,K] fp32 = dY^T X."""
     G, T, N = dy.shape
     K = x.shape[2]
     return gemm(dy, x, out, M=N, N=K, K=T, groups=G, a_mn=True, b_mn=True, lda=N, ldb=K, ldo=K, a_gs=T * N,
-                b_gs=T * K, out_gs=N * K, accumulate=accumulate)
+                b_gs=T * K, out_gs=N * K, accumulate=accumulate, split_k=split_k)
 
 
 def ln_fwd(x, gamma, beta, y, mean, rstd, *, rows_per_group, groups, C, x_row_stride=None, x_gs=None, eps=1e-5):
@@ -99,16 +99,18 @@ def _i32arr(v):
     return (C.c_int32 * len(v))(*v)
 
 
-def ln_fusion_fwd(streams, gamma, beta, y, mean, rstd, *, B, N, C_, cls_src, tok_src, eps=1e-5):
+def ln_fusion_fwd(streams, x_cls, gamma, beta, y, mean, rstd, *, B, N, C_, cls_src, tok_src, eps=1e-5):
     K = len(cls_src)
-    check(lib().cavit_ln_fusion_fwd(streams.data_ptr(), B * N * C_, B, N, C_, K, _i32arr(cls_src), _i32arr(tok_src),
+    check(lib().cavit_ln_fusion_fwd(streams.data_ptr(), B * N * C_, x_cls.data_ptr(), B, N, C_, K, _i32arr(cls_src), _i32arr(tok_src),
                                     gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), mean.data_ptr(),
                                     rstd.data_ptr(), _stream()), "cavit_ln_fusion_fwd")
 
 
-def ln_fusion_bwd(dy, streams, mean, rstd, gamma, dstreams, dgamma, dbeta, partials, *, B, N, C_, cls_src, tok_src):
+def ln_fusion_bwd(dy, streams, x_cls, mean, rstd, gamma, dstreams, dgamma, dbeta, partials, *, B, N, C_, cls_src,
+                  tok_src, dy_cls=None):
     K = len(cls_src)
-    check(lib().cavit_ln_fusion_bwd(dy.data_ptr(), streams.data_ptr(), B * N * C_, mean.data_ptr(), rstd.data_ptr(),
+    check(lib().cavit_ln_fusion_bwd(dy.data_ptr(), _p(dy_cls), streams.data_ptr(), B * N * C_, x_cls.data_ptr(),
+                                    mean.data_ptr(), rstd.data_ptr(),
                                     gamma.data_ptr(), B, N, C_, K, _i32arr(cls_src), _i32arr(tok_src),
                                     dstreams.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), partials.data_ptr(),
                                     _stream()), "cavit_ln_fusion_bwd")
@@ -134,10 +136,11 @@ def xattn_bwd(q, kv, probs, dout, dq, dkv, *, K, B, N, H, scale):
                                 dkv.data_ptr(), K, B, N, H, scale, _stream()), "cavit_xattn_bwd")
 
 
-def patchify(img, patches, *, patch_size):
+def patchify(img, patches, *, patch_size, sample_major=False):
     B, M, _, D, H, W = img.shape
     dp, hp, wp = patch_size
-    check(lib().cavit_patchify(img.data_ptr(), patches.data_ptr(), B, M, D, H, W, dp, hp, wp, _stream()),
+    check(lib().cavit_patchify(img.data_ptr(), patches.data_ptr(), B, M, D, H, W, dp, hp, wp, int(sample_major),
+                               _stream()),
           "cavit_patchify")
 
 
@@ -163,9 +166,26 @@ def colsum_bf16(x, out, *, rows, C_, groups, ldx=None, x_gs=None, out_gs=None):
           "cavit_colsum_bf16")
 
 
-def gather_rows_f32(src, dst, *, rows, C_, groups, src_row_stride, src_gs, dst_row_stride, dst_gs, accumulate=False):
+def gather_rows_f32(src, dst, *, rows, C_, groups, src_row_stride, src_gs, dst_row_stride, dst_gs, accumulate=False,
+                    zero_src=False):
     check(lib().cavit_gather_rows_f32(src.data_ptr(), src_row_stride, src_gs, dst.data_ptr(), dst_row_stride, dst_gs,
-                                      rows, C_, groups, int(accumulate), _stream()), "cavit_gather_rows_f32")
+                                      rows, C_, groups, int(accumulate), int(zero_src), _stream()),
+          "cavit_gather_rows_f32")
+
+
+def add_bf16_f32(a, b_bf16, out):
+    check(lib().cavit_add_bf16_f32(a.data_ptr(), b_bf16.data_ptr(), out.data_ptr(), a.numel(), _stream()),
+          "cavit_add_bf16_f32")
+
+
+def gelu_bwd_bf16(dh, u, du):
+    check(lib().cavit_gelu_bwd_bf16(dh.data_ptr(), u.data_ptr(), du.data_ptr(), dh.numel(), _stream()),
+          "cavit_gelu_bwd_bf16")
+
+
+def compact_patch_rows_bf16(src, dst, *, S, Np, C_):
+    check(lib().cavit_compact_patch_rows_bf16(src.data_ptr(), dst.data_ptr(), S, Np, C_, _stream()),
+          "cavit_compact_patch_rows_bf16")
 
 
 def head_loss_fwd(h, W2, b2, labels, logits, loss, *, M, B, F, classes, smoothing):
@@ -173,7 +193,8 @@ def head_loss_fwd(h, W2, b2, labels, logits, loss, *, M, B, F, classes, smoothin
                                     loss.data_ptr(), M, B, F, classes, smoothing, _stream()), "cavit_head_loss_fwd")
 
 
-def head_loss_bwd(h, W2, labels, logits, dh, dW2, db2, *, M, B, F, classes, smoothing, loss_scale=1.0):
+def head_loss_bwd(h, W2, labels, logits, dh, dW2, db2, *, M, B, F, classes, smoothing, loss_scale=1.0,
+                  loss_scale_dev=None):
     check(lib().cavit_head_loss_bwd(h.data_ptr(), W2.data_ptr(), labels.data_ptr(), logits.data_ptr(), loss_scale,
-                                    dh.data_ptr(), dW2.data_ptr(), db2.data_ptr(), M, B, F, classes, smoothing,
+                                    _p(loss_scale_dev), dh.data_ptr(), dW2.data_ptr(), db2.data_ptr(), M, B, F, classes, smoothing,
                                     _stream()), "cavit_head_loss_bwd")

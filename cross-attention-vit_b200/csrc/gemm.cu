@@ -23,7 +23,7 @@ constexpr int GEMM_THREADS = 192;
 
 struct GemmDev {
   int M, N, K, groups;
-  int a_mn, b_mn, epi, out_fp32, accumulate, embed_np;
+  int a_mn, b_mn, epi, out_fp32, accumulate, embed_np, split_k, kb_per_split;
   void* out; long long ldo, out_gs;
   const float* bias; long long bias_gs;
   const float* resid; long long ldr, resid_gs;
@@ -121,6 +121,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, int g, long lon
     }
   }
 
+  if (p.split_k > 1) {  // partial tile of a split-K reduction: combine with fp32 atomics
+    float* o = reinterpret_cast<float*>(p.out) + (long long)g * p.out_gs + out_row * p.ldo + col0;
+    for (int i = 0; i < ncols; ++i) atomicAdd(o + i, v[i]);
+    return;
+  }
   if (p.out_fp32) {
     float* o = reinterpret_cast<float*>(p.out) + (long long)g * p.out_gs + out_row * p.ldo + col0;
     if (full && (p.ldo % 4 == 0)) {
@@ -200,21 +205,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int splits = p.split_k > 1 ? p.split_k : 1;
   const int tiles_per_group = p.tiles_m * p.tiles_n;
-  const int total_tiles = tiles_per_group * p.groups;
+  const int total_tiles = tiles_per_group * p.groups * splits;  // work item = (group, m tile, n tile, k split)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+        const int split = work % splits;
+        const int tile = work / splits;
         const int g = tile / tiles_per_group;
         const int rem = tile - g * tiles_per_group;
         const int m0 = (rem / p.tiles_n) * GEMM_BM;
         const int n0 = (rem % p.tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, abort_flag, p.status, ERR_TIMEOUT_EMPTY);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::A_BYTES;
@@ -250,7 +260,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+        const int split = work % splits;
+        const int kb0 = split * p.kb_per_split;
+        const int num_kb = min(num_kb_total, kb0 + p.kb_per_split) - kb0;
         mbar_wait(tempty_bar(as), aphase ^ 1u, abort_flag, p.status, ERR_TIMEOUT_TMEM_EMPTY);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -278,7 +291,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      const int tile = work / splits;
       const int g = tile / tiles_per_group;
       const int rem = tile - g * tiles_per_group;
       const int m0 = (rem / p.tiles_n) * GEMM_BM;
@@ -324,7 +338,12 @@ static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d,
   }
   d.tiles_m = (d.M + GEMM_BM - 1) / GEMM_BM;
   d.tiles_n = (d.N + BN - 1) / BN;
-  const long long total = (long long)d.tiles_m * d.tiles_n * d.groups;
+  const int num_kb = (d.K + GEMM_BK - 1) / GEMM_BK;
+  if (d.split_k > num_kb) d.split_k = num_kb;
+  if (d.split_k < 1) d.split_k = 1;
+  d.kb_per_split = (num_kb + d.split_k - 1) / d.split_k;
+  d.split_k = (num_kb + d.kb_per_split - 1) / d.kb_per_split;  // no empty splits
+  const long long total = (long long)d.tiles_m * d.tiles_n * d.groups * d.split_k;
   const int grid = (int)(total < sm_count() ? total : sm_count());
   gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, d);
   count_launch();
@@ -354,6 +373,8 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
     return fail(CAVIT_E_BADARG, "cavit_gemm: residual epilogues need resid and fp32 out");
   if (a->epi == CAVIT_EPI_EMBED && a->embed_np <= 0) return fail(CAVIT_E_BADARG, "cavit_gemm: embed_np");
   if (a->accumulate && !a->out_fp32) return fail(CAVIT_E_BADARG, "cavit_gemm: accumulate needs fp32 out");
+  if (a->split_k > 1 && (!a->out_fp32 || a->epi != CAVIT_EPI_NONE))
+    return fail(CAVIT_E_BADARG, "cavit_gemm: split_k needs fp32 out and EPI_NONE");
   int* status = status_word();
   if (!status) return fail(CAVIT_E_DEVICE, "cavit_gemm: no device status word");
 
@@ -380,7 +401,19 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   d.resid = a->resid; d.ldr = a->ldr; d.resid_gs = a->resid_gs;
   d.aux = a->aux; d.ldaux = a->ldaux; d.aux_gs = a->aux_gs;
   d.tiles_m = d.tiles_n = 0;
+  d.split_k = a->split_k > 1 ? a->split_k : 1;
+  d.kb_per_split = 0;
   d.status = status;
+  if (d.split_k > 1 && !a->accumulate) {  // atomics combine into a zeroed output
+    cudaStream_t st = as_stream(stream);
+    if (a->ldo == a->N && (a->groups == 1 || a->out_gs == (int64_t)a->M * a->N)) {
+      cudaMemsetAsync(a->out, 0, sizeof(float) * (size_t)a->groups * a->M * a->N, st);
+    } else {
+      for (int g = 0; g < a->groups; ++g)
+        cudaMemset2DAsync(reinterpret_cast<float*>(a->out) + (size_t)g * a->out_gs, sizeof(float) * a->ldo, 0,
+                          sizeof(float) * a->N, a->M, st);
+    }
+  }
   if (BN == 256) return launch_gemm<256>(ta, tb, d, as_stream(stream));
   return launch_gemm<128>(ta, tb, d, as_stream(stream));
 }

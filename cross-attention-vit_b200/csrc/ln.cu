@@ -25,13 +25,24 @@ constexpr int LN_MAX_FUSIONS = 16;
 struct RowMap {
   int fusion;  // 0: plain rows; 1: fusion gather
   int N;       // tokens per sample (fusion mode)
+  int B;       // samples (fusion mode)
+  const float* x_cls;   // fusion: CLS inputs [K][B][C] (row 0 of every sample is read from here)
+  const float* dy_cls;  // fusion bwd: optional extra fp32 gradient [K][B][C] added to dy on row 0
   int cls_src[LN_MAX_FUSIONS];
   int tok_src[LN_MAX_FUSIONS];
 };
 
-__device__ __forceinline__ long long src_offset(const RowMap& rm, int g, long long r, long long row_stride,
-                                                long long gs) {
-  if (!rm.fusion) return (long long)g * gs + r * row_stride;
+// Pointer to the source row (x) of logical row r of group g.
+__device__ __forceinline__ const float* src_row(const RowMap& rm, const float* x, int g, long long r, long long row_stride,
+                                                long long gs, int C) {
+  if (!rm.fusion) return x + (long long)g * gs + r * row_stride;
+  const int n = (int)(r % rm.N);
+  if (n == 0) return rm.x_cls + ((long long)g * rm.B + r / rm.N) * C;
+  return x + (long long)rm.tok_src[g] * gs + r * row_stride;
+}
+// Offset of the destination row (dx) in fusion mode: scatter back into the donor streams.
+__device__ __forceinline__ long long fusion_dst_offset(const RowMap& rm, int g, long long r, long long row_stride,
+                                                       long long gs) {
   const int n = (int)(r % rm.N);
   const int s = (n == 0) ? rm.cls_src[g] : rm.tok_src[g];
   return (long long)s * gs + r * row_stride;
@@ -49,7 +60,7 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
   for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < total; row += (long long)gridDim.x * LN_WARPS) {
     const int g = (int)(row / rows_per_group);
     const long long r = row - (long long)g * rows_per_group;
-    const float4* xr = reinterpret_cast<const float4*>(x + src_offset(rm, g, r, row_stride, gs));
+    const float4* xr = reinterpret_cast<const float4*>(src_row(rm, x, g, r, row_stride, gs, C));
     float4 v[NV];
     float s = 0.f;
 #pragma unroll
@@ -116,9 +127,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
   }
   for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows_per_group; r += (long long)gridDim.x * LN_WARPS) {
     const long long row = (long long)g * rows_per_group + r;
-    const long long soff = src_offset(rm, g, r, row_stride, gs);
-    const float4* xr = reinterpret_cast<const float4*>(x + soff);
+    const float4* xr = reinterpret_cast<const float4*>(src_row(rm, x, g, r, row_stride, gs, C));
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * C);
+    const float4* dyc = nullptr;  // extra fp32 gradient on the CLS row of a fusion
+    if (rm.fusion && rm.dy_cls && (r % rm.N) == 0)
+      dyc = reinterpret_cast<const float4*>(rm.dy_cls + ((long long)g * rm.B + r / rm.N) * C);
     const float mu = mean[row], rs = rstd[row];
     float4 xh[NV], gy[NV];
     float s1 = 0.f, s2 = 0.f;
@@ -128,7 +141,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
       if (c4 < C4) {
         const float4 xv = __ldg(xr + c4);
         const uint2 d2 = __ldg(dyr + c4);
-        const float2 d01 = unpack_bf16(d2.x), d23 = unpack_bf16(d2.y);
+        float2 d01 = unpack_bf16(d2.x), d23 = unpack_bf16(d2.y);
+        if (dyc) {
+          const float4 e = __ldg(dyc + c4);
+          d01.x += e.x; d01.y += e.y; d23.x += e.z; d23.y += e.w;
+        }
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         dg[i].x += d01.x * xh[i].x; dg[i].y += d01.y * xh[i].y; dg[i].z += d23.x * xh[i].z; dg[i].w += d23.y * xh[i].w;
         db[i].x += d01.x; db[i].y += d01.y; db[i].z += d23.x; db[i].w += d23.y;
@@ -139,7 +156,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
     }
     const float m1 = warp_sum(s1) * inv_c, m2 = warp_sum(s2) * inv_c;
     long long doff;
-    if (rm.fusion) doff = soff;  // scatter back to where the row was gathered from
+    if (rm.fusion) doff = fusion_dst_offset(rm, g, r, row_stride, gs);  // scatter back into the donor stream
     else doff = (long long)g * dx_gs + r * dx_row_stride;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -304,27 +321,32 @@ int cavit_ln_bwd(const void* dy, const float* x, int64_t x_row_stride, int64_t x
                        dx_row_stride, dx_gs, dx_bf16, dgamma, dbeta, partials, rm, as_stream(stream));
 }
 
-int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, int32_t B, int32_t N, int32_t C, int32_t K,
-                        const int32_t* cls_src, const int32_t* tok_src, const float* gamma, const float* beta,
+int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, const float* x_cls, int32_t B, int32_t N, int32_t C,
+                        int32_t K, const int32_t* cls_src, const int32_t* tok_src, const float* gamma, const float* beta,
                         float eps, void* y, float* mean, float* rstd, void* stream) {
-  if (!streams || !cls_src || !tok_src || !gamma || !beta || !y) return fail(CAVIT_E_BADARG, "cavit_ln_fusion_fwd: null pointer");
+  if (!streams || !x_cls || !cls_src || !tok_src || !gamma || !beta || !y) return fail(CAVIT_E_BADARG, "cavit_ln_fusion_fwd: null pointer");
   if (K <= 0 || K > LN_MAX_FUSIONS) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_ln_fusion_fwd: K=%d (max %d)", K, LN_MAX_FUSIONS);
   RowMap rm{};
   rm.fusion = 1;
   rm.N = N;
+  rm.B = B;
+  rm.x_cls = x_cls;
   for (int k = 0; k < K; ++k) { rm.cls_src[k] = cls_src[k]; rm.tok_src[k] = tok_src[k]; }
   return ln_fwd_launch(streams, C, stream_gs, B * N, K, C, gamma, beta, eps, y, mean, rstd, rm, as_stream(stream));
 }
 
-int cavit_ln_fusion_bwd(const void* dy, const float* streams, int64_t stream_gs, const float* mean, const float* rstd,
-                        const float* gamma, int32_t B, int32_t N, int32_t C, int32_t K, const int32_t* cls_src,
-                        const int32_t* tok_src, float* dstreams, float* dgamma, float* dbeta, float* partials,
-                        void* stream) {
-  if (!dy || !streams || !cls_src || !tok_src || !dstreams) return fail(CAVIT_E_BADARG, "cavit_ln_fusion_bwd: null pointer");
+int cavit_ln_fusion_bwd(const void* dy, const float* dy_cls, const float* streams, int64_t stream_gs, const float* x_cls,
+                        const float* mean, const float* rstd, const float* gamma, int32_t B, int32_t N, int32_t C,
+                        int32_t K, const int32_t* cls_src, const int32_t* tok_src, float* dstreams, float* dgamma,
+                        float* dbeta, float* partials, void* stream) {
+  if (!dy || !streams || !x_cls || !cls_src || !tok_src || !dstreams) return fail(CAVIT_E_BADARG, "cavit_ln_fusion_bwd: null pointer");
   if (K <= 0 || K > LN_MAX_FUSIONS) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_ln_fusion_bwd: K=%d", K);
   RowMap rm{};
   rm.fusion = 1;
   rm.N = N;
+  rm.B = B;
+  rm.x_cls = x_cls;
+  rm.dy_cls = dy_cls;
   for (int k = 0; k < K; ++k) { rm.cls_src[k] = cls_src[k]; rm.tok_src[k] = tok_src[k]; }
   return ln_bwd_launch(dy, streams, C, stream_gs, mean, rstd, gamma, B * N, K, C, nullptr, dstreams, C, stream_gs,
                        nullptr, dgamma, dbeta, partials, rm, as_stream(stream));

@@ -25,7 +25,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
 //   t = (hi*Wn + wi)*Dn + di   (d fastest),   f = (a*hp + bb)*wp + c      
 // One thread produces two consecutive features (one 4-byte bf16x2 store).
 __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int M, int D, int H,
-                                int W, int dp, int hp, int wp) {
+                                int W, int dp, int hp, int wp, int sample_major) {
   const int Dn = D / dp, Hn = H / hp, Wn = W / wp;
   const long long Np = (long long)Dn * Hn * Wn;
   const int P = dp * hp * wp;
@@ -37,8 +37,9 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
     e /= P;
     const long long t = e % Np;
     e /= Np;
-    const int b = (int)(e % B);
-    const int m = (int)(e / B);
+    int b, m;
+    if (sample_major) { m = (int)(e % M); b = (int)(e / M); }
+    else { b = (int)(e % B); m = (int)(e / B); }
     const int di = (int)(t % Dn), wi = (int)((t / Dn) % Wn), hi = (int)(t / ((long long)Dn * Wn));
     const float* vol = img + ((long long)b * M + m) * ((long long)D * H * W);
     float v[2];
@@ -114,8 +115,9 @@ __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, lo
 }
 
 // ------------------------------------------------------------------------------------------ gather rows
-__global__ void gather_rows_f32_kernel(const float* __restrict__ src, long long srs, long long sgs, float* __restrict__ dst,
-                                       long long drs, long long dgs, int rows, int C, int groups, int accumulate) {
+__global__ void gather_rows_f32_kernel(float* __restrict__ src, long long srs, long long sgs, float* __restrict__ dst,
+                                       long long drs, long long dgs, int rows, int C, int groups, int accumulate,
+                                       int zero_src) {
   const int C4 = C >> 2;
   const long long total = (long long)groups * rows * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -123,7 +125,9 @@ __global__ void gather_rows_f32_kernel(const float* __restrict__ src, long long 
     long long e = i / C4;
     const int r = (int)(e % rows);
     const int g = (int)(e / rows);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)g * sgs + (long long)r * srs) + c4);
+    float4* sp = reinterpret_cast<float4*>(src + (long long)g * sgs + (long long)r * srs) + c4;
+    const float4 v = *sp;
+    if (zero_src) *sp = make_float4(0.f, 0.f, 0.f, 0.f);
     float4* d = reinterpret_cast<float4*>(dst + (long long)g * dgs + (long long)r * drs) + c4;
     if (accumulate) {
       float4 o = *d;
@@ -132,6 +136,36 @@ __global__ void gather_rows_f32_kernel(const float* __restrict__ src, long long 
     } else {
       *d = v;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ elementwise
+__global__ void add_bf16_f32_kernel(const float* a, const bf16* __restrict__ b, float* out, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(a)[i];
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(b) + i);
+    const float2 lo = unpack_bf16(q.x), hi = unpack_bf16(q.y);
+    v.x += lo.x; v.y += lo.y; v.z += hi.x; v.w += hi.y;
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+__global__ void gelu_bwd_bf16_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ u, bf16* __restrict__ du, long long n2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const float2 d = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(dh) + i));
+    const float2 x = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(u) + i));
+    reinterpret_cast<uint32_t*>(du)[i] = pack_bf16(d.x * gelu_erf_grad(x.x), d.y * gelu_erf_grad(x.y));
+  }
+}
+
+// out[s*Np + t][:] = in[s*(Np+1) + 1 + t][:]   (16-byte chunks)
+__global__ void compact_patch_rows_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int S, int Np, int C8) {
+  const long long total = (long long)S * Np * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const long long row = i / C8;
+    const long long s_ = row / Np, t = row % Np;
+    out[i] = __ldg(in + (s_ * (Np + 1) + 1 + t) * C8 + c);
   }
 }
 
@@ -214,9 +248,10 @@ __device__ __forceinline__ void dlogits_row(const float* z, long long label, int
 
 // grid = (B, M): dh[m][b][f] = sum_k dz[b][k] W2[m][k][f],  dz = dlogits / M
 __global__ void head_dh_kernel(const float* __restrict__ W2, const long long* __restrict__ labels,
-                               const float* __restrict__ logits, float scale, bf16* __restrict__ dh, int M, int B, int F,
-                               int classes, float smoothing) {
+                               const float* __restrict__ logits, float scale, const float* __restrict__ scale_dev,
+                               bf16* __restrict__ dh, int M, int B, int F, int classes, float smoothing) {
   const int b = blockIdx.x, m = blockIdx.y;
+  if (scale_dev) scale *= __ldg(scale_dev);
   float dz[HEAD_MAX_CLASSES];
   dlogits_row(logits + b * classes, labels[b], classes, smoothing, scale / ((float)B * (float)M), dz);
   bf16* o = dh + ((long long)m * B + b) * F;
@@ -229,9 +264,11 @@ __global__ void head_dh_kernel(const float* __restrict__ W2, const long long* __
 
 // grid = (ceil(F/256), M): dW2[m][k][f] = sum_b dz[b][k] h[m][b][f];  block (0, m) also writes db2.
 __global__ void head_dw_kernel(const bf16* __restrict__ h, const long long* __restrict__ labels,
-                               const float* __restrict__ logits, float scale, float* __restrict__ dW2,
-                               float* __restrict__ db2, int M, int B, int F, int classes, float smoothing) {
+                               const float* __restrict__ logits, float scale, const float* __restrict__ scale_dev,
+                               float* __restrict__ dW2, float* __restrict__ db2, int M, int B, int F, int classes,
+                               float smoothing) {
   const int m = blockIdx.y;
+  if (scale_dev) scale *= __ldg(scale_dev);
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   float acc[HEAD_MAX_CLASSES], accb[HEAD_MAX_CLASSES];
 #pragma unroll
@@ -275,7 +312,7 @@ int cavit_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
 }
 
 int cavit_patchify(const float* img, void* patches, int32_t B, int32_t M, int32_t D, int32_t H, int32_t W, int32_t dp,
-                   int32_t hp, int32_t wp, void* stream) {
+                   int32_t hp, int32_t wp, int32_t sample_major, void* stream) {
   if (!img || !patches) return fail(CAVIT_E_BADARG, "cavit_patchify: null pointer");
   if (dp <= 0 || hp <= 0 || wp <= 0 || D % dp || H % hp || W % wp)
     return fail(CAVIT_E_BADARG, "image dimensions must be divisible by the patch size");
@@ -283,7 +320,7 @@ int cavit_patchify(const float* img, void* patches, int32_t B, int32_t M, int32_
   if (P % 2) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_patchify: patch_dim must be even");
   const long long pairs = (long long)M * B * (D / dp) * (H / hp) * (W / wp) * P / 2;
   patchify_kernel<<<grid_for(pairs, 256), 256, 0, as_stream(stream)>>>(img, reinterpret_cast<bf16*>(patches), B, M, D, H, W,
-                                                                        dp, hp, wp);
+                                                                        dp, hp, wp, sample_major);
   count_launch();
   return check_launch("cavit_patchify");
 }
@@ -318,14 +355,37 @@ int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, in
   return check_launch("cavit_colsum_bf16");
 }
 
-int cavit_gather_rows_f32(const float* src, int64_t srs, int64_t sgs, float* dst, int64_t drs, int64_t dgs, int32_t rows,
-                          int32_t C, int32_t groups, int32_t accumulate, void* stream) {
+int cavit_gather_rows_f32(float* src, int64_t srs, int64_t sgs, float* dst, int64_t drs, int64_t dgs, int32_t rows,
+                          int32_t C, int32_t groups, int32_t accumulate, int32_t zero_src, void* stream) {
   if (!src || !dst || (C % 4) || (srs % 4) || (sgs % 4) || (drs % 4) || (dgs % 4))
     return fail(CAVIT_E_BADARG, "cavit_gather_rows_f32: bad args");
   gather_rows_f32_kernel<<<grid_for((long long)groups * rows * C / 4, 256), 256, 0, as_stream(stream)>>>(
-      src, srs, sgs, dst, drs, dgs, rows, C, groups, accumulate);
+      src, srs, sgs, dst, drs, dgs, rows, C, groups, accumulate, zero_src);
   count_launch();
   return check_launch("cavit_gather_rows_f32");
+}
+
+int cavit_add_bf16_f32(const float* a, const void* b, float* out, int64_t n, void* stream) {
+  if (!a || !b || !out || n <= 0 || (n % 4)) return fail(CAVIT_E_BADARG, "cavit_add_bf16_f32: bad args");
+  add_bf16_f32_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(a, reinterpret_cast<const bf16*>(b), out, n / 4);
+  count_launch();
+  return check_launch("cavit_add_bf16_f32");
+}
+
+int cavit_gelu_bwd_bf16(const void* dh, const void* u, void* du, int64_t n, void* stream) {
+  if (!dh || !u || !du || n <= 0 || (n % 2)) return fail(CAVIT_E_BADARG, "cavit_gelu_bwd_bf16: bad args");
+  gelu_bwd_bf16_kernel<<<grid_for(n / 2, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const bf16*>(dh), reinterpret_cast<const bf16*>(u), reinterpret_cast<bf16*>(du), n / 2);
+  count_launch();
+  return check_launch("cavit_gelu_bwd_bf16");
+}
+
+int cavit_compact_patch_rows_bf16(const void* in, void* out, int32_t S, int32_t Np, int32_t C, void* stream) {
+  if (!in || !out || S <= 0 || Np <= 0 || C <= 0 || (C % 8)) return fail(CAVIT_E_BADARG, "cavit_compact_patch_rows_bf16: bad args");
+  compact_patch_rows_kernel<<<grid_for((long long)S * Np * (C / 8), 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), S, Np, C / 8);
+  count_launch();
+  return check_launch("cavit_compact_patch_rows_bf16");
 }
 
 int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const int64_t* labels, float* logits, float* loss,
@@ -340,15 +400,16 @@ int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const i
 }
 
 int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, const float* logits, float loss_scale,
-                        void* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing,
+                        const float* loss_scale_dev, void* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing,
                         void* stream) {
   if (!h || !W2 || !labels || !logits || !dh || !dW2 || !db2) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: null pointer");
   if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d", classes);
   cudaStream_t st = as_stream(stream);
   const long long* lab = reinterpret_cast<const long long*>(labels);
-  head_dh_kernel<<<dim3(B, M), 256, 0, st>>>(W2, lab, logits, loss_scale, reinterpret_cast<bf16*>(dh), M, B, F, classes, smoothing);
-  head_dw_kernel<<<dim3((F + 255) / 256, M), 256, 0, st>>>(reinterpret_cast<const bf16*>(h), lab, logits, loss_scale, dW2, db2,
-                                                           M, B, F, classes, smoothing);
+  head_dh_kernel<<<dim3(B, M), 256, 0, st>>>(W2, lab, logits, loss_scale, loss_scale_dev, reinterpret_cast<bf16*>(dh), M, B, F, classes,
+                                             smoothing);
+  head_dw_kernel<<<dim3((F + 255) / 256, M), 256, 0, st>>>(reinterpret_cast<const bf16*>(h), lab, logits, loss_scale,
+                                                           loss_scale_dev, dW2, db2, M, B, F, classes, smoothing);
   count_launch(2);
   return check_launch("cavit_head_loss_bwd");
 }

@@ -81,7 +81,10 @@ typedef struct cavit_gemm_args {
   const float* bias; int64_t bias_gs;               /* [groups][N] fp32 (NULL allowed for EPI_NONE) */
   const float* resid; int64_t ldr, resid_gs;        /* EPI_BIAS_RESID: fp32 [M][N]; EPI_EMBED: pos [1+Np][N] */
   void* aux; int64_t ldaux, aux_gs;                 /* EPI_BIAS_GELU: bf16 out u; EPI_GELU_BWD: bf16 in u */
-  int32_t accumulate;  /* 1: out (fp32 only) += result (used by split wgrad accumulation) */
+  int32_t accumulate;  /* 1: out (fp32 only) += result */
+  int32_t split_k;     /* >1: the K range is split over that many CTAs whose partial tiles are combined with
+                          fp32 atomics into `out` (fp32, EPI_NONE only; zeroed by the call unless accumulate).
+                          0/1: no split. Used by wgrad, whose reduction axis (tokens) is the long one. */
   int32_t embed_np;    /* EPI_EMBED: patches per sample (row m -> out row (m / Np) * (Np + 1) + 1 + m % Np) */
 } cavit_gemm_args;
 int cavit_gemm(const cavit_gemm_args* a, void* stream);
@@ -107,20 +110,20 @@ int cavit_ln_bwd(const void* dy_bf16, const float* x, int64_t x_row_stride, int6
                  float* dgamma, float* dbeta, float* partials, void* stream);
 
 /* Fused gather + LayerNorm for the cross-modal fusion input `cat(cls_i, patches_j)`
- * (/root/reference/model_cross.py:140, 109): row 0 of every sample comes from stream cls_src[k],
- * rows 1.. from stream tok_src[k]; fusion k uses gamma/beta[k]. streams: fp32 [M][B*N][C].
- * y: bf16 [K][B*N][C]. cls_src/tok_src are HOST int arrays of length K (K <= 16). */
-int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, int32_t B, int32_t N, int32_t C,
-                        int32_t K, const int32_t* cls_src, const int32_t* tok_src, const float* gamma,
+ * (/root/reference/model_cross.py:140, 109): row 0 of every sample is read from x_cls[k][b]
+ * (the saved CLS row of stream cls_src[k]), rows 1.. from stream tok_src[k]; fusion k uses
+ * gamma/beta[k]. streams: fp32 [M][B*N][C]; x_cls: fp32 [K][B][C]; y: bf16 [K][B*N][C].
+ * cls_src/tok_src are HOST int arrays of length K (K <= 16). */
+int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, const float* x_cls, int32_t B, int32_t N,
+                        int32_t C, int32_t K, const int32_t* cls_src, const int32_t* tok_src, const float* gamma,
                         const float* beta, float eps, void* y_bf16, float* mean, float* rstd, void* stream);
-/* Backward of the above: scatters LN'(dy) into the fp32 stream gradients (+=): row 0 into stream
- * cls_src[k], rows 1.. into stream tok_src[k]. Rows of one destination stream never collide
- * between fusions (a stream is CLS donor of at most one fusion; patch rows of a stream that feed
- * several fusions are accumulated with atomics). */
-int cavit_ln_fusion_bwd(const void* dy_bf16, const float* streams, int64_t stream_gs, const float* mean,
-                        const float* rstd, const float* gamma, int32_t B, int32_t N, int32_t C, int32_t K,
-                        const int32_t* cls_src, const int32_t* tok_src, float* dstreams, float* dgamma,
-                        float* dbeta, float* partials, void* stream);
+/* Backward of the above: adds LN'(dy) into the fp32 stream gradients with atomics: row 0 into
+ * stream cls_src[k], rows 1.. into stream tok_src[k] (a stream can donate patches to several
+ * fusions). dy_cls (optional, fp32 [K][B][C]) is added to dy on the CLS rows (the query path). */
+int cavit_ln_fusion_bwd(const void* dy_bf16, const float* dy_cls, const float* streams, int64_t stream_gs,
+                        const float* x_cls, const float* mean, const float* rstd, const float* gamma, int32_t B,
+                        int32_t N, int32_t C, int32_t K, const int32_t* cls_src, const int32_t* tok_src,
+                        float* dstreams, float* dgamma, float* dbeta, float* partials, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Self-attention core softmax(Q K^T * scale) V, head_dim 64, fused online softmax on tcgen05;
@@ -155,8 +158,10 @@ int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const fl
  * fp32 batch into bf16 patch rows [M][B*Np][P] (bit-exact index map).
  * Replaces: einops.rearrange at /root/reference/model_cross.py:193, modelv3.py:129.
  * ------------------------------------------------------------------------------------------- */
+/* sample_major = 0: rows ordered [m][b][t] (ModelCross, one token stream per modality);
+ * sample_major = 1: rows ordered [b][m][t] (ModelVIT, streams concatenated on the token axis). */
 int cavit_patchify(const float* img, void* patches_bf16, int32_t B, int32_t M, int32_t D, int32_t H, int32_t W,
-                   int32_t dp, int32_t hp, int32_t wp, void* stream);
+                   int32_t dp, int32_t hp, int32_t wp, int32_t sample_major, void* stream);
 /* tokens[m][b*N + 0][:] = cls + pos[0]  for all streams/samples (/root/reference/model_cross.py:195-197). */
 int cavit_cls_rows(const float* cls, const float* pos, float* tokens, int32_t M, int32_t B, int32_t N,
                    int32_t C, void* stream);
@@ -172,21 +177,32 @@ int cavit_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 /* out[g][c] (+)= sum_r x[g][r][c];  x bf16 [groups][rows][C] (bias gradients). */
 int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C, int32_t groups,
                       float* out, int64_t out_gs, void* stream);
-/* Strided row copy / gather: dst[g][r][:] = src[g][r * src_row_stride ...][:C] (fp32). */
-int cavit_gather_rows_f32(const float* src, int64_t src_row_stride, int64_t src_gs, float* dst,
+/* Strided row copy / gather: dst[g][r][:] (+)= src[g][r][:C] (fp32), independent row / group strides.
+ * zero_src != 0 additionally clears the source rows ("move"). */
+int cavit_gather_rows_f32(float* src, int64_t src_row_stride, int64_t src_gs, float* dst,
                           int64_t dst_row_stride, int64_t dst_gs, int32_t rows, int32_t C, int32_t groups,
-                          int32_t accumulate, void* stream);
+                          int32_t accumulate, int32_t zero_src, void* stream);
+/* out[i] = a[i] + (float) b_bf16[i]   (residual add for the heads == 1 case where the reference's
+ * attention has no output projection, /root/reference/model_cross.py:37,44-48). out may alias a. */
+int cavit_add_bf16_f32(const float* a, const void* b_bf16, float* out, int64_t n, void* stream);
+/* du[i] = dh[i] * GELU'(u[i])  (bf16 in/out; the classification head's GELU backward). */
+int cavit_gelu_bwd_bf16(const void* dh, const void* u, void* du, int64_t n, void* stream);
+/* Compact the patch rows of a token tensor (drop the CLS row of every sample):
+ * out[s*Np + t][:] = in[s*(Np+1) + 1 + t][:], bf16, s in [0, S). (embedding wgrad operand) */
+int cavit_compact_patch_rows_bf16(const void* in, void* out, int32_t S, int32_t Np, int32_t C, void* stream);
 
 /* Classification tail: logits = mean_m(h_m W2_m^T + b2_m); loss = CE(logits, labels, smoothing).
  * Replaces: mlp_head[*][3], torch.mean, F.cross_entropy (/root/reference/model_cross.py:181,205-211).
  * h: bf16 [M][B][F]; W2: fp32 [M][classes][F]; b2: fp32 [M][classes]; labels: int64 [B].
- * logits fp32 [B][classes]; loss fp32 [1]. Backward: dh bf16 [M][B][F], dW2, db2 (overwritten). */
+ * logits fp32 [B][classes]; loss fp32 [1]. Backward: dh bf16 [M][B][F], dW2, db2 (overwritten);
+ * the upstream gradient of the loss is loss_scale * (loss_scale_dev ? *loss_scale_dev : 1), the
+ * device scalar lets autograd's d(loss) be consumed without a host synchronisation. */
 int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const int64_t* labels, float* logits,
                         float* loss, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing,
                         void* stream);
 int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, const float* logits,
-                        float loss_scale, void* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F,
-                        int32_t classes, float smoothing, void* stream);
+                        float loss_scale, const float* loss_scale_dev, void* dh, float* dW2, float* db2, int32_t M,
+                        int32_t B, int32_t F, int32_t classes, float smoothing, void* stream);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,11 @@ def test_gemm_wgrad_layout(G, T, N, K):
     ops.linear_wgrad(dy, x, out, accumulate=True)
     status_ok()
     assert rel(out, 2 * want) < 1e-5
+    for sk in (2, 5, 64):
+        out.fill_(float("nan"))
+        ops.linear_wgrad(dy, x, out, split_k=sk)
+        status_ok()
+        assert rel(out, want) < 1e-5, sk
 
 
 def test_gemm_epilogues():
@@ -180,7 +185,8 @@ def test_layernorm_fusion_gather_and_scatter():
     y = torch.empty(K, B * N, C, device=DEV, dtype=torch.bfloat16)
     mean = torch.empty(K, B * N, device=DEV)
     rstd = torch.empty(K, B * N, device=DEV)
-    ops.ln_fusion_fwd(streams, gamma, beta, y, mean, rstd, B=B, N=N, C_=C, cls_src=cls_src, tok_src=tok_src)
+    x_cls = torch.stack([streams[i].view(B, N, C)[:, 0] for i in cls_src]).contiguous()
+    ops.ln_fusion_fwd(streams, x_cls, gamma, beta, y, mean, rstd, B=B, N=N, C_=C, cls_src=cls_src, tok_src=tok_src)
     sd = streams.double().requires_grad_(True)
     s4 = sd.view(M, B, N, C)
     outs = []
@@ -196,9 +202,24 @@ def test_layernorm_fusion_gather_and_scatter():
     dg = torch.empty(K, C, device=DEV)
     db = torch.empty(K, C, device=DEV)
     ws = ops.ln_bwd_workspace(K, C, DEV)
-    ops.ln_fusion_bwd(dy, streams, mean, rstd, gamma, dstreams, dg, db, ws, B=B, N=N, C_=C, cls_src=cls_src,
+    ops.ln_fusion_bwd(dy, streams, x_cls, mean, rstd, gamma, dstreams, dg, db, ws, B=B, N=N, C_=C, cls_src=cls_src,
                       tok_src=tok_src)
     assert rel(dstreams - base, sd.grad) < 1e-4
+    # extra fp32 gradient on the CLS rows (the query path of the fusion)
+    dy_cls = torch.randn(K, B, C, device=DEV)
+    sd.grad = None
+    outs2 = []
+    for k in range(K):
+        tmp = torch.cat((s4[cls_src[k]][:, 0:1], s4[tok_src[k]][:, 1:]), dim=1)
+        outs2.append(torch.nn.functional.layer_norm(tmp, (C,), gamma[k].double(), beta[k].double(), 1e-5))
+    want2 = torch.stack(outs2).view(K, B, N, C)
+    dy2 = dy.double().view(K, B, N, C).clone()
+    dy2[:, :, 0] += dy_cls.double()
+    want2.backward(dy2)
+    dstreams2 = torch.zeros(M, B * N, C, device=DEV)
+    ops.ln_fusion_bwd(dy, streams, x_cls, mean, rstd, gamma, dstreams2, dg, db, ws, B=B, N=N, C_=C, cls_src=cls_src,
+                      tok_src=tok_src, dy_cls=dy_cls)
+    assert rel(dstreams2, sd.grad) < 1e-4
     status_ok()
 
 
@@ -217,6 +238,11 @@ def test_patchify_bit_exact(img_size, patch):
     for m in range(M):
         want = patchify(img[:, m].cpu(), patch).to(torch.bfloat16).reshape(B * Np, P)
         assert torch.equal(out[m].cpu(), want)   # bit-exact indexing (values are the same RNE cast)
+    out2 = torch.empty(B, M * Np, P, device=DEV, dtype=torch.bfloat16)
+    ops.patchify(img, out2, patch_size=patch, sample_major=True)
+    for m in range(M):
+        want = patchify(img[:, m].cpu(), patch).to(torch.bfloat16)
+        assert torch.equal(out2[:, m * Np:(m + 1) * Np].cpu(), want)
     status_ok()
 
 
@@ -264,6 +290,28 @@ def test_colsum_cast_gather():
     ops.gather_rows_f32(s, d, rows=5, C_=128, groups=G, src_row_stride=9 * 128, src_gs=45 * 128, dst_row_stride=128,
                         dst_gs=5 * 128)
     assert torch.equal(d, s.view(G, 5, 9, 128)[:, :, 0])
+    s2 = s.clone()
+    ops.gather_rows_f32(s2, d, rows=5, C_=128, groups=G, src_row_stride=9 * 128, src_gs=45 * 128, dst_row_stride=128,
+                        dst_gs=5 * 128, accumulate=True, zero_src=True)
+    assert torch.equal(d, 2 * s.view(G, 5, 9, 128)[:, :, 0])
+    assert float(s2.view(G, 5, 9, 128)[:, :, 0].abs().max()) == 0.0
+    assert torch.equal(s2.view(G, 5, 9, 128)[:, :, 1:], s.view(G, 5, 9, 128)[:, :, 1:])
+    a = torch.randn(4096, device=DEV)
+    b = bf(torch.randn(4096, device=DEV))
+    o = torch.empty_like(a)
+    ops.add_bf16_f32(a, b, o)
+    assert torch.equal(o, a + b.float())
+    u = bf(torch.randn(4096, device=DEV))
+    dh = bf(torch.randn(4096, device=DEV))
+    du = torch.empty_like(u)
+    ops.gelu_bwd_bf16(dh, u, du)
+    uu = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uu).backward(dh.float())
+    assert rel(du, uu.grad) < 5e-3
+    tok = bf(torch.randn(6 * 10, 64, device=DEV))
+    comp = torch.empty(6 * 9, 64, device=DEV, dtype=torch.bfloat16)
+    ops.compact_patch_rows_bf16(tok, comp, S=6, Np=9, C_=64)
+    assert torch.equal(comp.view(6, 9, 64), tok.view(6, 10, 64)[:, 1:])
     status_ok()
 
 
