@@ -129,8 +129,7 @@ class _CavitFn(torch.autograd.Function):
     """One autograd node for the whole model: forward and backward are static kernel sequences."""
 
     @staticmethod
-    def forward(ctx, engine, img, labels, *params):
-        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, engine, train, img, labels, *params):
         logits, loss = engine.forward(img, labels, train=train)
         ctx.engine = engine
         ctx.train = train
@@ -152,7 +151,7 @@ class _CavitFn(torch.autograd.Function):
                 grads.append(flat[off:off + p.numel()].view(shp))
             else:
                 grads.append(None)
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
 class _CavitModel(_Base):
@@ -202,7 +201,9 @@ class _CavitModel(_Base):
                                   "use dropout=0.0 or eval()")
         eng = self.engine()
         params = list(eng.params.values())
-        return _CavitFn.apply(eng, img, labels, *params)
+        # grad mode is off inside autograd.Function.forward, so decide here whether to save activations
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _CavitFn.apply(eng, train, img, labels, *params)
 
     # ---------------------------------------------------------------- Lightning-style hooks
     def training_step(self, batch, batch_idx):

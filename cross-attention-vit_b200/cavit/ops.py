@@ -198,3 +198,38 @@ def head_loss_bwd(h, W2, labels, logits, dh, dW2, db2, *, M, B, F, classes, smoo
     check(lib().cavit_head_loss_bwd(h.data_ptr(), W2.data_ptr(), labels.data_ptr(), logits.data_ptr(), loss_scale,
                                     _p(loss_scale_dev), dh.data_ptr(), dW2.data_ptr(), db2.data_ptr(), M, B, F, classes, smoothing,
                                     _stream()), "cavit_head_loss_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# Optional per-launch timing (bench.py's roofline leg): when PROFILE is a list, every wrapper above
+# brackets its launch with CUDA events on the launching stream and appends
+# (name, start_event, end_event, info) to it. Off (None) in normal operation.
+PROFILE = None
+
+
+def _instrument(name, fn):
+    def wrapped(*args, **kw):
+        if PROFILE is None:
+            return fn(*args, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+        out = fn(*args, **kw)
+        e1.record(torch.cuda.current_stream())
+        info = {}
+        if name == "gemm":
+            info = {"flops": 2.0 * kw["M"] * kw["N"] * kw["K"] * kw.get("groups", 1),
+                    "shape": (kw["M"], kw["N"], kw["K"], kw.get("groups", 1), int(kw.get("a_mn", False)), int(kw.get("b_mn", False)))}
+        elif name in ("attn_fwd", "attn_bwd"):
+            mult = 4.0 if name == "attn_fwd" else 10.0   # QK^T + PV ; S, dP, dV, dK, dQ
+            info = {"flops": mult * kw["G"] * kw["B"] * kw["H"] * kw["N"] * kw["N"] * 64}
+        PROFILE.append((name, e0, e1, info))
+        return out
+    wrapped.__name__ = fn.__name__
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+
+
+for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_fwd", "attn_bwd", "xattn_fwd", "xattn_bwd",
+           "patchify", "cls_rows", "embed_param_grads", "cast_bf16", "colsum_bf16", "gather_rows_f32", "add_bf16_f32",
+           "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd"):
+    globals()[_n] = _instrument(_n, globals()[_n])

@@ -1,0 +1,61 @@
+"""CPU, world_size 2, gloo: the slab bookkeeping of cavit.ddp (coalescing of backward-ordered flat
+ranges, in-place averaging) — the host-side logic of the multi-GPU path."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cavit.ddp import SlabReducer
+    from cavit.engine import build_layout
+    from oracle.cases import CASES
+    from oracle.functional import make_config
+    cfg = make_config(**CASES["cross_ring4"][1])
+    lay = build_layout("cross", cfg)
+    flat = torch.full((lay.total,), float(rank + 1))
+    red = SlabReducer(min_elems=lay.total // 4)
+    order = [r for r in lay.layer_ranges if r[0] == "head"]
+    order += sorted([r for r in lay.layer_ranges if r[0] not in ("head", "embed")], key=lambda r: -r[1])
+    order += [r for r in lay.layer_ranges if r[0] == "embed"]
+    n_slabs = 0
+    for tag, s, e in order:
+        ready = red.add(s, e)
+        if tag == "embed":
+            ready += red.flush()
+        for a, b in ready:
+            red.reduce_(flat, a, b)
+            n_slabs += 1
+    covered = sorted(red.issued)
+    ok = covered[0][0] == 0 and covered[-1][1] == lay.total and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    q.put((rank, bool(ok), n_slabs, float(flat.min()), float(flat.max())))
+    dist.destroy_process_group()
+
+
+def test_slab_reducer_covers_flat_buffer_and_averages():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, n_slabs, lo, hi in res:
+        assert ok
+        assert 2 <= n_slabs <= 6
+        assert lo == hi == 1.5      # mean of 1 and 2 everywhere: every element reduced exactly once
