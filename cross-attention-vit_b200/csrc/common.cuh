@@ -200,9 +200,32 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int a_mn, int b_mn
 }
 
 // ---------------------------------------------------------------- math
-__device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU default) evaluated with the Abramowitz-Stegun 7.1.26 rational form of
+// erfc (|abs err| < 1.5e-7, far below bf16 resolution) so that the fused GEMM epilogues need one
+// MUFU.EX2, one MUFU.RCP and ~10 FMAs per element instead of libdevice erff + expf:
+//   Phi(u) = 0.5 erfc(-u / sqrt 2);  erfc(z) = poly(t) e^{-z^2}, t = 1 / (1 + p z), z >= 0
+//   gelu(u) = u Phi(u);  gelu'(u) = Phi(u) + u e^{-u^2/2} / sqrt(2 pi)   (same exponential)
+__device__ __forceinline__ void gelu_phi_terms(float u, float& phi, float& e) {
+  const float z = fabsf(u) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));  // e = exp(-u^2/2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * e;  // 0.5 erfc(|u| / sqrt 2)
+  phi = (u >= 0.f) ? 1.0f - half_erfc : half_erfc;
+}
+__device__ __forceinline__ float gelu_erf(float u) {
+  float phi, e;
+  gelu_phi_terms(u, phi, e);
+  return u * phi;
+}
 __device__ __forceinline__ float gelu_erf_grad(float u) {
-  return 0.5f * (1.0f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+  float phi, e;
+  gelu_phi_terms(u, phi, e);
+  return fmaf(u * 0.3989422804014327f, e, phi);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -2,10 +2,10 @@
 //
 //   D[g][m][n] = sum_k A_g(m,k) * B_g(n,k)      bf16 operands, fp32 accumulation in TMEM
 //
-// One CTA per SM, 192 threads:
+// One CTA per SM, 320 threads:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, mbarrier ring)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1, 128 x BN x 16 per instruction) + TMEM alloc
-//   warps 2..5  epilogue       (tcgen05.ld -> bias / GELU / residual / ... -> global)
+//   warps 2..9  epilogue       (tcgen05.ld -> smem transpose -> bias / GELU / residual / ... -> coalesced global)
 // Two TMEM accumulator stages (2 x BN fp32 columns) let the epilogue of tile i overlap the
 // mainloop of tile i+1. Tiles are walked in a static persistent schedule (tile = cta + i*grid).
 // Operands may be K-major or MN-major (the latter is what dgrad's W and wgrad's dY / X are), so
@@ -19,7 +19,7 @@ namespace cavit {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 
 struct GemmDev {
   int M, N, K, groups;
@@ -29,6 +29,7 @@ struct GemmDev {
   const float* resid; long long ldr, resid_gs;
   void* aux; long long ldaux, aux_gs;
   int tiles_m, tiles_n;
+  int vec_ok;  // all epilogue pointers / leading dimensions allow 16-byte (fp32) / 8-byte (bf16) vector access
   int* status;
 };
 
@@ -39,128 +40,232 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue transpose stages*/;
 };
 
-// Epilogue for one 32-column chunk held by one thread (one output row).
-__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, int g, long long row, int col0, bool row_ok,
-                                               uint32_t (&acc)[32]) {
-  if (!row_ok) return;
-  const int ncols = min(32, p.N - col0);
-  if (ncols <= 0) return;
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+// ---------------------------------------------------------------------------------------- epilogue
+// tcgen05.ld hands every thread one ROW of a 32x32 fp32 accumulator chunk; storing that directly
+// would make each warp store touch 32 different rows (32 sectors per instruction). Each chunk is
+// therefore transposed through a 4 KB XOR-swizzled shared-memory stage (conflict-free both ways) so
+// that afterwards each group of 8 lanes owns one 128-byte row segment: residual / aux loads and all
+// stores are fully coalesced (4 rows x 128 B per warp instruction). The loads a chunk needs
+// (residual, positional embedding, GELU pre-activation) are issued one chunk AHEAD into registers
+// (for the first chunk of a tile even before the accumulator is ready), so that the epilogue
+// streams HBM instead of waiting on it. Eight epilogue warps (two per TMEM lane quadrant, each
+// taking half of the tile's columns) keep this off the critical path of the short-K mainloops.
+// Output modes of the fast path (compile-time): bf16 store, fp32 store, fp32 split-K reduction.
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_RED = 2 };
 
-  const float* bias = p.bias ? p.bias + (long long)g * p.bias_gs + col0 : nullptr;
-  long long out_row = row;
-  if (p.epi == CAVIT_EPI_EMBED) {
-    const long long b = row / p.embed_np, t = row % p.embed_np;
-    out_row = b * (p.embed_np + 1) + 1 + t;
-  }
-  const bool full = (ncols == 32);
+__device__ __forceinline__ void stg_v2(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(p)), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void stg_v4f(void* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void red_add_f32(void* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(a) : "memory");
+}
+__device__ __forceinline__ float4 ldg_v4f(const void* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(__cvta_generic_to_global(p))
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ldg_v2(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(__cvta_generic_to_global(p)) : "memory");
+  return v;
+}
 
-  if (bias) {
-    if (full) {
+// Per-lane addressing of the transposed domain, computed once per tile: lane (rsub = lane/8,
+// c4 = lane%8) owns columns [c4*4, c4*4+4) of rows rsub, rsub+4, ... of the warp's 32-row slab.
+struct EpiLane {
+  char* out;          // &out[g][row0 + rsub][0]
+  const char* resid;  // &resid[g][row0 + rsub][0]
+  char* aux;          // &aux[g][row0 + rsub][0]
+  const float* bias;  // &bias[g][0]
+  long long out_step, resid_step, aux_step;  // byte strides for 4 rows
+  int rows_left;      // rows of this lane's 8 that are inside M: iteration `it` is valid iff it*4 < rows_left
+};
+
+template <int EPI>
+struct EpiPre {
+  float4 r[(EPI == CAVIT_EPI_BIAS_RESID) ? 8 : 1];
+  uint2 a[(EPI == CAVIT_EPI_GELU_BWD) ? 8 : 1];
+};
+
+template <int EPI>
+__device__ __forceinline__ void epi_prefetch(const EpiLane& L, int col, EpiPre<EPI>& pre) {
+  if (EPI != CAVIT_EPI_BIAS_RESID && EPI != CAVIT_EPI_GELU_BWD) return;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + i));
-        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-      }
-    } else {
-      for (int i = 0; i < ncols; ++i) v[i] += __ldg(bias + i);
+  for (int it = 0; it < 8; ++it) {
+    if (it * 4 < L.rows_left) {
+      if (EPI == CAVIT_EPI_BIAS_RESID) pre.r[it] = ldg_v4f(L.resid + it * L.resid_step + col * 4);
+      else pre.a[it] = ldg_v2(L.aux + it * L.aux_step + col * 2);
     }
   }
+}
 
-  if (p.epi == CAVIT_EPI_BIAS_GELU) {
-    bf16* aux = reinterpret_cast<bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col0;
-    if (full && (p.ldaux % 8 == 0)) {
+// Fast path: all pointers / leading dimensions vector-aligned and the chunk's 32 columns inside N.
+template <int EPI, int OUT>
+__device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const float* stage, int lane, const EpiPre<EPI>& pre) {
+  const int c4 = lane & 7, rsub = lane >> 3;
+  float4 t[8];
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 q;
-        q.x = pack_bf16(v[i], v[i + 1]); q.y = pack_bf16(v[i + 2], v[i + 3]);
-        q.z = pack_bf16(v[i + 4], v[i + 5]); q.w = pack_bf16(v[i + 6], v[i + 7]);
-        *reinterpret_cast<uint4*>(aux + i) = q;
-      }
-    } else {
-      for (int i = 0; i < ncols; ++i) aux[i] = __float2bfloat16(v[i]);
-    }
-    // GELU is applied to the bf16-rounded pre-activation so that backward (which reads u as
-    // bf16) differentiates exactly the function the forward evaluated.
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(__bfloat162float(__float2bfloat16(v[i])));
-  } else if (p.epi == CAVIT_EPI_GELU_BWD) {
-    const bf16* aux = reinterpret_cast<const bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col0;
-    if (full && (p.ldaux % 8 == 0)) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        const uint4 q = *reinterpret_cast<const uint4*>(aux + i);
-        float2 f;
-        f = unpack_bf16(q.x); v[i] *= gelu_erf_grad(f.x); v[i + 1] *= gelu_erf_grad(f.y);
-        f = unpack_bf16(q.y); v[i + 2] *= gelu_erf_grad(f.x); v[i + 3] *= gelu_erf_grad(f.y);
-        f = unpack_bf16(q.z); v[i + 4] *= gelu_erf_grad(f.x); v[i + 5] *= gelu_erf_grad(f.y);
-        f = unpack_bf16(q.w); v[i + 6] *= gelu_erf_grad(f.x); v[i + 7] *= gelu_erf_grad(f.y);
-      }
-    } else {
-      for (int i = 0; i < ncols; ++i) v[i] *= gelu_erf_grad(__bfloat162float(aux[i]));
-    }
-  } else if (p.epi == CAVIT_EPI_BIAS_RESID || p.epi == CAVIT_EPI_EMBED) {
-    const float* r;
-    if (p.epi == CAVIT_EPI_BIAS_RESID)
-      r = p.resid + (long long)g * p.resid_gs + row * p.ldr + col0;
-    else
-      r = p.resid + (1 + row % p.embed_np) * p.ldr + col0;  // positional embedding row 1 + t
-    if (full && (p.ldr % 4 == 0)) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 r4 = *reinterpret_cast<const float4*>(r + i);
-        v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
-      }
-    } else {
-      for (int i = 0; i < ncols; ++i) v[i] += r[i];
-    }
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    t[it] = reinterpret_cast<const float4*>(stage + r * 32)[c4 ^ (r & 7)];
   }
-
-  if (p.split_k > 1) {  // partial tile of a split-K reduction: combine with fp32 atomics
-    float* o = reinterpret_cast<float*>(p.out) + (long long)g * p.out_gs + out_row * p.ldo + col0;
-    for (int i = 0; i < ncols; ++i) atomicAdd(o + i, v[i]);
-    return;
-  }
-  if (p.out_fp32) {
-    float* o = reinterpret_cast<float*>(p.out) + (long long)g * p.out_gs + out_row * p.ldo + col0;
-    if (full && (p.ldo % 4 == 0)) {
-      if (p.accumulate) {
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr bool kBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID);
+  if (kBias) b = __ldg(reinterpret_cast<const float4*>(L.bias + col));
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 o4 = *reinterpret_cast<float4*>(o + i);
-          o4.x += v[i]; o4.y += v[i + 1]; o4.z += v[i + 2]; o4.w += v[i + 3];
-          *reinterpret_cast<float4*>(o + i) = o4;
-        }
+  for (int it = 0; it < 8; ++it) {
+    if (it * 4 < L.rows_left) {
+      float v0 = t[it].x, v1 = t[it].y, v2 = t[it].z, v3 = t[it].w;
+      if (kBias) { v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w; }
+      if (EPI == CAVIT_EPI_BIAS_GELU) {
+        const uint32_t q0 = pack_bf16(v0, v1), q1 = pack_bf16(v2, v3);
+        stg_v2(L.aux + it * L.aux_step + col * 2, q0, q1);
+        // GELU of the bf16-rounded pre-activation: backward differentiates exactly what forward evaluated
+        const float2 u0 = unpack_bf16(q0), u1 = unpack_bf16(q1);
+        v0 = gelu_erf(u0.x); v1 = gelu_erf(u0.y); v2 = gelu_erf(u1.x); v3 = gelu_erf(u1.y);
+      } else if (EPI == CAVIT_EPI_GELU_BWD) {
+        const float2 u0 = unpack_bf16(pre.a[it].x), u1 = unpack_bf16(pre.a[it].y);
+        v0 *= gelu_erf_grad(u0.x); v1 *= gelu_erf_grad(u0.y); v2 *= gelu_erf_grad(u1.x); v3 *= gelu_erf_grad(u1.y);
+      } else if (EPI == CAVIT_EPI_BIAS_RESID) {
+        v0 += pre.r[it].x; v1 += pre.r[it].y; v2 += pre.r[it].z; v3 += pre.r[it].w;
+      }
+      char* o = L.out + it * L.out_step;
+      if (OUT == OUT_RED) {
+        float* of = reinterpret_cast<float*>(o) + col;
+        red_add_f32(of, v0); red_add_f32(of + 1, v1); red_add_f32(of + 2, v2); red_add_f32(of + 3, v3);
+      } else if (OUT == OUT_F32) {
+        stg_v4f(o + col * 4, v0, v1, v2, v3);
       } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        stg_v2(o + col * 2, pack_bf16(v0, v1), pack_bf16(v2, v3));
       }
-    } else {
-      for (int i = 0; i < ncols; ++i) o[i] = p.accumulate ? o[i] + v[i] : v[i];
     }
-  } else {
-    bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)g * p.out_gs + out_row * p.ldo + col0;
-    if (full && (p.ldo % 8 == 0)) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 q;
-        q.x = pack_bf16(v[i], v[i + 1]); q.y = pack_bf16(v[i + 2], v[i + 3]);
-        q.z = pack_bf16(v[i + 4], v[i + 5]); q.w = pack_bf16(v[i + 6], v[i + 7]);
-        *reinterpret_cast<uint4*>(o + i) = q;
+  }
+}
+
+// Generic path (ragged N, unaligned leading dimensions, accumulate, the CLS-skipping row map of the embedding).
+template <int EPI>
+__device__ __noinline__ void epi_chunk_slow(const GemmDev* pp, int g, long long row0, int col0, const float* stage, int lane) {
+  const GemmDev& p = *pp;
+  const int c4 = lane & 7, rsub = lane >> 3;
+  const int col = col0 + c4 * 4;
+  const int ncols = min(4, p.N - col);
+  if (ncols <= 0) return;
+  float b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias)
+    for (int i = 0; i < ncols; ++i) b[i] = __ldg(p.bias + (long long)g * p.bias_gs + col + i);
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    const long long row = row0 + r;
+    if (row >= p.M) break;
+    const float4 t = reinterpret_cast<const float4*>(stage + r * 32)[c4 ^ (r & 7)];
+    float v[4] = {t.x + b[0], t.y + b[1], t.z + b[2], t.w + b[3]};
+    long long out_row = row;
+    if (EPI == CAVIT_EPI_EMBED) out_row = (row / p.embed_np) * (p.embed_np + 1) + 1 + row % p.embed_np;
+    if (EPI == CAVIT_EPI_BIAS_GELU) {
+      bf16* aux = reinterpret_cast<bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col;
+      for (int i = 0; i < ncols; ++i) {
+        const bf16 u = __float2bfloat16(v[i]);
+        aux[i] = u;
+        v[i] = gelu_erf(__bfloat162float(u));
+      }
+    } else if (EPI == CAVIT_EPI_GELU_BWD) {
+      const bf16* aux = reinterpret_cast<const bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col;
+      for (int i = 0; i < ncols; ++i) v[i] *= gelu_erf_grad(__bfloat162float(aux[i]));
+    } else if (EPI == CAVIT_EPI_BIAS_RESID || EPI == CAVIT_EPI_EMBED) {
+      const float* rp = (EPI == CAVIT_EPI_BIAS_RESID) ? p.resid + (long long)g * p.resid_gs + row * p.ldr + col
+                                                      : p.resid + (1 + row % p.embed_np) * p.ldr + col;
+      for (int i = 0; i < ncols; ++i) v[i] += rp[i];
+    }
+    if (p.out_fp32) {
+      float* o = reinterpret_cast<float*>(p.out) + (long long)g * p.out_gs + out_row * p.ldo + col;
+      for (int i = 0; i < ncols; ++i) {
+        if (p.split_k > 1) red_add_f32(o + i, v[i]);
+        else o[i] = p.accumulate ? o[i] + v[i] : v[i];
       }
     } else {
+      bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)g * p.out_gs + out_row * p.ldo + col;
       for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(v[i]);
     }
   }
 }
 
-template <int BN>
+// Body of one epilogue warp: q = TMEM lane quadrant (rows q*32..), half = which half of the tile's columns.
+template <int BN, int EPI, int OUT>
+__device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                              float* stage, volatile int* abort_flag, int q, int half, int lane,
+                                              int total_tiles, int splits, int tiles_per_group) {
+  constexpr int CH = BN / 64;  // 32-column chunks per warp
+  const int c4 = lane & 7, rsub = lane >> 3;
+  const bool fast_kind = p.vec_ok && EPI != CAVIT_EPI_EMBED;
+  constexpr int osz = (OUT == OUT_BF16) ? 2 : 4;
+  int as = 0;
+  uint32_t aphase = 0;
+  for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+    const int tile = work / splits;
+    const int g = tile / tiles_per_group;
+    const int rem = tile - g * tiles_per_group;
+    const int m0 = (rem / p.tiles_n) * GEMM_BM;
+    const int n0 = (rem % p.tiles_n) * BN + half * (BN / 2);
+    const long long row0 = (long long)m0 + q * 32;
+    EpiLane L;
+    {
+      const long long r = row0 + rsub;
+      L.out = reinterpret_cast<char*>(p.out) + ((long long)g * p.out_gs + r * p.ldo) * osz;
+      L.out_step = 4 * p.ldo * osz;
+      L.resid = reinterpret_cast<const char*>(p.resid) + ((long long)g * p.resid_gs + r * p.ldr) * 4;
+      L.resid_step = 16 * p.ldr;
+      L.aux = reinterpret_cast<char*>(p.aux) + ((long long)g * p.aux_gs + r * p.ldaux) * 2;
+      L.aux_step = 8 * p.ldaux;
+      L.bias = p.bias + (long long)g * p.bias_gs;
+      const long long left = (long long)p.M - r;
+      L.rows_left = left > 32 ? 32 : (left < 0 ? 0 : (int)left);
+    }
+    EpiPre<EPI> pre;
+    if (fast_kind && n0 + 32 <= p.N) epi_prefetch<EPI>(L, n0 + c4 * 4, pre);  // overlaps the tile's mainloop
+    mbar_wait(tfull0 + 8u * as, aphase, abort_flag, p.status, ERR_TIMEOUT_TMEM_FULL);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * (BN / 2);
+#pragma unroll 1
+    for (int c = 0; c < CH; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) break;  // warp-uniform
+      uint32_t acc[32];
+      tmem_ld32(t_row + c * 32, acc);
+      tmem_ld_wait();
+      float4* srow = reinterpret_cast<float4*>(stage + lane * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        srow[j ^ (lane & 7)] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                           __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+      __syncwarp();
+      if (fast_kind && (col0 + 32 <= p.N)) {  // warp-uniform
+        const EpiPre<EPI> cur = pre;
+        if (c + 1 < CH && col0 + 64 <= p.N) epi_prefetch<EPI>(L, col0 + 32 + c4 * 4, pre);
+        epi_chunk_fast<EPI, OUT>(L, col0 + c4 * 4, stage, lane, cur);
+      } else {
+        epi_chunk_slow<EPI>(&p, g, row0, col0, stage, lane);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty0 + 8u * as);
+    as ^= 1;
+    if (as == 0) aphase ^= 1u;
+  }
+}
+
+template <int BN, int EPI, int OUT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmDev p) {
@@ -178,6 +283,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* epi_stage = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -190,7 +296,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 8);
     }
     fence_barrier_init();
     prefetch_tmap(&tmA);
@@ -287,35 +393,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-      const int tile = work / splits;
-      const int g = tile / tiles_per_group;
-      const int rem = tile - g * tiles_per_group;
-      const int m0 = (rem / p.tiles_n) * GEMM_BM;
-      const int n0 = (rem % p.tiles_n) * BN;
-      mbar_wait(tfull_bar(as), aphase, abort_flag, p.status, ERR_TIMEOUT_TMEM_FULL);
-      tc_fence_after();
-      const long long row = (long long)m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n0 + c * 32 >= p.N) break;  // warp-uniform
-        uint32_t acc[32];
-        tmem_ld32(t_row + c * 32, acc);
-        tmem_ld_wait();
-        epilogue_chunk(p, g, row, n0 + c * 32, row_ok, acc);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
-      as ^= 1;
-      if (as == 0) aphase ^= 1u;
-    }
+    // ------------------------------------------------------------------ epilogue warps (2..9)
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // column half of the tile
+    float* stage = epi_stage + (warp - 2) * 1024;
+    epilogue_role<BN, EPI, OUT>(p, tmem_base, tfull_bar(0), tempty_bar(0), stage, abort_flag, q, half, lane, total_tiles, splits,
+                           tiles_per_group);
   }
 
   tc_fence_before();
@@ -326,16 +409,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
+template <int BN, int EPI, int OUT>
+static int launch_gemm_epi(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, OUT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "gemm smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  const long long total = (long long)d.tiles_m * d.tiles_n * d.groups * d.split_k;
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  gemm_bf16_tcgen05_kernel<BN, EPI, OUT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, d);
+  count_launch();
+  return check_launch("cavit_gemm");
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
   d.tiles_m = (d.M + GEMM_BM - 1) / GEMM_BM;
   d.tiles_n = (d.N + BN - 1) / BN;
   const int num_kb = (d.K + GEMM_BK - 1) / GEMM_BK;
@@ -343,11 +435,21 @@ static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d,
   if (d.split_k < 1) d.split_k = 1;
   d.kb_per_split = (num_kb + d.split_k - 1) / d.split_k;
   d.split_k = (num_kb + d.kb_per_split - 1) / d.kb_per_split;  // no empty splits
-  const long long total = (long long)d.tiles_m * d.tiles_n * d.groups * d.split_k;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, d);
-  count_launch();
-  return check_launch("cavit_gemm");
+  if (d.accumulate) d.vec_ok = 0;  // read-modify-write outputs take the generic path
+  const int out = d.split_k > 1 ? OUT_RED : (d.out_fp32 ? OUT_F32 : OUT_BF16);
+#define CAVIT_GEMM_CASE(E, O) \
+  if (d.epi == E && out == O) return launch_gemm_epi<BN, E, O>(ta, tb, d, stream);
+  CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_BF16)
+  CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_F32)
+  CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_RED)
+  CAVIT_GEMM_CASE(CAVIT_EPI_BIAS, OUT_BF16)
+  CAVIT_GEMM_CASE(CAVIT_EPI_BIAS, OUT_F32)
+  CAVIT_GEMM_CASE(CAVIT_EPI_BIAS_GELU, OUT_BF16)
+  CAVIT_GEMM_CASE(CAVIT_EPI_BIAS_RESID, OUT_F32)
+  CAVIT_GEMM_CASE(CAVIT_EPI_GELU_BWD, OUT_BF16)
+  CAVIT_GEMM_CASE(CAVIT_EPI_EMBED, OUT_F32)
+#undef CAVIT_GEMM_CASE
+  return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_gemm: epilogue %d with output mode %d is not instantiated", d.epi, out);
 }
 
 }  // namespace cavit
@@ -372,6 +474,8 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   if ((a->epi == CAVIT_EPI_BIAS_RESID || a->epi == CAVIT_EPI_EMBED) && (!a->resid || !a->out_fp32))
     return fail(CAVIT_E_BADARG, "cavit_gemm: residual epilogues need resid and fp32 out");
   if (a->epi == CAVIT_EPI_EMBED && a->embed_np <= 0) return fail(CAVIT_E_BADARG, "cavit_gemm: embed_np");
+  if ((a->epi == CAVIT_EPI_BIAS || a->epi == CAVIT_EPI_BIAS_GELU || a->epi == CAVIT_EPI_BIAS_RESID || a->epi == CAVIT_EPI_EMBED) && !a->bias)
+    return fail(CAVIT_E_BADARG, "cavit_gemm: epilogue %d needs bias", a->epi);
   if (a->accumulate && !a->out_fp32) return fail(CAVIT_E_BADARG, "cavit_gemm: accumulate needs fp32 out");
   if (a->split_k > 1 && (!a->out_fp32 || a->epi != CAVIT_EPI_NONE))
     return fail(CAVIT_E_BADARG, "cavit_gemm: split_k needs fp32 out and EPI_NONE");
@@ -401,6 +505,13 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   d.resid = a->resid; d.ldr = a->ldr; d.resid_gs = a->resid_gs;
   d.aux = a->aux; d.ldaux = a->ldaux; d.aux_gs = a->aux_gs;
   d.tiles_m = d.tiles_n = 0;
+  {
+    auto al = [](const void* q, uintptr_t m) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & (m - 1)) == 0; };
+    const bool out_ok = a->out_fp32 ? (al(a->out, 16) && a->ldo % 4 == 0 && a->out_gs % 4 == 0)
+                                    : (al(a->out, 8) && a->ldo % 4 == 0 && a->out_gs % 4 == 0);
+    d.vec_ok = out_ok && al(a->bias, 16) && a->bias_gs % 4 == 0 && al(a->resid, 16) && a->ldr % 4 == 0 &&
+               a->resid_gs % 4 == 0 && al(a->aux, 8) && a->ldaux % 4 == 0 && a->aux_gs % 4 == 0;
+  }
   d.split_k = a->split_k > 1 ? a->split_k : 1;
   d.kb_per_split = 0;
   d.status = status;
