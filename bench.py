@@ -234,7 +234,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _abi.launch_count()
+    def n_launches():
+        return _abi.launch_count() + model.engine().graph_launches
+    launches0 = n_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -242,7 +244,7 @@ def main():
         loss = step_resident()
     e1.record()
     barrier()
-    launches = _abi.launch_count() - launches0
+    launches = n_launches() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
@@ -255,7 +257,7 @@ def main():
         loss.backward()
         for p in model.parameters():
             p.grad = None
-        return float(loss)          # device -> host read of the step's result
+        return float(loss.detach())   # device -> host read of the step's result
 
     step_e2e()
     barrier()

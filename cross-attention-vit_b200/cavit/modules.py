@@ -139,7 +139,7 @@ class _CavitFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _dlogits, dloss):
         eng = ctx.engine
-        hook = getattr(eng, "on_range_done", None)
+        hook = eng.on_range_done
         scale_dev = None
         if dloss is not None:  # consumed on the device: no host synchronisation between fwd and bwd
             scale_dev = dloss.detach().to(device=eng.device, dtype=torch.float32).reshape(1).contiguous()

@@ -51,6 +51,26 @@ __device__ __forceinline__ void store_row_chunk_sw128(uint8_t* tile, int r, int 
   }
 }
 
+// Same for 16 consecutive values (c0 multiple of 16).
+__device__ __forceinline__ void store_row_16_sw128(uint8_t* tile, int r, int c0, const float (&v)[16]) {
+  const int half = c0 >> 6;
+  const int c16_0 = (c0 & 63) >> 3;
+  uint8_t* row = tile + half * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 q;
+    q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+    q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(row + (((c16_0 + i) ^ (r & 7)) << 4)) = q;
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 struct AttnFwdParams {
   bf16* out;
   float* lse;
@@ -60,10 +80,11 @@ struct AttnFwdParams {
   int* status;
 };
 
-// smem: Q | K0 | K1 | V0 | V1 | P(2 chunks) | barriers
-constexpr int ATT_FWD_SMEM = 7 * ATT_TILE_BYTES + 1024 + 128;
+// smem: Q | K0 | K1 | V0 | V1 | P(2 chunks) | row max / sum exchange [2][128] x2 | barriers
+constexpr int ATT_FWD_THREADS = 256;  // 8 warps: two per TMEM lane quadrant, each owning half of the key columns
+constexpr int ATT_FWD_SMEM = 7 * ATT_TILE_BYTES + 1024 + 2048 + 128;
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -71,12 +92,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   const uint32_t sQ = base, sK = base + ATT_TILE_BYTES, sV = base + 3 * ATT_TILE_BYTES;
   const uint32_t sP = base + 5 * ATT_TILE_BYTES;
   uint8_t* genP = gen + 5 * ATT_TILE_BYTES;
-  const uint32_t bar0 = base + 7 * ATT_TILE_BYTES;
+  float* s_max = reinterpret_cast<float*>(gen + 7 * ATT_TILE_BYTES);  // [2][128]
+  float* s_sum = s_max + 2 * ATT_TILE;                                 // [2][128]
+  const uint32_t bar0 = base + 7 * ATT_TILE_BYTES + 2048;
   const uint32_t bar_q = bar0, bar_kv0 = bar0 + 8, bar_s = bar0 + 24, bar_o = bar0 + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 7 * ATT_TILE_BYTES + 40);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 7 * ATT_TILE_BYTES + 2048 + 40);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2;  // TMEM lane quadrant; column half
+  const int row = quad * 32 + lane;             // query row inside the tile (= TMEM lane)
   const int g = blockIdx.z, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int q0 = blockIdx.x * ATT_TILE;
   const int row_base = b * p.N;
@@ -112,11 +137,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
 
   const uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);
   const uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);
-  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
 
-  float o[ATT_D];
+  float o[32];  // this thread's half (32 of 64) of the output row
 #pragma unroll
-  for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
+  for (int i = 0; i < 32; ++i) o[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
 
   for (int j = 0; j < nkv; ++j) {
@@ -143,38 +168,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     tc_fence_after();
 
     const int kv_valid = min(ATT_TILE, p.N - j * ATT_TILE);  // columns < kv_valid are real keys
-    // pass 1: row maximum (log2 domain)
-    float m_tile = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tS + t_lane + c * 32, r);
-      tmem_ld_wait();
+    const int cbase = part * 64;                              // this warp's 64 key columns
+    uint32_t s0[32], s1[32];
+    tmem_ld32(tS + t_lane + cbase, s0);
+    tmem_ld32(tS + t_lane + cbase + 32, s1);
+    tmem_ld_wait();
+    float m_part = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c * 32 + i < kv_valid) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+    for (int i = 0; i < 32; ++i) {
+      if (cbase + i < kv_valid) m_part = fmaxf(m_part, __uint_as_float(s0[i]));
+      if (cbase + 32 + i < kv_valid) m_part = fmaxf(m_part, __uint_as_float(s1[i]));
     }
+    s_max[part * ATT_TILE + row] = m_part;
+    named_bar_sync(1 + quad, 64);  // the two warps of this lane quadrant
+    const float m_tile = fmaxf(m_part, s_max[(part ^ 1) * ATT_TILE + row]);
     const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
     const float alpha = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
-    float l_tile = 0.f;
-    // pass 2: probabilities -> bf16 -> swizzled smem
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tS + t_lane + c * 32, r);
-      tmem_ld_wait();
+    float l_part = 0.f;
+    {
       float pv[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float e = ex2_approx(__uint_as_float(r[i]) * p.scale_log2 - m_new);
-        pv[i] = (c * 32 + i < kv_valid) ? e : 0.f;
-        // sum what the MMA will actually see (bf16-rounded probabilities)
-        l_tile += __bfloat162float(__float2bfloat16(pv[i]));
+        const float e = ex2_approx(__uint_as_float(s0[i]) * p.scale_log2 - m_new);
+        pv[i] = (cbase + i < kv_valid) ? e : 0.f;
+        l_part += pv[i];
       }
-      store_row_chunk_sw128(genP, tid, c * 32, pv);
+      store_row_chunk_sw128(genP, row, cbase, pv);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e = ex2_approx(__uint_as_float(s1[i]) * p.scale_log2 - m_new);
+        pv[i] = (cbase + 32 + i < kv_valid) ? e : 0.f;
+        l_part += pv[i];
+      }
+      store_row_chunk_sw128(genP, row, cbase + 32, pv);
     }
-    l_run = l_run * alpha + l_tile;
-    m_run = m_new;
+    s_sum[part * ATT_TILE + row] = l_part;
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
@@ -188,26 +216,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       }
       umma_commit(bar_o);
     }
+    l_run = l_run * alpha + (l_part + s_sum[(part ^ 1) * ATT_TILE + row]);
+    m_run = m_new;
     mbar_wait(bar_o, j & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t r[32];
-      tmem_ld32(tO + t_lane + c * 32, r);
+      tmem_ld32(tO + t_lane + part * 32, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(r[i]);
     }
     tc_fence_before();
-    __syncthreads();  // everyone is done with S / O / P of this tile before thread 0 reuses them
+    __syncthreads();  // everyone is done with S / O / P / exchange buffers before they are reused
   }
 
-  const int q = q0 + tid;
+  const int q = q0 + row;
   if (q < p.N) {
     const float inv_l = 1.0f / l_run;
-    bf16* orow = p.out + (long long)g * p.out_gs + (long long)(row_base + q) * p.C + h * ATT_D;
+    bf16* orow = p.out + (long long)g * p.out_gs + (long long)(row_base + q) * p.C + h * ATT_D + part * 32;
 #pragma unroll
-    for (int i = 0; i < ATT_D; i += 8) {
+    for (int i = 0; i < 32; i += 8) {
       uint4 w;
       w.x = pack_bf16(o[i] * inv_l, o[i + 1] * inv_l);
       w.y = pack_bf16(o[i + 2] * inv_l, o[i + 3] * inv_l);
@@ -215,7 +244,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       w.w = pack_bf16(o[i + 6] * inv_l, o[i + 7] * inv_l);
       *reinterpret_cast<uint4*>(orow + i) = w;
     }
-    p.lse[(((long long)g * p.B + b) * p.H + h) * p.N + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+    if (part == 0)
+      p.lse[(((long long)g * p.B + b) * p.H + h) * p.N + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
   }
   tc_fence_before();
   __syncthreads();
@@ -261,7 +291,9 @@ struct AttnBwdParams {
 // smem: K | V | Q0 | Q1 | dO0 | dO1 | PT(2 chunks) | dST(2 chunks) | lse[128] delta[128] | barriers
 constexpr int ATT_BWD_SMEM = 10 * ATT_TILE_BYTES + 1024 + 1024 + 128;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+constexpr int ATT_BWD_THREADS = 512;  // 16 warps: four per TMEM lane quadrant, each owning 32 of the 128 query columns
+
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -278,7 +310,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 10 * ATT_TILE_BYTES + 1024 + 40);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2;  // TMEM lane quadrant; 32-column slice of the query tile
+  const int trow = quad * 32 + lane;            // row inside the tile (= TMEM lane)
   const int g = blockIdx.z, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int kv0 = blockIdx.x * ATT_TILE;
   const int row_base = b * p.N;
@@ -304,7 +338,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
-  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_kv, 2 * ATT_TILE_BYTES);
@@ -319,13 +353,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t idesc_kmn = umma_idesc_bf16(64, 0, 1);   // dV, dK    : A K-major (smem P^T/dS^T), B MN-major, N = 64
   const uint32_t idesc_mnmn = umma_idesc_bf16(64, 1, 1);  // dQ        : A = dS^T viewed MN-major, B = K MN-major
   const long long lse_base = (((long long)g * p.B + b) * p.H + h) * p.N;
-  const bool kv_ok = (kv0 + tid) < p.N;
+  const bool kv_ok = (kv0 + trow) < p.N;
 
   for (int i = 0; i < nq; ++i) {
     const int buf = i & 1;
     const int q0 = i * ATT_TILE;
     // stage LSE / delta of this query tile (log2 domain for LSE)
-    {
+    if (tid < ATT_TILE) {
       const int q = q0 + tid;
       s_lse[tid] = (q < p.N) ? p.lse[lse_base + q] * 1.4426950408889634f : 0.f;
       s_delta[tid] = (q < p.N) ? p.delta[lse_base + q] : 0.f;
@@ -358,23 +392,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_wait(bar_s, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
     tc_fence_after();
     const int q_valid = min(ATT_TILE, p.N - q0);
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tST + t_lane + c * 32, rs);
-      tmem_ld32(tDPT + t_lane + c * 32, rp);
-      tmem_ld_wait();
-      float pt[32], dst[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = c * 32 + j;
+    for (int hc = 0; hc < 2; ++hc) {  // this warp's 32 query columns, 16 at a time (register budget)
+      const int cb = part * 32 + hc * 16;
+      uint32_t rs[16], rp[16];
+      tmem_ld16(tST + t_lane + cb, rs);
+      tmem_ld16(tDPT + t_lane + cb, rp);
+      tmem_ld_wait();
+      float pt[16], dst[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = cb + j;
         const bool ok = kv_ok && (col < q_valid);
         const float pr = ok ? ex2_approx(__uint_as_float(rs[j]) * p.scale_log2 - s_lse[col]) : 0.f;
         pt[j] = pr;
         dst[j] = pr * (__uint_as_float(rp[j]) - s_delta[col]);
       }
-      store_row_chunk_sw128(genPT, tid, c * 32, pt);
-      store_row_chunk_sw128(genDST, tid, c * 32, dst);
+      store_row_16_sw128(genPT, trow, cb, pt);
+      store_row_16_sw128(genDST, trow, cb, dst);
     }
     tc_fence_before();
     fence_proxy_async_smem();
@@ -407,47 +442,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_wait(bar_d, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
     tc_fence_after();
     {
-      const int q = q0 + tid;
-      float* acc = p.dq_acc + (long long)g * p.acc_gs + (long long)(row_base + q) * p.C + h * ATT_D;
+      const int q = q0 + trow;
+      float* acc = p.dq_acc + (long long)g * p.acc_gs + (long long)(row_base + q) * p.C + h * ATT_D + part * 16;
+      uint32_t r[16];
+      tmem_ld16(tDQ + t_lane + part * 16, r);
+      tmem_ld_wait();
+      if (q < p.N) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tDQ + t_lane + c * 32, r);
-        tmem_ld_wait();
-        if (q < p.N) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(acc + c * 32 + j, __uint_as_float(r[j]) * p.scale);
-        }
+        for (int j = 0; j < 16; ++j) atomicAdd(acc + j, __uint_as_float(r[j]) * p.scale);
       }
     }
     tc_fence_before();
     __syncthreads();
   }
 
-  // write dK (scaled) and dV for this key/value tile
+  // write dK (scaled) and dV for this key/value tile: each warp stores a 16-column slice of both
   {
-    const int kv = kv0 + tid;
-    bf16* drow = p.dqkv + (long long)g * p.qkv_gs + (long long)(row_base + kv) * (3 * p.C) + h * ATT_D;
+    const int kv = kv0 + trow;
+    bf16* drow = p.dqkv + (long long)g * p.qkv_gs + (long long)(row_base + kv) * (3 * p.C) + h * ATT_D + part * 16;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const uint32_t t = which == 0 ? tDK : tDV;
       const float sc = which == 0 ? p.scale : 1.0f;
       bf16* dst = drow + (which == 0 ? p.C : 2 * p.C);
+      uint32_t r[16];
+      tmem_ld16(t + t_lane + part * 16, r);
+      tmem_ld_wait();
+      if (kv < p.N) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t + t_lane + c * 32, r);
-        tmem_ld_wait();
-        if (kv < p.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 w;
-            w.x = pack_bf16(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc);
-            w.y = pack_bf16(__uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
-            w.z = pack_bf16(__uint_as_float(r[j + 4]) * sc, __uint_as_float(r[j + 5]) * sc);
-            w.w = pack_bf16(__uint_as_float(r[j + 6]) * sc, __uint_as_float(r[j + 7]) * sc);
-            *reinterpret_cast<uint4*>(dst + c * 32 + j) = w;
-          }
+        for (int j = 0; j < 16; j += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc);
+          w.y = pack_bf16(__uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
+          w.z = pack_bf16(__uint_as_float(r[j + 4]) * sc, __uint_as_float(r[j + 5]) * sc);
+          w.w = pack_bf16(__uint_as_float(r[j + 6]) * sc, __uint_as_float(r[j + 7]) * sc);
+          *reinterpret_cast<uint4*>(dst + j) = w;
         }
       }
     }
@@ -504,7 +533,7 @@ int cavit_attn_fwd(const void* qkv, void* out, float* lse, int32_t G, int32_t B,
   p.status = status_word();
   if (!p.status) return fail(CAVIT_E_DEVICE, "no status word");
   dim3 grid((N + ATT_TILE - 1) / ATT_TILE, B * H, G);
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_FWD_SMEM, as_stream(stream)>>>(*tm, p);
+  attn_fwd_kernel<<<grid, ATT_FWD_THREADS, ATT_FWD_SMEM, as_stream(stream)>>>(*tm, p);
   count_launch();
   return check_launch("cavit_attn_fwd");
 }
@@ -547,7 +576,7 @@ int cavit_attn_bwd(const void* qkv, const void* out, const void* dout, const flo
   p.status = status_word();
   if (!p.status) return fail(CAVIT_E_DEVICE, "no status word");
   dim3 grid((N + ATT_TILE - 1) / ATT_TILE, B * H, G);
-  attn_bwd_kernel<<<grid, ATT_THREADS, ATT_BWD_SMEM, st>>>(*tq, *td, p);
+  attn_bwd_kernel<<<grid, ATT_BWD_THREADS, ATT_BWD_SMEM, st>>>(*tq, *td, p);
   count_launch();
   int rc = check_launch("cavit_attn_bwd");
   if (rc) return rc;

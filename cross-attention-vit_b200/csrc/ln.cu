@@ -19,7 +19,7 @@ namespace cavit {
 
 constexpr int LN_THREADS = 256;
 constexpr int LN_WARPS = LN_THREADS / 32;
-constexpr int LN_MAX_BLOCKS_PER_GROUP = 64;
+constexpr int LN_MAX_BLOCKS_PER_GROUP = 256;
 constexpr int LN_MAX_FUSIONS = 16;
 
 struct RowMap {
@@ -105,7 +105,7 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
   }
 }
 
-// grid = (blocks_per_group, groups). partials: [groups][blocks_per_group*LN_WARPS][2][C]
+// grid = (blocks_per_group, groups). partials: [groups][blocks_per_group][2][C]
 template <int NV>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long long row_stride, long long gs,
@@ -132,6 +132,22 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
     const float4* dyc = nullptr;  // extra fp32 gradient on the CLS row of a fusion
     if (rm.fusion && rm.dy_cls && (r % rm.N) == 0)
       dyc = reinterpret_cast<const float4*>(rm.dy_cls + ((long long)g * rm.B + r / rm.N) * C);
+    long long doff;
+    if (rm.fusion) doff = fusion_dst_offset(rm, g, r, row_stride, gs);  // scatter back into the donor stream
+    else doff = (long long)g * dx_gs + r * dx_row_stride;
+    // issue every load of the row up front (x, dy, residual gradient) before the reductions
+    float4 xv[NV], dr[NV];
+    uint2 d2[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < C4) {
+        xv[i] = __ldg(xr + c4);
+        d2[i] = __ldg(dyr + c4);
+        if (!rm.fusion && dresid) dr[i] = *(reinterpret_cast<const float4*>(dresid + doff) + c4);
+        else dr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
     float4 xh[NV], gy[NV];
     float s1 = 0.f, s2 = 0.f;
@@ -139,14 +155,12 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
       if (c4 < C4) {
-        const float4 xv = __ldg(xr + c4);
-        const uint2 d2 = __ldg(dyr + c4);
-        float2 d01 = unpack_bf16(d2.x), d23 = unpack_bf16(d2.y);
+        float2 d01 = unpack_bf16(d2[i].x), d23 = unpack_bf16(d2[i].y);
         if (dyc) {
           const float4 e = __ldg(dyc + c4);
           d01.x += e.x; d01.y += e.y; d23.x += e.z; d23.y += e.w;
         }
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        xh[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);
         dg[i].x += d01.x * xh[i].x; dg[i].y += d01.y * xh[i].y; dg[i].z += d23.x * xh[i].z; dg[i].w += d23.y * xh[i].w;
         db[i].x += d01.x; db[i].y += d01.y; db[i].z += d23.x; db[i].w += d23.y;
         gy[i] = make_float4(d01.x * gm[i].x, d01.y * gm[i].y, d23.x * gm[i].z, d23.y * gm[i].w);
@@ -155,9 +169,6 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
       }
     }
     const float m1 = warp_sum(s1) * inv_c, m2 = warp_sum(s2) * inv_c;
-    long long doff;
-    if (rm.fusion) doff = fusion_dst_offset(rm, g, r, row_stride, gs);  // scatter back into the donor stream
-    else doff = (long long)g * dx_gs + r * dx_row_stride;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
@@ -171,10 +182,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
           float* d = dx + doff + c4 * 4;
           atomicAdd(d + 0, o.x); atomicAdd(d + 1, o.y); atomicAdd(d + 2, o.z); atomicAdd(d + 3, o.w);
         } else {
-          if (dresid) {
-            const float4 dr = *(reinterpret_cast<const float4*>(dresid + doff) + c4);
-            o.x += dr.x; o.y += dr.y; o.z += dr.z; o.w += dr.w;
-          }
+          o.x += dr[i].x; o.y += dr[i].y; o.z += dr[i].z; o.w += dr[i].w;
           *(reinterpret_cast<float4*>(dx + doff) + c4) = o;
           if (dx_bf16) {
             uint2 q;
@@ -186,18 +194,24 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
       }
     }
   }
-  // per-warp partial rows of d(gamma), d(beta)
-  const long long prow = ((long long)g * gridDim.x + blockIdx.x) * LN_WARPS + warp;
-  float4* pg = reinterpret_cast<float4*>(partials + prow * 2 * C);
-  float4* pb = reinterpret_cast<float4*>(partials + prow * 2 * C + C);
+  // d(gamma), d(beta): combine the block's 8 warps in shared memory, then one partial row per block
+  __shared__ float s_part[2 * 1024];
+  for (int i = threadIdx.x; i < 2 * C; i += LN_THREADS) s_part[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c4 = lane + 32 * i;
     if (c4 < C4) {
-      pg[c4] = dg[i];
-      pb[c4] = db[i];
+      float* pg = s_part + c4 * 4;
+      float* pb = s_part + C + c4 * 4;
+      atomicAdd(pg + 0, dg[i].x); atomicAdd(pg + 1, dg[i].y); atomicAdd(pg + 2, dg[i].z); atomicAdd(pg + 3, dg[i].w);
+      atomicAdd(pb + 0, db[i].x); atomicAdd(pb + 1, db[i].y); atomicAdd(pb + 2, db[i].z); atomicAdd(pb + 3, db[i].w);
     }
   }
+  __syncthreads();
+  const long long prow = (long long)g * gridDim.x + blockIdx.x;
+  float* po = partials + prow * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += LN_THREADS) po[i] = s_part[i];
 }
 
 // grid = (ceil(C/32), groups); block = (32, 8)
@@ -227,9 +241,11 @@ __global__ void ln_param_grad_finalize(const float* __restrict__ partials, int p
   }
 }
 
-static int blocks_per_group(long long rows) {
+static int blocks_per_group(long long rows, int groups) {
   long long b = (rows + LN_WARPS - 1) / LN_WARPS;
-  if (b > LN_MAX_BLOCKS_PER_GROUP) b = LN_MAX_BLOCKS_PER_GROUP;
+  long long want = ((long long)sm_count() * 8 + groups - 1) / groups;  // ~8 resident blocks (64 warps) per SM in total
+  if (want > LN_MAX_BLOCKS_PER_GROUP) want = LN_MAX_BLOCKS_PER_GROUP;
+  if (b > want) b = want;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -267,7 +283,7 @@ static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, l
   if ((row_stride % 4) || (gs % 4) || (dx_rs % 4) || (dx_gs % 4))
     return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: strides must be multiples of 4");
   if (!partials || !dgamma || !dbeta) return fail(CAVIT_E_BADARG, "layernorm bwd: null workspace / outputs");
-  const int bpg = blocks_per_group(rpg);
+  const int bpg = blocks_per_group(rpg, groups);
   dim3 grid(bpg, groups);
   const int nv = (C / 4 + 31) / 32;
 #define LN_BWD_CASE(NVV)                                                                                       \
@@ -285,7 +301,7 @@ static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, l
   int rc = check_launch("cavit_ln_bwd");
   if (rc) return rc;
   dim3 fgrid((C + 31) / 32, groups), fblock(32, 8);
-  ln_param_grad_finalize<<<fgrid, fblock, 0, st>>>(partials, bpg * LN_WARPS, C, dgamma, dbeta);
+  ln_param_grad_finalize<<<fgrid, fblock, 0, st>>>(partials, bpg, C, dgamma, dbeta);
   count_launch();
   return check_launch("cavit_ln_bwd(finalize)");
 }
@@ -307,7 +323,7 @@ int cavit_ln_fwd(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t row
 }
 
 size_t cavit_ln_bwd_workspace_floats(int32_t groups, int32_t C) {
-  return (size_t)groups * LN_MAX_BLOCKS_PER_GROUP * LN_WARPS * 2 * (size_t)C;
+  return (size_t)groups * LN_MAX_BLOCKS_PER_GROUP * 2 * (size_t)C;
 }
 
 int cavit_ln_bwd(const void* dy, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,

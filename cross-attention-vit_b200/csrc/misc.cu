@@ -82,35 +82,44 @@ __global__ void embed_param_grads_kernel(const float* __restrict__ dtok, float* 
 }
 
 // ------------------------------------------------------------------------------------------ colsum
-// out[g][c] = sum_r x[g][r][c]. grid = (ceil(C/64), groups, row_slices); block = (32, 8); each
-// thread owns 2 columns. Row slices are combined with atomics into a zero-initialised out.
-__global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, long long gs, int rows, int C,
-                                   float* __restrict__ out, long long out_gs) {
-  __shared__ float2 sm[8][33];
+// out[g][c] = sum_r x[g][r][c]. grid = (ceil(C/256), groups, row_slices); block = 256 (8 warps). Each lane
+// owns 8 consecutive columns (one 16-byte load per row), each warp strides over the rows of its slice;
+// the 8 warps are combined through shared memory and the row slices with fp32 atomics into a
+// zero-initialised out.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, long long gs, int rows, int C, float* __restrict__ out,
+                   long long out_gs) {
+  __shared__ float sm[8][256 + 8];
   const int g = blockIdx.y;
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 256 + lane * 8;
   const int slices = gridDim.z;
   const int rows_per = (rows + slices - 1) / slices;
   const int r0 = blockIdx.z * rows_per, r1 = min(rows, r0 + rows_per);
-  float2 acc = make_float2(0.f, 0.f);
-  if (c < C) {
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c < C) {  // C % 8 == 0 is checked by the launcher
     const bf16* p = x + (long long)g * gs + c;
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
-      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(p + (long long)r * ldx));
-      acc.x += v.x;
-      acc.y += v.y;
+#pragma unroll 4
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + (long long)r * ldx));
+      float2 f;
+      f = unpack_bf16(v.x); acc[0] += f.x; acc[1] += f.y;
+      f = unpack_bf16(v.y); acc[2] += f.x; acc[3] += f.y;
+      f = unpack_bf16(v.z); acc[4] += f.x; acc[5] += f.y;
+      f = unpack_bf16(v.w); acc[6] += f.x; acc[7] += f.y;
     }
   }
-  sm[threadIdx.y][threadIdx.x] = acc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[warp][lane * 8 + i] = acc[i];
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int r = 1; r < 8; ++r) {
-      acc.x += sm[r][threadIdx.x].x;
-      acc.y += sm[r][threadIdx.x].y;
-    }
-    float* o = out + (long long)g * out_gs + c;
-    atomicAdd(o, acc.x);
-    if (c + 1 < C) atomicAdd(o + 1, acc.y);
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < C) {
+    float s_ = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s_ += sm[w][threadIdx.x];
+    atomicAdd(out + (long long)g * out_gs + cc, s_);
   }
 }
 
@@ -343,14 +352,21 @@ int cavit_embed_param_grads(const float* dtokens, float* dpos, float* dcls, int3
 
 int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C, int32_t groups, float* out,
                       int64_t out_gs, void* stream) {
-  if (!x || !out || rows <= 0 || C <= 0 || (C % 2) || (ldx % 2)) return fail(CAVIT_E_BADARG, "cavit_colsum_bf16: bad args");
+  if (!x || !out || rows <= 0 || C <= 0 || (C % 8) || (ldx % 8) || (x_gs % 8) || (reinterpret_cast<uintptr_t>(x) & 15))
+    return fail(CAVIT_E_BADARG, "cavit_colsum_bf16: bad args (C, ld must be multiples of 8; 16-byte aligned base)");
   cudaStream_t st = as_stream(stream);
-  for (int g = 0; g < groups; ++g) cudaMemsetAsync(out + (long long)g * out_gs, 0, sizeof(float) * C, st);
-  int slices = rows / 512;
+  if (out_gs == C) {
+    cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C * groups, st);
+  } else {
+    for (int g = 0; g < groups; ++g) cudaMemsetAsync(out + (long long)g * out_gs, 0, sizeof(float) * C, st);
+  }
+  const int cblocks = (C + 255) / 256;
+  int slices = (sm_count() * 4) / (cblocks * groups);  // ~4 blocks per SM in total
+  const int max_slices = (rows + 63) / 64;             // at least 8 rows per warp
+  if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
-  if (slices > 64) slices = 64;
-  dim3 grid((C + 63) / 64, groups, slices), block(32, 8);
-  colsum_bf16_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, x_gs, rows, C, out, out_gs);
+  dim3 grid(cblocks, groups, slices);
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, x_gs, rows, C, out, out_gs);
   count_launch();
   return check_launch("cavit_colsum_bf16");
 }
