@@ -19,6 +19,7 @@ Reference semantics followed: /root/reference/model_cross.py:186-212 (ModelCross
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
@@ -204,7 +205,7 @@ class Engine:
         # CUDA graphs: the forward / backward kernel sequences are static for a given (batch, mode), so after
         # two eager runs they are captured once and replayed (removes ~1.5k launch calls per step from the
         # critical path). Disabled while per-launch profiling is on or a data-parallel hook is installed.
-        self.use_graphs = True
+        self.use_graphs = os.environ.get("CAVIT_NO_GRAPHS", "0") != "1"
         self._fwd_graphs: Dict = {}
         self._bwd_graphs: Dict = {}
         self.on_range_done = None
