@@ -288,10 +288,21 @@ struct AttnBwdParams {
   int* status;
 };
 
-// smem: K | V | Q0 | Q1 | dO0 | dO1 | PT(2 chunks) | dST(2 chunks) | lse[128] delta[128] | barriers
-constexpr int ATT_BWD_SMEM = 10 * ATT_TILE_BYTES + 1024 + 1024 + 128;
+// Backward, pipelined. 17 warps: warps 0..15 compute (quad = TMEM lane quadrant, part = 32-column slice of the
+// query tile), warp 16 is the control warp whose lane 0 issues every TMA load and tcgen05.mma.
+// Per query tile i the tensor pipe runs  S^T,dP^T(i+1)  right after the compute warps have pulled
+// S^T,dP^T(i) into registers, and  dV,dK,dQ(i)  once P^T,dS^T(i) are in shared memory, so the
+// elementwise work of tile i+1 overlaps the five MMAs of tile i. dQ partial tiles are transposed in
+// shared memory and accumulated with 16-byte vector reductions (red.global.add.v4.f32).
+// smem: K | V | Q0 | Q1 | dO0 | dO1 | PT(2 chunks) | dST(2 chunks) | dQ stages 16 x 2 KB | lse/delta [3][128] x2 | barriers
+constexpr int ATT_BWD_COMPUTE_WARPS = 16;
+constexpr int ATT_BWD_THREADS = (ATT_BWD_COMPUTE_WARPS + 1) * 32;
+constexpr int ATT_BWD_SMEM = 10 * ATT_TILE_BYTES + 16 * 2048 + 3072 + 1024 + 128;
 
-constexpr int ATT_BWD_THREADS = 512;  // 16 warps: four per TMEM lane quadrant, each owning 32 of the 128 query columns
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
@@ -303,20 +314,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t sPT = base + 6 * ATT_TILE_BYTES, sDST = base + 8 * ATT_TILE_BYTES;
   uint8_t* genPT = gen + 6 * ATT_TILE_BYTES;
   uint8_t* genDST = gen + 8 * ATT_TILE_BYTES;
-  float* s_lse = reinterpret_cast<float*>(gen + 10 * ATT_TILE_BYTES);
-  float* s_delta = s_lse + ATT_TILE;
-  const uint32_t bar0 = base + 10 * ATT_TILE_BYTES + 1024;
-  const uint32_t bar_kv = bar0, bar_q0 = bar0 + 8, bar_s = bar0 + 24, bar_d = bar0 + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 10 * ATT_TILE_BYTES + 1024 + 40);
+  float* dq_stage = reinterpret_cast<float*>(gen + 10 * ATT_TILE_BYTES);           // [16 warps][32 rows][16 cols]
+  // LSE / delta of a query tile are staged one tile ahead into a ring of 3 buffers: buffer (i+1)%3 is written at
+  // the top of iteration i (before this warp's bar_sfree arrival, which orders it before S^T(i+1) becomes
+  // visible) and its previous contents (tile i-2) were last read before bar_p(i-2), which every warp has passed.
+  float* s_lse = reinterpret_cast<float*>(gen + 10 * ATT_TILE_BYTES + 16 * 2048);  // [3][128]
+  float* s_delta = s_lse + 3 * ATT_TILE;                                           // [3][128]
+  const uint32_t bar0 = base + 10 * ATT_TILE_BYTES + 16 * 2048 + 3072;
+  const uint32_t bar_kv = bar0, bar_q0 = bar0 + 8, bar_s = bar0 + 24, bar_sfree = bar0 + 32, bar_p = bar0 + 40,
+                 bar_d = bar0 + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 10 * ATT_TILE_BYTES + 16 * 2048 + 3072 + 64);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, part = warp >> 2;  // TMEM lane quadrant; 32-column slice of the query tile
-  const int trow = quad * 32 + lane;            // row inside the tile (= TMEM lane)
+  const int quad = warp & 3, part = (warp >> 2) & 3;
+  const int trow = quad * 32 + lane;  // row inside the tile (= TMEM lane)
   const int g = blockIdx.z, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int kv0 = blockIdx.x * ATT_TILE;
   const int row_base = b * p.N;
   const int nq = (p.N + ATT_TILE - 1) / ATT_TILE;
+  const long long lse_base = (((long long)g * p.B + b) * p.H + h) * p.N;
 
   if (tid == 0) {
     *abort_flag = 0;
@@ -324,6 +341,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(bar_q0, 1);
     mbar_init(bar_q0 + 8, 1);
     mbar_init(bar_s, 1);
+    mbar_init(bar_sfree, ATT_BWD_COMPUTE_WARPS);
+    mbar_init(bar_p, ATT_BWD_COMPUTE_WARPS);
     mbar_init(bar_d, 1);
     fence_barrier_init();
     prefetch_tmap(&tmQKV);
@@ -333,6 +352,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
+  if (tid < ATT_TILE) {  // LSE (log2 domain) / delta of query tile 0
+    s_lse[tid] = (tid < p.N) ? p.lse[lse_base + tid] * 1.4426950408889634f : 0.f;
+    s_delta[tid] = (tid < p.N) ? p.delta[lse_base + tid] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -340,143 +363,174 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
   const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_kv, 2 * ATT_TILE_BYTES);
-    tma_load_3d(&tmQKV, bar_kv, sK, p.C + h * ATT_D, row_base + kv0, g);
-    tma_load_3d(&tmQKV, bar_kv, sV, 2 * p.C + h * ATT_D, row_base + kv0, g);
-    mbar_arrive_expect_tx(bar_q0, 2 * ATT_TILE_BYTES);
-    tma_load_3d(&tmQKV, bar_q0, sQ, h * ATT_D, row_base, g);
-    tma_load_3d(&tmDO, bar_q0, sDO, h * ATT_D, row_base, g);
-  }
-
-  const uint32_t idesc_kk = umma_idesc_bf16(128, 0, 0);   // S^T, dP^T : both operands K-major, N = 128
-  const uint32_t idesc_kmn = umma_idesc_bf16(64, 0, 1);   // dV, dK    : A K-major (smem P^T/dS^T), B MN-major, N = 64
-  const uint32_t idesc_mnmn = umma_idesc_bf16(64, 1, 1);  // dQ        : A = dS^T viewed MN-major, B = K MN-major
-  const long long lse_base = (((long long)g * p.B + b) * p.H + h) * p.N;
-  const bool kv_ok = (kv0 + trow) < p.N;
-
-  for (int i = 0; i < nq; ++i) {
-    const int buf = i & 1;
-    const int q0 = i * ATT_TILE;
-    // stage LSE / delta of this query tile (log2 domain for LSE)
-    if (tid < ATT_TILE) {
-      const int q = q0 + tid;
-      s_lse[tid] = (q < p.N) ? p.lse[lse_base + q] * 1.4426950408889634f : 0.f;
-      s_delta[tid] = (q < p.N) ? p.delta[lse_base + q] : 0.f;
-    }
-    if (tid == 0) {
-      if (i + 1 < nq) {
-        const uint32_t bar = bar_q0 + 8 * ((i + 1) & 1);
+  if (warp == ATT_BWD_COMPUTE_WARPS) {
+    // ================================================================= control warp
+    if (lane == 0) {
+      const uint32_t idesc_kk = umma_idesc_bf16(128, 0, 0);   // S^T, dP^T : both operands K-major, N = 128
+      const uint32_t idesc_kmn = umma_idesc_bf16(64, 0, 1);   // dV, dK    : A K-major (smem P^T/dS^T), B MN-major, N = 64
+      const uint32_t idesc_mnmn = umma_idesc_bf16(64, 1, 1);  // dQ        : A = dS^T viewed MN-major, B = K MN-major
+      auto load_q = [&](int i) {
+        const uint32_t bar = bar_q0 + 8 * (i & 1);
         mbar_arrive_expect_tx(bar, 2 * ATT_TILE_BYTES);
-        tma_load_3d(&tmQKV, bar, sQ + ((i + 1) & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + q0 + ATT_TILE, g);
-        tma_load_3d(&tmDO, bar, sDO + ((i + 1) & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + q0 + ATT_TILE, g);
-      }
-      if (i == 0) mbar_wait(bar_kv, 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-      mbar_wait(bar_q0 + 8 * buf, (i >> 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        tma_load_3d(&tmQKV, bar, sQ + (i & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + i * ATT_TILE, g);
+        tma_load_3d(&tmDO, bar, sDO + (i & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + i * ATT_TILE, g);
+      };
+      auto issue_s = [&](int i) {  // S^T = K Q_i^T ; dP^T = V dO_i^T
+        const int buf = i & 1;
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) {
+          const uint64_t kd = umma_desc_sw128(sK + k * 32, 16, 1024);
+          const uint64_t qd = umma_desc_sw128(sQ + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
+          umma_bf16_ss(tST, kd, qd, idesc_kk, k != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) {
+          const uint64_t vd = umma_desc_sw128(sV + k * 32, 16, 1024);
+          const uint64_t dd = umma_desc_sw128(sDO + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
+          umma_bf16_ss(tDPT, vd, dd, idesc_kk, k != 0);
+        }
+        umma_commit(bar_s);
+      };
+      mbar_arrive_expect_tx(bar_kv, 2 * ATT_TILE_BYTES);
+      tma_load_3d(&tmQKV, bar_kv, sK, p.C + h * ATT_D, row_base + kv0, g);
+      tma_load_3d(&tmQKV, bar_kv, sV, 2 * p.C + h * ATT_D, row_base + kv0, g);
+      load_q(0);
+      if (nq > 1) load_q(1);
+      mbar_wait(bar_kv, 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+      mbar_wait(bar_q0, 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
       tc_fence_after();
+      issue_s(0);
+      for (int i = 0; i < nq; ++i) {
+        const int buf = i & 1;
+        // S^T,dP^T(i) are in registers everywhere -> the tensor pipe may start on tile i+1
+        mbar_wait(bar_sfree, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        if (i + 1 < nq) {
+          mbar_wait(bar_q0 + 8 * ((i + 1) & 1), ((i + 1) >> 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          tc_fence_after();
+          issue_s(i + 1);
+        }
+        // P^T,dS^T(i) are in shared memory (and dQ(i-1) has been drained) -> dV, dK, dQ of tile i
+        mbar_wait(bar_p, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < ATT_D / 16; ++k) {
-        const uint64_t kd = umma_desc_sw128(sK + k * 32, 16, 1024);
-        const uint64_t qd = umma_desc_sw128(sQ + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
-        umma_bf16_ss(tST, kd, qd, idesc_kk, k != 0);
-      }
+        for (int k = 0; k < ATT_TILE / 16; ++k) {  // dV[kv][d] += P^T[kv][q] dO[q][d]
+          const uint64_t ad = umma_desc_sw128(sPT + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(sDO + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
+          umma_bf16_ss(tDV, ad, bd, idesc_kmn, (i | k) != 0);
+        }
 #pragma unroll
-      for (int k = 0; k < ATT_D / 16; ++k) {
-        const uint64_t vd = umma_desc_sw128(sV + k * 32, 16, 1024);
-        const uint64_t dd = umma_desc_sw128(sDO + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
-        umma_bf16_ss(tDPT, vd, dd, idesc_kk, k != 0);
+        for (int k = 0; k < ATT_TILE / 16; ++k) {  // dK[kv][d] += dS^T[kv][q] Q[q][d]
+          const uint64_t ad = umma_desc_sw128(sDST + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(sQ + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
+          umma_bf16_ss(tDK, ad, bd, idesc_kmn, (i | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < ATT_TILE / 16; ++k) {  // dQ[q][d] = dS[q][kv] K[kv][d]  (A = dS^T viewed MN-major)
+          const uint64_t ad = umma_desc_sw128(sDST + k * 2048, ATT_TILE_BYTES, 1024);
+          const uint64_t bd = umma_desc_sw128(sK + k * 2048, ATT_TILE_BYTES, 1024);
+          umma_bf16_ss(tDQ, ad, bd, idesc_mnmn, k != 0);
+        }
+        umma_commit(bar_d);
+        if (i + 2 < nq) {  // refill this Q/dO buffer once the MMAs that read it have retired
+          mbar_wait(bar_d, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          load_q(i + 2);
+        }
       }
-      umma_commit(bar_s);
     }
-    __syncthreads();  // s_lse / s_delta visible
-    mbar_wait(bar_s, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-    tc_fence_after();
-    const int q_valid = min(ATT_TILE, p.N - q0);
-#pragma unroll
-    for (int hc = 0; hc < 2; ++hc) {  // this warp's 32 query columns, 16 at a time (register budget)
-      const int cb = part * 32 + hc * 16;
-      uint32_t rs[16], rp[16];
-      tmem_ld16(tST + t_lane + cb, rs);
-      tmem_ld16(tDPT + t_lane + cb, rp);
-      tmem_ld_wait();
-      float pt[16], dst[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = cb + j;
-        const bool ok = kv_ok && (col < q_valid);
-        const float pr = ok ? ex2_approx(__uint_as_float(rs[j]) * p.scale_log2 - s_lse[col]) : 0.f;
-        pt[j] = pr;
-        dst[j] = pr * (__uint_as_float(rp[j]) - s_delta[col]);
-      }
-      store_row_16_sw128(genPT, trow, cb, pt);
-      store_row_16_sw128(genDST, trow, cb, dst);
-    }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      // dV[kv][d] += P^T[kv][q] dO[q][d]      A: sPT (K-major over q), B: sDO tile as MN-major (N = d)
-#pragma unroll
-      for (int k = 0; k < ATT_TILE / 16; ++k) {
-        const uint64_t ad = umma_desc_sw128(sPT + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
-        const uint64_t bd = umma_desc_sw128(sDO + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
-        umma_bf16_ss(tDV, ad, bd, idesc_kmn, (i | k) != 0);
-      }
-      // dK[kv][d] += dS^T[kv][q] Q[q][d]
-#pragma unroll
-      for (int k = 0; k < ATT_TILE / 16; ++k) {
-        const uint64_t ad = umma_desc_sw128(sDST + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
-        const uint64_t bd = umma_desc_sw128(sQ + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
-        umma_bf16_ss(tDK, ad, bd, idesc_kmn, (i | k) != 0);
-      }
-      // dQ[q][d] = dS[q][kv] K[kv][d]         A: sDST viewed MN-major (M = q contiguous, K = kv rows)
-#pragma unroll
-      for (int k = 0; k < ATT_TILE / 16; ++k) {
-        const uint64_t ad = umma_desc_sw128(sDST + k * 2048, ATT_TILE_BYTES, 1024);
-        const uint64_t bd = umma_desc_sw128(sK + k * 2048, ATT_TILE_BYTES, 1024);
-        umma_bf16_ss(tDQ, ad, bd, idesc_mnmn, k != 0);
-      }
-      umma_commit(bar_d);
-    }
-    mbar_wait(bar_d, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-    tc_fence_after();
-    {
-      const int q = q0 + trow;
-      float* acc = p.dq_acc + (long long)g * p.acc_gs + (long long)(row_base + q) * p.C + h * ATT_D + part * 16;
+  } else {
+    // ================================================================= compute warps
+    const bool kv_ok = (kv0 + trow) < p.N;
+    float* my_stage = dq_stage + warp * 512;
+    // drains dQ of query tile `qi` from TMEM: transpose through smem, 16-byte vector reductions
+    auto drain_dq = [&](int qi) {
       uint32_t r[16];
       tmem_ld16(tDQ + t_lane + part * 16, r);
       tmem_ld_wait();
-      if (q < p.N) {
+      float4* srow = reinterpret_cast<float4*>(my_stage + lane * 16);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(acc + j, __uint_as_float(r[j]) * p.scale);
+      for (int j = 0; j < 4; ++j)
+        srow[j ^ ((lane >> 1) & 3)] = make_float4(__uint_as_float(r[4 * j]) * p.scale, __uint_as_float(r[4 * j + 1]) * p.scale,
+                                                  __uint_as_float(r[4 * j + 2]) * p.scale, __uint_as_float(r[4 * j + 3]) * p.scale);
+      __syncwarp();
+      const int j = lane & 3;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2);
+        const float4 v = reinterpret_cast<const float4*>(my_stage + rr * 16)[j ^ ((rr >> 1) & 3)];
+        const int q = qi * ATT_TILE + quad * 32 + rr;
+        if (q < p.N)
+          red_add_v4(p.dq_acc + (long long)g * p.acc_gs + (long long)(row_base + q) * p.C + h * ATT_D + part * 16 + j * 4, v.x, v.y,
+                     v.z, v.w);
       }
-    }
-    tc_fence_before();
-    __syncthreads();
-  }
+      __syncwarp();
+    };
 
-  // write dK (scaled) and dV for this key/value tile: each warp stores a 16-column slice of both
-  {
-    const int kv = kv0 + trow;
-    bf16* drow = p.dqkv + (long long)g * p.qkv_gs + (long long)(row_base + kv) * (3 * p.C) + h * ATT_D + part * 16;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t t = which == 0 ? tDK : tDV;
-      const float sc = which == 0 ? p.scale : 1.0f;
-      bf16* dst = drow + (which == 0 ? p.C : 2 * p.C);
-      uint32_t r[16];
-      tmem_ld16(t + t_lane + part * 16, r);
+    for (int i = 0; i < nq; ++i) {
+      const int q0 = i * ATT_TILE;
+      const float* lse_i = s_lse + (i % 3) * ATT_TILE;
+      const float* delta_i = s_delta + (i % 3) * ATT_TILE;
+      if (i + 1 < nq && tid < ATT_TILE) {  // stage LSE / delta of the next query tile
+        const int q = q0 + ATT_TILE + tid;
+        s_lse[((i + 1) % 3) * ATT_TILE + tid] = (q < p.N) ? p.lse[lse_base + q] * 1.4426950408889634f : 0.f;
+        s_delta[((i + 1) % 3) * ATT_TILE + tid] = (q < p.N) ? p.delta[lse_base + q] : 0.f;
+      }
+      mbar_wait(bar_s, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+      tc_fence_after();
+      const int cb = part * 32;
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tST + t_lane + cb, rs);
+      tmem_ld32(tDPT + t_lane + cb, rp);
       tmem_ld_wait();
-      if (kv < p.N) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree);
+      const int q_valid = min(ATT_TILE, p.N - q0);
+      float pt[32], dst[32];
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc);
-          w.y = pack_bf16(__uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
-          w.z = pack_bf16(__uint_as_float(r[j + 4]) * sc, __uint_as_float(r[j + 5]) * sc);
-          w.w = pack_bf16(__uint_as_float(r[j + 6]) * sc, __uint_as_float(r[j + 7]) * sc);
-          *reinterpret_cast<uint4*>(dst + j) = w;
+      for (int j = 0; j < 32; ++j) {
+        const int col = cb + j;
+        const bool ok = kv_ok && (col < q_valid);
+        const float pr = ok ? ex2_approx(__uint_as_float(rs[j]) * p.scale_log2 - lse_i[col]) : 0.f;
+        pt[j] = pr;
+        dst[j] = pr * (__uint_as_float(rp[j]) - delta_i[col]);
+      }
+      if (i > 0) {  // MMAs of tile i-1 done: P^T/dS^T buffers are free and dQ(i-1) is complete
+        mbar_wait(bar_d, (i - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        tc_fence_after();
+        drain_dq(i - 1);
+      }
+      store_row_chunk_sw128(genPT, trow, cb, pt);
+      store_row_chunk_sw128(genDST, trow, cb, dst);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_d, (nq - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+    drain_dq(nq - 1);
+    // write dK (scaled) and dV for this key/value tile: each warp stores a 16-column slice of both
+    {
+      const int kv = kv0 + trow;
+      bf16* drow = p.dqkv + (long long)g * p.qkv_gs + (long long)(row_base + kv) * (3 * p.C) + h * ATT_D + part * 16;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t t = which == 0 ? tDK : tDV;
+        const float sc = which == 0 ? p.scale : 1.0f;
+        bf16* dstp = drow + (which == 0 ? p.C : 2 * p.C);
+        uint32_t r[16];
+        tmem_ld16(t + t_lane + part * 16, r);
+        tmem_ld_wait();
+        if (kv < p.N) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc);
+            w.y = pack_bf16(__uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
+            w.z = pack_bf16(__uint_as_float(r[j + 4]) * sc, __uint_as_float(r[j + 5]) * sc);
+            w.w = pack_bf16(__uint_as_float(r[j + 6]) * sc, __uint_as_float(r[j + 7]) * sc);
+            *reinterpret_cast<uint4*>(dstp + j) = w;
+          }
         }
       }
     }

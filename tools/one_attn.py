@@ -1,4 +1,5 @@
-"""Runs the attention forward/backward kernels a few times at the cfg2 shape (target for ncu)."""
+"""Runs the attention forward/backward kernels a few times (target for ncu).
+usage: one_attn.py [G B N H]"""
 import os
 import sys
 
@@ -9,7 +10,7 @@ import torch  # noqa: E402
 
 from cavit import _abi, ops  # noqa: E402
 
-G, B, N, H = 4, 256, 197, 6
+G, B, N, H = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 else (4, 256, 197, 6)
 C = H * 64
 T = B * N
 qkv = torch.randn(G, T, 3 * C, device="cuda").to(torch.bfloat16)
