@@ -74,184 +74,292 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 struct AttnFwdParams {
   bf16* out;
   float* lse;
-  int N, H, C, B;
+  int N, H, C, B, G;
   long long out_gs;  // elements between groups in out
   float scale_log2;  // scale * log2(e)
   int* status;
 };
 
-// smem: Q | K0 | K1 | V0 | V1 | P(2 chunks) | row max / sum exchange [2][128] x2 | barriers
-constexpr int ATT_FWD_THREADS = 256;  // 8 warps: two per TMEM lane quadrant, each owning half of the key columns
-constexpr int ATT_FWD_SMEM = 7 * ATT_TILE_BYTES + 1024 + 2048 + 128;
+// Forward, persistent + pipelined ("ping-pong"). One CTA per SM walks work items = 256 query rows (two
+// 128-row tiles, "slots") of one (stream, sample, head). 18 warps:
+//   warps 0-7   softmax group of slot 0     (quad = TMEM lane quadrant, part = 64-column half of the key tile)
+//   warps 8-15  softmax group of slot 1
+//   warp 16     TMA producer: Q0,Q1 per item; K/V tiles through a 3-stage ring shared by both slots
+//   warp 17     MMA issuer:   S[s] = Q[s] K_j^T, O[s] = P[s] V_j  (issue order PV0(j), S0(j+1), PV1(j), S1(j+1))
+// While one slot's warps run the softmax of tile j the tensor pipe works for the other slot, and the
+// producer runs up to 3 K/V tiles ahead (also across work items), so neither TMA latency nor MMA
+// latency sits on a softmax warp's critical path. O_j is produced fresh in TMEM and folded into
+// register accumulators one tile later (o = o*alpha + O_j), so there is no TMEM read-modify-write.
+// smem: Q0 | Q1 | (K,V) x 3 | P0(2 chunks) | P1(2 chunks) | max/sum exchange [2 slots][2 parts][128] x2 | barriers
+constexpr int ATT_FWD_THREADS = 18 * 32;
+constexpr int ATT_FWD_KV_STAGES = 3;
+constexpr int ATT_FWD_SMEM = (2 + 2 * ATT_FWD_KV_STAGES + 4) * ATT_TILE_BYTES + 4096 + 1024 + 256;
 
-__global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base, sK = base + ATT_TILE_BYTES, sV = base + 3 * ATT_TILE_BYTES;
-  const uint32_t sP = base + 5 * ATT_TILE_BYTES;
-  uint8_t* genP = gen + 5 * ATT_TILE_BYTES;
-  float* s_max = reinterpret_cast<float*>(gen + 7 * ATT_TILE_BYTES);  // [2][128]
-  float* s_sum = s_max + 2 * ATT_TILE;                                 // [2][128]
-  const uint32_t bar0 = base + 7 * ATT_TILE_BYTES + 2048;
-  const uint32_t bar_q = bar0, bar_kv0 = bar0 + 8, bar_s = bar0 + 24, bar_o = bar0 + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 7 * ATT_TILE_BYTES + 2048 + 40);
+  const uint32_t sQ = base;                                       // 2 tiles
+  const uint32_t sKV = base + 2 * ATT_TILE_BYTES;                 // stage: K then V
+  const uint32_t sP = base + (2 + 2 * ATT_FWD_KV_STAGES) * ATT_TILE_BYTES;  // slot s at + s * 2 tiles
+  uint8_t* genP = gen + (2 + 2 * ATT_FWD_KV_STAGES) * ATT_TILE_BYTES;
+  float* s_xchg = reinterpret_cast<float*>(gen + (6 + 2 * ATT_FWD_KV_STAGES) * ATT_TILE_BYTES);  // [slot][max|sum][part][128]
+  const uint32_t bar0 = base + (6 + 2 * ATT_FWD_KV_STAGES) * ATT_TILE_BYTES + 4096;
+  const uint32_t bar_qfull = bar0, bar_qempty = bar0 + 8;
+  auto bar_kvfull = [&](int st) { return bar0 + 16 + 8u * st; };
+  auto bar_kvempty = [&](int st) { return bar0 + 16 + 8u * (ATT_FWD_KV_STAGES + st); };
+  const uint32_t bar_x = bar0 + 16 + 16 * ATT_FWD_KV_STAGES;  // then per slot: s_full, s_free, p_full, o_full
+  auto bar_sfull = [&](int sl) { return bar_x + 32u * sl; };
+  auto bar_sfree = [&](int sl) { return bar_x + 32u * sl + 8; };
+  auto bar_pfull = [&](int sl) { return bar_x + 32u * sl + 16; };
+  auto bar_ofull = [&](int sl) { return bar_x + 32u * sl + 24; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (6 + 2 * ATT_FWD_KV_STAGES) * ATT_TILE_BYTES + 4096 + 192);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, part = warp >> 2;  // TMEM lane quadrant; column half
-  const int row = quad * 32 + lane;             // query row inside the tile (= TMEM lane)
-  const int g = blockIdx.z, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
-  const int q0 = blockIdx.x * ATT_TILE;
-  const int row_base = b * p.N;
   const int nkv = (p.N + ATT_TILE - 1) / ATT_TILE;
+  const int nqp = (p.N + 2 * ATT_TILE - 1) / (2 * ATT_TILE);
+  const int BH = p.B * p.H;
+  const long long items = (long long)p.G * BH * nqp;
 
   if (tid == 0) {
     *abort_flag = 0;
-    mbar_init(bar_q, 1);
-    mbar_init(bar_kv0, 1);
-    mbar_init(bar_kv0 + 8, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
+    mbar_init(bar_qfull, 1);
+    mbar_init(bar_qempty, 1);
+    for (int st = 0; st < ATT_FWD_KV_STAGES; ++st) {
+      mbar_init(bar_kvfull(st), 1);
+      mbar_init(bar_kvempty(st), 1);
+    }
+    for (int sl = 0; sl < 2; ++sl) {
+      mbar_init(bar_sfull(sl), 1);
+      mbar_init(bar_sfree(sl), 8);
+      mbar_init(bar_pfull(sl), 8);
+      mbar_init(bar_ofull(sl), 1);
+    }
     fence_barrier_init();
     prefetch_tmap(&tmQKV);
   }
-  if (warp == 0) {
-    tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 16) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 128;
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, ATT_TILE_BYTES);
-    tma_load_3d(&tmQKV, bar_q, sQ, h * ATT_D, row_base + q0, g);
-    mbar_arrive_expect_tx(bar_kv0, 2 * ATT_TILE_BYTES);
-    tma_load_3d(&tmQKV, bar_kv0, sK, p.C + h * ATT_D, row_base, g);
-    tma_load_3d(&tmQKV, bar_kv0, sV, 2 * p.C + h * ATT_D, row_base, g);
-  }
-
-  const uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);
-  const uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);
-  const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
-
-  float o[32];  // this thread's half (32 of 64) of the output row
-#pragma unroll
-  for (int i = 0; i < 32; ++i) o[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-
-  for (int j = 0; j < nkv; ++j) {
-    const int buf = j & 1;
-    if (tid == 0) {
-      if (j + 1 < nkv) {  // prefetch next K/V tile into the other buffer (its readers finished at j-1)
-        const uint32_t bar = bar_kv0 + 8 * ((j + 1) & 1);
-        mbar_arrive_expect_tx(bar, 2 * ATT_TILE_BYTES);
-        tma_load_3d(&tmQKV, bar, sK + ((j + 1) & 1) * ATT_TILE_BYTES, p.C + h * ATT_D, row_base + (j + 1) * ATT_TILE, g);
-        tma_load_3d(&tmQKV, bar, sV + ((j + 1) & 1) * ATT_TILE_BYTES, 2 * p.C + h * ATT_D, row_base + (j + 1) * ATT_TILE, g);
+  if (warp == 16) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int qp = (int)(item % nqp);
+        const long long gbh = item / nqp;
+        const int bh = (int)(gbh % BH), g = (int)(gbh / BH);
+        const int b = bh / p.H, h = bh % p.H;
+        const int row_base = b * p.N;
+        mbar_wait(bar_qempty, (it & 1) ^ 1u, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        mbar_arrive_expect_tx(bar_qfull, 2 * ATT_TILE_BYTES);
+        tma_load_3d(&tmQKV, bar_qfull, sQ, h * ATT_D, row_base + qp * 2 * ATT_TILE, g);
+        tma_load_3d(&tmQKV, bar_qfull, sQ + ATT_TILE_BYTES, h * ATT_D, row_base + qp * 2 * ATT_TILE + ATT_TILE, g);
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(bar_kvempty(st), ph ^ 1u, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          mbar_arrive_expect_tx(bar_kvfull(st), 2 * ATT_TILE_BYTES);
+          tma_load_3d(&tmQKV, bar_kvfull(st), sKV + st * 2 * ATT_TILE_BYTES, p.C + h * ATT_D, row_base + j * ATT_TILE, g);
+          tma_load_3d(&tmQKV, bar_kvfull(st), sKV + st * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, 2 * p.C + h * ATT_D,
+                      row_base + j * ATT_TILE, g);
+          if (++st == ATT_FWD_KV_STAGES) { st = 0; ph ^= 1u; }
+        }
       }
-      if (j == 0) mbar_wait(bar_q, 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-      mbar_wait(bar_kv0 + 8 * buf, (j >> 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+    }
+  } else if (warp == 17) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);
+      int st = 0;
+      uint32_t ph = 0;
+      uint32_t t = 0;  // global tile counter of this CTA (same for both slots)
+      int it = 0;
+      auto issue_s = [&](int sl, int stage) {
+        // S[sl] may be overwritten once the slot's softmax warps have read the previous tile
+        mbar_wait(bar_sfree(sl), (t & 1) ^ 1u, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(sQ + sl * ATT_TILE_BYTES + k * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(sKV + stage * 2 * ATT_TILE_BYTES + k * 32, 16, 1024);
+          umma_bf16_ss(tmem + sl * 128, ad, bd, idesc_s, k != 0);
+        }
+        umma_commit(bar_sfull(sl));
+      };
+      auto issue_pv = [&](int sl, int stage, uint32_t tt) {
+        mbar_wait(bar_pfull(sl), tt & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_TILE / 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(sP + sl * 2 * ATT_TILE_BYTES + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
+          umma_bf16_ss(tmem + 256 + sl * 64, ad, bd, idesc_o, k != 0);
+        }
+        umma_commit(bar_ofull(sl));
+      };
+      for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        mbar_wait(bar_qfull, it & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        mbar_wait(bar_kvfull(st), ph, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        issue_s(0, st);
+        issue_s(1, st);
+        for (int j = 0; j < nkv; ++j) {
+          int nst = st + 1;
+          uint32_t nph = ph;
+          if (nst == ATT_FWD_KV_STAGES) { nst = 0; nph ^= 1u; }
+          const bool more = (j + 1 < nkv);
+          if (more) mbar_wait(bar_kvfull(nst), nph, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          issue_pv(0, st, t);
+          if (more) { ++t; issue_s(0, nst); --t; }
+          issue_pv(1, st, t);
+          if (more) { ++t; issue_s(1, nst); --t; }
+          umma_commit(bar_kvempty(st));  // K_j / V_j no longer needed once everything issued so far retires
+          ++t;
+          st = nst;
+          ph = nph;
+        }
+        umma_commit(bar_qempty);  // all S MMAs of this item have been issued: Q buffers free when they retire
+      }
+    }
+  } else {
+    // ================================================================= softmax warps
+    const int sl = warp >> 3;                       // slot
+    const int quad = warp & 3, part = (warp >> 2) & 1;
+    const int row = quad * 32 + lane;               // query row inside the slot's tile (= TMEM lane)
+    const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem + sl * 128, tO = tmem + 256 + sl * 64;
+    uint8_t* myP = genP + sl * 2 * ATT_TILE_BYTES;
+    float* x_max = s_xchg + sl * 512;               // [part][128]
+    float* x_sum = x_max + 256;
+    const int bar_id = 1 + sl * 4 + quad;           // the two warps (parts) of this slot's lane quadrant
+    const int cbase = part * 64;
+    uint32_t t = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+      const int qp = (int)(item % nqp);
+      const long long gbh = item / nqp;
+      const int bh = (int)(gbh % BH), g = (int)(gbh / BH);
+      const int b = bh / p.H, h = bh % p.H;
+      const int row_base = b * p.N;
+      float o[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, alpha = 0.f;
+      for (int j = 0; j < nkv; ++j, ++t) {
+        mbar_wait(bar_sfull(sl), t & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        tc_fence_after();
+        const int kv_valid = min(ATT_TILE, p.N - j * ATT_TILE);
+        // pass 1: row maximum of this warp's 64 columns
+        float m_part = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tS + t_lane + cbase + c * 32, r);
+          tmem_ld_wait();
+          if (cbase + c * 32 + 32 <= kv_valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m_part = fmaxf(m_part, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (cbase + c * 32 + i < kv_valid) m_part = fmaxf(m_part, __uint_as_float(r[i]));
+          }
+        }
+        x_max[part * ATT_TILE + row] = m_part;
+        named_bar_sync(bar_id, 64);
+        const float m_tile = fmaxf(m_part, x_max[(part ^ 1) * ATT_TILE + row]);
+        const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
+        // fold the previous tile's O into the accumulators (its P.V finished long ago; this also
+        // guarantees that the MMA no longer reads the P buffer we are about to overwrite)
+        if (j > 0) {
+          mbar_wait(bar_ofull(sl), (t - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          tc_fence_after();
+          uint32_t r[32];
+          tmem_ld32(tO + t_lane + part * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(r[i]);
+        }
+        const float alpha_new = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
+        // pass 2: probabilities -> bf16 -> swizzled smem
+        float l_part = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tS + t_lane + cbase + c * 32, r);
+          tmem_ld_wait();
+          float pv[32];
+          if (cbase + c * 32 + 32 <= kv_valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              pv[i] = ex2_approx(__uint_as_float(r[i]) * p.scale_log2 - m_new);
+              l_part += pv[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float e = ex2_approx(__uint_as_float(r[i]) * p.scale_log2 - m_new);
+              pv[i] = (cbase + c * 32 + i < kv_valid) ? e : 0.f;
+              l_part += pv[i];
+            }
+          }
+          store_row_chunk_sw128(myP, row, cbase + c * 32, pv);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sfree(sl));   // S[sl] fully read by this warp
+        x_sum[part * ATT_TILE + row] = l_part;
+        fence_proxy_async_smem();                     // P stores visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pfull(sl));
+        named_bar_sync(bar_id, 64);
+        l_run = l_run * alpha_new + (l_part + x_sum[(part ^ 1) * ATT_TILE + row]);
+        m_run = m_new;
+        alpha = alpha_new;
+      }
+      // last tile's O
+      mbar_wait(bar_ofull(sl), (t - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
       tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(tO + t_lane + part * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < ATT_D / 16; ++k) {
-        const uint64_t ad = umma_desc_sw128(sQ + k * 32, 16, 1024);
-        const uint64_t bd = umma_desc_sw128(sK + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
-        umma_bf16_ss(tS, ad, bd, idesc_s, k != 0);
+        for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(r[i]);
       }
-      umma_commit(bar_s);
-    }
-    mbar_wait(bar_s, j & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-    tc_fence_after();
-
-    const int kv_valid = min(ATT_TILE, p.N - j * ATT_TILE);  // columns < kv_valid are real keys
-    const int cbase = part * 64;                              // this warp's 64 key columns
-    uint32_t s0[32], s1[32];
-    tmem_ld32(tS + t_lane + cbase, s0);
-    tmem_ld32(tS + t_lane + cbase + 32, s1);
-    tmem_ld_wait();
-    float m_part = -INFINITY;
+      tc_fence_before();
+      const int q = qp * 2 * ATT_TILE + sl * ATT_TILE + row;
+      if (q < p.N) {
+        const float inv_l = 1.0f / l_run;
+        bf16* orow = p.out + (long long)g * p.out_gs + (long long)(row_base + q) * p.C + h * ATT_D + part * 32;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (cbase + i < kv_valid) m_part = fmaxf(m_part, __uint_as_float(s0[i]));
-      if (cbase + 32 + i < kv_valid) m_part = fmaxf(m_part, __uint_as_float(s1[i]));
-    }
-    s_max[part * ATT_TILE + row] = m_part;
-    named_bar_sync(1 + quad, 64);  // the two warps of this lane quadrant
-    const float m_tile = fmaxf(m_part, s_max[(part ^ 1) * ATT_TILE + row]);
-    const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
-    const float alpha = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
-    float l_part = 0.f;
-    {
-      float pv[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = ex2_approx(__uint_as_float(s0[i]) * p.scale_log2 - m_new);
-        pv[i] = (cbase + i < kv_valid) ? e : 0.f;
-        l_part += pv[i];
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16(o[i] * inv_l, o[i + 1] * inv_l);
+          w.y = pack_bf16(o[i + 2] * inv_l, o[i + 3] * inv_l);
+          w.z = pack_bf16(o[i + 4] * inv_l, o[i + 5] * inv_l);
+          w.w = pack_bf16(o[i + 6] * inv_l, o[i + 7] * inv_l);
+          *reinterpret_cast<uint4*>(orow + i) = w;
+        }
+        if (part == 0)
+          p.lse[(((long long)g * p.B + b) * p.H + h) * p.N + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
       }
-      store_row_chunk_sw128(genP, row, cbase, pv);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = ex2_approx(__uint_as_float(s1[i]) * p.scale_log2 - m_new);
-        pv[i] = (cbase + 32 + i < kv_valid) ? e : 0.f;
-        l_part += pv[i];
-      }
-      store_row_chunk_sw128(genP, row, cbase + 32, pv);
     }
-    s_sum[part * ATT_TILE + row] = l_part;
-    tc_fence_before();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < ATT_TILE / 16; ++k) {
-        const uint64_t ad = umma_desc_sw128(sP + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
-        const uint64_t bd = umma_desc_sw128(sV + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
-        umma_bf16_ss(tO, ad, bd, idesc_o, k != 0);
-      }
-      umma_commit(bar_o);
-    }
-    l_run = l_run * alpha + (l_part + s_sum[(part ^ 1) * ATT_TILE + row]);
-    m_run = m_new;
-    mbar_wait(bar_o, j & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-    tc_fence_after();
-    {
-      uint32_t r[32];
-      tmem_ld32(tO + t_lane + part * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(r[i]);
-    }
-    tc_fence_before();
-    __syncthreads();  // everyone is done with S / O / P / exchange buffers before they are reused
-  }
-
-  const int q = q0 + row;
-  if (q < p.N) {
-    const float inv_l = 1.0f / l_run;
-    bf16* orow = p.out + (long long)g * p.out_gs + (long long)(row_base + q) * p.C + h * ATT_D + part * 32;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      uint4 w;
-      w.x = pack_bf16(o[i] * inv_l, o[i + 1] * inv_l);
-      w.y = pack_bf16(o[i + 2] * inv_l, o[i + 3] * inv_l);
-      w.z = pack_bf16(o[i + 4] * inv_l, o[i + 5] * inv_l);
-      w.w = pack_bf16(o[i + 6] * inv_l, o[i + 7] * inv_l);
-      *reinterpret_cast<uint4*>(orow + i) = w;
-    }
-    if (part == 0)
-      p.lse[(((long long)g * p.B + b) * p.H + h) * p.N + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 16) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -581,12 +689,13 @@ int cavit_attn_fwd(const void* qkv, void* out, float* lse, int32_t G, int32_t B,
   AttnFwdParams p;
   p.out = reinterpret_cast<bf16*>(out);
   p.lse = lse;
-  p.N = N; p.H = H; p.C = C; p.B = B;
+  p.N = N; p.H = H; p.C = C; p.B = B; p.G = G;
   p.out_gs = T * C;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.status = status_word();
   if (!p.status) return fail(CAVIT_E_DEVICE, "no status word");
-  dim3 grid((N + ATT_TILE - 1) / ATT_TILE, B * H, G);
+  const long long items = (long long)G * B * H * ((N + 2 * ATT_TILE - 1) / (2 * ATT_TILE));
+  const int grid = (int)(items < sm_count() ? items : sm_count());
   attn_fwd_kernel<<<grid, ATT_FWD_THREADS, ATT_FWD_SMEM, as_stream(stream)>>>(*tm, p);
   count_launch();
   return check_launch("cavit_attn_fwd");
