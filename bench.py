@@ -191,6 +191,10 @@ def main():
     _abi.require_device(local_rank)
     if world > 1:
         import torch.distributed as dist
+        if "CAVIT_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["CAVIT_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)   # the version banner would go to stdout next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = make_config(**wl["cfg"])
     B = args.batch or wl["batch"]
@@ -199,7 +203,7 @@ def main():
     runner = model
     if world > 1:
         from cavit.ddp import DataParallel
-        runner = DataParallel(model)
+        runner = DataParallel(model, mode=os.environ.get("CAVIT_DDP_MODE", "auto"))
     g = torch.Generator().manual_seed(1234 + rank)
     D, H, W = cfg.img_size
     img_host = torch.randn((B, cfg.num_modalities, 1, D, H, W), generator=g).pin_memory()
@@ -311,7 +315,7 @@ def main():
             "config": {"workload": f"{args.workload}: ModelCross C={cfg.hidden_dim} H={cfg.num_heads} F={cfg.mlp_dim} "
                                    f"{cfg.num_multi_blocks}x{cfg.num_self_blocks} blocks, img {tuple(cfg.img_size)} patch {tuple(cfg.patch_size)}, "
                                    f"M=4 ring cross-attention, per-GPU batch {B}",
-                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "global_batch": B * world, "parallelism": f"dp{world}" + (f" ({runner.mode} all-reduce)" if world > 1 else ""),
                        "l2": "per-step working set (activations + weights, several GB) far exceeds the 126 MB L2; no explicit flush",
                        "precision": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LayerNorm / softmax statistics"},
             "model_tflops": value * fpv / 1e12,
@@ -323,7 +327,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernel_breakdown_ms": breakdown,
-            "loss": float(loss),
+            "loss": float(loss.detach()),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -70,7 +70,13 @@ class SlabReducer:
 class DataParallel:
     """Wraps a cavit model: `dp = DataParallel(model); logits, loss = dp(img, labels); loss.backward()`."""
 
-    def __init__(self, model, group=None, min_slab_elems: int = 8 << 20):
+    def __init__(self, model, group=None, min_slab_elems: int = 8 << 20, mode: str = "auto"):
+        """mode = "overlap": backward runs eagerly and every finished gradient slab is all-reduced on a
+        communication stream while the remaining backward kernels run (best when the all-reduce is a
+        visible fraction of the step, i.e. large models / small per-GPU batches);
+        mode = "post": backward replays its CUDA graph and the flat gradient buffer is all-reduced
+        afterwards in one call (best when launch overhead would cost more than the un-overlapped
+        all-reduce); "auto" picks "post" below 512 MB of gradients."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.model, self.group = model, group
@@ -78,7 +84,13 @@ class DataParallel:
         self.comm_stream = torch.cuda.Stream(device=self.engine.device)
         self.min_slab_elems = min_slab_elems
         self._reducer: Optional[SlabReducer] = None
-        self.engine.on_range_done = self._on_range_done
+        if mode == "auto":
+            mode = "post" if self.engine.layout.total * 4 < (512 << 20) else "overlap"
+        self.mode = mode
+        if mode == "overlap":
+            self.engine.on_range_done = self._on_range_done
+        else:
+            self.engine.post_backward = self._post_backward
         self.broadcast_parameters()
 
     def broadcast_parameters(self, src: int = 0):
@@ -96,6 +108,9 @@ class DataParallel:
         if tag == "embed":
             torch.cuda.current_stream().wait_stream(self.comm_stream)
             self._reducer = None
+
+    def _post_backward(self, flat: torch.Tensor):
+        SlabReducer(0, self.group).reduce_(flat, 0, flat.numel())
 
     def _launch(self, start: int, end: int):
         ev = torch.cuda.Event()

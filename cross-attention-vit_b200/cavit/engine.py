@@ -209,6 +209,7 @@ class Engine:
         self._fwd_graphs: Dict = {}
         self._bwd_graphs: Dict = {}
         self.on_range_done = None
+        self.post_backward = None
         self.graph_launches = 0   # kernels executed through graph replays (the library counter only sees eager launches)
 
     # ------------------------------------------------------------------ parameters
@@ -497,6 +498,12 @@ class Engine:
             raise _abi.CavitError("backward() without a preceding training forward()")
         self.saved_valid = False
         self.grad = self._next_grad_buffer()
+        out = self._backward_dispatch(loss_scale, on_range_done, loss_scale_dev)
+        if self.post_backward is not None:   # e.g. cavit.ddp's whole-buffer gradient all-reduce
+            self.post_backward(out)
+        return out
+
+    def _backward_dispatch(self, loss_scale, on_range_done, loss_scale_dev):
         if not (self.use_graphs and ops.PROFILE is None and on_range_done is None):
             return self._backward_impl(loss_scale, on_range_done, loss_scale_dev)
         st = self._bwd_graphs.setdefault((self.B, self._grad_idx), {"runs": 0, "graph": None})

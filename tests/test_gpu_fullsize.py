@@ -1,0 +1,116 @@
+"""GPU, BASELINE.json full sizes (cfg2: B=256, 224x224 slices, C=384, 3x2 blocks, M=4 ring): the fp64 CPU
+oracle cannot run these in seconds, so parity is checked through size-independent properties of the
+path: sample independence, data-parallel linearity of the gradient, a directional
+finite-difference check of backward, the analytically-zero key-bias gradient, and stream independence
+when there is no cross-attention."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RING4 = {"0": "1", "1": "2", "2": "3", "3": "0"}
+CFG2 = dict(hidden_dim=384, mlp_dim=1536, num_heads=6, num_multi_blocks=3, num_self_blocks=2, patch_size=(16, 16, 1),
+            img_size=(224, 224, 1), num_modalities=4, attn_order=RING4, num_classes=2, dropout=0.0, label_smoothing=0.0)
+
+
+def _model(attn_order=RING4, seed=0):
+    from cavit.modules import ModelCross
+    from oracle.functional import make_config
+    cfg = make_config(**{**CFG2, "attn_order": attn_order})
+    torch.manual_seed(seed)
+    m = ModelCross(cfg)
+    with torch.no_grad():   # non-trivial biases / LayerNorm affine
+        g = torch.Generator().manual_seed(seed + 1)
+        for p in m.parameters():
+            if p.ndim == 1:
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+    return cfg, m.cuda().train()
+
+
+def _batch(cfg, B, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn((B, cfg.num_modalities, 1, *cfg.img_size), generator=g)
+    labels = torch.randint(0, 2, (B,), generator=g)
+    return img.cuda(), labels.cuda()
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _flat_grad(model):
+    return torch.cat([p.grad.detach().flatten() for p in model.parameters()])
+
+
+def test_full_size_sample_independence_and_dp_linearity():
+    cfg, model = _model()
+    B = 256
+    img, labels = _batch(cfg, B)
+    logits, loss = model(img, labels)
+    loss.backward()
+    g_full = _flat_grad(model).clone()
+    logits_full = logits.clone()
+    for p in model.parameters():
+        p.grad = None
+    halves, grads = [], []
+    for lo in (0, B // 2):
+        l, s = model(img[lo:lo + B // 2].contiguous(), labels[lo:lo + B // 2].contiguous())
+        s.backward()
+        halves.append(l.clone())
+        grads.append(_flat_grad(model).clone())
+        for p in model.parameters():
+            p.grad = None
+    # samples never interact (LayerNorm, per-sample attention): same logits whatever the batch split
+    assert rel(torch.cat(halves), logits_full) < 1e-5
+    # mean loss => the full-batch gradient is the average of the shard gradients (what the DP all-reduce computes)
+    assert rel(0.5 * (grads[0] + grads[1]), g_full) < 2e-3
+    from cavit import _abi
+    assert _abi.device_status() == 0
+
+
+def test_full_size_directional_derivative_matches_gradient():
+    cfg, model = _model(seed=3)
+    img, labels = _batch(cfg, 256, seed=5)
+    _, loss = model(img, labels)
+    loss.backward()
+    params = [p for p in model.parameters()]
+    g = [p.grad.detach().clone() for p in params]
+    gnorm = float(torch.sqrt(sum((x.double() ** 2).sum() for x in g)))
+    eps = 2e-2 / gnorm     # expected |dL| ~ 2e-2 per side along the normalised gradient
+    vals = []
+    with torch.no_grad():
+        for sgn in (+1.0, -1.0):
+            for p, gi in zip(params, g):
+                p.add_(sgn * eps * gi / gnorm * gnorm)   # step eps * g  (|step| = eps * |g|)
+            _, l = model(img, labels)
+            vals.append(float(l))
+            for p, gi in zip(params, g):
+                p.sub_(sgn * eps * gi / gnorm * gnorm)
+    fd = (vals[0] - vals[1]) / (2 * eps)       # ~ <g, g> = |g|^2
+    assert abs(fd - gnorm ** 2) < 0.1 * gnorm ** 2, (fd, gnorm ** 2)
+
+
+def test_full_size_key_bias_gradient_is_zero_and_streams_independent_without_fusion():
+    cfg, model = _model()
+    img, labels = _batch(cfg, 256, seed=9)
+    _, loss = model(img, labels)
+    loss.backward()
+    gmax = max(float(p.grad.norm()) for p in model.parameters())
+    for n, p in model.named_parameters():
+        if n.endswith("attn.fn.wk.bias"):
+            assert float(p.grad.norm()) < 2e-3 * gmax, n
+    # no cross-attention: perturbing stream 1 must leave the other streams' tokens bit-identical
+    cfg2, model2 = _model(attn_order={}, seed=4)
+    img2, labels2 = _batch(cfg2, 64, seed=11)
+    with torch.no_grad():
+        model2(img2, labels2)
+        eng = model2.engine()
+        toks = eng._x_fin.clone()
+        img3 = img2.clone()
+        img3[:, 1] = torch.randn_like(img3[:, 1])
+        model2(img3, labels2)
+        toks2 = eng._x_fin
+        for m in (0, 2, 3):
+            assert torch.equal(toks[m], toks2[m])
+        assert not torch.equal(toks[1], toks2[1])
