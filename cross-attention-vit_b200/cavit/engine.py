@@ -199,6 +199,7 @@ class Engine:
         self.grad_bufs = [torch.zeros(self.layout.total, dtype=F32, device=self.device)]
         self._grad_idx = 0
         self._bf16_version = -1
+        self._frozen = False
         self.adopt_parameters()
         self._plan_key = None
         self.saved_valid = False
@@ -233,12 +234,20 @@ class Engine:
         return True
 
     def refresh_operands(self):
+        """Re-derive the bf16 operand copy from the fp32 master weights. Parameters are views of the flat
+        buffer whose in-place updates (optimizer steps) are not visible through any version counter of
+        the flat tensor, so the cast (one launch, ~6 bytes per parameter) runs on every forward unless
+        the caller froze the weights with `freeze_operands()` (inference)."""
         if not self._params_in_place():
             self.adopt_parameters()
-        v = self.flat._version
-        if v != self._bf16_version:
+        if not self._frozen or self._bf16_version < 0:
             ops.cast_bf16(self.flat, self.flat_bf16)
-            self._bf16_version = v
+            self._bf16_version = 1
+
+    def freeze_operands(self, frozen: bool = True):
+        """Inference helper: skip the per-forward fp32 -> bf16 weight cast until unfrozen."""
+        self._frozen = frozen
+        self._bf16_version = -1
 
     def _seg(self, buf, name):
         off, shp = self.layout.segments[name]
@@ -382,7 +391,6 @@ class Engine:
         st["graph"].replay()
         self.graph_launches += st["launches"]
         self._labels = st["labels"]
-        self._bf16_version = self.flat._version
         self.saved_valid = train
         return self.a["logits"], self.a["loss"]
 

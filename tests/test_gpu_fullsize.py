@@ -77,18 +77,18 @@ def test_full_size_directional_derivative_matches_gradient():
     params = [p for p in model.parameters()]
     g = [p.grad.detach().clone() for p in params]
     gnorm = float(torch.sqrt(sum((x.double() ** 2).sum() for x in g)))
-    eps = 2e-2 / gnorm     # expected |dL| ~ 2e-2 per side along the normalised gradient
+    eps = 5e-3 / gnorm ** 2     # expected |dL| = eps * |g|^2 = 5e-3 per side
     vals = []
     with torch.no_grad():
         for sgn in (+1.0, -1.0):
             for p, gi in zip(params, g):
-                p.add_(sgn * eps * gi / gnorm * gnorm)   # step eps * g  (|step| = eps * |g|)
+                p.add_(sgn * eps * gi)   # step eps * g
             _, l = model(img, labels)
             vals.append(float(l))
             for p, gi in zip(params, g):
                 p.sub_(sgn * eps * gi / gnorm * gnorm)
     fd = (vals[0] - vals[1]) / (2 * eps)       # ~ <g, g> = |g|^2
-    assert abs(fd - gnorm ** 2) < 0.1 * gnorm ** 2, (fd, gnorm ** 2)
+    assert abs(fd - gnorm ** 2) < 0.15 * gnorm ** 2, (fd, gnorm ** 2)
 
 
 def test_full_size_key_bias_gradient_is_zero_and_streams_independent_without_fusion():

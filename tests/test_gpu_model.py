@@ -142,3 +142,26 @@ def test_cuda_graph_replay_matches_eager():
         num = sum(float((g1[k].double() - g0[k].double()).norm()) ** 2 for k in g0)
         den = sum(float(g0[k].double().norm()) ** 2 for k in g0)
         assert (num / den) ** 0.5 < 1e-3      # split-K / dQ atomics reorder fp32 sums slightly
+
+
+def test_eager_mode_sees_in_place_weight_updates():
+    """Parameters are views of the engine's flat buffer; an optimizer step must reach the bf16 operands
+    also when CUDA graphs are off (regression: the flat tensor's version counter does not change)."""
+    kind, cfg, state, img, labels = build_case("cross_chain3")
+    from cavit.modules import ModelCross
+    model = ModelCross(cfg)
+    model.load_state_dict(state)
+    model = model.cuda().train()
+    model.engine().use_graphs = False
+    x, y = img.cuda(), labels.cuda()
+    l0, s0 = model(x, y)
+    s0.backward()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.sub_(0.5 * p.grad)
+            p.grad = None
+    l1, s1 = model(x, y)
+    assert float(s1) < float(s0) - 1e-3
+    ref_state = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    ref_logits, _ = OF.model_cross_forward(ref_state, img.double(), labels, cfg)
+    assert rel(l1, ref_logits) < 2e-2
