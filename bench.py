@@ -122,7 +122,7 @@ def cpu_port_throughput(wl, steps: int, warmup: int):
     """The reference's algorithm (oracle port) fwd+bwd on the host cores, bounded batch."""
     from oracle import functional as OF
     from oracle.weights import make_inputs, make_state, state_schema_cross
-    cfg = OF.make_config(**wl["cfg"])
+    cfg = OF.make_config(**wl["cfg"])   # oracle-side config: this leg IS the CPU checker being timed
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     state = make_state(state_schema_cross(cfg), seed=0, init="reference")
@@ -184,7 +184,7 @@ def main():
 
     from cavit import _abi, ops
     from cavit.modules import ModelCross
-    from oracle.functional import make_config
+    from cavit.config import make_config
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

@@ -48,8 +48,10 @@ _SIGS = {
                                     C.POINTER(c_i32), C.POINTER(c_i32), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cavit_attn_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
     "cavit_attn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
-    "cavit_xattn_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
-    "cavit_xattn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_xattn_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp, C.c_uint32, c_vp]),
+    "cavit_xattn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp,
+                                C.c_uint32, c_vp]),
+    "cavit_dropout": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, C.c_uint32, c_vp]),
     "cavit_patchify": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cavit_cls_rows": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cavit_embed_param_grads": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
@@ -59,9 +61,10 @@ _SIGS = {
     "cavit_add_bf16_f32": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "cavit_gelu_bwd_bf16": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "cavit_compact_patch_rows_bf16": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
-    "cavit_head_loss_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_head_loss_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp,
+                                    C.c_uint32, c_vp]),
     "cavit_head_loss_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
-                                    c_f32, c_vp]),
+                                    c_f32, c_f32, c_vp, C.c_uint32, c_vp]),
 }
 
 EXPORTS = tuple(_SIGS)

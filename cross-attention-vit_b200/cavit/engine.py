@@ -188,6 +188,10 @@ class Engine:
             self.smoothing = 0.0
         self.K = len(self.cls_src)
         self.scale = 64 ** -0.5
+        self.p_drop = float(cfg.dropout)
+        self.drop = False                      # dropout active for the current forward/backward pair
+        self.seed_buf = torch.zeros(1, dtype=torch.int64, device=self.device)   # per-step dropout seed (device scalar)
+        self._step = 0
         self.layout = build_layout(kind, cfg)
         missing = [k for k in named_params if k not in self.layout.slots]
         extra = [k for k in self.layout.slots if k not in named_params]
@@ -268,9 +272,30 @@ class Engine:
     def has(self, name):
         return name in self.layout.segments
 
+    # ------------------------------------------------------------------ dropout sites
+    # One id per nn.Dropout module instance on the path (model_cross.py:25,27,47,84,86,170,180,182).
+    SITE_EMBED, SITE_HEAD_GELU, SITE_HEAD_LOGITS = 1, 2, 3
+
+    @staticmethod
+    def site_layer(l: int, which: str) -> int:      # which in out | gelu | fc2
+        return 16 + 4 * l + {"out": 0, "gelu": 1, "fc2": 2}[which]
+
+    @staticmethod
+    def site_fusion(mb: int, which: str) -> int:    # which in attn | proj | gelu | fc2
+        return 4096 + 4 * mb + {"attn": 0, "proj": 1, "gelu": 2, "fc2": 3}[which]
+
+    def _dropout(self, mode, a, b, out, site):
+        ops.dropout(mode, a, b, out, n=out.numel(), p=self.p_drop, seed=self.seed_buf, site=site)
+
+    def _new_seed(self):
+        """Fresh per-step seed derived from torch's global seed (so torch.manual_seed controls it)."""
+        self._step += 1
+        x = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._step * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+        self.seed_buf.fill_(x)
+
     # ------------------------------------------------------------------ planning
-    def _plan(self, B: int, train: bool):
-        key = (B, train)
+    def _plan(self, B: int, train: bool, drop: bool = False):
+        key = (B, train, drop)
         if self._plan_key == key:
             return
         dev = self.device
@@ -299,6 +324,10 @@ class Engine:
                                 ("f_rstdy", (K, B), F32), ("f_u", (K, B, F), BF16), ("f_h", (K, B, F), BF16),
                                 ("f_z", (K, B, C), F32)]:
                 a[nm] = [e(shp, dt) for _ in range(nF)]
+        if drop:   # bf16 branch outputs that get dropped before the residual add
+            a["br"] = e((G, T, C), BF16)
+            if K:
+                a["br_f"] = e((K, B, C), BF16)
         a["clsn"] = e((G, B, C), BF16)
         a["meanc"], a["rstdc"] = e((G, B)), e((G, B))
         a["uh"], a["hh"] = e((G, B, F), BF16), e((G, B, F), BF16)
@@ -356,8 +385,9 @@ class Engine:
         ops.colsum_bf16(x, out, rows=T, C_=N, groups=G)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, img: torch.Tensor, labels: torch.Tensor, train: bool):
-        """Validates inputs, then runs the forward kernel sequence (eagerly, or by replaying its CUDA graph)."""
+    def forward(self, img: torch.Tensor, labels: torch.Tensor, train: bool, drop: bool = False):
+        """Validates inputs, then runs the forward kernel sequence (eagerly, or by replaying its CUDA graph).
+        drop: apply the configured dropout (module in training mode with dropout > 0)."""
         cfg = self.cfg
         if img.dim() != 6 or img.shape[1] != self.Mimg or tuple(img.shape[3:]) != tuple(cfg.img_size) or img.shape[2] != 1:
             raise _abi.CavitError(f"img must be [B, {self.Mimg}, 1, {tuple(cfg.img_size)}], got {tuple(img.shape)}")
@@ -366,12 +396,16 @@ class Engine:
         img = img.contiguous()
         labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
         B = img.shape[0]
-        self._plan(B, train)
+        drop = bool(drop and self.p_drop > 0.0)
+        self._plan(B, train, drop)
+        self.drop = drop
+        if drop:
+            self._new_seed()
         if not self._params_in_place():
             self.adopt_parameters()
         if not (self.use_graphs and ops.PROFILE is None):
             return self._forward_impl(img, labels, train)
-        st = self._fwd_graphs.setdefault((B, train), {"runs": 0, "graph": None})
+        st = self._fwd_graphs.setdefault((B, train, drop), {"runs": 0, "graph": None})
         if st["graph"] is None:
             st["runs"] += 1
             if st["runs"] <= 2:   # eager warm-up: sets kernel attributes, fills the TMA descriptor cache
@@ -409,6 +443,9 @@ class Engine:
         ops.gemm(a["patches"], self.wb("embed.w"), X0, M=self.Mimg * B * self.Np, N=C, K=self.P, lda=self.P,
                  ldb=self.P, ldo=C, epi=EPI_EMBED, bias=self.w("embed.b"), resid=self.w("pos"), ldr=C, embed_np=np_seq)
         ops.cls_rows(self.w("cls"), self.w("pos"), X0, M=G, B=B, N=N, C_=C)
+        drop = self.drop
+        if drop:   # x = dropout(x) after the positional add (model_cross.py:198)
+            self._dropout(ops.DROP_F32, X0, None, X0, self.SITE_EMBED)
         xi = 0
         for l in range(self.L):
             s = l if train else 0
@@ -422,17 +459,25 @@ class Engine:
                        rows_per_group=T, groups=G, C=C)
             self._fwd(a["xn1"][s], self.wb(f"{tag}.wqkv"), a["qkv"][s], G=G, T=T, N=3 * C, K=C)
             ops.attn_fwd(a["qkv"][s], a["ao"][s], a["lse"][s], G=G, B=B, N=N, H=H, scale=self.scale)
-            if H != 1:
+            if H != 1 and drop:   # to_out = Linear, Dropout: x_mid = x_in + D(ao Wo^T + bo)
+                self._fwd(a["ao"][s], self.wb(f"{tag}.wo"), a["br"], G=G, T=T, N=C, K=C, epi=EPI_BIAS, bias=self.w(f"{tag}.bo"))
+                self._dropout(ops.DROP_ADD, x_in, a["br"], x_mid, self.site_layer(l, "out"))
+            elif H != 1:
                 self._fwd(a["ao"][s], self.wb(f"{tag}.wo"), x_mid, G=G, T=T, N=C, K=C, epi=EPI_BIAS_RESID,
                           bias=self.w(f"{tag}.bo"), resid=x_in)
-            else:  # to_out = nn.Identity() when heads == 1 (model_cross.py:37,44-48)
+            else:  # to_out = nn.Identity() when heads == 1 (model_cross.py:37,44-48): no projection, no dropout
                 ops.add_bf16_f32(x_in, a["ao"][s], x_mid)
             ops.ln_fwd(x_mid, self.w(f"{tag}.ln2.w"), self.w(f"{tag}.ln2.b"), a["xn2"][s], a["mean2"][s], a["rstd2"][s],
                        rows_per_group=T, groups=G, C=C)
             self._fwd(a["xn2"][s], self.wb(f"{tag}.w1"), a["h"][s], G=G, T=T, N=F, K=C, epi=EPI_BIAS_GELU,
                       bias=self.w(f"{tag}.b1"), aux=a["u"][s])
-            self._fwd(a["h"][s], self.wb(f"{tag}.w2"), x_out, G=G, T=T, N=C, K=F, epi=EPI_BIAS_RESID,
-                      bias=self.w(f"{tag}.b2"), resid=x_mid)
+            if drop:
+                self._dropout(ops.DROP_BF16, a["h"][s], None, a["h"][s], self.site_layer(l, "gelu"))
+                self._fwd(a["h"][s], self.wb(f"{tag}.w2"), a["br"], G=G, T=T, N=C, K=F, epi=EPI_BIAS, bias=self.w(f"{tag}.b2"))
+                self._dropout(ops.DROP_ADD, x_mid, a["br"], x_out, self.site_layer(l, "fc2"))
+            else:
+                self._fwd(a["h"][s], self.wb(f"{tag}.w2"), x_out, G=G, T=T, N=C, K=F, epi=EPI_BIAS_RESID,
+                          bias=self.w(f"{tag}.b2"), resid=x_mid)
             if self.kind == "cross" and K and (l + 1) % cfg.num_self_blocks == 0:
                 self._fusion_fwd(l // cfg.num_self_blocks, x_out, train)
         x_fin = a["X"][2 * self.L] if train else a["X"][xi]
@@ -442,8 +487,11 @@ class Engine:
                    groups=G, C=C, x_row_stride=N * C, x_gs=T * C)
         self._fwd(a["clsn"], self.wb("head.w1"), a["hh"], G=G, T=B, N=F, K=C, epi=EPI_BIAS_GELU, bias=self.w("head.b1"),
                   aux=a["uh"])
+        if drop:
+            self._dropout(ops.DROP_BF16, a["hh"], None, a["hh"], self.SITE_HEAD_GELU)
         ops.head_loss_fwd(a["hh"], self.w("head.w2"), self.w("head.b2"), labels, a["logits"], a["loss"], M=G, B=B, F=F,
-                          classes=self.classes, smoothing=self.smoothing)
+                          classes=self.classes, smoothing=self.smoothing, p_drop=self.p_drop if drop else 0.0,
+                          seed=self.seed_buf, site=self.SITE_HEAD_LOGITS)
         self._labels = labels
         self.saved_valid = train
         return a["logits"], a["loss"]
@@ -466,16 +514,27 @@ class Engine:
         # query from the CLS row only: rows b*N of xn (row stride N*C)
         self._fwd(a["f_xn"][s], self.wb(f"{tag}.wq"), a["f_q"][s], G=K, T=B, N=C, K=C, epi=EPI_BIAS,
                   bias=self.w(f"{tag}.bq"), lda=N * C, a_gs=T * C)
-        ops.xattn_fwd(a["f_q"][s], a["f_kv"][s], a["f_xo"][s], a["f_probs"][s], K=K, B=B, N=N, H=H, scale=self.scale)
+        drop = self.drop
+        ops.xattn_fwd(a["f_q"][s], a["f_kv"][s], a["f_xo"][s], a["f_probs"][s], K=K, B=B, N=N, H=H, scale=self.scale,
+                      p_drop=self.p_drop if drop else 0.0, seed=self.seed_buf, site=self.site_fusion(mb, "attn"))
         ops.cast_bf16(a["f_xo"][s], a["f_xob"][s])
-        self._fwd(a["f_xob"][s], self.wb(f"{tag}.wp"), a["f_y"][s], G=K, T=B, N=C, K=C, epi=EPI_BIAS_RESID,
-                  bias=self.w(f"{tag}.bp"), resid=f_cls)
+        if drop:
+            self._fwd(a["f_xob"][s], self.wb(f"{tag}.wp"), a["br_f"], G=K, T=B, N=C, K=C, epi=EPI_BIAS, bias=self.w(f"{tag}.bp"))
+            self._dropout(ops.DROP_ADD, f_cls, a["br_f"], a["f_y"][s], self.site_fusion(mb, "proj"))
+        else:
+            self._fwd(a["f_xob"][s], self.wb(f"{tag}.wp"), a["f_y"][s], G=K, T=B, N=C, K=C, epi=EPI_BIAS_RESID,
+                      bias=self.w(f"{tag}.bp"), resid=f_cls)
         ops.ln_fwd(a["f_y"][s], self.w(f"{tag}.lnF.w"), self.w(f"{tag}.lnF.b"), a["f_yn"][s], a["f_meany"][s],
                    a["f_rstdy"][s], rows_per_group=B, groups=K, C=C)
         self._fwd(a["f_yn"][s], self.wb(f"{tag}.w1"), a["f_h"][s], G=K, T=B, N=F, K=C, epi=EPI_BIAS_GELU,
                   bias=self.w(f"{tag}.b1"), aux=a["f_u"][s])
-        self._fwd(a["f_h"][s], self.wb(f"{tag}.w2"), a["f_z"][s], G=K, T=B, N=C, K=F, epi=EPI_BIAS_RESID,
-                  bias=self.w(f"{tag}.b2"), resid=a["f_y"][s])
+        if drop:
+            self._dropout(ops.DROP_BF16, a["f_h"][s], None, a["f_h"][s], self.site_fusion(mb, "gelu"))
+            self._fwd(a["f_h"][s], self.wb(f"{tag}.w2"), a["br_f"], G=K, T=B, N=C, K=F, epi=EPI_BIAS, bias=self.w(f"{tag}.b2"))
+            self._dropout(ops.DROP_ADD, a["f_y"][s], a["br_f"], a["f_z"][s], self.site_fusion(mb, "fc2"))
+        else:
+            self._fwd(a["f_h"][s], self.wb(f"{tag}.w2"), a["f_z"][s], G=K, T=B, N=C, K=F, epi=EPI_BIAS_RESID,
+                      bias=self.w(f"{tag}.b2"), resid=a["f_y"][s])
         for k in range(K):
             ops.gather_rows_f32(a["f_z"][s][k], X[self.cls_src[k]], rows=B, C_=C, groups=1, src_row_stride=C, src_gs=0,
                                 dst_row_stride=N * C, dst_gs=0)
@@ -514,7 +573,7 @@ class Engine:
     def _backward_dispatch(self, loss_scale, on_range_done, loss_scale_dev):
         if not (self.use_graphs and ops.PROFILE is None and on_range_done is None):
             return self._backward_impl(loss_scale, on_range_done, loss_scale_dev)
-        st = self._bwd_graphs.setdefault((self.B, self._grad_idx), {"runs": 0, "graph": None})
+        st = self._bwd_graphs.setdefault((self.B, self._grad_idx, self.drop), {"runs": 0, "graph": None})
         if st["graph"] is None:
             st["runs"] += 1
             if st["runs"] <= 2:
@@ -554,8 +613,12 @@ class Engine:
         # ---- loss, heads, final norm
         ops.head_loss_bwd(a["hh"], self.w("head.w2"), self._labels, a["logits"], a["dhh"], self.g("head.w2"),
                           self.g("head.b2"), M=G, B=B, F=F, classes=self.classes, smoothing=self.smoothing,
-                          loss_scale=loss_scale, loss_scale_dev=loss_scale_dev)
+                          loss_scale=loss_scale, loss_scale_dev=loss_scale_dev, p_drop=self.p_drop if self.drop else 0.0,
+                          seed=self.seed_buf, site=self.SITE_HEAD_LOGITS)
+        drop = self.drop
         ops.gelu_bwd_bf16(a["dhh"], a["uh"], a["duh"])
+        if drop:
+            self._dropout(ops.DROP_BF16, a["duh"], None, a["duh"], self.SITE_HEAD_GELU)
         self._dgrad(a["duh"], self.wb("head.w1"), a["dclsn"], G=G, T=B, N=F, K=C)
         self._wgrad(a["duh"], a["clsn"], self.g("head.w1"), G=G, T=B, N=F, K=C)
         self._colsum(a["duh"], self.g("head.b1"), G=G, T=B, N=F)
@@ -572,19 +635,29 @@ class Engine:
                 self._fusion_bwd(l // cfg.num_self_blocks, dX)
                 done(f"X{l // cfg.num_self_blocks}")
                 need_cast = True
-            if need_cast:
+            if drop:     # gradient of the dropped fc2 branch: mask_fc2 * dX / (1 - p)
+                self._dropout(ops.DROP_CAST, dX, None, dXb, self.site_layer(l, "fc2"))
+            elif need_cast:
                 ops.cast_bf16(dX, dXb)
-                need_cast = False
+            need_cast = False
             x_in, x_mid = a["X"][2 * l], a["X"][2 * l + 1]
             # FFN: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
             self._dgrad(dXb, self.wb(f"{tag}.w2"), a["dbig"], G=G, T=T, N=C, K=F, epi=EPI_GELU_BWD, aux=a["u"][l])
+            if drop:
+                self._dropout(ops.DROP_BF16, a["dbig"], None, a["dbig"], self.site_layer(l, "gelu"))
             self._wgrad(dXb, a["h"][l], self.g(f"{tag}.w2"), G=G, T=T, N=C, K=F)
             self._colsum(dXb, self.g(f"{tag}.b2"), G=G, T=T, N=C)
             self._dgrad(a["dbig"], self.wb(f"{tag}.w1"), a["dmid"], G=G, T=T, N=F, K=C)
             self._wgrad(a["dbig"], a["xn2"][l], self.g(f"{tag}.w1"), G=G, T=T, N=F, K=C)
             self._colsum(a["dbig"], self.g(f"{tag}.b1"), G=G, T=T, N=F)
             ops.ln_bwd(a["dmid"], x_mid, a["mean2"][l], a["rstd2"][l], self.w(f"{tag}.ln2.w"), dX, self.g(f"{tag}.ln2.w"),
-                       self.g(f"{tag}.ln2.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX, dx_bf16=dXb)
+                       self.g(f"{tag}.ln2.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX,
+                       dx_bf16=None if drop else dXb)
+            if drop:
+                if H != 1:
+                    self._dropout(ops.DROP_CAST, dX, None, dXb, self.site_layer(l, "out"))
+                else:
+                    ops.cast_bf16(dX, dXb)
             # attention: x_mid = x_in + Wo attn(LN1(x_in)) + bo
             if H != 1:
                 self._dgrad(dXb, self.wb(f"{tag}.wo"), a["dmid"], G=G, T=T, N=C, K=C)
@@ -598,9 +671,13 @@ class Engine:
             self._dgrad(a["dqkv"], self.wb(f"{tag}.wqkv"), a["dmid"], G=G, T=T, N=3 * C, K=C)
             self._wgrad(a["dqkv"], a["xn1"][l], self.g(f"{tag}.wqkv"), G=G, T=T, N=3 * C, K=C)
             ops.ln_bwd(a["dmid"], x_in, a["mean1"][l], a["rstd1"][l], self.w(f"{tag}.ln1.w"), dX, self.g(f"{tag}.ln1.w"),
-                       self.g(f"{tag}.ln1.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX, dx_bf16=dXb)
+                       self.g(f"{tag}.ln1.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX,
+                       dx_bf16=None if drop else dXb)
             done(tag)
         # ---- embedding: d(pos), d(cls), dW = dY^T unfold(x), db
+        if drop:   # through the embedding dropout; the bf16 copy is rebuilt from the masked gradient
+            self._dropout(ops.DROP_F32, dX, None, dX, self.SITE_EMBED)
+            ops.cast_bf16(dX, dXb)
         ops.embed_param_grads(dX, self.g("pos"), self.g("cls"), M=G, B=B, N=N, C_=C)
         np_seq = self.N - 1
         ops.compact_patch_rows_bf16(dXb, a["dcomp"], S=G * B, Np=np_seq, C_=C)
@@ -620,9 +697,15 @@ class Engine:
         for k in range(K):
             ops.gather_rows_f32(dX[self.cls_src[k]], d_z[k], rows=B, C_=C, groups=1, src_row_stride=N * C, src_gs=0,
                                 dst_row_stride=C, dst_gs=0, zero_src=True)
-        ops.cast_bf16(d_z, a["d_zb"])
+        drop = self.drop
+        if drop:
+            self._dropout(ops.DROP_CAST, d_z, None, a["d_zb"], self.site_fusion(mb, "fc2"))
+        else:
+            ops.cast_bf16(d_z, a["d_zb"])
         # FFN on the single CLS token
         self._dgrad(a["d_zb"], self.wb(f"{tag}.w2"), a["d_u"], G=K, T=B, N=C, K=F, epi=EPI_GELU_BWD, aux=a["f_u"][s])
+        if drop:
+            self._dropout(ops.DROP_BF16, a["d_u"], None, a["d_u"], self.site_fusion(mb, "gelu"))
         self._wgrad(a["d_zb"], a["f_h"][s], self.g(f"{tag}.w2"), G=K, T=B, N=C, K=F)
         self._colsum(a["d_zb"], self.g(f"{tag}.b2"), G=K, T=B, N=C)
         self._dgrad(a["d_u"], self.wb(f"{tag}.w1"), a["d_yn"], G=K, T=B, N=F, K=C)
@@ -630,13 +713,16 @@ class Engine:
         self._colsum(a["d_u"], self.g(f"{tag}.b1"), G=K, T=B, N=F)
         ops.ln_bwd(a["d_yn"], a["f_y"][s], a["f_meany"][s], a["f_rstdy"][s], self.w(f"{tag}.lnF.w"), a["d_y"],
                    self.g(f"{tag}.lnF.w"), self.g(f"{tag}.lnF.b"), ws, rows_per_group=B, groups=K, C=C, dresid=d_z,
-                   dx_bf16=a["d_yb"])
+                   dx_bf16=None if drop else a["d_yb"])
+        if drop:
+            self._dropout(ops.DROP_CAST, a["d_y"], None, a["d_yb"], self.site_fusion(mb, "proj"))
         # y = proj(xattn) + cls_in
         self._dgrad(a["d_yb"], self.wb(f"{tag}.wp"), a["d_xo"], G=K, T=B, N=C, K=C)
         self._wgrad(a["d_yb"], a["f_xob"][s], self.g(f"{tag}.wp"), G=K, T=B, N=C, K=C)
         self._colsum(a["d_yb"], self.g(f"{tag}.bp"), G=K, T=B, N=C)
         ops.xattn_bwd(a["f_q"][s], a["f_kv"][s], a["f_probs"][s], a["d_xo"], a["d_q"], a["d_kv"], K=K, B=B, N=N, H=H,
-                      scale=self.scale)
+                      scale=self.scale, p_drop=self.p_drop if drop else 0.0, seed=self.seed_buf,
+                      site=self.site_fusion(mb, "attn"))
         # query path (CLS row of xn only)
         ops.cast_bf16(a["d_q"], a["d_qb"])
         self._dgrad(a["d_qb"], self.wb(f"{tag}.wq"), a["d_xncls"], G=K, T=B, N=C, K=C)

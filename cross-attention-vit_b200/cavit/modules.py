@@ -129,8 +129,8 @@ class _CavitFn(torch.autograd.Function):
     """One autograd node for the whole model: forward and backward are static kernel sequences."""
 
     @staticmethod
-    def forward(ctx, engine, train, img, labels, *params):
-        logits, loss = engine.forward(img, labels, train=train)
+    def forward(ctx, engine, train, drop, img, labels, *params):
+        logits, loss = engine.forward(img, labels, train=train, drop=drop)
         ctx.engine = engine
         ctx.train = train
         ctx.mark_non_differentiable(logits_out := logits.clone())
@@ -151,7 +151,7 @@ class _CavitFn(torch.autograd.Function):
                 grads.append(flat[off:off + p.numel()].view(shp))
             else:
                 grads.append(None)
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 class _CavitModel(_Base):
@@ -196,14 +196,12 @@ class _CavitModel(_Base):
         return eng
 
     def forward(self, img, labels):
-        if self.training and self._dropout_p > 0.0:
-            raise _abi.CavitError("dropout > 0 in training mode is not implemented in the cavit kernel path yet; "
-                                  "use dropout=0.0 or eval()")
         eng = self.engine()
         params = list(eng.params.values())
         # grad mode is off inside autograd.Function.forward, so decide here whether to save activations
         train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _CavitFn.apply(eng, train, img, labels, *params)
+        drop = self.training and self._dropout_p > 0.0   # nn.Dropout semantics: active in train() mode only
+        return _CavitFn.apply(eng, train, drop, img, labels, *params)
 
     # ---------------------------------------------------------------- Lightning-style hooks
     def training_step(self, batch, batch_idx):

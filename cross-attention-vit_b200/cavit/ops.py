@@ -126,14 +126,22 @@ def attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, *, G, B, N, H, scale):
                                delta.data_ptr(), dq_acc.data_ptr(), G, B, N, H, scale, _stream()), "cavit_attn_bwd")
 
 
-def xattn_fwd(q, kv, out, probs, *, K, B, N, H, scale):
+def xattn_fwd(q, kv, out, probs, *, K, B, N, H, scale, p_drop=0.0, seed=None, site=0):
     check(lib().cavit_xattn_fwd(q.data_ptr(), kv.data_ptr(), out.data_ptr(), probs.data_ptr(), K, B, N, H, scale,
-                                _stream()), "cavit_xattn_fwd")
+                                p_drop, _p(seed), site, _stream()), "cavit_xattn_fwd")
 
 
-def xattn_bwd(q, kv, probs, dout, dq, dkv, *, K, B, N, H, scale):
+def xattn_bwd(q, kv, probs, dout, dq, dkv, *, K, B, N, H, scale, p_drop=0.0, seed=None, site=0):
     check(lib().cavit_xattn_bwd(q.data_ptr(), kv.data_ptr(), probs.data_ptr(), dout.data_ptr(), dq.data_ptr(),
-                                dkv.data_ptr(), K, B, N, H, scale, _stream()), "cavit_xattn_bwd")
+                                dkv.data_ptr(), K, B, N, H, scale, p_drop, _p(seed), site, _stream()), "cavit_xattn_bwd")
+
+
+DROP_F32, DROP_BF16, DROP_ADD, DROP_CAST, DROP_MASK = range(5)
+
+
+def dropout(mode, a, b, out, *, n, p, seed, site):
+    """Counter-based dropout (include/cavit.h: cavit_dropout). seed: int64/uint64 device scalar tensor."""
+    check(lib().cavit_dropout(mode, _p(a), _p(b), out.data_ptr(), n, p, seed.data_ptr(), site, _stream()), "cavit_dropout")
 
 
 def patchify(img, patches, *, patch_size, sample_major=False):
@@ -188,16 +196,17 @@ def compact_patch_rows_bf16(src, dst, *, S, Np, C_):
           "cavit_compact_patch_rows_bf16")
 
 
-def head_loss_fwd(h, W2, b2, labels, logits, loss, *, M, B, F, classes, smoothing):
+def head_loss_fwd(h, W2, b2, labels, logits, loss, *, M, B, F, classes, smoothing, p_drop=0.0, seed=None, site=0):
     check(lib().cavit_head_loss_fwd(h.data_ptr(), W2.data_ptr(), b2.data_ptr(), labels.data_ptr(), logits.data_ptr(),
-                                    loss.data_ptr(), M, B, F, classes, smoothing, _stream()), "cavit_head_loss_fwd")
+                                    loss.data_ptr(), M, B, F, classes, smoothing, p_drop, _p(seed), site, _stream()),
+          "cavit_head_loss_fwd")
 
 
 def head_loss_bwd(h, W2, labels, logits, dh, dW2, db2, *, M, B, F, classes, smoothing, loss_scale=1.0,
-                  loss_scale_dev=None):
+                  loss_scale_dev=None, p_drop=0.0, seed=None, site=0):
     check(lib().cavit_head_loss_bwd(h.data_ptr(), W2.data_ptr(), labels.data_ptr(), logits.data_ptr(), loss_scale,
                                     _p(loss_scale_dev), dh.data_ptr(), dW2.data_ptr(), db2.data_ptr(), M, B, F, classes, smoothing,
-                                    _stream()), "cavit_head_loss_bwd")
+                                    p_drop, _p(seed), site, _stream()), "cavit_head_loss_bwd")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,5 +240,5 @@ def _instrument(name, fn):
 
 for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_fwd", "attn_bwd", "xattn_fwd", "xattn_bwd",
            "patchify", "cls_rows", "embed_param_grads", "cast_bf16", "colsum_bf16", "gather_rows_f32", "add_bf16_f32",
-           "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd"):
+           "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout"):
     globals()[_n] = _instrument(_n, globals()[_n])

@@ -227,6 +227,36 @@ __device__ __forceinline__ float gelu_erf_grad(float u) {
   gelu_phi_terms(u, phi, e);
   return fmaf(u * 0.3989422804014327f, e, phi);
 }
+// ---------------------------------------------------------------- dropout
+// Counter-based Bernoulli masks: keep(i) is a pure function of (seed, site, element index), so the
+// backward pass regenerates exactly the mask the forward pass used without storing it. One
+// splitmix64 evaluation yields two 32-bit uniforms (elements 2j and 2j+1 of a site).
+struct DropCfg {
+  const unsigned long long* seed;  // device scalar (changes every step; graph-replay safe)
+  uint32_t site;                   // which dropout module
+  uint32_t thresh;                 // p * 2^32: keep iff uniform >= thresh
+  float inv_keep;                  // 1 / (1 - p)
+};
+__device__ __forceinline__ uint64_t drop_hash(uint64_t seed, uint32_t site, uint64_t pair_idx) {
+  uint64_t x = pair_idx * 0x9E3779B97F4A7C15ull + (seed ^ (static_cast<uint64_t>(site) * 0xD1B54A32D192ED03ull));
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+// multiplier (0 or 1/(1-p)) for element idx
+__device__ __forceinline__ float drop_mult(const DropCfg& d, uint64_t seed, uint64_t idx) {
+  const uint64_t h = drop_hash(seed, d.site, idx >> 1);
+  const uint32_t u = (idx & 1) ? static_cast<uint32_t>(h >> 32) : static_cast<uint32_t>(h);
+  return u >= d.thresh ? d.inv_keep : 0.f;
+}
+// multipliers for elements idx (even) and idx+1
+__device__ __forceinline__ float2 drop_mult2(const DropCfg& d, uint64_t seed, uint64_t even_idx) {
+  const uint64_t h = drop_hash(seed, d.site, even_idx >> 1);
+  return make_float2(static_cast<uint32_t>(h) >= d.thresh ? d.inv_keep : 0.f,
+                     static_cast<uint32_t>(h >> 32) >= d.thresh ? d.inv_keep : 0.f);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

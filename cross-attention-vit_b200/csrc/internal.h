@@ -26,6 +26,13 @@ const CUtensorMap* tensor_map_bf16_4d(const void* base, const uint64_t dims[4], 
                                       const uint32_t box[4]);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+// p * 2^32 threshold for the counter-based dropout masks (common.cuh); p in [0, 1)
+inline uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
 int sm_count();
 
 }  // namespace cavit

@@ -178,18 +178,80 @@ __global__ void compact_patch_rows_kernel(const uint4* __restrict__ in, uint4* _
   }
 }
 
+// ------------------------------------------------------------------------------------------ dropout
+// mode 0: out_f32 = m*a_f32            mode 1: out_bf16 = m*a_bf16
+// mode 2: out_f32 = a_f32 + m*b_bf16   mode 3: out_bf16 = bf16(m*a_f32)      mode 4: out_u8 = keep
+// m = keep / (1 - p); two elements per thread (one hash).
+__global__ void dropout_kernel(int mode, const void* a, const void* b, void* out, long long n, DropCfg d) {
+  const unsigned long long seed = *d.seed;
+  const long long pairs = (n + 1) >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (long long)gridDim.x * blockDim.x) {
+    const float2 m = drop_mult2(d, seed, (uint64_t)i * 2);
+    const long long e = i * 2;
+    const bool two = e + 1 < n;
+    if (mode == 0) {
+      const float* x = reinterpret_cast<const float*>(a);
+      float* o = reinterpret_cast<float*>(out);
+      if (two) {
+        const float2 v = *reinterpret_cast<const float2*>(x + e);
+        *reinterpret_cast<float2*>(o + e) = make_float2(v.x * m.x, v.y * m.y);
+      } else {
+        o[e] = x[e] * m.x;
+      }
+    } else if (mode == 1) {
+      const bf16* x = reinterpret_cast<const bf16*>(a);
+      bf16* o = reinterpret_cast<bf16*>(out);
+      if (two) {
+        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + e));
+        *reinterpret_cast<uint32_t*>(o + e) = pack_bf16(v.x * m.x, v.y * m.y);
+      } else {
+        o[e] = __float2bfloat16(__bfloat162float(x[e]) * m.x);
+      }
+    } else if (mode == 2) {
+      const float* r = reinterpret_cast<const float*>(a);
+      const bf16* x = reinterpret_cast<const bf16*>(b);
+      float* o = reinterpret_cast<float*>(out);
+      if (two) {
+        const float2 rv = *reinterpret_cast<const float2*>(r + e);
+        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + e));
+        *reinterpret_cast<float2*>(o + e) = make_float2(rv.x + v.x * m.x, rv.y + v.y * m.y);
+      } else {
+        o[e] = r[e] + __bfloat162float(x[e]) * m.x;
+      }
+    } else if (mode == 3) {
+      const float* x = reinterpret_cast<const float*>(a);
+      bf16* o = reinterpret_cast<bf16*>(out);
+      if (two) {
+        const float2 v = *reinterpret_cast<const float2*>(x + e);
+        *reinterpret_cast<uint32_t*>(o + e) = pack_bf16(v.x * m.x, v.y * m.y);
+      } else {
+        o[e] = __float2bfloat16(x[e] * m.x);
+      }
+    } else {
+      uint8_t* o = reinterpret_cast<uint8_t*>(out);
+      o[e] = m.x != 0.f;
+      if (two) o[e + 1] = m.y != 0.f;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ classification tail
 constexpr int HEAD_MAX_CLASSES = 8;
 
-// grid = B, block = 256. logits[b][k] = (1/M) sum_m ( b2[m][k] + sum_f h[m][b][f] W2[m][k][f] )
+// grid = B, block = 256. logits[b][k] = (1/M) sum_m D_m( b2[m][k] + sum_f h[m][b][f] W2[m][k][f] ), where D_m is the
+// (optional) dropout the reference applies to every head's logits (model_cross.py:182) before the mean.
 __global__ void head_logits_kernel(const bf16* __restrict__ h, const float* __restrict__ W2, const float* __restrict__ b2,
-                                   float* __restrict__ logits, int M, int B, int F, int classes) {
+                                   float* __restrict__ logits, int M, int B, int F, int classes, DropCfg d, int use_drop) {
   __shared__ float red[HEAD_MAX_CLASSES][8];
+  __shared__ float total[HEAD_MAX_CLASSES];
   const int b = blockIdx.x;
-  float acc[HEAD_MAX_CLASSES];
-#pragma unroll
-  for (int k = 0; k < HEAD_MAX_CLASSES; ++k) acc[k] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < HEAD_MAX_CLASSES) total[threadIdx.x] = 0.f;
+  const unsigned long long seed = use_drop ? *d.seed : 0ull;
   for (int m = 0; m < M; ++m) {
+    float acc[HEAD_MAX_CLASSES];
+#pragma unroll
+    for (int k = 0; k < HEAD_MAX_CLASSES; ++k) acc[k] = 0.f;
     const bf16* hr = h + ((long long)m * B + b) * F;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
       const float hv = __bfloat162float(hr[f]);
@@ -197,20 +259,22 @@ __global__ void head_logits_kernel(const bf16* __restrict__ h, const float* __re
       for (int k = 0; k < HEAD_MAX_CLASSES; ++k)
         if (k < classes) acc[k] += hv * __ldg(W2 + ((long long)m * classes + k) * F + f);
     }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
 #pragma unroll
-  for (int k = 0; k < HEAD_MAX_CLASSES; ++k) {
-    const float s = warp_sum(acc[k]);
-    if (lane == 0) red[k][warp] = s;
+    for (int k = 0; k < HEAD_MAX_CLASSES; ++k) {
+      const float s_ = warp_sum(acc[k]);
+      if (lane == 0) red[k][warp] = s_;
+    }
+    __syncthreads();
+    if (threadIdx.x < classes) {
+      float s_ = b2[m * classes + threadIdx.x];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s_ += red[threadIdx.x][w];
+      if (use_drop) s_ *= drop_mult(d, seed, ((uint64_t)m * B + b) * classes + threadIdx.x);
+      total[threadIdx.x] += s_;
+    }
   }
   __syncthreads();
-  if (threadIdx.x < classes) {
-    float s = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
-    for (int m = 0; m < M; ++m) s += b2[m * classes + threadIdx.x];
-    logits[b * classes + threadIdx.x] = s / (float)M;
-  }
+  if (threadIdx.x < classes) logits[b * classes + threadIdx.x] = total[threadIdx.x] / (float)M;
 }
 
 // single block: loss = mean_b CE(logits[b], label[b]) with label smoothing
@@ -258,11 +322,16 @@ __device__ __forceinline__ void dlogits_row(const float* z, long long label, int
 // grid = (B, M): dh[m][b][f] = sum_k dz[b][k] W2[m][k][f],  dz = dlogits / M
 __global__ void head_dh_kernel(const float* __restrict__ W2, const long long* __restrict__ labels,
                                const float* __restrict__ logits, float scale, const float* __restrict__ scale_dev,
-                               bf16* __restrict__ dh, int M, int B, int F, int classes, float smoothing) {
+                               bf16* __restrict__ dh, int M, int B, int F, int classes, float smoothing, DropCfg d,
+                               int use_drop) {
   const int b = blockIdx.x, m = blockIdx.y;
   if (scale_dev) scale *= __ldg(scale_dev);
   float dz[HEAD_MAX_CLASSES];
   dlogits_row(logits + b * classes, labels[b], classes, smoothing, scale / ((float)B * (float)M), dz);
+  if (use_drop) {
+    const unsigned long long seed = *d.seed;
+    for (int k = 0; k < classes; ++k) dz[k] *= drop_mult(d, seed, ((uint64_t)m * B + b) * classes + k);
+  }
   bf16* o = dh + ((long long)m * B + b) * F;
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
     float s = 0.f;
@@ -275,9 +344,10 @@ __global__ void head_dh_kernel(const float* __restrict__ W2, const long long* __
 __global__ void head_dw_kernel(const bf16* __restrict__ h, const long long* __restrict__ labels,
                                const float* __restrict__ logits, float scale, const float* __restrict__ scale_dev,
                                float* __restrict__ dW2, float* __restrict__ db2, int M, int B, int F, int classes,
-                               float smoothing) {
+                               float smoothing, DropCfg d, int use_drop) {
   const int m = blockIdx.y;
   if (scale_dev) scale *= __ldg(scale_dev);
+  const unsigned long long seed = use_drop ? *d.seed : 0ull;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   float acc[HEAD_MAX_CLASSES], accb[HEAD_MAX_CLASSES];
 #pragma unroll
@@ -285,6 +355,8 @@ __global__ void head_dw_kernel(const bf16* __restrict__ h, const long long* __re
   for (int b = 0; b < B; ++b) {
     float dz[HEAD_MAX_CLASSES];
     dlogits_row(logits + b * classes, labels[b], classes, smoothing, scale / ((float)B * (float)M), dz);
+    if (use_drop)
+      for (int k = 0; k < classes; ++k) dz[k] *= drop_mult(d, seed, ((uint64_t)m * B + b) * classes + k);
     const float hv = (f < F) ? __bfloat162float(h[((long long)m * B + b) * F + f]) : 0.f;
 #pragma unroll
     for (int k = 0; k < HEAD_MAX_CLASSES; ++k)
@@ -404,12 +476,40 @@ int cavit_compact_patch_rows_bf16(const void* in, void* out, int32_t S, int32_t 
   return check_launch("cavit_compact_patch_rows_bf16");
 }
 
+static int make_drop(float p, const uint64_t* seed_dev, uint32_t site, DropCfg* d) {
+  d->seed = reinterpret_cast<const unsigned long long*>(seed_dev);
+  d->site = site;
+  d->thresh = 0;
+  d->inv_keep = 1.f;
+  if (p <= 0.f) return 0;
+  if (p >= 1.f || !seed_dev) return -1;
+  d->thresh = drop_threshold(p);
+  d->inv_keep = 1.0f / (1.0f - p);
+  return 1;
+}
+
+int cavit_dropout(int32_t mode, const void* a, const void* b, void* out, int64_t n, float p, const uint64_t* seed_dev,
+                  uint32_t site, void* stream) {
+  if (mode < 0 || mode > 4 || !out || n <= 0 || (mode != 4 && !a) || (mode == 2 && !b))
+    return fail(CAVIT_E_BADARG, "cavit_dropout: bad args");
+  DropCfg d;
+  const int use = make_drop(p, seed_dev, site, &d);
+  if (use < 0 || !seed_dev) return fail(CAVIT_E_BADARG, "cavit_dropout: p must be in [0, 1) and seed_dev non-null");
+  dropout_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, as_stream(stream)>>>(mode, a, b, out, n, d);
+  count_launch();
+  return check_launch("cavit_dropout");
+}
+
 int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const int64_t* labels, float* logits, float* loss,
-                        int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing, void* stream) {
+                        int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing, float p_drop,
+                        const uint64_t* seed_dev, uint32_t site, void* stream) {
   if (!h || !W2 || !b2 || !labels || !logits || !loss) return fail(CAVIT_E_BADARG, "cavit_head_loss_fwd: null pointer");
   if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d (max %d)", classes, HEAD_MAX_CLASSES);
   cudaStream_t st = as_stream(stream);
-  head_logits_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const bf16*>(h), W2, b2, logits, M, B, F, classes);
+  DropCfg d;
+  const int use = make_drop(p_drop, seed_dev, site, &d);
+  if (use < 0) return fail(CAVIT_E_BADARG, "cavit_head_loss_fwd: bad dropout arguments");
+  head_logits_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const bf16*>(h), W2, b2, logits, M, B, F, classes, d, use);
   ce_loss_kernel<<<1, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), loss, B, classes, smoothing);
   count_launch(2);
   return check_launch("cavit_head_loss_fwd");
@@ -417,15 +517,18 @@ int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const i
 
 int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, const float* logits, float loss_scale,
                         const float* loss_scale_dev, void* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing,
-                        void* stream) {
+                        float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream) {
   if (!h || !W2 || !labels || !logits || !dh || !dW2 || !db2) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: null pointer");
   if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d", classes);
   cudaStream_t st = as_stream(stream);
   const long long* lab = reinterpret_cast<const long long*>(labels);
+  DropCfg d;
+  const int use = make_drop(p_drop, seed_dev, site, &d);
+  if (use < 0) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: bad dropout arguments");
   head_dh_kernel<<<dim3(B, M), 256, 0, st>>>(W2, lab, logits, loss_scale, loss_scale_dev, reinterpret_cast<bf16*>(dh), M, B, F, classes,
-                                             smoothing);
+                                             smoothing, d, use);
   head_dw_kernel<<<dim3((F + 255) / 256, M), 256, 0, st>>>(reinterpret_cast<const bf16*>(h), lab, logits, loss_scale,
-                                                           loss_scale_dev, dW2, db2, M, B, F, classes, smoothing);
+                                                           loss_scale_dev, dW2, db2, M, B, F, classes, smoothing, d, use);
   count_launch(2);
   return check_launch("cavit_head_loss_bwd");
 }

@@ -45,7 +45,7 @@ __device__ __forceinline__ float dot64(const float* qs, const bf16* row) {
 // grid = (H, B, K)
 __global__ void __launch_bounds__(XA_THREADS)
 xattn_fwd_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, float* __restrict__ out, float* __restrict__ probs,
-                 int B, int N, int H, float scale) {
+                 int B, int N, int H, float scale, DropCfg dcfg, int use_drop) {
   extern __shared__ float sm[];
   float* s_p = sm;           // [N]
   float* s_q = sm + N;       // [64]
@@ -76,10 +76,12 @@ xattn_fwd_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, float
   sum = block_reduce(sum, s_red, false);
   const float inv = 1.0f / sum;
   float* pr = probs + (((long long)k * B + b) * H + h) * N;
+  const unsigned long long seed = use_drop ? *dcfg.seed : 0ull;
+  const unsigned long long pbase = (((unsigned long long)k * B + b) * H + h) * (unsigned long long)N;
   for (int n = tid; n < N; n += XA_THREADS) {
     const float pn = s_p[n] * inv;
-    s_p[n] = pn;
-    pr[n] = pn;
+    pr[n] = pn;  // saved pre-dropout (softmax backward needs it); attn_drop (model_cross.py:97) applies to the weights used below
+    s_p[n] = use_drop ? pn * drop_mult(dcfg, seed, pbase + n) : pn;
   }
   __syncthreads();
   float a0 = 0.f, a1 = 0.f;
@@ -104,7 +106,7 @@ xattn_fwd_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, float
 __global__ void __launch_bounds__(XA_THREADS)
 xattn_bwd_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, const float* __restrict__ probs,
                  const float* __restrict__ dout, float* __restrict__ dq, bf16* __restrict__ dkv, int B, int N, int H,
-                 float scale) {
+                 float scale, DropCfg dcfg, int use_drop) {
   extern __shared__ float sm[];
   float* s_ds = sm;           // [N]
   float* s_q = sm + N;        // [64] (unscaled q)
@@ -126,10 +128,13 @@ xattn_bwd_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, const
   float dov[XA_D];
 #pragma unroll
   for (int i = 0; i < XA_D; ++i) dov[i] = s_do[i];
-  // dp_n = <dout, V[n]>;  dot_pd = sum_n p_n dp_n
+  // dp_n = m_n <dout, V[n]> (m_n = attention-dropout multiplier);  dot_pd = sum_n p_n dp_n
+  const unsigned long long seed = use_drop ? *dcfg.seed : 0ull;
+  const unsigned long long pbase = (kb * H + h) * (unsigned long long)N;
   float part = 0.f;
   for (int n = tid; n < N; n += XA_THREADS) {
-    const float dp = dot64(dov, kvb + (long long)n * 2 * C + C + h * XA_D);
+    float dp = dot64(dov, kvb + (long long)n * 2 * C + C + h * XA_D);
+    if (use_drop) dp *= drop_mult(dcfg, seed, pbase + n);
     s_ds[n] = dp;
     part += pr[n] * dp;
   }
@@ -139,6 +144,7 @@ xattn_bwd_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, const
     const float pn = pr[n];
     const float ds = pn * (s_ds[n] - dot_pd);
     s_ds[n] = ds;
+    const float pv = use_drop ? pn * drop_mult(dcfg, seed, pbase + n) : pn;  // dropped weight that multiplied V[n]
     bf16* dk = dkvb + (long long)n * 2 * C + h * XA_D;
     bf16* dv = dk + C;
     const float dss = ds * scale;
@@ -150,10 +156,10 @@ xattn_bwd_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, const
       w.z = pack_bf16(dss * s_q[i + 4], dss * s_q[i + 5]);
       w.w = pack_bf16(dss * s_q[i + 6], dss * s_q[i + 7]);
       *reinterpret_cast<uint4*>(dk + i) = w;
-      w.x = pack_bf16(pn * dov[i], pn * dov[i + 1]);
-      w.y = pack_bf16(pn * dov[i + 2], pn * dov[i + 3]);
-      w.z = pack_bf16(pn * dov[i + 4], pn * dov[i + 5]);
-      w.w = pack_bf16(pn * dov[i + 6], pn * dov[i + 7]);
+      w.x = pack_bf16(pv * dov[i], pv * dov[i + 1]);
+      w.y = pack_bf16(pv * dov[i + 2], pv * dov[i + 3]);
+      w.z = pack_bf16(pv * dov[i + 4], pv * dov[i + 5]);
+      w.w = pack_bf16(pv * dov[i + 6], pv * dov[i + 7]);
       *reinterpret_cast<uint4*>(dv + i) = w;
     }
   }
@@ -183,8 +189,20 @@ using namespace cavit;
 
 extern "C" {
 
+static int xa_drop(float p, const uint64_t* seed_dev, uint32_t site, DropCfg* d) {
+  d->seed = reinterpret_cast<const unsigned long long*>(seed_dev);
+  d->site = site;
+  d->thresh = 0;
+  d->inv_keep = 1.f;
+  if (p <= 0.f) return 0;
+  if (p >= 1.f || !seed_dev) return -1;
+  d->thresh = drop_threshold(p);
+  d->inv_keep = 1.0f / (1.0f - p);
+  return 1;
+}
+
 int cavit_xattn_fwd(const float* q, const void* kv, float* out, float* probs, int32_t K, int32_t B, int32_t N, int32_t H,
-                    float scale, void* stream) {
+                    float scale, float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream) {
   if (!q || !kv || !out || !probs) return fail(CAVIT_E_BADARG, "cavit_xattn_fwd: null pointer");
   if (K <= 0 || B <= 0 || N <= 0 || H <= 0) return fail(CAVIT_E_BADARG, "cavit_xattn_fwd: bad extents");
   const size_t smem = sizeof(float) * ((size_t)N + XA_D + 4 + 4 * XA_D);
@@ -194,14 +212,18 @@ int cavit_xattn_fwd(const float* q, const void* kv, float* out, float* probs, in
     cudaFuncSetAttribute(xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cur = smem;
   }
+  DropCfg d;
+  const int use = xa_drop(p_drop, seed_dev, site, &d);
+  if (use < 0) return fail(CAVIT_E_BADARG, "cavit_xattn_fwd: bad dropout arguments");
   xattn_fwd_kernel<<<dim3(H, B, K), XA_THREADS, smem, as_stream(stream)>>>(q, reinterpret_cast<const bf16*>(kv), out, probs,
-                                                                           B, N, H, scale);
+                                                                           B, N, H, scale, d, use);
   count_launch();
   return check_launch("cavit_xattn_fwd");
 }
 
 int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const float* dout, float* dq, void* dkv, int32_t K,
-                    int32_t B, int32_t N, int32_t H, float scale, void* stream) {
+                    int32_t B, int32_t N, int32_t H, float scale, float p_drop, const uint64_t* seed_dev, uint32_t site,
+                    void* stream) {
   if (!q || !kv || !probs || !dout || !dq || !dkv) return fail(CAVIT_E_BADARG, "cavit_xattn_bwd: null pointer");
   if (K <= 0 || B <= 0 || N <= 0 || H <= 0) return fail(CAVIT_E_BADARG, "cavit_xattn_bwd: bad extents");
   const size_t smem = sizeof(float) * ((size_t)N + 2 * XA_D + 4 + 4 * XA_D);
@@ -211,8 +233,11 @@ int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const fl
     cudaFuncSetAttribute(xattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cur = smem;
   }
+  DropCfg d;
+  const int use = xa_drop(p_drop, seed_dev, site, &d);
+  if (use < 0) return fail(CAVIT_E_BADARG, "cavit_xattn_bwd: bad dropout arguments");
   xattn_bwd_kernel<<<dim3(H, B, K), XA_THREADS, smem, as_stream(stream)>>>(q, reinterpret_cast<const bf16*>(kv), probs, dout,
-                                                                           dq, reinterpret_cast<bf16*>(dkv), B, N, H, scale);
+                                                                           dq, reinterpret_cast<bf16*>(dkv), B, N, H, scale, d, use);
   count_launch();
   return check_launch("cavit_xattn_bwd");
 }

@@ -146,12 +146,16 @@ int cavit_attn_bwd(const void* qkv, const void* out, const void* dout, const flo
  * Replaces: CrossAttention.forward's matmul / softmax / matmul (/root/reference/model_cross.py:95-99).
  * q: fp32 [K][B][C]; kv: bf16 [K][B*N][2*C] (k | v halves); out: fp32 [K][B][C];
  * probs: fp32 [K][B][H][N] saved for backward.
- * ------------------------------------------------------------------------------------------- */
+ * -------------------------------------------------------------------------------------------
+ * p_drop > 0 applies the attention-probability dropout of CrossAttention (attn_drop, model_cross.py:84,97)
+ * with the counter-based mask of cavit_dropout (site / seed as there); probs are saved pre-dropout.
+ */
 int cavit_xattn_fwd(const float* q, const void* kv, float* out, float* probs, int32_t K, int32_t B, int32_t N,
-                    int32_t H, float scale, void* stream);
+                    int32_t H, float scale, float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream);
 /* dq: fp32 [K][B][C]; dkv: bf16 [K][B*N][2*C]. */
 int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const float* dout, float* dq,
-                    void* dkv, int32_t K, int32_t B, int32_t N, int32_t H, float scale, void* stream);
+                    void* dkv, int32_t K, int32_t B, int32_t N, int32_t H, float scale, float p_drop,
+                    const uint64_t* seed_dev, uint32_t site, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Patch extraction: 'b c (d p1)(h p2)(w p3) -> b (h w d)(p1 p2 p3 c)' gather of one [B, M, 1, D, H, W]
@@ -199,10 +203,26 @@ int cavit_compact_patch_rows_bf16(const void* in, void* out, int32_t S, int32_t 
  * device scalar lets autograd's d(loss) be consumed without a host synchronisation. */
 int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const int64_t* labels, float* logits,
                         float* loss, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing,
-                        void* stream);
+                        float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream);
 int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, const float* logits,
                         float loss_scale, const float* loss_scale_dev, void* dh, float* dW2, float* db2, int32_t M,
-                        int32_t B, int32_t F, int32_t classes, float smoothing, void* stream);
+                        int32_t B, int32_t F, int32_t classes, float smoothing, float p_drop,
+                        const uint64_t* seed_dev, uint32_t site, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dropout (nn.Dropout on the path: model_cross.py:25,27,47,84,86,170,180,182). Masks are counter-based:
+ * keep(i) = hash(*seed_dev, site, i) >= p * 2^32, a pure function of the per-step device seed, the
+ * dropout module ("site") and the element index, so backward regenerates the forward mask instead
+ * of storing it. m = keep / (1 - p).
+ *   mode 0: out_f32  = m * a_f32              mode 1: out_bf16 = m * a_bf16
+ *   mode 2: out_f32  = a_f32 + m * b_bf16     (residual add of a dropped branch)
+ *   mode 3: out_bf16 = bf16(m * a_f32)        (masked gradient operand)
+ *   mode 4: out_u8   = keep                   (mask export for tests)
+ * out may alias a. The reference's ATen Philox stream cannot be reproduced bit-for-bit;
+ * parity with p > 0 is checked by replaying these masks in the CPU oracle.
+ * ------------------------------------------------------------------------------------------- */
+int cavit_dropout(int32_t mode, const void* a, const void* b, void* out, int64_t n, float p,
+                  const uint64_t* seed_dev, uint32_t site, void* stream);
 
 #ifdef __cplusplus
 }

@@ -6,8 +6,18 @@ bag, runs in whatever dtype the tensors have (fp32 for the stated tolerances, fp
 tight reference) and is differentiable through autograd, so ``loss.backward()`` on leaf
 copies of the weights gives the reference gradients.
 
-Each function cites the reference lines it restates. Dropout is the identity here
-(parity runs use ``dropout=0.0``; /root/reference/model_cross.py:25,27,47,84,86,170).
+Each function cites the reference lines it restates. Dropout
+(/root/reference/model_cross.py:25,27,47,84,86,170,180,182) is the identity unless a ``dm``
+mapping of multiplier tensors (0 or 1/(1-p), one per nn.Dropout call site) is passed: ATen's
+Philox stream cannot be reproduced by another implementation, so p > 0 parity is checked by
+replaying the masks the CUDA path used (tests/test_gpu_dropout.py).
+
+Dropout site keys (all multipliers shaped like the tensor they scale):
+  ("embed", m)                      x = dropout(x + pos)              model_cross.py:198 / modelv3.py:141
+  ("out" | "gelu" | "fc2", l, m)    to_out / FeedForward dropouts of self block l (0-based over the
+                                    whole depth) of stream m          model_cross.py:47,25,27
+  ("f_attn" | "f_proj" | "f_gelu" | "f_fc2", mb, k)   fusion k of multi-scale block mb   :97,101,25,27
+  ("head_gelu", m), ("head_logits", m)                                :180,182 / modelv3.py:115,117
 """
 from __future__ import annotations
 
@@ -91,18 +101,25 @@ def gelu_erf(x: Tensor) -> Tensor:
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
+def _drop(dm, key, x: Tensor) -> Tensor:
+    """nn.Dropout with an externally supplied multiplier tensor (identity when dm is None)."""
+    if dm is None:
+        return x
+    return x * dm[key].to(x.dtype).reshape(x.shape)
+
+
 def linear(x: Tensor, w: Tensor, b: Tensor | None = None) -> Tensor:
     y = x @ w.transpose(-1, -2)
     return y if b is None else y + b
 
 
-def feed_forward(p: Params, pre: str, x: Tensor) -> Tensor:
-    """FeedForward.net: Linear, GELU, (drop), Linear, (drop) (/root/reference/model_cross.py:19-31)."""
-    h = gelu_erf(linear(x, p[pre + "net.0.weight"], p[pre + "net.0.bias"]))
-    return linear(h, p[pre + "net.3.weight"], p[pre + "net.3.bias"])
+def feed_forward(p: Params, pre: str, x: Tensor, dm=None, k_gelu=None, k_out=None) -> Tensor:
+    """FeedForward.net: Linear, GELU, Dropout, Linear, Dropout (/root/reference/model_cross.py:19-31)."""
+    h = _drop(dm, k_gelu, gelu_erf(linear(x, p[pre + "net.0.weight"], p[pre + "net.0.bias"])))
+    return _drop(dm, k_out, linear(h, p[pre + "net.3.weight"], p[pre + "net.3.bias"]))
 
 
-def self_attention(p: Params, pre: str, x: Tensor, heads: int) -> Tensor:
+def self_attention(p: Params, pre: str, x: Tensor, heads: int, dm=None, k_out=None) -> Tensor:
     """Attention.forward (/root/reference/model_cross.py:50-61): bias-free packed QKV,
     'b n (h d) -> b h n d', softmax(q k^T * d^-0.5) v, merge heads, to_out (+bias)."""
     B, N, C = x.shape
@@ -119,19 +136,19 @@ def self_attention(p: Params, pre: str, x: Tensor, heads: int) -> Tensor:
     out = (attn @ v).permute(0, 2, 1, 3).reshape(B, N, C)
     if heads == 1:  # project_out is False when heads == 1 and dim_head == hidden_dim
         return out  # (/root/reference/model_cross.py:37,44-48: to_out = nn.Identity())
-    return linear(out, p[pre + "to_out.0.weight"], p[pre + "to_out.0.bias"])
+    return _drop(dm, k_out, linear(out, p[pre + "to_out.0.weight"], p[pre + "to_out.0.bias"]))
 
 
-def self_attention_block(p: Params, pre: str, x: Tensor, heads: int) -> Tensor:
+def self_attention_block(p: Params, pre: str, x: Tensor, heads: int, dm=None, l: int = 0, m: int = 0) -> Tensor:
     """SelfAttentionBlock.forward (/root/reference/model_cross.py:69-72) with PreNorm (:11-17)."""
     xn = layer_norm(x, p[pre + "attn.norm.weight"], p[pre + "attn.norm.bias"])
-    x = self_attention(p, pre + "attn.fn.", xn, heads) + x
+    x = self_attention(p, pre + "attn.fn.", xn, heads, dm, ("out", l, m)) + x
     xn = layer_norm(x, p[pre + "ffn.norm.weight"], p[pre + "ffn.norm.bias"])
-    x = feed_forward(p, pre + "ffn.fn.", xn) + x
+    x = feed_forward(p, pre + "ffn.fn.", xn, dm, ("gelu", l, m), ("fc2", l, m)) + x
     return x
 
 
-def cross_attention(p: Params, pre: str, x: Tensor, heads: int) -> Tensor:
+def cross_attention(p: Params, pre: str, x: Tensor, heads: int, dm=None, mb: int = 0, kf: int = 0) -> Tensor:
     """CrossAttention.forward (/root/reference/model_cross.py:88-102): query from token 0
     only, keys/values from all N tokens (token 0 included), biased projections."""
     B, N, C = x.shape
@@ -139,21 +156,21 @@ def cross_attention(p: Params, pre: str, x: Tensor, heads: int) -> Tensor:
     q = linear(x[:, 0:1], p[pre + "wq.weight"], p[pre + "wq.bias"]).reshape(B, 1, heads, d).permute(0, 2, 1, 3)
     k = linear(x, p[pre + "wk.weight"], p[pre + "wk.bias"]).reshape(B, N, heads, d).permute(0, 2, 1, 3)
     v = linear(x, p[pre + "wv.weight"], p[pre + "wv.bias"]).reshape(B, N, heads, d).permute(0, 2, 1, 3)
-    attn = torch.softmax((q @ k.transpose(-2, -1)) * (d ** -0.5), dim=-1)
+    attn = _drop(dm, ("f_attn", mb, kf), torch.softmax((q @ k.transpose(-2, -1)) * (d ** -0.5), dim=-1))
     y = (attn @ v).transpose(1, 2).reshape(B, 1, C)
-    return linear(y, p[pre + "proj.weight"], p[pre + "proj.bias"])
+    return _drop(dm, ("f_proj", mb, kf), linear(y, p[pre + "proj.weight"], p[pre + "proj.bias"]))
 
 
-def cross_attention_block(p: Params, pre: str, x: Tensor, heads: int) -> Tensor:
+def cross_attention_block(p: Params, pre: str, x: Tensor, heads: int, dm=None, mb: int = 0, kf: int = 0) -> Tensor:
     """CrossAttentionBlock.forward (/root/reference/model_cross.py:111-114): residual uses
     the UN-normalised CLS row; FFN runs on that single token."""
     xn = layer_norm(x, p[pre + "attn.norm.weight"], p[pre + "attn.norm.bias"])
-    y = cross_attention(p, pre + "attn.fn.", xn, heads) + x[:, 0:1]
+    y = cross_attention(p, pre + "attn.fn.", xn, heads, dm, mb, kf) + x[:, 0:1]
     yn = layer_norm(y, p[pre + "ffn.norm.weight"], p[pre + "ffn.norm.bias"])
-    return feed_forward(p, pre + "ffn.fn.", yn) + y
+    return feed_forward(p, pre + "ffn.fn.", yn, dm, ("f_gelu", mb, kf), ("f_fc2", mb, kf)) + y
 
 
-def multi_scale_block(p: Params, pre: str, xs: List[Tensor], cfg) -> List[Tensor]:
+def multi_scale_block(p: Params, pre: str, xs: List[Tensor], cfg, dm=None, mb: int = 0) -> List[Tensor]:
     """MultiScaleBlock.forward (/root/reference/model_cross.py:128-148). All fusions read
     the post-self-attention streams of THIS block; fusion modules are indexed by a running
     count over ascending i among the keys present."""
@@ -162,7 +179,7 @@ def multi_scale_block(p: Params, pre: str, xs: List[Tensor], cfg) -> List[Tensor
     for m in range(M):
         x = xs[m]
         for sb in range(cfg.num_self_blocks):
-            x = self_attention_block(p, f"{pre}blocks.{m}.{sb}.", x, cfg.num_heads)
+            x = self_attention_block(p, f"{pre}blocks.{m}.{sb}.", x, cfg.num_heads, dm, mb * cfg.num_self_blocks + sb, m)
         attn.append(x)
     outs = []
     k = 0
@@ -170,7 +187,7 @@ def multi_scale_block(p: Params, pre: str, xs: List[Tensor], cfg) -> List[Tensor
         if str(i) in cfg.attn_order:
             j = int(cfg.attn_order[str(i)])
             tmp = torch.cat((attn[i][:, 0:1], attn[j][:, 1:]), dim=1)
-            tmp = cross_attention_block(p, f"{pre}fusion.{k}.", tmp, cfg.num_heads)
+            tmp = cross_attention_block(p, f"{pre}fusion.{k}.", tmp, cfg.num_heads, dm, mb, k)
             outs.append(torch.cat((tmp, attn[i][:, 1:]), dim=1))
             k += 1
         else:
@@ -198,19 +215,19 @@ def cross_entropy(logits: Tensor, labels: Tensor, label_smoothing: float = 0.0) 
     return ((1.0 - label_smoothing) * nll + label_smoothing * smooth).mean()
 
 
-def model_cross_forward(p: Params, img: Tensor, labels: Tensor, cfg, return_tokens: bool = False):
+def model_cross_forward(p: Params, img: Tensor, labels: Tensor, cfg, return_tokens: bool = False, dm=None):
     """ModelCross.forward (/root/reference/model_cross.py:186-212).
     img [B, M, 1, D, H, W]; labels int64 [B]. Returns (logits [B, classes], loss)."""
     M = img.shape[1]
-    xs = [embed_stream(p, img[:, m], cfg) for m in range(M)]
+    xs = [_drop(dm, ("embed", m), embed_stream(p, img[:, m], cfg)) for m in range(M)]
     for mb in range(cfg.num_multi_blocks):
-        xs = multi_scale_block(p, f"transformer.{mb}.", xs, cfg)
+        xs = multi_scale_block(p, f"transformer.{mb}.", xs, cfg, dm, mb)
     tokens = xs
     heads = []
     for m in range(M):
         xn = layer_norm(xs[m], p[f"norm.{m}.weight"], p[f"norm.{m}.bias"])[:, 0]
-        h = gelu_erf(linear(xn, p[f"mlp_head.{m}.0.weight"], p[f"mlp_head.{m}.0.bias"]))
-        heads.append(linear(h, p[f"mlp_head.{m}.3.weight"], p[f"mlp_head.{m}.3.bias"]))
+        h = _drop(dm, ("head_gelu", m), gelu_erf(linear(xn, p[f"mlp_head.{m}.0.weight"], p[f"mlp_head.{m}.0.bias"])))
+        heads.append(_drop(dm, ("head_logits", m), linear(h, p[f"mlp_head.{m}.3.weight"], p[f"mlp_head.{m}.3.bias"])))
     logits = torch.stack(heads).mean(dim=0)
     loss = cross_entropy(logits, labels, cfg.label_smoothing)
     if return_tokens:
@@ -218,7 +235,7 @@ def model_cross_forward(p: Params, img: Tensor, labels: Tensor, cfg, return_toke
     return logits, loss
 
 
-def model_vit_forward(p: Params, img: Tensor, labels: Tensor, cfg):
+def model_vit_forward(p: Params, img: Tensor, labels: Tensor, cfg, dm=None):
     """ModelVIT.forward (/root/reference/modelv3.py:123-147): streams concatenated on the
     token axis BEFORE the single CLS / positional embedding; `num_layers` pre-norm blocks;
     head = LN, Linear, GELU, Linear on the CLS row; plain CE."""
@@ -227,15 +244,16 @@ def model_vit_forward(p: Params, img: Tensor, labels: Tensor, cfg):
                    p["patch_to_embedding.bias"]) for m in range(M)]
     x = torch.cat(toks, dim=1)
     x = torch.cat((p["cls_token"].expand(img.shape[0], -1, -1), x), dim=1) + p["pos_embedding"]
+    x = _drop(dm, ("embed", 0), x)
     for l in range(cfg.num_layers):
         pre = f"transformer.layers.{l}."
         xn = layer_norm(x, p[pre + "0.norm.weight"], p[pre + "0.norm.bias"])
-        x = self_attention(p, pre + "0.fn.", xn, cfg.num_heads) + x
+        x = self_attention(p, pre + "0.fn.", xn, cfg.num_heads, dm, ("out", l, 0)) + x
         xn = layer_norm(x, p[pre + "2.norm.weight"], p[pre + "2.norm.bias"])
-        x = feed_forward(p, pre + "2.fn.", xn) + x
+        x = feed_forward(p, pre + "2.fn.", xn, dm, ("gelu", l, 0), ("fc2", l, 0)) + x
     c = layer_norm(x[:, 0], p["mlp_head.0.weight"], p["mlp_head.0.bias"])
-    h = gelu_erf(linear(c, p["mlp_head.1.weight"], p["mlp_head.1.bias"]))
-    logits = linear(h, p["mlp_head.4.weight"], p["mlp_head.4.bias"])
+    h = _drop(dm, ("head_gelu", 0), gelu_erf(linear(c, p["mlp_head.1.weight"], p["mlp_head.1.bias"])))
+    logits = _drop(dm, ("head_logits", 0), linear(h, p["mlp_head.4.weight"], p["mlp_head.4.bias"]))
     return logits, cross_entropy(logits, labels, 0.0)
 
 
@@ -246,11 +264,11 @@ def leaf_params(p: Params, dtype=torch.float64) -> Dict[str, Tensor]:
 
 
 def forward_backward(p: Params, img: Tensor, labels: Tensor, cfg, kind: str = "cross",
-                     dtype=torch.float64):
+                     dtype=torch.float64, dm=None):
     """Run fwd+bwd of the restatement; returns (logits, loss, grads dict)."""
     lp = leaf_params(p, dtype)
     fwd = model_cross_forward if kind == "cross" else model_vit_forward
-    logits, loss = fwd(lp, img.to(dtype), labels, cfg)
+    logits, loss = fwd(lp, img.to(dtype), labels, cfg, dm=dm)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in lp.items()}
     return logits.detach(), loss.detach(), grads
