@@ -18,6 +18,8 @@
 //   dQ_i = dS K                             (A = dS^T tile viewed MN-major) -> fp32 red.global.add
 //
 // Ragged tails (N = tile + 1): out-of-range keys get P = 0; out-of-range query rows are not stored.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -708,6 +710,10 @@ int cavit_attn_bwd(const void* qkv, const void* out, const void* dout, const flo
   const int C = H * ATT_D;
   const long long T = (long long)B * N;
   cudaStream_t st = as_stream(stream);
+  // N <= 256 (all 2-D slice configs): whole-head persistent kernel, no delta / dQ helper kernels (attn_short.cu).
+  // CAVIT_ATTN_GENERIC=1 forces the generic tile kernel below (A/B measurements, tests of both paths).
+  static const bool force_generic = [] { const char* e = getenv("CAVIT_ATTN_GENERIC"); return e && e[0] == '1'; }();
+  if (N <= 256 && !force_generic) return launch_attn_bwd_short(qkv, out, dout, lse, dqkv, G, B, N, H, scale, st);
   const CUtensorMap* tq = tensor_map_bf16_3d(qkv, 3 * C, T, G, 3 * C, T * 3 * C, 64, ATT_TILE);
   const CUtensorMap* td = tensor_map_bf16_3d(dout, C, T, G, C, T * C, 64, ATT_TILE);
   if (!tq || !td) return CAVIT_E_BADARG;

@@ -35,4 +35,8 @@ inline uint32_t drop_threshold(float p) {
 }
 int sm_count();
 
+// Short-sequence (N <= 256) attention backward: one persistent CTA per SM walks whole heads (attn_short.cu).
+int launch_attn_bwd_short(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int G, int B,
+                          int N, int H, float scale, cudaStream_t stream);
+
 }  // namespace cavit

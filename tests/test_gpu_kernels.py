@@ -374,7 +374,12 @@ def test_attention_fwd(G, B, N, H):
     assert rel(lse, l) < 1e-3
 
 
-@pytest.mark.parametrize("G,B,N,H", [(1, 1, 128, 1), (1, 2, 64, 2), (2, 2, 197, 3), (1, 1, 513, 2), (1, 3, 9, 2)])
+@pytest.mark.parametrize("G,B,N,H", [(1, 1, 128, 1), (1, 2, 64, 2), (2, 2, 197, 3), (1, 1, 513, 2), (1, 3, 9, 2),
+                                     # short-sequence kernel (N <= 256): one / two key tiles, one / two query halves,
+                                     # ragged tails, and enough heads that every persistent CTA walks several of them
+                                     (1, 2, 16, 1), (1, 2, 17, 2), (1, 1, 31, 1), (1, 2, 129, 2), (1, 1, 144, 1),
+                                     (1, 1, 200, 2), (1, 2, 255, 1), (1, 1, 256, 2), (2, 40, 197, 6), (1, 50, 65, 4),
+                                     (1, 1, 257, 1)])
 def test_attention_bwd(G, B, N, H):
     from cavit import ops
     torch.manual_seed(11)
