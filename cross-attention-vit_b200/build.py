@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "cavit", "libcavit_sm100a.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-cudart", "static", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-cudart", "static", "--expt-relaxed-constexpr"] + os.environ.get("NVCC_EXTRA", "").split()
 
 
 def _newer(src, dst, deps):

@@ -13,12 +13,16 @@
 //   * dQ accumulates over the key tiles INSIDE TMEM, so it is written once, as bf16, straight into the packed
 //     dQKV activation: no fp32 atomics, no memset, no conversion kernel;
 //   * delta = rowsum(dO o O) and LSE*log2e of the NEXT head are staged by two helper warps while the
-//     current head is being processed (no separate delta kernel);
+//     current head is being processed (no separate delta kernel); padded query columns get LSE = +inf,
+//     which makes their probabilities exactly 0 without any per-element masking;
 //   * the control thread prefetches the next head's K/V/Q/dO tiles by TMA as soon as the last MMA reading
 //     a buffer has retired, and issues S^T,dP^T of step t+1 as soon as step t's scores are in registers,
 //     so the tensor pipe, the TMA engine and the 16 elementwise warps overlap across steps and heads.
+// The kernel is specialised at compile time on (key tiles, query halves) so that the step loop unrolls.
 //
 // Reference semantics: autograd of Attention.forward (/root/reference/model_cross.py:50-61), SURVEY.md §A.9.
+#include <stdio.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -44,27 +48,72 @@ struct AttnBwdShortParams {
   const bf16* dout;
   bf16* dqkv;
   int N, H, C, B, G;
-  int nkv, nh, hN0, hN1;  // key tiles, query halves, columns per half (multiples of 16, <= 128)
+  int hN0, hN1;  // query columns per half (multiples of 16, <= 128; hN1 = 0 with a single half)
   float scale, scale_log2;
   int* status;
 };
+
+// Optional timeline trace (build with NVCC_EXTRA=-DCAVIT_SB_TRACE): CTA 0 records clock64() at protocol points.
+#ifdef CAVIT_SB_TRACE
+__device__ unsigned long long g_sb_trace[2][4096];
+__device__ __forceinline__ void sb_trace(int role, uint32_t& n, int tag) {
+  if (blockIdx.x == 0 && n < 2047) {
+    g_sb_trace[role][2 * n] = clock64();
+    g_sb_trace[role][2 * n + 1] = tag;
+    ++n;
+  }
+}
+#define SB_TRACE(role, n, tag) sb_trace(role, n, tag)
+#else
+#define SB_TRACE(role, n, tag)
+#endif
 
 __device__ __forceinline__ float sb_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ uint64_t sb_desc_add(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 
+// 8 score columns of one key row -> packed bf16 P^T and dS^T
+__device__ __forceinline__ void sb_group(const uint32_t (&rs)[8], const uint32_t (&rp)[8], const float* lse2, const float* dlt,
+                                         float sl2, uint4& wp, uint4& wd) {
+  const float4 la = *reinterpret_cast<const float4*>(lse2), lb = *reinterpret_cast<const float4*>(lse2 + 4);
+  const float4 da = *reinterpret_cast<const float4*>(dlt), db = *reinterpret_cast<const float4*>(dlt + 4);
+  const float p0 = sb_ex2(fmaf(__uint_as_float(rs[0]), sl2, -la.x)), p1 = sb_ex2(fmaf(__uint_as_float(rs[1]), sl2, -la.y));
+  const float p2 = sb_ex2(fmaf(__uint_as_float(rs[2]), sl2, -la.z)), p3 = sb_ex2(fmaf(__uint_as_float(rs[3]), sl2, -la.w));
+  const float p4 = sb_ex2(fmaf(__uint_as_float(rs[4]), sl2, -lb.x)), p5 = sb_ex2(fmaf(__uint_as_float(rs[5]), sl2, -lb.y));
+  const float p6 = sb_ex2(fmaf(__uint_as_float(rs[6]), sl2, -lb.z)), p7 = sb_ex2(fmaf(__uint_as_float(rs[7]), sl2, -lb.w));
+  wp = make_uint4(pack_bf16(p0, p1), pack_bf16(p2, p3), pack_bf16(p4, p5), pack_bf16(p6, p7));
+  wd = make_uint4(pack_bf16(p0 * (__uint_as_float(rp[0]) - da.x), p1 * (__uint_as_float(rp[1]) - da.y)),
+                  pack_bf16(p2 * (__uint_as_float(rp[2]) - da.z), p3 * (__uint_as_float(rp[3]) - da.w)),
+                  pack_bf16(p4 * (__uint_as_float(rp[4]) - db.x), p5 * (__uint_as_float(rp[5]) - db.y)),
+                  pack_bf16(p6 * (__uint_as_float(rp[6]) - db.z), p7 * (__uint_as_float(rp[7]) - db.w)));
+}
+
+// 16 fp32 accumulator columns of one row -> 32 bytes of bf16
+__device__ __forceinline__ void sb_store16(bf16* dst, const uint32_t (&r)[16], float sc) {
+#pragma unroll
+  for (int c = 0; c < 16; c += 8) {
+    uint4 w;
+    w.x = pack_bf16(__uint_as_float(r[c]) * sc, __uint_as_float(r[c + 1]) * sc);
+    w.y = pack_bf16(__uint_as_float(r[c + 2]) * sc, __uint_as_float(r[c + 3]) * sc);
+    w.z = pack_bf16(__uint_as_float(r[c + 4]) * sc, __uint_as_float(r[c + 5]) * sc);
+    w.w = pack_bf16(__uint_as_float(r[c + 6]) * sc, __uint_as_float(r[c + 7]) * sc);
+    *reinterpret_cast<uint4*>(dst + c) = w;
+  }
+}
+
+template <int NKV, int NH>
 __global__ void __launch_bounds__(SB_THREADS, 1)
 attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ16,
                       const __grid_constant__ CUtensorMap tmDO16, const AttnBwdShortParams p) {
+  constexpr int NS = NKV * NH;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sK = base + SB_OFF_K, sV = base + SB_OFF_V, sQ = base + SB_OFF_Q, sDO = base + SB_OFF_DO;
   const uint32_t sPT = base + SB_OFF_PT, sDST = base + SB_OFF_DST;
-  uint8_t* genPT = gen + SB_OFF_PT;
-  uint8_t* genDST = gen + SB_OFF_DST;
   float* s_aux = reinterpret_cast<float*>(gen + SB_OFF_AUX);
   const uint32_t bar0 = base + SB_OFF_BAR;
   auto bar_kv = [&](int j) { return bar0 + 8u * j; };
@@ -77,8 +126,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BH = p.B * p.H;
-  const long long items = (long long)p.G * BH;
-  const int ns = p.nkv * p.nh;
+  const int items = p.G * BH;
 
   if (tid == 0) {
     *abort_flag = 0;
@@ -109,26 +157,33 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
   const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
 
   if (warp == SB_EW_WARPS) {
-    // ================================================================= control warp (lane 0): TMA + MMA issue
-    if (lane == 0) {
+    // ================================================================= control warp: TMA + MMA issue
+    // The whole warp runs the protocol (waits are executed by all lanes, converged); one elected lane issues.
+    {
       const uint32_t idesc_kmn = umma_idesc_bf16(64, 0, 1);   // dV, dK: A K-major (P^T / dS^T), B MN-major, N = 64
       const uint32_t idesc_mnmn = umma_idesc_bf16(64, 1, 1);  // dQ:     A = dS^T viewed MN-major, B = K MN-major
-      auto decode = [&](long long item, int& g, int& h, int& row_base) {
-        const int bh = (int)(item % BH);
-        g = (int)(item / BH);
+      const uint32_t idesc_s0 = umma_idesc_bf16(p.hN0, 0, 0), idesc_s1 = umma_idesc_bf16(NH == 2 ? p.hN1 : p.hN0, 0, 0);
+      // descriptor bases (byte offsets are added in units of 16 B)
+      const uint64_t dK_k = umma_desc_sw128(sK, 16, 1024), dV_k = umma_desc_sw128(sV, 16, 1024);       // K-major reads
+      const uint64_t dQ_k = umma_desc_sw128(sQ, 16, 1024), dDO_k = umma_desc_sw128(sDO, 16, 1024);
+      const uint64_t dPT_k = umma_desc_sw128(sPT, 16, 1024), dDST_k = umma_desc_sw128(sDST, 16, 1024);
+      const uint64_t dK_mn = umma_desc_sw128(sK, SB_TILE, 1024), dQ_mn = umma_desc_sw128(sQ, SB_TILE, 1024);  // MN-major reads
+      const uint64_t dDO_mn = umma_desc_sw128(sDO, SB_TILE, 1024), dDST_mn = umma_desc_sw128(sDST, SB_TILE, 1024);
+      const int nq16_0 = p.hN0 >> 4, nq16_1 = p.hN1 >> 4;
+      const int nk16_last = (min(128, p.N - (NKV - 1) * 128) + 15) >> 4;  // key rows beyond ceil16(N) are never read
+      const uint32_t rowb1 = p.hN0 * 128;
+      auto decode = [&](int item, int& g, int& h, int& row_base) {
+        const int bh = item % BH;
+        g = item / BH;
         h = bh % p.H;
         row_base = (bh / p.H) * p.N;
       };
-      auto load_kv = [&](int j, long long item) {
-        int g, h, row_base;
-        decode(item, g, h, row_base);
+      auto load_kv = [&](int j, int g, int h, int row_base) {
         mbar_arrive_expect_tx(bar_kv(j), 2 * SB_TILE);
         tma_load_3d(&tmKV, bar_kv(j), sK + j * SB_TILE, p.C + h * 64, row_base + j * 128, g);
         tma_load_3d(&tmKV, bar_kv(j), sV + j * SB_TILE, 2 * p.C + h * 64, row_base + j * 128, g);
       };
-      auto load_q = [&](int hf, long long item) {
-        int g, h, row_base;
-        decode(item, g, h, row_base);
+      auto load_q = [&](int hf, int g, int h, int row_base) {
         const int row0 = hf ? p.hN0 : 0, n = hf ? p.hN1 : p.hN0;
         mbar_arrive_expect_tx(bar_q(hf), 2 * n * 128);
         for (int r = 0; r < n; r += 16) {
@@ -137,97 +192,109 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
         }
       };
       auto issue_s = [&](int j, int hf) {  // S^T = K_j Q_half^T ; dP^T = V_j dO_half^T
-        const uint32_t row0 = hf ? p.hN0 : 0;
-        const uint32_t idesc = umma_idesc_bf16(hf ? p.hN1 : p.hN0, 0, 0);
+        const uint32_t rowb = hf ? rowb1 : 0u;
+        const uint32_t idesc = hf ? idesc_s1 : idesc_s0;
+        const uint64_t a0 = sb_desc_add(dK_k, j * SB_TILE), b0 = sb_desc_add(dQ_k, rowb);
+        const uint64_t a1 = sb_desc_add(dV_k, j * SB_TILE), b1 = sb_desc_add(dDO_k, rowb);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t kd = umma_desc_sw128(sK + j * SB_TILE + k * 32, 16, 1024);
-          const uint64_t qd = umma_desc_sw128(sQ + row0 * 128 + k * 32, 16, 1024);
-          umma_bf16_ss(tST, kd, qd, idesc, k != 0);
-        }
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tST, a0 + 2 * k, b0 + 2 * k, idesc, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t vd = umma_desc_sw128(sV + j * SB_TILE + k * 32, 16, 1024);
-          const uint64_t dd = umma_desc_sw128(sDO + row0 * 128 + k * 32, 16, 1024);
-          umma_bf16_ss(tDPT, vd, dd, idesc, k != 0);
-        }
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tDPT, a1 + 2 * k, b1 + 2 * k, idesc, k != 0);
         umma_commit(bar_s);
       };
       auto issue_d = [&](int j, int hf) {
-        const uint32_t row0 = hf ? p.hN0 : 0;
-        const int nq16 = (hf ? p.hN1 : p.hN0) >> 4;
-        for (int k = 0; k < nq16; ++k) {  // dV_j[kv][d] += P^T[kv][q] dO[q][d]
-          const uint64_t ad = umma_desc_sw128(sPT + (k >> 2) * SB_TILE + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(sDO + (row0 + 16 * k) * 128, SB_TILE, 1024);
-          umma_bf16_ss(tDV, ad, bd, idesc_kmn, (hf | k) != 0);
-        }
-        for (int k = 0; k < nq16; ++k) {  // dK_j[kv][d] += dS^T[kv][q] Q[q][d]
-          const uint64_t ad = umma_desc_sw128(sDST + (k >> 2) * SB_TILE + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(sQ + (row0 + 16 * k) * 128, SB_TILE, 1024);
-          umma_bf16_ss(tDK, ad, bd, idesc_kmn, (hf | k) != 0);
-        }
-        const int nk16 = (min(128, p.N - j * 128) + 15) >> 4;  // key rows beyond N hold dS^T = 0: skip their k-steps
-        for (int k = 0; k < nk16; ++k) {  // dQ_half[q][d] += dS[q][kv] K_j[kv][d]   (A = dS^T viewed MN-major)
-          const uint64_t ad = umma_desc_sw128(sDST + k * 2048, SB_TILE, 1024);
-          const uint64_t bd = umma_desc_sw128(sK + j * SB_TILE + k * 2048, SB_TILE, 1024);
-          umma_bf16_ss(tDQ + hf * 64, ad, bd, idesc_mnmn, (j | k) != 0);
-        }
+        const uint32_t rowb = hf ? rowb1 : 0u;
+        const int nq16 = hf ? nq16_1 : nq16_0;
+        const uint64_t bdo = sb_desc_add(dDO_mn, rowb), bq = sb_desc_add(dQ_mn, rowb), bk = sb_desc_add(dK_mn, j * SB_TILE);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV_j[kv][d] += P^T[kv][q] dO[q][d]
+          if (k < nq16)
+            umma_bf16_ss(tDV, dPT_k + (((k >> 2) * SB_TILE + (k & 3) * 32) >> 4), bdo + k * 128, idesc_kmn, (hf | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK_j[kv][d] += dS^T[kv][q] Q[q][d]
+          if (k < nq16)
+            umma_bf16_ss(tDK, dDST_k + (((k >> 2) * SB_TILE + (k & 3) * 32) >> 4), bq + k * 128, idesc_kmn, (hf | k) != 0);
+        const int nk16 = (j == NKV - 1) ? nk16_last : 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ_half[q][d] += dS[q][kv] K_j[kv][d]   (A = dS^T viewed MN-major)
+          if (k < nk16) umma_bf16_ss(tDQ + hf * 64, dDST_mn + k * 128, bk + k * 128, idesc_mnmn, (j | k) != 0);
         umma_commit(bar_d);
       };
       // With two key tiles and two halves every buffer of the next head is refilled at least one step before
       // the step that issues the next head's first S^T; otherwise that issue waits for the last step's prefetch.
-      const bool early_next = (p.nkv == 2 && p.nh == 2);
-      long long item = blockIdx.x;
+      constexpr bool kEarlyNext = (NKV == 2 && NH == 2);
+      int item = blockIdx.x;
+      int g, h, row_base;
       if (item < items) {
-        for (int j = 0; j < p.nkv; ++j) load_kv(j, item);
-        for (int hf = 0; hf < p.nh; ++hf) load_q(hf, item);
+        decode(item, g, h, row_base);
+        if (elect_one()) {
+          for (int j = 0; j < NKV; ++j) load_kv(j, g, h, row_base);
+          for (int hf = 0; hf < NH; ++hf) load_q(hf, g, h, row_base);
+        }
+        __syncwarp();
         mbar_wait(bar_kv(0), 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
         mbar_wait(bar_q(0), 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
         tc_fence_after();
-        issue_s(0, 0);
+        if (elect_one()) issue_s(0, 0);
+        __syncwarp();
       }
       uint32_t t = 0;
+      [[maybe_unused]] uint32_t ntr = (lane == 0) ? 0u : 4096u;
       for (int it = 0; item < items; item += gridDim.x, ++it) {
-        const long long next_item = item + gridDim.x;
+        const int next_item = item + gridDim.x;
         const bool has_next = next_item < items;
+        if (has_next) decode(next_item, g, h, row_base);
         const uint32_t hp = it & 1, hpn = hp ^ 1u;
-        for (int s = 0; s < ns; ++s, ++t) {
-          const int j = s / p.nh, hf = s % p.nh;
+#pragma unroll
+        for (int s = 0; s < NS; ++s, ++t) {
+          const int j = s / NH, hf = s % NH;
           // step t's scores are in registers everywhere -> the tensor pipe may overwrite S^T / dP^T
+          SB_TRACE(0, ntr, 0);
           mbar_wait(bar_sfree, t & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-          bool next_s_pending = false;
-          if (s + 1 < ns) {
-            const int j2 = (s + 1) / p.nh, h2 = (s + 1) % p.nh;
+          SB_TRACE(0, ntr, 1);
+          if (s + 1 < NS) {
+            const int j2 = (s + 1) / NH, h2 = (s + 1) % NH;
             mbar_wait(bar_kv(j2), hp, abort_flag, p.status, ERR_TIMEOUT_ATTN);
             mbar_wait(bar_q(h2), hp, abort_flag, p.status, ERR_TIMEOUT_ATTN);
             tc_fence_after();
-            issue_s(j2, h2);
-          } else if (has_next) {
-            if (early_next) {
-              mbar_wait(bar_kv(0), hpn, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-              mbar_wait(bar_q(0), hpn, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-              tc_fence_after();
-              issue_s(0, 0);
-            } else {
-              next_s_pending = true;
-            }
+            if (elect_one()) issue_s(j2, h2);
+            __syncwarp();
+          } else if (kEarlyNext && has_next) {
+            mbar_wait(bar_kv(0), hpn, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+            mbar_wait(bar_q(0), hpn, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+            tc_fence_after();
+            if (elect_one()) issue_s(0, 0);
+            __syncwarp();
           }
           // P^T, dS^T of step t are in shared memory (and the accumulators they overwrite have been drained)
+          SB_TRACE(0, ntr, 2);
           mbar_wait(bar_p, t & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          SB_TRACE(0, ntr, 3);
           tc_fence_after();
-          issue_d(j, hf);
+          if (elect_one()) issue_d(j, hf);
+          __syncwarp();
+          SB_TRACE(0, ntr, 4);
+#ifdef CAVIT_SB_TRACE
+          mbar_wait(bar_d, t & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          SB_TRACE(0, ntr, 5);
+#endif
           if (has_next) {
-            const bool kv_free = (hf == p.nh - 1), q_free = (j == p.nkv - 1);
+            const bool kv_free = (hf == NH - 1), q_free = (j == NKV - 1);
             if (kv_free || q_free) {  // refill buffers whose last reader (an MMA of this step) has retired
               mbar_wait(bar_d, t & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-              if (kv_free) load_kv(j, next_item);
-              if (q_free) load_q(hf, next_item);
+              if (elect_one()) {
+                if (kv_free) load_kv(j, g, h, row_base);
+                if (q_free) load_q(hf, g, h, row_base);
+              }
+              __syncwarp();
+              SB_TRACE(0, ntr, 6);
             }
-            if (next_s_pending) {
+            if (!kEarlyNext && s + 1 == NS) {
               mbar_wait(bar_kv(0), hpn, abort_flag, p.status, ERR_TIMEOUT_ATTN);
               mbar_wait(bar_q(0), hpn, abort_flag, p.status, ERR_TIMEOUT_ATTN);
               tc_fence_after();
-              issue_s(0, 0);
+              if (elect_one()) issue_s(0, 0);
+              __syncwarp();
             }
           }
         }
@@ -237,17 +304,17 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
     // ================================================================= helper warps: LSE*log2e and delta of the next head
     const int atid = tid - (SB_EW_WARPS + 1) * 32;  // 0..63
     int ait = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++ait) {
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++ait) {
       const int buf = ait & 1;
       if (ait >= 2) mbar_wait(bar_auxfree(buf), ((ait >> 1) - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-      const int bh = (int)(item % BH), g = (int)(item / BH);
+      const int bh = item % BH, g = item / BH;
       const int b = bh / p.H, h = bh % p.H;
       const long long lse_base = (((long long)g * p.B + b) * p.H + h) * p.N;
       const long long row0 = ((long long)g * p.B + b) * p.N;
       float* o_lse = s_aux + buf * 512;
       float* o_del = o_lse + 256;
       for (int q = atid; q < 256; q += SB_AUX_WARPS * 32) {
-        float l2 = 0.f, dl = 0.f;
+        float l2 = INFINITY, dl = 0.f;  // padded query columns: exp2(s - inf) = 0 exactly, so P = dS = 0 there
         if (q < p.N) {
           l2 = p.lse[lse_base + q] * 1.4426950408889634f;
           const uint4* po = reinterpret_cast<const uint4*>(p.o + (row0 + q) * p.C + h * 64);
@@ -271,138 +338,136 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
     const int quad = warp & 3, part = warp >> 2;
     const int trow = quad * 32 + lane;  // key row inside the tile = TMEM lane (scores) / query row (dQ)
     const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
-    // drains the accumulators that step (pj, phf) of head (pg, pb, ph) finalised
-    auto drain = [&](int pg, int pb, int ph, int pj, int phf) {
-      const long long rowb = ((long long)pg * p.B + pb) * p.N;
-      if (phf == p.nh - 1) {  // dK_j (scaled) and dV_j: each warp stores a 16-column slice of both
+    const uint32_t t_col = t_lane + part * 16;                 // this warp's 16-column slice of a 64-wide accumulator
+    uint8_t* const myPT = gen + SB_OFF_PT + trow * 128;        // this key row inside chunk 0 of P^T
+    const uint32_t sw = static_cast<uint32_t>(trow & 7);
+    const float sl2 = p.scale_log2, scale = p.scale;
+    const int N = p.N;
+    // last key tile: rows >= N are masked to zero; warps entirely beyond ceil16(valid rows) are never read by an MMA
+    const int last_valid = N - (NKV - 1) * 128;
+    const bool row_ok_last = trow < last_valid;
+    const bool warp_active_last = quad * 32 < ((last_valid + 15) & ~15);
+    // drains the accumulators finalised by step (pj, phf) of the head whose dQKV rows start at `hb`
+    auto drain = [&](bf16* hb, int pj, int phf) {
+      if (phf == NH - 1) {  // dK_j (scaled) and dV_j of key row kv: each warp stores a 16-column slice of both
         const int kv = pj * 128 + trow;
-        bf16* drow = p.dqkv + (rowb + kv) * (3 * p.C) + ph * 64 + part * 16;
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {  // one 16-column slice at a time (register pressure)
-          uint32_t r[16];
-          tmem_ld16((which == 0 ? tDK : tDV) + t_lane + part * 16, r);
-          tmem_ld_wait();
-          const float sc = which == 0 ? p.scale : 1.0f;
-          if (kv < p.N) {
-#pragma unroll
-            for (int c = 0; c < 16; c += 8) {
-              uint4 w;
-              w.x = pack_bf16(__uint_as_float(r[c]) * sc, __uint_as_float(r[c + 1]) * sc);
-              w.y = pack_bf16(__uint_as_float(r[c + 2]) * sc, __uint_as_float(r[c + 3]) * sc);
-              w.z = pack_bf16(__uint_as_float(r[c + 4]) * sc, __uint_as_float(r[c + 5]) * sc);
-              w.w = pack_bf16(__uint_as_float(r[c + 6]) * sc, __uint_as_float(r[c + 7]) * sc);
-              *reinterpret_cast<uint4*>(drow + (which + 1) * p.C + c) = w;
-            }
-          }
-        }
+        bf16* drow = hb + (long long)kv * (3 * p.C) + part * 16;
+        uint32_t r[16];
+        tmem_ld16(tDK + t_col, r);
+        tmem_ld_wait();
+        if (kv < N) sb_store16(drow + p.C, r, scale);
+        tmem_ld16(tDV + t_col, r);
+        tmem_ld_wait();
+        if (kv < N) sb_store16(drow + 2 * p.C, r, 1.0f);
       }
-      if (pj == p.nkv - 1) {  // dQ of this half is complete (accumulated over the key tiles in TMEM)
+      if (pj == NKV - 1) {  // dQ of this half is complete (accumulated over the key tiles in TMEM)
         const int hn = phf ? p.hN1 : p.hN0;
         const int q = (phf ? p.hN0 : 0) + trow;
         uint32_t r[16];
-        tmem_ld16(tDQ + phf * 64 + t_lane + part * 16, r);
+        tmem_ld16(tDQ + phf * 64 + t_col, r);
         tmem_ld_wait();
-        if (trow < hn && q < p.N) {
-          bf16* drow = p.dqkv + (rowb + q) * (3 * p.C) + ph * 64 + part * 16;
-#pragma unroll
-          for (int c = 0; c < 16; c += 8) {
-            uint4 w;
-            w.x = pack_bf16(__uint_as_float(r[c]) * p.scale, __uint_as_float(r[c + 1]) * p.scale);
-            w.y = pack_bf16(__uint_as_float(r[c + 2]) * p.scale, __uint_as_float(r[c + 3]) * p.scale);
-            w.z = pack_bf16(__uint_as_float(r[c + 4]) * p.scale, __uint_as_float(r[c + 5]) * p.scale);
-            w.w = pack_bf16(__uint_as_float(r[c + 6]) * p.scale, __uint_as_float(r[c + 7]) * p.scale);
-            *reinterpret_cast<uint4*>(drow + c) = w;
-          }
-        }
+        if (trow < hn && q < N) sb_store16(hb + (long long)q * (3 * p.C) + part * 16, r, scale);
       }
     };
 
     uint32_t t = 0;
-    int pg = 0, pb = 0, ph = 0, pj = 0, phf = 0;
+    [[maybe_unused]] uint32_t ntr = (tid == 0) ? 0u : 4096u;
+    bf16* prev_hb = nullptr;
     int it = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-      const int bh = (int)(item % BH), g = (int)(item / BH);
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int bh = item % BH, g = item / BH;
       const int b = bh / p.H, h = bh % p.H;
+      bf16* const hb = p.dqkv + (((long long)g * p.B + b) * N) * (3 * p.C) + h * 64;
       const float* lse2 = s_aux + (it & 1) * 512;
-      const float* dlt = lse2 + 256;
       mbar_wait(bar_auxfull(it & 1), (it >> 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-      for (int s = 0; s < ns; ++s, ++t) {
-        const int j = s / p.nh, hf = s % p.nh;
+#pragma unroll
+      for (int s = 0; s < NS; ++s, ++t) {
+        const int j = s / NH, hf = s % NH;
         const int row0 = hf ? p.hN0 : 0;
         const int ngrp = (hf ? p.hN1 : p.hN0) >> 3;  // groups of 8 query columns in this half
         const int g0 = (part * ngrp) >> 2;
         const int cnt = (((part + 1) * ngrp) >> 2) - g0;  // <= 4 groups for this warp
+        const bool active = (j < NKV - 1) || warp_active_last;
+        SB_TRACE(1, ntr, 10);
         mbar_wait(bar_s, t & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        SB_TRACE(1, ntr, 11);
         tc_fence_after();
-        // Two passes of <= 2 column groups keep the live register set small: raw scores of a pass are folded into
-        // packed bf16 before the next pass is read; S^T / dP^T are released to the tensor pipe after the last read.
-        const bool kv_ok = (j * 128 + trow) < p.N;
         uint4 wp[4], wd[4];
+        // Two passes of <= 2 column groups keep the live register set small; S^T / dP^T are released to the tensor
+        // pipe right after the last read.
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
           uint32_t rs[2][8], rp[2][8];
+          if (active) {
 #pragma unroll
-          for (int gg = 0; gg < 2; ++gg) {
-            const int gi = pass * 2 + gg;
-            if (gi < cnt) {
-              tmem_ld8(tST + t_lane + (g0 + gi) * 8, rs[gg]);
-              tmem_ld8(tDPT + t_lane + (g0 + gi) * 8, rp[gg]);
+            for (int gg = 0; gg < 2; ++gg) {
+              const int gi = pass * 2 + gg;
+              if (gi < cnt) {
+                tmem_ld8(tST + t_lane + (g0 + gi) * 8, rs[gg]);
+                tmem_ld8(tDPT + t_lane + (g0 + gi) * 8, rp[gg]);
+              }
             }
+            tmem_ld_wait();
           }
-          tmem_ld_wait();
           if (pass == 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sfree);
           }
+          if (active) {
 #pragma unroll
-          for (int gg = 0; gg < 2; ++gg) {
-            const int gi = pass * 2 + gg;
-            if (gi < cnt) {
-              const int q0 = row0 + (g0 + gi) * 8;
-              const float4 la = *reinterpret_cast<const float4*>(lse2 + q0), lb = *reinterpret_cast<const float4*>(lse2 + q0 + 4);
-              const float4 da = *reinterpret_cast<const float4*>(dlt + q0), db = *reinterpret_cast<const float4*>(dlt + q0 + 4);
-              const float l[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
-              const float d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-              float pr[8], ds[8];
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const bool ok = kv_ok && (q0 + c < p.N);
-                pr[c] = ok ? sb_ex2(fmaf(__uint_as_float(rs[gg][c]), p.scale_log2, -l[c])) : 0.f;
-                ds[c] = pr[c] * (__uint_as_float(rp[gg][c]) - d[c]);
+            for (int gg = 0; gg < 2; ++gg) {
+              const int gi = pass * 2 + gg;
+              if (gi < cnt) {
+                const float* l = lse2 + row0 + (g0 + gi) * 8;
+                sb_group(rs[gg], rp[gg], l, l + 256, sl2, wp[gi], wd[gi]);
+                if (j == NKV - 1 && !row_ok_last) {
+                  wp[gi] = make_uint4(0u, 0u, 0u, 0u);
+                  wd[gi] = make_uint4(0u, 0u, 0u, 0u);
+                }
               }
-              wp[gi] = make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]), pack_bf16(pr[4], pr[5]), pack_bf16(pr[6], pr[7]));
-              wd[gi] = make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
             }
           }
         }
-        if (t > 0) {  // MMAs of the previous step done: P^T / dS^T buffers are free, its finished accumulators can be drained
+        SB_TRACE(1, ntr, 12);
+        // MMAs of the previous step done: P^T / dS^T buffers are free, accumulators it finalised can be drained
+        if (s > 0) {
           mbar_wait(bar_d, (t - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
           tc_fence_after();
-          drain(pg, pb, ph, pj, phf);
+          SB_TRACE(1, ntr, 13);
+          drain(hb, (s - 1) / NH, (s - 1) % NH);
+        } else if (t > 0) {
+          mbar_wait(bar_d, (t - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          tc_fence_after();
+          SB_TRACE(1, ntr, 13);
+          drain(prev_hb, NKV - 1, NH - 1);
         }
+        SB_TRACE(1, ntr, 14);
+        if (active) {
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          if (gi < cnt) {
-            const int cg = g0 + gi;
-            const uint32_t off = (cg >> 3) * SB_TILE + trow * 128 + (((cg & 7) ^ (trow & 7)) << 4);
-            *reinterpret_cast<uint4*>(genPT + off) = wp[gi];
-            *reinterpret_cast<uint4*>(genDST + off) = wd[gi];
+          for (int gi = 0; gi < 4; ++gi) {
+            if (gi < cnt) {
+              const uint32_t cg = g0 + gi;
+              uint8_t* dst = myPT + (cg >> 3) * SB_TILE + (((cg & 7) ^ sw) << 4);
+              *reinterpret_cast<uint4*>(dst) = wp[gi];
+              *reinterpret_cast<uint4*>(dst + (SB_OFF_DST - SB_OFF_PT)) = wd[gi];
+            }
           }
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p);
-        pg = g; pb = b; ph = h; pj = j; phf = hf;
+        SB_TRACE(1, ntr, 15);
       }
+      prev_hb = hb;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_auxfree(it & 1));
     }
     if (t > 0) {
       mbar_wait(bar_d, (t - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
       tc_fence_after();
-      drain(pg, pb, ph, pj, phf);
+      drain(prev_hb, NKV - 1, NH - 1);
     }
   }
   tc_fence_before();
@@ -413,20 +478,28 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
   }
 }
 
+template <int NKV, int NH>
+static int launch_short(const CUtensorMap* tkv, const CUtensorMap* tq, const CUtensorMap* td, const AttnBwdShortParams& p,
+                        int grid, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_short_kernel<NKV, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM);
+    if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "attn bwd (short) smem attribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  attn_bwd_short_kernel<NKV, NH><<<grid, SB_THREADS, SB_SMEM, stream>>>(*tkv, *tq, *td, p);
+  return CAVIT_OK;
+}
+
 int launch_attn_bwd_short(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int G, int B,
                           int N, int H, float scale, cudaStream_t stream) {
   const int C = H * 64;
   const long long T = (long long)B * N;
+  if ((long long)G * B * H > 0x7fffffffLL) return fail(CAVIT_E_BADARG, "cavit_attn_bwd: too many heads");
   const CUtensorMap* tkv = tensor_map_bf16_3d(qkv, 3 * C, T, G, 3 * C, T * 3 * C, 64, 128);
   const CUtensorMap* tq = tensor_map_bf16_3d(qkv, 3 * C, T, G, 3 * C, T * 3 * C, 64, 16);
   const CUtensorMap* td = tensor_map_bf16_3d(dout, C, T, G, C, T * C, 64, 16);
   if (!tkv || !tq || !td) return CAVIT_E_BADARG;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM);
-    if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "attn bwd (short) smem attribute: %s", cudaGetErrorString(e));
-    attr = true;
-  }
   AttnBwdShortParams p;
   p.lse = lse;
   p.o = reinterpret_cast<const bf16*>(out);
@@ -434,18 +507,35 @@ int launch_attn_bwd_short(const void* qkv, const void* out, const void* dout, co
   p.dqkv = reinterpret_cast<bf16*>(dqkv);
   p.N = N; p.H = H; p.C = C; p.B = B; p.G = G;
   const int NP = (N + 15) & ~15;
-  p.nkv = (N + 127) / 128;
+  const int nkv = (N + 127) / 128;
   p.hN0 = NP >= 32 ? ((NP / 2 + 15) & ~15) : NP;
   p.hN1 = NP - p.hN0;
-  p.nh = p.hN1 > 0 ? 2 : 1;
+  const int nh = p.hN1 > 0 ? 2 : 1;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.status = status_word();
   if (!p.status) return fail(CAVIT_E_DEVICE, "no status word");
-  const long long items = (long long)G * B * H;
-  const int grid = (int)(items < sm_count() ? items : sm_count());
-  attn_bwd_short_kernel<<<grid, SB_THREADS, SB_SMEM, stream>>>(*tkv, *tq, *td, p);
+  const int items = G * B * H;
+  const int grid = items < sm_count() ? items : sm_count();
+  int rc;
+  if (nkv == 2 && nh == 2) rc = launch_short<2, 2>(tkv, tq, td, p, grid, stream);
+  else if (nkv == 1 && nh == 2) rc = launch_short<1, 2>(tkv, tq, td, p, grid, stream);
+  else if (nkv == 1 && nh == 1) rc = launch_short<1, 1>(tkv, tq, td, p, grid, stream);
+  else return fail(CAVIT_E_UNSUPPORTED_SHAPE, "attn bwd (short): N=%d", N);
+  if (rc) return rc;
   count_launch();
+#ifdef CAVIT_SB_TRACE
+  {
+    static int dumps = 0;
+    if (++dumps == 3) {
+      cudaStreamSynchronize(stream);
+      static unsigned long long h[2][4096];
+      cudaMemcpyFromSymbol(h, g_sb_trace, sizeof(h));
+      for (int role = 0; role < 2; ++role)
+        for (int i = 0; i < 400; ++i) fprintf(stderr, "SBTRACE %d %d %llu %llu\n", role, i, h[role][2 * i] - h[0][0], h[role][2 * i + 1]);
+    }
+  }
+#endif
   return check_launch("cavit_attn_bwd(short)");
 }
 

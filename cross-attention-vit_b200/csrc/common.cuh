@@ -79,6 +79,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
   }
 }
 
+// One elected lane of a fully converged warp (the compiler turns `if (elect_one())` into ELECT + predicated
+// issue; with `if (lane == 0)` it cannot prove a single active thread and wraps every tcgen05.mma in a loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
