@@ -119,34 +119,42 @@ __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const 
     const int r = it * 4 + rsub;
     t[it] = reinterpret_cast<const float4*>(stage + r * 32)[c4 ^ (r & 7)];
   }
-  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 b01 = make_float2(0.f, 0.f), b23 = make_float2(0.f, 0.f);
   constexpr bool kBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID);
-  if (kBias) b = __ldg(reinterpret_cast<const float4*>(L.bias + col));
+  if (kBias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(L.bias + col));
+    b01 = make_float2(b.x, b.y);
+    b23 = make_float2(b.z, b.w);
+  }
+  // running row pointers (4 rows per step) instead of 64-bit it * stride products in every iteration
+  char* o = L.out + col * ((OUT == OUT_BF16) ? 2 : 4);
+  char* ax = L.aux + col * 2;
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
+  for (int it = 0; it < 8; ++it, o += L.out_step, ax += L.aux_step) {
     if (it * 4 < L.rows_left) {
-      float v0 = t[it].x, v1 = t[it].y, v2 = t[it].z, v3 = t[it].w;
-      if (kBias) { v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w; }
+      // two packed fp32 pairs per lane: columns (col, col+1) and (col+2, col+3)
+      float2 v01 = make_float2(t[it].x, t[it].y), v23 = make_float2(t[it].z, t[it].w);
+      if (kBias) { v01 = add2(v01, b01); v23 = add2(v23, b23); }
       if (EPI == CAVIT_EPI_BIAS_GELU) {
-        const uint32_t q0 = pack_bf16(v0, v1), q1 = pack_bf16(v2, v3);
-        stg_v2(L.aux + it * L.aux_step + col * 2, q0, q1);
+        const uint32_t q0 = pack_bf16(v01.x, v01.y), q1 = pack_bf16(v23.x, v23.y);
+        stg_v2(ax, q0, q1);
         // GELU of the bf16-rounded pre-activation: backward differentiates exactly what forward evaluated
-        const float2 u0 = unpack_bf16(q0), u1 = unpack_bf16(q1);
-        v0 = gelu_erf(u0.x); v1 = gelu_erf(u0.y); v2 = gelu_erf(u1.x); v3 = gelu_erf(u1.y);
+        v01 = gelu_pair(unpack_bf16_fast(q0));
+        v23 = gelu_pair(unpack_bf16_fast(q1));
       } else if (EPI == CAVIT_EPI_GELU_BWD) {
-        const float2 u0 = unpack_bf16(pre.a[it].x), u1 = unpack_bf16(pre.a[it].y);
-        v0 *= gelu_erf_grad(u0.x); v1 *= gelu_erf_grad(u0.y); v2 *= gelu_erf_grad(u1.x); v3 *= gelu_erf_grad(u1.y);
+        v01 = mul2(v01, gelu_grad_pair(unpack_bf16_fast(pre.a[it].x)));
+        v23 = mul2(v23, gelu_grad_pair(unpack_bf16_fast(pre.a[it].y)));
       } else if (EPI == CAVIT_EPI_BIAS_RESID) {
-        v0 += pre.r[it].x; v1 += pre.r[it].y; v2 += pre.r[it].z; v3 += pre.r[it].w;
+        v01 = add2(v01, make_float2(pre.r[it].x, pre.r[it].y));
+        v23 = add2(v23, make_float2(pre.r[it].z, pre.r[it].w));
       }
-      char* o = L.out + it * L.out_step;
       if (OUT == OUT_RED) {
-        float* of = reinterpret_cast<float*>(o) + col;
-        red_add_f32(of, v0); red_add_f32(of + 1, v1); red_add_f32(of + 2, v2); red_add_f32(of + 3, v3);
+        float* of = reinterpret_cast<float*>(o);
+        red_add_f32(of, v01.x); red_add_f32(of + 1, v01.y); red_add_f32(of + 2, v23.x); red_add_f32(of + 3, v23.y);
       } else if (OUT == OUT_F32) {
-        stg_v4f(o + col * 4, v0, v1, v2, v3);
+        stg_v4f(o, v01.x, v01.y, v23.x, v23.y);
       } else {
-        stg_v2(o + col * 2, pack_bf16(v0, v1), pack_bf16(v2, v3));
+        stg_v2(o, pack_bf16(v01.x, v01.y), pack_bf16(v23.x, v23.y));
       }
     }
   }
@@ -356,12 +364,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the schedule (converged waits); one elected lane issues, so that the compiler emits
+    // ELECT + predicated UTCHMMA instead of a per-instruction election loop.
+    {
       const uint32_t idesc = umma_idesc_bf16(BN, p.a_mn, p.b_mn);
       // descriptor strides: K-major: SBO = 1024 (8 rows x 128 B); MN-major: LBO = 64-wide chunk
       // pitch (BK rows x 128 B), SBO = 1024 (8 k-rows x 128 B).
       const uint32_t a_lbo = p.a_mn ? GEMM_BK * 128 : 16, b_lbo = p.b_mn ? GEMM_BK * 128 : 16;
-      const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;
+      const uint32_t a_kstep = (p.a_mn ? 16 * 128 : 32) >> 4, b_kstep = (p.b_mn ? 16 * 128 : 32) >> 4;  // in 16-byte units
+      const uint64_t adesc0 = umma_desc_sw128(smem_base, a_lbo, 1024);
+      const uint64_t bdesc0 = umma_desc_sw128(smem_base + Cfg::A_BYTES, b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -376,18 +388,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, abort_flag, p.status, ERR_TIMEOUT_FULL);
           tc_fence_after();
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + Cfg::A_BYTES;
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + static_cast<uint32_t>(stage * (Cfg::STAGE_BYTES >> 4));
+            const uint64_t bd = bdesc0 + static_cast<uint32_t>(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t adesc = umma_desc_sw128(sA + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = umma_desc_sw128(sB + k * b_kstep, b_lbo, 1024);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_bf16_ss(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+            if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
