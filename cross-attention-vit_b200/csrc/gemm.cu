@@ -12,6 +12,8 @@
 // no transposed copies of weights or activations are ever materialised.
 //
 // Replaces the reference's cuBLAS `addmm`/`mm` call sites (SURVEY.md §2.2 G1-G4, X2, B*).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -33,12 +35,16 @@ struct GemmDev {
   int* status;
 };
 
-template <int BN>
+// CTAS = 1: one CTA computes a 128 x BN tile. CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a
+// 256 x BN tile; each CTA stages its own 128 rows of A and HALF of the B tile, so the L2 -> SM traffic per FLOP drops
+// by a third at BN = 256 (the K = 384 GEMMs of cfg2 run into the L2 fabric limit with 128 x 256 tiles) and the
+// shared-memory ring gets deeper for the same footprint.
+template <int BN, int CTAS>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (CTAS == 2) ? ((BN == 128) ? 8 : 6) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue transpose stages*/;
 };
@@ -208,21 +214,22 @@ __device__ __noinline__ void epi_chunk_slow(const GemmDev* pp, int g, long long 
 }
 
 // Body of one epilogue warp: q = TMEM lane quadrant (rows q*32..), half = which half of the tile's columns.
-template <int BN, int EPI, int OUT>
+template <int BN, int EPI, int OUT, int CTAS>
 __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               float* stage, volatile int* abort_flag, int q, int half, int lane,
-                                              int total_tiles, int splits, int tiles_per_group) {
+                                              int total_tiles, int splits, int tiles_per_group, int unit, int num_units,
+                                              int cta_rank) {
   constexpr int CH = BN / 64;  // 32-column chunks per warp
   const int c4 = lane & 7, rsub = lane >> 3;
   const bool fast_kind = p.vec_ok && EPI != CAVIT_EPI_EMBED;
   constexpr int osz = (OUT == OUT_BF16) ? 2 : 4;
   int as = 0;
   uint32_t aphase = 0;
-  for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+  for (int work = unit; work < total_tiles; work += num_units) {
     const int tile = work / splits;
     const int g = tile / tiles_per_group;
     const int rem = tile - g * tiles_per_group;
-    const int m0 = (rem / p.tiles_n) * GEMM_BM;
+    const int m0 = (rem / p.tiles_n) * (GEMM_BM * CTAS) + cta_rank * GEMM_BM;
     const int n0 = (rem % p.tiles_n) * BN + half * (BN / 2);
     const long long row0 = (long long)m0 + q * 32;
     EpiLane L;
@@ -267,17 +274,20 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty0 + 8u * as);
+    if (lane == 0) {  // the MMA issuer (leader CTA) waits for the epilogue warps of BOTH CTAs of a pair
+      if (CTAS == 2 && cta_rank != 0) mbar_arrive_remote(tempty0 + 8u * as, 0);
+      else mbar_arrive(tempty0 + 8u * as);
+    }
     as ^= 1;
     if (as == 0) aphase ^= 1u;
   }
 }
 
-template <int BN, int EPI, int OUT>
+template <int BN, int EPI, int OUT, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -295,6 +305,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = (CTAS == 2) ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CTAS, num_units = gridDim.x / CTAS;  // a "unit" owns a tile: a CTA or a CTA pair
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
@@ -304,18 +316,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);
+      mbar_init(tempty_bar(s), 8 * CTAS);
     }
     fence_barrier_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      tmem_alloc_pair(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -325,49 +342,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int total_tiles = tiles_per_group * p.groups * splits;  // work item = (group, m tile, n tile, k split)
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (each CTA stages its own rows)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      for (int work = unit; work < total_tiles; work += num_units) {
         const int split = work % splits;
         const int tile = work / splits;
         const int g = tile / tiles_per_group;
         const int rem = tile - g * tiles_per_group;
-        const int m0 = (rem / p.tiles_n) * GEMM_BM;
-        const int n0 = (rem % p.tiles_n) * BN;
+        const int m0 = (rem / p.tiles_n) * (GEMM_BM * CTAS) + cta_rank * GEMM_BM;
+        const int n0 = (rem % p.tiles_n) * BN + cta_rank * (BN / CTAS);  // this CTA's share of the B tile
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, abort_flag, p.status, ERR_TIMEOUT_EMPTY);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          // the pair's transactions are all credited to the leader's barrier (see tma_load_3d_pair)
+          if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CTAS);
           const int k0 = kb * GEMM_BK;
+          auto load = [&](const CUtensorMap* m, uint32_t dst, int c0, int c1) {
+            if (CTAS == 2) tma_load_3d_pair(m, full_bar(stage), dst, c0, c1, g);
+            else tma_load_3d(m, full_bar(stage), dst, c0, c1, g);
+          };
           if (!p.a_mn) {
-            tma_load_3d(&tmA, full_bar(stage), sA, k0, m0, g);
+            load(&tmA, sA, k0, m0);
           } else {
 #pragma unroll
-            for (int c = 0; c < GEMM_BM / 64; ++c)
-              tma_load_3d(&tmA, full_bar(stage), sA + c * (GEMM_BK * 128), m0 + c * 64, k0, g);
+            for (int c = 0; c < GEMM_BM / 64; ++c) load(&tmA, sA + c * (GEMM_BK * 128), m0 + c * 64, k0);
           }
           if (!p.b_mn) {
-            tma_load_3d(&tmB, full_bar(stage), sB, k0, n0, g);
+            load(&tmB, sB, k0, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_3d(&tmB, full_bar(stage), sB + c * (GEMM_BK * 128), n0 + c * 64, k0, g);
+            for (int c = 0; c < BN / CTAS / 64; ++c) load(&tmB, sB + c * (GEMM_BK * 128), n0 + c * 64, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair only)
     // The whole warp walks the schedule (converged waits); one elected lane issues, so that the compiler emits
     // ELECT + predicated UTCHMMA instead of a per-instruction election loop.
-    {
-      const uint32_t idesc = umma_idesc_bf16(BN, p.a_mn, p.b_mn);
+    if (cta_rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BN, p.a_mn, p.b_mn, GEMM_BM * CTAS);
       // descriptor strides: K-major: SBO = 1024 (8 rows x 128 B); MN-major: LBO = 64-wide chunk
       // pitch (BK rows x 128 B), SBO = 1024 (8 k-rows x 128 B).
       const uint32_t a_lbo = p.a_mn ? GEMM_BK * 128 : 16, b_lbo = p.b_mn ? GEMM_BK * 128 : 16;
@@ -378,7 +398,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      for (int work = unit; work < total_tiles; work += num_units) {
         const int split = work % splits;
         const int kb0 = split * p.kb_per_split;
         const int num_kb = min(num_kb_total, kb0 + p.kb_per_split) - kb0;
@@ -392,10 +412,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint64_t ad = adesc0 + static_cast<uint32_t>(stage * (Cfg::STAGE_BYTES >> 4));
             const uint64_t bd = bdesc0 + static_cast<uint32_t>(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k)
-              umma_bf16_ss(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
-            if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              if (CTAS == 2) umma_bf16_ss_pair(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if (CTAS == 2) {
+              umma_commit_pair(empty_bar(stage));  // frees the stage in BOTH CTAs once these MMAs retire
+              if (kb == num_kb - 1) umma_commit_pair(tfull_bar(as));
+            } else {
+              umma_commit(empty_bar(stage));
+              if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -409,38 +436,53 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;   // column half of the tile
     float* stage = epi_stage + (warp - 2) * 1024;
-    epilogue_role<BN, EPI, OUT>(p, tmem_base, tfull_bar(0), tempty_bar(0), stage, abort_flag, q, half, lane, total_tiles, splits,
-                           tiles_per_group);
+    epilogue_role<BN, EPI, OUT, CTAS>(p, tmem_base, tfull_bar(0), tempty_bar(0), stage, abort_flag, q, half, lane, total_tiles,
+                                      splits, tiles_per_group, unit, num_units, cta_rank);
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();  // the peer may still read this CTA's smem / barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI, int OUT>
+template <int BN, int EPI, int OUT, int CTAS>
 static int launch_gemm_epi(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, OUT>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, OUT, CTAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "gemm smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const long long total = (long long)d.tiles_m * d.tiles_n * d.groups * d.split_k;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
-  gemm_bf16_tcgen05_kernel<BN, EPI, OUT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, d);
+  const int max_units = sm_count() / CTAS;
+  const int units = (int)(total < max_units ? total : max_units);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * CTAS, 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, OUT, CTAS>, *ta, *tb, d);
+  if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "cavit_gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("cavit_gemm");
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
-  d.tiles_m = (d.M + GEMM_BM - 1) / GEMM_BM;
+  d.tiles_m = (d.M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS);
   d.tiles_n = (d.N + BN - 1) / BN;
   const int num_kb = (d.K + GEMM_BK - 1) / GEMM_BK;
   if (d.split_k > num_kb) d.split_k = num_kb;
@@ -450,7 +492,7 @@ static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d,
   if (d.accumulate) d.vec_ok = 0;  // read-modify-write outputs take the generic path
   const int out = d.split_k > 1 ? OUT_RED : (d.out_fp32 ? OUT_F32 : OUT_BF16);
 #define CAVIT_GEMM_CASE(E, O) \
-  if (d.epi == E && out == O) return launch_gemm_epi<BN, E, O>(ta, tb, d, stream);
+  if (d.epi == E && out == O) return launch_gemm_epi<BN, E, O, CTAS>(ta, tb, d, stream);
   CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_BF16)
   CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_F32)
   CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_RED)
@@ -494,8 +536,14 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   int* status = status_word();
   if (!status) return fail(CAVIT_E_DEVICE, "cavit_gemm: no device status word");
 
-  // N tile: 256 when it divides the work well, else 128 (short N) — both keep 128-row M tiles.
-  const int BN = (a->N >= 256 && (a->N % 256 == 0 || a->N > 1024)) ? 256 : 128;
+  // N tile: 256 when it divides the work well, else 128 (short N). CTA pairs (256-row tiles, each CTA staging half
+  // of the B tile) whenever there is more than one 128-row tile; CAVIT_GEMM_1CTA=1 forces single-CTA tiles.
+  // wgrad (MN-major A: few, short tiles with a long split-K reduction) keeps single-CTA tiles. With pairs and a K-major
+  // B operand, N tiles of 192 remove the 10-25 % padding of N = 1152 (QKV) and N = 384 (out-proj, fc2).
+  static const bool force_1cta = [] { const char* e = getenv("CAVIT_GEMM_1CTA"); return e && e[0] == '1'; }();
+  const int CTAS = (!force_1cta && a->M > GEMM_BM && !a->a_mn) ? 2 : 1;
+  int BN = (a->N >= 256 && (a->N % 256 == 0 || a->N > 1024)) ? 256 : 128;
+  if (CTAS == 2 && !a->b_mn && a->N % 192 == 0 && a->N % 256 != 0) BN = 192;
   const CUtensorMap *ta, *tb;
   if (!a->a_mn)
     ta = tensor_map_bf16_3d(a->A, a->K, a->M, a->groups, a->lda, a->a_gs, 64, GEMM_BM);
@@ -503,7 +551,7 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
     ta = tensor_map_bf16_3d(a->A, a->M, a->K, a->groups, a->lda, a->a_gs, 64, GEMM_BK);
   if (!ta) return CAVIT_E_BADARG;
   if (!a->b_mn)
-    tb = tensor_map_bf16_3d(a->B, a->K, a->N, a->groups, a->ldb, a->b_gs, 64, BN);
+    tb = tensor_map_bf16_3d(a->B, a->K, a->N, a->groups, a->ldb, a->b_gs, 64, BN / CTAS);
   else
     tb = tensor_map_bf16_3d(a->B, a->N, a->K, a->groups, a->ldb, a->b_gs, 64, GEMM_BK);
   if (!tb) return CAVIT_E_BADARG;
@@ -537,6 +585,11 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
                           sizeof(float) * a->N, a->M, st);
     }
   }
-  if (BN == 256) return launch_gemm<256>(ta, tb, d, as_stream(stream));
-  return launch_gemm<128>(ta, tb, d, as_stream(stream));
+  if (CTAS == 2) {
+    if (BN == 256) return launch_gemm<256, 2>(ta, tb, d, as_stream(stream));
+    if (BN == 192) return launch_gemm<192, 2>(ta, tb, d, as_stream(stream));
+    return launch_gemm<128, 2>(ta, tb, d, as_stream(stream));
+  }
+  if (BN == 256) return launch_gemm<256, 1>(ta, tb, d, as_stream(stream));
+  return launch_gemm<128, 1>(ta, tb, d, as_stream(stream));
 }
