@@ -51,6 +51,13 @@ _SIGS = {
     "cavit_xattn_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp, C.c_uint32, c_vp]),
     "cavit_xattn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp,
                                 C.c_uint32, c_vp]),
+    "cavit_xfold_scratch_floats": (c_i64, [c_i32, c_i32, c_i32, c_i32]),
+    "cavit_xfold_fwd": (c_i32, [c_vp] * 11 + [c_i32] * 5 + [C.POINTER(c_i32), C.POINTER(c_i32), c_f32, c_f32, c_f32, c_vp,
+                                C.c_uint32, c_vp]),
+    "cavit_xfold_bwd": (c_i32, [c_vp] * 14 + [c_i32] * 5 + [C.POINTER(c_i32), C.POINTER(c_i32), c_f32, c_f32, c_vp,
+                                C.c_uint32, c_vp]),
+    "cavit_expand_heads": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_fold_heads": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cavit_dropout": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, C.c_uint32, c_vp]),
     "cavit_patchify": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cavit_cls_rows": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

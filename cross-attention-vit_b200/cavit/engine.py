@@ -187,6 +187,9 @@ class Engine:
             self.cls_src, self.tok_src = [], []
             self.smoothing = 0.0
         self.K = len(self.cls_src)
+        self.fold_ok = (self.H in (1, 2, 3, 4, 6, 8, 12, 16) and self.C <= 1024 and self.K <= 16
+                        and os.environ.get("CAVIT_XFOLD", "1") != "0")
+        self.fold = False
         self.scale = 64 ** -0.5
         self.p_drop = float(cfg.dropout)
         self.drop = False                      # dropout active for the current forward/backward pair
@@ -306,6 +309,10 @@ class Engine:
             return torch.empty(shape, dtype=dt, device=dev)
 
         a: Dict[str, torch.Tensor] = {}
+        # Folded single-query cross attention (csrc/xfold.cu): no K/V projection of the fused sequence, no materialised
+        # LayerNorm of it. Attention dropout breaks the fold (probabilities stop summing to one): unfolded path then.
+        self.fold = bool(K) and not drop and self.fold_ok
+        fold = self.fold
         a["patches"] = e((self.Mimg * B * self.Np, self.P), BF16)
         nL = self.L if train else 1
         nX = 2 * self.L + 1 if train else 3
@@ -317,13 +324,19 @@ class Engine:
             a[nm] = [e(shp, dt) for _ in range(nL)]
         if K:
             nF = self.cfg.num_multi_blocks if train else 1
-            for nm, shp, dt in [("f_cls", (K, B, C), F32), ("f_xn", (K, T, C), BF16), ("f_mean", (K, T), F32),
-                                ("f_rstd", (K, T), F32), ("f_kv", (K, T, 2 * C), BF16), ("f_q", (K, B, C), F32),
+            unfolded = [("f_xn", (K, T, C), BF16), ("f_kv", (K, T, 2 * C), BF16), ("f_q", (K, B, C), F32)]
+            folded = [("f_xncls", (K, B, C), BF16), ("f_mean0", (K, B), F32), ("f_rstd0", (K, B), F32),
+                      ("f_qb", (K, B, C), BF16), ("f_qp", (K, B, H * C), F32), ("f_zhat", (K, B, H * C), F32),
+                      ("f_zb", (K, B, H * C), BF16), ("f_Ekv", (K, 2, C, H * C), BF16)]
+            for nm, shp, dt in (folded if fold else unfolded) + [
+                                ("f_cls", (K, B, C), F32), ("f_mean", (K, T), F32), ("f_rstd", (K, T), F32),
                                 ("f_probs", (K, B, H, N), F32), ("f_xo", (K, B, C), F32), ("f_xob", (K, B, C), BF16),
                                 ("f_y", (K, B, C), F32), ("f_yn", (K, B, C), BF16), ("f_meany", (K, B), F32),
                                 ("f_rstdy", (K, B), F32), ("f_u", (K, B, F), BF16), ("f_h", (K, B, F), BF16),
                                 ("f_z", (K, B, C), F32)]:
                 a[nm] = [e(shp, dt) for _ in range(nF)]
+            if fold:
+                a["xf_scratch"] = ops.xfold_scratch(K, B, N, H, dev)
         if drop:   # bf16 branch outputs that get dropped before the residual add
             a["br"] = e((G, T, C), BF16)
             if K:
@@ -346,9 +359,18 @@ class Engine:
                 a["d_z"], a["d_zb"] = e((K, B, C)), e((K, B, C), BF16)
                 a["d_u"], a["d_yn"] = e((K, B, F), BF16), e((K, B, C), BF16)
                 a["d_y"], a["d_yb"] = e((K, B, C)), e((K, B, C), BF16)
-                a["d_xo"], a["d_q"], a["d_qb"] = e((K, B, C)), e((K, B, C)), e((K, B, C), BF16)
-                a["d_kv"], a["d_xn"] = e((K, T, 2 * C), BF16), e((K, T, C), BF16)
-                a["d_xncls"] = e((K, B, C))
+                a["d_qb"] = e((K, B, C), BF16)
+                if fold:
+                    a["d_xob"], a["d_gz"] = e((K, B, C), BF16), e((K, B, H * C))
+                    a["d_qp"], a["d_qpb"] = e((K, B, H * C)), e((K, B, H * C), BF16)
+                    a["d_Ekv"] = e((K, 2, C, H * C))
+                    a["d_lnA"] = e((2, K, C))          # dgamma | dbeta of the folded LayerNorm (atomically accumulated)
+                    a["d_bv"] = e((K, C))
+                    a["d_xnclsb"], a["d_clsq"] = e((K, B, C), BF16), e((K, B, C))
+                else:
+                    a["d_xo"], a["d_q"] = e((K, B, C)), e((K, B, C))
+                    a["d_kv"], a["d_xn"] = e((K, T, 2 * C), BF16), e((K, T, C), BF16)
+                    a["d_xncls"] = e((K, B, C))
         self.a = a
         self._plan_key = key
         self.B, self.T = B, T
@@ -506,17 +528,35 @@ class Engine:
         for k in range(K):  # save the CLS rows the fusions read (they are overwritten below)
             ops.gather_rows_f32(X[self.cls_src[k]], f_cls[k], rows=B, C_=C, groups=1, src_row_stride=N * C, src_gs=0,
                                 dst_row_stride=C, dst_gs=0)
-        ops.ln_fusion_fwd(X, f_cls, self.w(f"{tag}.lnA.w"), self.w(f"{tag}.lnA.b"), a["f_xn"][s], a["f_mean"][s],
-                          a["f_rstd"][s], B=B, N=N, C_=C, cls_src=self.cls_src, tok_src=self.tok_src)
-        # K | V projection of every token, one [T, 2C] GEMM per fusion (grouped)
-        self._fwd(a["f_xn"][s], self.wb(f"{tag}.wkv"), a["f_kv"][s], G=K, T=T, N=2 * C, K=C, epi=EPI_BIAS,
-                  bias=self.w(f"{tag}.bkv"))
-        # query from the CLS row only: rows b*N of xn (row stride N*C)
-        self._fwd(a["f_xn"][s], self.wb(f"{tag}.wq"), a["f_q"][s], G=K, T=B, N=C, K=C, epi=EPI_BIAS,
-                  bias=self.w(f"{tag}.bq"), lda=N * C, a_gs=T * C)
         drop = self.drop
-        ops.xattn_fwd(a["f_q"][s], a["f_kv"][s], a["f_xo"][s], a["f_probs"][s], K=K, B=B, N=N, H=H, scale=self.scale,
-                      p_drop=self.p_drop if drop else 0.0, seed=self.seed_buf, site=self.site_fusion(mb, "attn"))
+        if self.fold:
+            HC = H * C
+            # query from the normalised CLS row, then q'_h = Wk_h^T q_h against the head-expanded key weight
+            ops.ln_fwd(f_cls, self.w(f"{tag}.lnA.w"), self.w(f"{tag}.lnA.b"), a["f_xncls"][s], a["f_mean0"][s], a["f_rstd0"][s],
+                       rows_per_group=B, groups=K, C=C)
+            self._fwd(a["f_xncls"][s], self.wb(f"{tag}.wq"), a["f_qb"][s], G=K, T=B, N=C, K=C, epi=EPI_BIAS,
+                      bias=self.w(f"{tag}.bq"))
+            Ekv = a["f_Ekv"][s]
+            ops.expand_heads(self.wb(f"{tag}.wkv"), Ekv, groups=2 * K, C_=C, H=H)
+            ops.gemm(a["f_qb"][s], Ekv, a["f_qp"][s], M=B, N=HC, K=C, groups=K, b_mn=True, lda=C, ldb=HC, ldo=HC,
+                     a_gs=B * C, b_gs=2 * C * HC, out_gs=B * HC)
+            ops.xfold_fwd(X, f_cls, a["f_qp"][s], self.w(f"{tag}.lnA.w"), self.w(f"{tag}.lnA.b"), a["f_zhat"][s], a["f_zb"][s],
+                          a["f_probs"][s], a["f_mean"][s], a["f_rstd"][s], a["xf_scratch"], K=K, B=B, N=N, C_=C, H=H,
+                          cls_src=self.cls_src, tok_src=self.tok_src, scale=self.scale)
+            # o = Wv z + bv on the head-expanded value weight (second half of each fusion's Ekv / bkv)
+            ops.gemm(a["f_zb"][s], Ekv[:, 1], a["f_xo"][s], M=B, N=C, K=HC, groups=K, lda=HC, ldb=HC, ldo=C, a_gs=B * HC,
+                     b_gs=2 * C * HC, out_gs=B * C, epi=EPI_BIAS, bias=self.w(f"{tag}.bkv")[:, C:], bias_gs=2 * C)
+        else:
+            ops.ln_fusion_fwd(X, f_cls, self.w(f"{tag}.lnA.w"), self.w(f"{tag}.lnA.b"), a["f_xn"][s], a["f_mean"][s],
+                              a["f_rstd"][s], B=B, N=N, C_=C, cls_src=self.cls_src, tok_src=self.tok_src)
+            # K | V projection of every token, one [T, 2C] GEMM per fusion (grouped)
+            self._fwd(a["f_xn"][s], self.wb(f"{tag}.wkv"), a["f_kv"][s], G=K, T=T, N=2 * C, K=C, epi=EPI_BIAS,
+                      bias=self.w(f"{tag}.bkv"))
+            # query from the CLS row only: rows b*N of xn (row stride N*C)
+            self._fwd(a["f_xn"][s], self.wb(f"{tag}.wq"), a["f_q"][s], G=K, T=B, N=C, K=C, epi=EPI_BIAS,
+                      bias=self.w(f"{tag}.bq"), lda=N * C, a_gs=T * C)
+            ops.xattn_fwd(a["f_q"][s], a["f_kv"][s], a["f_xo"][s], a["f_probs"][s], K=K, B=B, N=N, H=H, scale=self.scale,
+                          p_drop=self.p_drop if drop else 0.0, seed=self.seed_buf, site=self.site_fusion(mb, "attn"))
         ops.cast_bf16(a["f_xo"][s], a["f_xob"][s])
         if drop:
             self._fwd(a["f_xob"][s], self.wb(f"{tag}.wp"), a["br_f"], G=K, T=B, N=C, K=C, epi=EPI_BIAS, bias=self.w(f"{tag}.bp"))
@@ -717,28 +757,76 @@ class Engine:
         if drop:
             self._dropout(ops.DROP_CAST, a["d_y"], None, a["d_yb"], self.site_fusion(mb, "proj"))
         # y = proj(xattn) + cls_in
-        self._dgrad(a["d_yb"], self.wb(f"{tag}.wp"), a["d_xo"], G=K, T=B, N=C, K=C)
-        self._wgrad(a["d_yb"], a["f_xob"][s], self.g(f"{tag}.wp"), G=K, T=B, N=C, K=C)
-        self._colsum(a["d_yb"], self.g(f"{tag}.bp"), G=K, T=B, N=C)
-        ops.xattn_bwd(a["f_q"][s], a["f_kv"][s], a["f_probs"][s], a["d_xo"], a["d_q"], a["d_kv"], K=K, B=B, N=N, H=H,
-                      scale=self.scale, p_drop=self.p_drop if drop else 0.0, seed=self.seed_buf,
-                      site=self.site_fusion(mb, "attn"))
-        # query path (CLS row of xn only)
-        ops.cast_bf16(a["d_q"], a["d_qb"])
-        self._dgrad(a["d_qb"], self.wb(f"{tag}.wq"), a["d_xncls"], G=K, T=B, N=C, K=C)
-        self._wgrad(a["d_qb"], a["f_xn"][s], self.g(f"{tag}.wq"), G=K, T=B, N=C, K=C, ldx=N * C, x_gs=T * C)
-        self._colsum(a["d_qb"], self.g(f"{tag}.bq"), G=K, T=B, N=C)
-        # key / value path (all tokens)
-        self._dgrad(a["d_kv"], self.wb(f"{tag}.wkv"), a["d_xn"], G=K, T=T, N=2 * C, K=C)
-        self._wgrad(a["d_kv"], a["f_xn"][s], self.g(f"{tag}.wkv"), G=K, T=T, N=2 * C, K=C)
-        self._colsum(a["d_kv"], self.g(f"{tag}.bkv"), G=K, T=T, N=2 * C)
-        # LayerNorm of cat(cls_i, patches_j): scatter-add into the stream gradients
-        ops.ln_fusion_bwd(a["d_xn"], self._x_for_fusion(mb), a["f_cls"][s], a["f_mean"][s], a["f_rstd"][s],
-                          self.w(f"{tag}.lnA.w"), dX, self.g(f"{tag}.lnA.w"), self.g(f"{tag}.lnA.b"), ws, B=B, N=N, C_=C,
-                          cls_src=self.cls_src, tok_src=self.tok_src, dy_cls=a["d_xncls"])
+        if self.fold:
+            self._fusion_bwd_folded(mb, dX)
+        else:
+            self._dgrad(a["d_yb"], self.wb(f"{tag}.wp"), a["d_xo"], G=K, T=B, N=C, K=C)
+            self._wgrad(a["d_yb"], a["f_xob"][s], self.g(f"{tag}.wp"), G=K, T=B, N=C, K=C)
+            self._colsum(a["d_yb"], self.g(f"{tag}.bp"), G=K, T=B, N=C)
+            ops.xattn_bwd(a["f_q"][s], a["f_kv"][s], a["f_probs"][s], a["d_xo"], a["d_q"], a["d_kv"], K=K, B=B, N=N, H=H,
+                          scale=self.scale, p_drop=self.p_drop if drop else 0.0, seed=self.seed_buf,
+                          site=self.site_fusion(mb, "attn"))
+            # query path (CLS row of xn only)
+            ops.cast_bf16(a["d_q"], a["d_qb"])
+            self._dgrad(a["d_qb"], self.wb(f"{tag}.wq"), a["d_xncls"], G=K, T=B, N=C, K=C)
+            self._wgrad(a["d_qb"], a["f_xn"][s], self.g(f"{tag}.wq"), G=K, T=B, N=C, K=C, ldx=N * C, x_gs=T * C)
+            self._colsum(a["d_qb"], self.g(f"{tag}.bq"), G=K, T=B, N=C)
+            # key / value path (all tokens)
+            self._dgrad(a["d_kv"], self.wb(f"{tag}.wkv"), a["d_xn"], G=K, T=T, N=2 * C, K=C)
+            self._wgrad(a["d_kv"], a["f_xn"][s], self.g(f"{tag}.wkv"), G=K, T=T, N=2 * C, K=C)
+            self._colsum(a["d_kv"], self.g(f"{tag}.bkv"), G=K, T=T, N=2 * C)
+            # LayerNorm of cat(cls_i, patches_j): scatter-add into the stream gradients
+            ops.ln_fusion_bwd(a["d_xn"], self._x_for_fusion(mb), a["f_cls"][s], a["f_mean"][s], a["f_rstd"][s],
+                              self.w(f"{tag}.lnA.w"), dX, self.g(f"{tag}.lnA.w"), self.g(f"{tag}.lnA.b"), ws, B=B, N=N, C_=C,
+                              cls_src=self.cls_src, tok_src=self.tok_src, dy_cls=a["d_xncls"])
         # residual path of the CLS token: y = ... + cls_in
         for k in range(K):
             ops.gather_rows_f32(a["d_y"][k], dX[self.cls_src[k]], rows=B, C_=C, groups=1, src_row_stride=C, src_gs=0,
+                                dst_row_stride=N * C, dst_gs=0, accumulate=True)
+
+    def _fusion_bwd_folded(self, mb: int, dX: torch.Tensor):
+        """Adjoint of the folded forward (see csrc/xfold.cu): everything left of the token streams is a [B, .] problem."""
+        a, N, C, H, K, B = self.a, self.N, self.C, self.H, self.K, self.B
+        tag, s, ws, HC = f"X{mb}", mb, self.a["ln_ws"], self.H * self.C
+        Ekv, dE = a["f_Ekv"][s], a["d_Ekv"]
+        gkv, gbkv = self.g(f"{tag}.wkv"), self.g(f"{tag}.bkv").view(K, 2, C)
+        self._dgrad(a["d_yb"], self.wb(f"{tag}.wp"), a["d_xob"], G=K, T=B, N=C, K=C)
+        self._wgrad(a["d_yb"], a["f_xob"][s], self.g(f"{tag}.wp"), G=K, T=B, N=C, K=C)
+        self._colsum(a["d_yb"], self.g(f"{tag}.bp"), G=K, T=B, N=C)
+        # value side: gz_h = Wv_h^T do_h, dWv (expanded), dbv = sum_b do, dbk = 0 (scores are shift invariant)
+        ops.gemm(a["d_xob"], Ekv[:, 1], a["d_gz"], M=B, N=HC, K=C, groups=K, b_mn=True, lda=C, ldb=HC, ldo=HC, a_gs=B * C,
+                 b_gs=2 * C * HC, out_gs=B * HC)
+        ops.gemm(a["d_xob"], a["f_zb"][s], dE[:, 1], M=C, N=HC, K=B, groups=K, a_mn=True, b_mn=True, lda=C, ldb=HC, ldo=HC,
+                 a_gs=B * C, b_gs=B * HC, out_gs=2 * C * HC)
+        self._colsum(a["d_xob"], a["d_bv"], G=K, T=B, N=C)
+        ops.gather_rows_f32(a["d_bv"], gbkv[:, 1], rows=K, C_=C, groups=1, src_row_stride=C, src_gs=0, dst_row_stride=2 * C,
+                            dst_gs=0)
+        a["d_lnA"].zero_()
+        ops.gather_rows_f32(a["d_lnA"][0], gbkv[:, 0], rows=K, C_=C, groups=1, src_row_stride=C, src_gs=0,
+                            dst_row_stride=2 * C, dst_gs=0)     # dbk = 0
+        ops.xfold_bwd(self._x_for_fusion(mb), a["f_cls"][s], a["f_qp"][s], self.w(f"{tag}.lnA.w"), a["f_zhat"][s],
+                      a["f_probs"][s], a["f_mean"][s], a["f_rstd"][s], a["d_gz"], a["xf_scratch"], dX, a["d_qp"],
+                      a["d_lnA"][0], a["d_lnA"][1], K=K, B=B, N=N, C_=C, H=H, cls_src=self.cls_src, tok_src=self.tok_src,
+                      scale=self.scale)
+        # key side: dq_h = Wk_h dq'_h, dWk (expanded) = q^T dq'
+        ops.cast_bf16(a["d_qp"], a["d_qpb"])
+        ops.gemm(a["d_qpb"], Ekv, a["d_qb"], M=B, N=C, K=HC, groups=K, lda=HC, ldb=HC, ldo=C, a_gs=B * HC, b_gs=2 * C * HC,
+                 out_gs=B * C)
+        ops.gemm(a["f_qb"][s], a["d_qpb"], dE, M=C, N=HC, K=B, groups=K, a_mn=True, b_mn=True, lda=C, ldb=HC, ldo=HC,
+                 a_gs=B * C, b_gs=B * HC, out_gs=2 * C * HC)
+        ops.fold_heads(dE, gkv, groups=2 * K, C_=C, H=H)
+        # query path through the LayerNorm of the CLS rows
+        self._dgrad(a["d_qb"], self.wb(f"{tag}.wq"), a["d_xnclsb"], G=K, T=B, N=C, K=C)
+        self._wgrad(a["d_qb"], a["f_xncls"][s], self.g(f"{tag}.wq"), G=K, T=B, N=C, K=C)
+        self._colsum(a["d_qb"], self.g(f"{tag}.bq"), G=K, T=B, N=C)
+        ops.ln_bwd(a["d_xnclsb"], a["f_cls"][s], a["f_mean0"][s], a["f_rstd0"][s], self.w(f"{tag}.lnA.w"), a["d_clsq"],
+                   self.g(f"{tag}.lnA.w"), self.g(f"{tag}.lnA.b"), ws, rows_per_group=B, groups=K, C=C)
+        ops.gather_rows_f32(a["d_lnA"][0], self.g(f"{tag}.lnA.w"), rows=K, C_=C, groups=1, src_row_stride=C, src_gs=0,
+                            dst_row_stride=C, dst_gs=0, accumulate=True)
+        ops.gather_rows_f32(a["d_lnA"][1], self.g(f"{tag}.lnA.b"), rows=K, C_=C, groups=1, src_row_stride=C, src_gs=0,
+                            dst_row_stride=C, dst_gs=0, accumulate=True)
+        for k in range(K):
+            ops.gather_rows_f32(a["d_clsq"][k], dX[self.cls_src[k]], rows=B, C_=C, groups=1, src_row_stride=C, src_gs=0,
                                 dst_row_stride=N * C, dst_gs=0, accumulate=True)
 
     def _x_for_fusion(self, mb: int) -> torch.Tensor:

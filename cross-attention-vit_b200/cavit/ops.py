@@ -136,6 +136,36 @@ def xattn_bwd(q, kv, probs, dout, dq, dkv, *, K, B, N, H, scale, p_drop=0.0, see
                                 dkv.data_ptr(), K, B, N, H, scale, p_drop, _p(seed), site, _stream()), "cavit_xattn_bwd")
 
 
+def xfold_scratch(K, B, N, H, device) -> torch.Tensor:
+    return torch.empty(lib().cavit_xfold_scratch_floats(K, B, N, H), dtype=F32, device=device)
+
+
+def xfold_fwd(x, cls, qp, gamma, beta, zhat, z, probs, mean, rstd, scratch, *, K, B, N, C_, H, cls_src, tok_src, scale,
+              eps=1e-5, p_drop=0.0, seed=None, site=0):
+    """Folded single-query cross attention, forward (include/cavit.h: cavit_xfold_fwd)."""
+    check(lib().cavit_xfold_fwd(x.data_ptr(), cls.data_ptr(), qp.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                zhat.data_ptr(), z.data_ptr(), probs.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                scratch.data_ptr(), K, B, N, C_, H, _i32arr(cls_src), _i32arr(tok_src), scale, eps, p_drop,
+                                _p(seed), site, _stream()), "cavit_xfold_fwd")
+
+
+def xfold_bwd(x, cls, qp, gamma, zhat, probs, mean, rstd, gz, scratch, dx, dqp, dgamma, dbeta, *, K, B, N, C_, H,
+              cls_src, tok_src, scale, p_drop=0.0, seed=None, site=0):
+    check(lib().cavit_xfold_bwd(x.data_ptr(), cls.data_ptr(), qp.data_ptr(), gamma.data_ptr(), zhat.data_ptr(),
+                                probs.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gz.data_ptr(), scratch.data_ptr(),
+                                dx.data_ptr(), dqp.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), K, B, N,
+                                C_, H, _i32arr(cls_src), _i32arr(tok_src), scale, p_drop, _p(seed), site, _stream()),
+          "cavit_xfold_bwd")
+
+
+def expand_heads(W, E, *, groups, C_, H):
+    check(lib().cavit_expand_heads(W.data_ptr(), E.data_ptr(), groups, C_, H, _stream()), "cavit_expand_heads")
+
+
+def fold_heads(dE, dW, *, groups, C_, H):
+    check(lib().cavit_fold_heads(dE.data_ptr(), dW.data_ptr(), groups, C_, H, _stream()), "cavit_fold_heads")
+
+
 DROP_F32, DROP_BF16, DROP_ADD, DROP_CAST, DROP_MASK = range(5)
 
 
@@ -240,5 +270,6 @@ def _instrument(name, fn):
 
 for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_fwd", "attn_bwd", "xattn_fwd", "xattn_bwd",
            "patchify", "cls_rows", "embed_param_grads", "cast_bf16", "colsum_bf16", "gather_rows_f32", "add_bf16_f32",
-           "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout"):
+           "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout", "xfold_fwd", "xfold_bwd",
+           "expand_heads", "fold_heads"):
     globals()[_n] = _instrument(_n, globals()[_n])

@@ -1,0 +1,647 @@
+// cavit-sm100 — K-XFOLD: the single-query cross attention of CrossAttentionBlock with the key / value projections
+// and the LayerNorm FOLDED AWAY (exact in real arithmetic, /root/reference/model_cross.py:88-114).
+//
+// CrossAttention projects ONE query (the CLS token) per sample against all N tokens of the fused sequence
+// cat(cls_i, patches_j). Because the query is a single vector per head,
+//     s_n = q_h . k_n = q_h . (Wk_h xn_n + bk_h) = (Wk_h^T q_h) . xn_n + const
+//     o_h = sum_n p_n v_n = Wv_h (sum_n p_n xn_n) + bv_h          (sum_n p_n = 1)
+// the [T, C] x [C, 2C] K/V GEMM (and its dgrad / wgrad), the materialised LayerNorm output of the fused sequence and
+// the [T, 2C] K/V activation and gradient are never needed: with q'_h = Wk_h^T q_h (a [B, C] x [C, H*C] GEMM),
+// a_h = q'_h o gamma and xhat_n = (x_n - mu_n) rstd_n,
+//     s_n   = scale * a_h . xhat_n                         (terms constant in n cancel in the softmax)
+//     zhat_h = sum_n p_n xhat_n,   z_h = gamma o zhat_h + beta,   o_h = Wv_h z_h + bv_h  (GEMM on [B, H*C])
+// so one pass over the fp32 token streams (read from HBM once, a second time out of L2) replaces
+// LayerNorm + K/V GEMM + attention; LayerNorm statistics are computed in the same pass. The backward kernel is the
+// exact adjoint: with w_h = (Wv_h^T do_h) o gamma,
+//     dp_n = w_h . xhat_n,  ds_n = p_n (dp_n - sum_j p_j dp_j),  dxhat_n = sum_h scale ds_hn a_h + p_hn w_h,
+//     dx_n = rstd_n (dxhat_n - mean(dxhat_n) - xhat_n mean(dxhat_n o xhat_n))     (both means follow from s_n, dp_n)
+//     da_h = scale sum_n ds_hn xhat_n  ->  dq'_h = da_h o gamma,  dgamma += da_h o q'_h + gz_h o zhat_h,  dbeta += gz_h.
+// Everything is fp32 (the token streams are fp32), so this path is also MORE accurate than the bf16 K/V route.
+//
+// One CTA per (fusion k, sample b), one thread per channel (C <= 1024). HBM-bound: 4*C bytes per token forward,
+// 12*C bytes per token backward (read x, read-modify-write the stream gradient).
+#include "common.cuh"
+#include "internal.h"
+
+namespace cavit {
+
+constexpr int XF_MAX_FUSIONS = 16;
+
+struct XfoldParams {
+  const float* x;       // token streams [M][B*N][C] fp32
+  const float* cls;     // CLS rows of the fused sequences [K][B][C] fp32 (row 0)
+  const float* qp;      // q' [K][B][H][C] fp32
+  const float* gamma;   // [K][C]
+  const float* beta;    // [K][C]
+  float* zhat;          // [K][B][H][C] fp32
+  bf16* z;              // [K][B][H][C] bf16 (forward only)
+  float* probs;         // [K][B][H][N] softmax (pre-dropout)
+  float* mean;          // [K][B][N]
+  float* rstd;          // [K][B][N]
+  float* scratch;       // forward: [K][B][N][HP]; backward: [K][B][N][2*HP + 2]
+  // backward only
+  const float* gz;      // [K][B][H][C] fp32 = Wv_h^T do_h
+  float* dx;            // stream gradients [M][B*N][C] fp32, atomically accumulated: rows n >= 1 of stream tok_src[k],
+                        // row 0 (the CLS row of the fused sequence) of stream cls_src[k]
+  float* dqp;           // [K][B][H][C] fp32
+  float* dgamma;        // [K][C] (atomically accumulated)
+  float* dbeta;         // [K][C] (atomically accumulated)
+  int B, N, C, H, K;
+  int cls_src[XF_MAX_FUSIONS], tok_src[XF_MAX_FUSIONS];
+  float scale, eps;
+  DropCfg drop;
+  int use_drop;
+  int disjoint;   // every token stream is read by at most one fusion: plain read-modify-write instead of atomics
+};
+
+__device__ __forceinline__ const float* xf_row(const XfoldParams& p, int k, int b, int n) {
+  if (n == 0) return p.cls + ((long long)k * p.B + b) * p.C;
+  return p.x + ((long long)p.tok_src[k] * p.B * p.N + (long long)b * p.N + n) * p.C;
+}
+
+__device__ __forceinline__ float xf_block_sum(float v, float* red, int nwarps) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < nwarps; ++w) r += red[w];
+  return r;
+}
+
+constexpr int XF_CHUNK = 64;  // token rows whose per-row coefficients are staged in shared memory at a time
+template <int H> struct XfCfg {
+  static constexpr int THREADS = 32 * H;                  // one thread per PAIR of channels (C = 64 H)
+  static constexpr int NVL = (H + 1) / 2;                 // float4 per lane of a warp that owns a token row
+  static constexpr int MINB = H <= 2 ? 8 : (H <= 4 ? 5 : (H <= 6 ? 4 : (H <= 8 ? 3 : 2)));
+  static constexpr int HP = (H + 3) & ~3;
+};
+
+// Sum V per-lane values across the 32 lanes with ~V + log2(32/V) shuffles instead of 5 V: at every halving step a lane
+// keeps one half of its values and trades the other half with its partner. Afterwards lane l holds the total of value
+// warp_multi_index<V>(l) (every index is held by 32 / V lanes).
+template <int V>
+__device__ __forceinline__ float warp_multi_reduce(float (&v)[V], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int cnt = V; cnt > 1; cnt >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt / 2; ++i) {
+      const float send = up ? v[i] : v[i + cnt / 2];
+      const float keep = up ? v[i + cnt / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    if (o <= off) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+template <int V>
+__device__ __forceinline__ int warp_multi_index(int lane) {
+  int idx = 0, bit = 4;
+#pragma unroll
+  for (int cnt = V; cnt > 1; cnt >>= 1, --bit) idx = (idx << 1) | ((lane >> bit) & 1);
+  return idx;
+}
+constexpr int xf_pow2(int h) { return h <= 1 ? 1 : (h <= 2 ? 2 : (h <= 4 ? 4 : (h <= 8 ? 8 : 16))); }
+
+// Dot products of NV row vectors (this lane's float4 slices of up to two token rows) with the H (or 2H) folded vectors
+// in shared memory. Processing two rows per sweep halves the shared-memory traffic, which bounds pass 1.
+template <int H, int NVL, int NVEC>
+__device__ __forceinline__ void xf_dots(const float* s_vec, int C, int nv, int lane, const float4 (&v0)[NVL],
+                                        const float4 (&v1)[NVL], float (&d0)[NVEC * H], float (&d1)[NVEC * H]) {
+#pragma unroll
+  for (int j = 0; j < NVEC * H; ++j) {
+    const float4* vec = reinterpret_cast<const float4*>(s_vec + j * C);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nv) {
+        const float4 a = vec[c4];
+        a0 += (a.x * v0[i].x + a.y * v0[i].y) + (a.z * v0[i].z + a.w * v0[i].w);
+        a1 += (a.x * v1[i].x + a.y * v1[i].y) + (a.z * v1[i].z + a.w * v1[i].w);
+      }
+    }
+    d0[j] = a0;   // per-lane partial sums; reduced across the warp by warp_multi_reduce
+    d1[j] = a1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// smem: a[H][C] | A[H] | m[H] | chunk[XF_CHUNK][HP]
+template <int H>
+__global__ void __launch_bounds__(XfCfg<H>::THREADS, XfCfg<H>::MINB)
+xfold_fwd_kernel(const XfoldParams p) {
+  constexpr int HP = XfCfg<H>::HP, NVL = XfCfg<H>::NVL;
+  extern __shared__ float sm[];
+  float* s_a = sm;                 // [H][C]
+  float* s_A = s_a + H * p.C;      // [H]
+  float* s_m = s_A + H;            // [H]
+  float* s_ch = s_m + H + ((4 - ((2 * H) & 3)) & 3);   // [XF_CHUNK][HP], 16-byte aligned
+  const int b = blockIdx.x, k = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int C = p.C, N = p.N;
+  const long long kb = (long long)k * p.B + b;
+  const float* qp = p.qp + kb * H * C;
+  const float* gamma = p.gamma + (long long)k * C;
+  float* wgt = p.scratch + kb * N * HP;   // [N][HP]: score, then p_eff * rstd
+  // a_h = q'_h o gamma; A_h = sum_c a_h[c]
+  for (int h = 0; h < H; ++h)
+    for (int c = tid; c < C; c += blockDim.x) s_a[h * C + c] = qp[h * C + c] * gamma[c];
+  __syncthreads();
+  for (int h = warp; h < H; h += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += s_a[h * C + c];
+    s = warp_sum(s);
+    if (lane == 0) s_A[h] = s;
+  }
+  __syncthreads();
+  // ---- pass 1: one warp per PAIR of token rows: LayerNorm statistics and the H scores of each
+  const int nv = C >> 2;  // float4 per row
+  for (int n = 2 * warp; n < N; n += 2 * nwarps) {
+    const bool two = n + 1 < N;
+    const float4* row0 = reinterpret_cast<const float4*>(xf_row(p, k, b, n));
+    const float4* row1 = reinterpret_cast<const float4*>(xf_row(p, k, b, two ? n + 1 : n));
+    float4 v0[NVL], v1[NVL];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nv) {
+        v0[i] = __ldg(row0 + c4);
+        v1[i] = __ldg(row1 + c4);
+        s0 += (v0[i].x + v0[i].y) + (v0[i].z + v0[i].w);
+        s1 += (v1[i].x + v1[i].y) + (v1[i].z + v1[i].w);
+      }
+    }
+    const float mu0 = warp_sum(s0) / (float)C, mu1 = warp_sum(s1) / (float)C;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nv) {
+        float d0 = v0[i].x - mu0, d1 = v0[i].y - mu0, d2 = v0[i].z - mu0, d3 = v0[i].w - mu0;
+        q0 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        d0 = v1[i].x - mu1; d1 = v1[i].y - mu1; d2 = v1[i].z - mu1; d3 = v1[i].w - mu1;
+        q1 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      }
+    }
+    const float rs0 = rsqrtf(warp_sum(q0) / (float)C + p.eps), rs1 = rsqrtf(warp_sum(q1) / (float)C + p.eps);
+    float d0[H], d1[H];
+    xf_dots<H, NVL, 1>(s_a, C, nv, lane, v0, v1, d0, d1);
+    constexpr int HQ = xf_pow2(H);
+    float red[2 * HQ];
+#pragma unroll
+    for (int h = 0; h < HQ; ++h) {
+      red[h] = h < H ? d0[h] : 0.f;
+      red[HQ + h] = h < H ? d1[h] : 0.f;
+    }
+    const float tot = warp_multi_reduce<2 * HQ>(red, lane);
+    const int idx = warp_multi_index<2 * HQ>(lane), r = idx / HQ, h = idx % HQ;
+    if (h < H && (r == 0 || two) && (lane & (32 / (2 * HQ) - 1)) == 0) {  // one lane per (row, head)
+      const float mu = r ? mu1 : mu0, rs = r ? rs1 : rs0;
+      wgt[(long long)(n + r) * HP + h] = p.scale * rs * (tot - mu * s_A[h]);  // score s_hn
+    }
+    if (lane == 0) {
+      p.mean[kb * N + n] = mu0;
+      p.rstd[kb * N + n] = rs0;
+      if (two) {
+        p.mean[kb * N + n + 1] = mu1;
+        p.rstd[kb * N + n + 1] = rs1;
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- softmax over n per head (one warp per head), weights p_eff * rstd back into the scratch
+  for (int h = warp; h < H; h += nwarps) {
+    float mx = -INFINITY;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, wgt[(long long)n * HP + h]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < N; n += 32) sum += __expf(wgt[(long long)n * HP + h] - mx);
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float* pr = p.probs + (kb * H + h) * N;
+    float m = 0.f;
+    for (int n = lane; n < N; n += 32) {
+      const float pn = __expf(wgt[(long long)n * HP + h] - mx) * inv;
+      pr[n] = pn;
+      const float w = pn * p.rstd[kb * N + n];
+      wgt[(long long)n * HP + h] = w;
+      m += w * p.mean[kb * N + n];
+    }
+    m = warp_sum(m);
+    if (lane == 0) s_m[h] = m;
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- pass 2: one thread per channel pair: zhat_h[c] = sum_n w_hn x_n[c] - m_h; weights staged per chunk of rows
+  {
+    const int c = 2 * tid;
+    float2 acc[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] = make_float2(0.f, 0.f);
+    const float* xs = p.x + ((long long)p.tok_src[k] * p.B * N + (long long)b * N) * C + c;
+    const float* x0 = p.cls + kb * C + c;
+    for (int n0 = 0; n0 < N; n0 += XF_CHUNK) {
+      const int rows = min(XF_CHUNK, N - n0);
+      __syncthreads();
+      for (int i = tid; i < rows * HP; i += blockDim.x) s_ch[i] = wgt[(long long)n0 * HP + i];
+      __syncthreads();
+      for (int r0 = 0; r0 < rows; r0 += 8) {
+        float2 xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // 8 independent 8-byte loads in flight per thread
+          const int n = n0 + r0 + j;
+          xv[j] = (r0 + j < rows) ? __ldg(reinterpret_cast<const float2*>(n == 0 ? x0 : xs + (long long)n * C)) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (r0 + j < rows) {
+            const float4* w4 = reinterpret_cast<const float4*>(s_ch + (r0 + j) * HP);
+#pragma unroll
+            for (int i = 0; i < HP / 4; ++i) {
+              const float4 t = w4[i];
+              const float wv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (4 * i + e < H) {
+                  acc[4 * i + e].x = fmaf(wv[e], xv[j].x, acc[4 * i + e].x);
+                  acc[4 * i + e].y = fmaf(wv[e], xv[j].y, acc[4 * i + e].y);
+                }
+            }
+          }
+        }
+      }
+    }
+    const float2 g = *reinterpret_cast<const float2*>(gamma + c);
+    const float2 be = *reinterpret_cast<const float2*>(p.beta + (long long)k * C + c);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float zx = acc[h].x - s_m[h], zy = acc[h].y - s_m[h];
+      *reinterpret_cast<float2*>(p.zhat + (kb * H + h) * C + c) = make_float2(zx, zy);
+      *reinterpret_cast<uint32_t*>(p.z + (kb * H + h) * C + c) = pack_bf16(fmaf(g.x, zx, be.x), fmaf(g.y, zy, be.y));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// scratch per token row (floats): sdot[HP] | dpraw[HP] | ds[HP] | peff[HP] | c1 | c2 | mu | rstd
+// smem: a[H][C] | w[H][C] | A[H] | W[H] | chunk[XF_CHUNK][2*HP + 4]
+template <int H>
+__global__ void __launch_bounds__(XfCfg<H>::THREADS, XfCfg<H>::MINB)
+xfold_bwd_kernel(const XfoldParams p) {
+  constexpr int HP = XfCfg<H>::HP, NVL = XfCfg<H>::NVL;
+  constexpr int RS = 4 * HP + 4;
+  constexpr int CS = 2 * HP + 4;   // staged part of a scratch row: ds[HP] | peff[HP] | c1 c2 mu rstd
+  extern __shared__ float sm[];
+  const int C = p.C, N = p.N;
+  float* s_a = sm;               // [H][C]  a_h = q'_h o gamma
+  float* s_w = s_a + H * C;      // [H][C]  w_h = gz_h o gamma   (contiguous after a: 2H vectors for xf_dots)
+  float* s_A = s_w + H * C;      // [H]
+  float* s_W = s_A + H;          // [H]
+  float* s_ch = s_W + H + ((4 - ((2 * H) & 3)) & 3);   // 16-byte aligned
+  const int b = blockIdx.x, k = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const long long kb = (long long)k * p.B + b;
+  const float* qp = p.qp + kb * H * C;
+  const float* gz = p.gz + kb * H * C;
+  const float* gamma = p.gamma + (long long)k * C;
+  float* rowc = p.scratch + kb * N * RS;
+  for (int h = 0; h < H; ++h)
+    for (int c = tid; c < C; c += blockDim.x) {
+      const float g = gamma[c];
+      s_a[h * C + c] = qp[h * C + c] * g;
+      s_w[h * C + c] = gz[h * C + c] * g;
+    }
+  __syncthreads();
+  for (int h = warp; h < 2 * H; h += nwarps) {
+    const float* v = s_a + h * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += v[c];
+    s = warp_sum(s);
+    if (lane == 0) { if (h < H) s_A[h] = s; else s_W[h - H] = s; }
+  }
+  __syncthreads();
+  // ---- pass 1: one warp per PAIR of token rows: sdot_h = scale a_h . xhat_n, dpraw_h = w_h . xhat_n
+  const int nv = C >> 2;
+  for (int n = 2 * warp; n < N; n += 2 * nwarps) {
+    const bool two = n + 1 < N;
+    const int n1 = two ? n + 1 : n;
+    const float4* row0 = reinterpret_cast<const float4*>(xf_row(p, k, b, n));
+    const float4* row1 = reinterpret_cast<const float4*>(xf_row(p, k, b, n1));
+    const float mu0 = p.mean[kb * N + n], rs0 = p.rstd[kb * N + n];
+    const float mu1 = p.mean[kb * N + n1], rs1 = p.rstd[kb * N + n1];
+    float4 v0[NVL], v1[NVL];
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nv) {
+        v0[i] = __ldg(row0 + c4);
+        v1[i] = __ldg(row1 + c4);
+      }
+    }
+    float d0[2 * H], d1[2 * H];
+    xf_dots<H, NVL, 2>(s_a, C, nv, lane, v0, v1, d0, d1);
+    constexpr int HQ = xf_pow2(H);
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {   // a-dots, then w-dots: [2 rows][HQ] values per reduction
+      float red[2 * HQ];
+#pragma unroll
+      for (int h = 0; h < HQ; ++h) {
+        red[h] = h < H ? d0[which * H + h] : 0.f;
+        red[HQ + h] = h < H ? d1[which * H + h] : 0.f;
+      }
+      const float tot = warp_multi_reduce<2 * HQ>(red, lane);
+      const int idx = warp_multi_index<2 * HQ>(lane), r = idx / HQ, h = idx % HQ;
+      if (h < H && (r == 0 || two) && (lane & (32 / (2 * HQ) - 1)) == 0) {
+        const float mu = r ? mu1 : mu0, rs = r ? rs1 : rs0;
+        float* row = rowc + (long long)(n + r) * RS;
+        if (which == 0) row[h] = p.scale * rs * (tot - mu * s_A[h]);
+        else row[HP + h] = rs * (tot - mu * s_W[h]);
+      }
+    }
+    if (lane == 0) {
+      float* r = rowc + (long long)n * RS;
+      r[4 * HP + 2] = mu0;
+      r[4 * HP + 3] = rs0;
+      if (two) {
+        r[RS + 4 * HP + 2] = mu1;
+        r[RS + 4 * HP + 3] = rs1;
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- softmax backward, one warp per head: D_h = sum_n p dpraw; ds_hn = p_hn (dpraw_hn - D_h)
+  for (int h = warp; h < H; h += nwarps) {
+    const float* pr = p.probs + (kb * H + h) * N;
+    float D = 0.f;
+    for (int n = lane; n < N; n += 32) {
+      const float pe = pr[n];
+      rowc[(long long)n * RS + 3 * HP + h] = pe;
+      D += pe * rowc[(long long)n * RS + HP + h];
+    }
+    D = warp_sum(D);
+    for (int n = lane; n < N; n += 32) rowc[(long long)n * RS + 2 * HP + h] = pr[n] * (rowc[(long long)n * RS + HP + h] - D);
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- per row: c1 = mean_c(dxhat), c2 = mean_c(dxhat o xhat)
+  const float invC = 1.0f / (float)C;
+  for (int n = tid; n < N; n += blockDim.x) {
+    float* r = rowc + (long long)n * RS;
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float ds = r[2 * HP + h], pe = r[3 * HP + h];
+      c1 += p.scale * ds * s_A[h] + pe * s_W[h];
+      c2 += ds * r[h] + pe * r[HP + h];
+    }
+    r[4 * HP] = c1 * invC;
+    r[4 * HP + 1] = c2 * invC;
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- pass 2: one thread per channel pair; the per-row coefficients are staged per chunk of rows in shared memory
+  {
+    const int c = 2 * tid;
+    float2 av[H], wv[H], dacc[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      av[h] = make_float2(s_a[h * C + c] * p.scale, s_a[h * C + c + 1] * p.scale);
+      wv[h] = make_float2(s_w[h * C + c], s_w[h * C + c + 1]);
+      dacc[h] = make_float2(0.f, 0.f);
+    }
+    const float* xs = p.x + ((long long)p.tok_src[k] * p.B * N + (long long)b * N) * C + c;
+    const float* x0 = p.cls + kb * C + c;
+    float* dxs = p.dx + ((long long)p.tok_src[k] * p.B * N + (long long)b * N) * C + c;
+    float* dx0 = p.dx + ((long long)p.cls_src[k] * p.B * N + (long long)b * N) * C + c;
+    for (int n0 = 0; n0 < N; n0 += XF_CHUNK) {
+      const int rows = min(XF_CHUNK, N - n0);
+      __syncthreads();
+      for (int i = tid; i < rows * CS; i += blockDim.x) s_ch[i] = rowc[(long long)(n0 + i / CS) * RS + 2 * HP + i % CS];
+      __syncthreads();
+      for (int r0 = 0; r0 < rows; r0 += 4) {
+        float2 xv[4], old[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // all loads first: the stores below may alias as far as the compiler knows
+          const int n = n0 + r0 + j;
+          const bool ok = r0 + j < rows;
+          xv[j] = ok ? __ldg(reinterpret_cast<const float2*>(n == 0 ? x0 : xs + (long long)n * C)) : make_float2(0.f, 0.f);
+          old[j] = (ok && p.disjoint) ? *reinterpret_cast<const float2*>(n == 0 ? dx0 : dxs + (long long)n * C)
+                                      : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + r0 + j;
+          if (r0 + j < rows) {
+            const float4* r4 = reinterpret_cast<const float4*>(s_ch + (r0 + j) * CS);
+            float ds[HP], pe[HP];
+#pragma unroll
+            for (int i = 0; i < HP / 4; ++i) {
+              const float4 t = r4[i];
+              ds[4 * i] = t.x; ds[4 * i + 1] = t.y; ds[4 * i + 2] = t.z; ds[4 * i + 3] = t.w;
+              const float4 u = r4[HP / 4 + i];
+              pe[4 * i] = u.x; pe[4 * i + 1] = u.y; pe[4 * i + 2] = u.z; pe[4 * i + 3] = u.w;
+            }
+            const float4 tl = r4[2 * (HP / 4)];  // c1 | c2 | mu | rstd
+            const float xhx = (xv[j].x - tl.z) * tl.w, xhy = (xv[j].y - tl.z) * tl.w;
+            float dx_ = 0.f, dy_ = 0.f;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+              dx_ = fmaf(ds[h], av[h].x, dx_);
+              dy_ = fmaf(ds[h], av[h].y, dy_);
+              dx_ = fmaf(pe[h], wv[h].x, dx_);
+              dy_ = fmaf(pe[h], wv[h].y, dy_);
+              dacc[h].x = fmaf(ds[h], xhx, dacc[h].x);
+              dacc[h].y = fmaf(ds[h], xhy, dacc[h].y);
+            }
+            const float ox = tl.w * (dx_ - tl.x - xhx * tl.y), oy = tl.w * (dy_ - tl.x - xhy * tl.y);
+            float* dst = (n == 0) ? dx0 : dxs + (long long)n * C;
+            if (p.disjoint) {
+              *reinterpret_cast<float2*>(dst) = make_float2(old[j].x + ox, old[j].y + oy);
+            } else {
+              atomicAdd(dst, ox);
+              atomicAdd(dst + 1, oy);
+            }
+          }
+        }
+      }
+    }
+    const float2 g = *reinterpret_cast<const float2*>(gamma + c);
+    float2 dg = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float dax = dacc[h].x * p.scale, day = dacc[h].y * p.scale;   // da_h[c] = scale sum_n ds_hn xhat_n[c]
+      *reinterpret_cast<float2*>(p.dqp + (kb * H + h) * C + c) = make_float2(dax * g.x, day * g.y);
+      const float2 gzh = *reinterpret_cast<const float2*>(gz + h * C + c);
+      const float2 qph = *reinterpret_cast<const float2*>(qp + h * C + c);
+      const float2 zh = *reinterpret_cast<const float2*>(p.zhat + (kb * H + h) * C + c);
+      dg.x += dax * qph.x + gzh.x * zh.x;
+      dg.y += day * qph.y + gzh.y * zh.y;
+      db.x += gzh.x;
+      db.y += gzh.y;
+    }
+    atomicAdd(p.dgamma + (long long)k * C + c, dg.x);
+    atomicAdd(p.dgamma + (long long)k * C + c + 1, dg.y);
+    atomicAdd(p.dbeta + (long long)k * C + c, db.x);
+    atomicAdd(p.dbeta + (long long)k * C + c + 1, db.y);
+  }
+}
+
+template <int H>
+static int xfold_launch(bool bwd, const XfoldParams& p, cudaStream_t st) {
+  constexpr int HP = XfCfg<H>::HP;
+  const int threads = XfCfg<H>::THREADS;
+  const size_t smem = sizeof(float) * (bwd ? (2 * (size_t)H * p.C + 2 * H + 4 + XF_CHUNK * (2 * HP + 4))
+                                           : ((size_t)H * p.C + 2 * H + 4 + XF_CHUNK * HP));
+  if (bwd) {
+    static size_t cur = 0;
+    if (smem > cur) {
+      if (cudaFuncSetAttribute(xfold_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return fail(CAVIT_E_LAUNCH, "xfold bwd smem attribute");
+      cur = smem;
+    }
+    xfold_bwd_kernel<H><<<dim3(p.B, p.K), threads, smem, st>>>(p);
+  } else {
+    static size_t cur = 0;
+    if (smem > cur) {
+      if (cudaFuncSetAttribute(xfold_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return fail(CAVIT_E_LAUNCH, "xfold fwd smem attribute");
+      cur = smem;
+    }
+    xfold_fwd_kernel<H><<<dim3(p.B, p.K), threads, smem, st>>>(p);
+  }
+  count_launch();
+  return check_launch(bwd ? "cavit_xfold_bwd" : "cavit_xfold_fwd");
+}
+
+static int xfold_dispatch(bool bwd, const XfoldParams& p, cudaStream_t st) {
+  switch (p.H) {
+    case 1: return xfold_launch<1>(bwd, p, st);
+    case 2: return xfold_launch<2>(bwd, p, st);
+    case 3: return xfold_launch<3>(bwd, p, st);
+    case 4: return xfold_launch<4>(bwd, p, st);
+    case 6: return xfold_launch<6>(bwd, p, st);
+    case 8: return xfold_launch<8>(bwd, p, st);
+    case 12: return xfold_launch<12>(bwd, p, st);
+    case 16: return xfold_launch<16>(bwd, p, st);
+    default: return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_xfold: num_heads %d is not instantiated (1,2,3,4,6,8,12,16)", p.H);
+  }
+}
+
+// 0/1 expansion of a per-head projection: E[c_out][h*C + c_in] = W[c_out][c_in] if c_out belongs to head h else 0
+__global__ void expand_heads_kernel(const bf16* __restrict__ W, bf16* __restrict__ E, int C, int H, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cin = (int)(i % C);
+    const long long t = i / C;
+    const int h = (int)(t % H);
+    const long long row = t / H;                 // g * C + c_out
+    const int cout = (int)(row % C);
+    E[i] = (cout / 64 == h) ? W[row * C + cin] : __float2bfloat16(0.f);
+  }
+}
+// dW[c_out][c_in] = dE[c_out][head(c_out)*C + c_in]
+__global__ void fold_heads_kernel(const float* __restrict__ dE, float* __restrict__ dW, int C, int H, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cin = (int)(i % C);
+    const long long row = i / C;
+    const int cout = (int)(row % C);
+    dW[i] = dE[(row * H + cout / 64) * C + cin];
+  }
+}
+
+}  // namespace cavit
+
+using namespace cavit;
+
+extern "C" {
+
+static int xfold_fill(XfoldParams& p, const float* x, const float* cls, const float* qp, const float* gamma, const float* beta,
+                      int32_t K, int32_t B, int32_t N, int32_t C, int32_t H, const int32_t* cls_src, const int32_t* tok_src,
+                      float scale, float eps, float p_drop, const uint64_t* seed_dev, uint32_t site) {
+  if (K <= 0 || K > XF_MAX_FUSIONS || B <= 0 || N <= 0 || H <= 0 || C != H * 64 || C > 1024)
+    return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_xfold: K=%d B=%d N=%d C=%d H=%d", K, B, N, C, H);
+  p.x = x; p.cls = cls; p.qp = qp; p.gamma = gamma; p.beta = beta;
+  p.B = B; p.N = N; p.C = C; p.H = H; p.K = K;
+  for (int i = 0; i < K; ++i) { p.cls_src[i] = cls_src[i]; p.tok_src[i] = tok_src[i]; }
+  p.scale = scale; p.eps = eps;
+  p.drop.seed = reinterpret_cast<const unsigned long long*>(seed_dev);
+  p.drop.site = site; p.drop.thresh = 0; p.drop.inv_keep = 1.f;
+  p.use_drop = 0;
+  p.disjoint = 1;
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < i; ++j)
+      if (tok_src[i] == tok_src[j]) p.disjoint = 0;
+  // With attention dropout the weights no longer sum to one, so beta / bv stop being constants of the fold:
+  // callers use the unfolded path (cavit_xattn_*) when dropout is active.
+  if (p_drop > 0.f) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_xfold: attention dropout needs the unfolded path");
+  return CAVIT_OK;
+}
+
+int64_t cavit_xfold_scratch_floats(int32_t K, int32_t B, int32_t N, int32_t H) {
+  const int HP = (H + 3) & ~3;
+  return (int64_t)K * B * N * (4 * HP + 4);
+}
+
+int cavit_xfold_fwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* beta, float* zhat,
+                    void* z, float* probs, float* mean, float* rstd, float* scratch, int32_t K, int32_t B, int32_t N,
+                    int32_t C, int32_t H, const int32_t* cls_src, const int32_t* tok_src, float scale, float eps, float p_drop,
+                    const uint64_t* seed_dev, uint32_t site, void* stream) {
+  if (!x || !cls || !qp || !gamma || !beta || !zhat || !z || !probs || !mean || !rstd || !scratch || !cls_src || !tok_src)
+    return fail(CAVIT_E_BADARG, "cavit_xfold_fwd: null pointer");
+  XfoldParams p = {};
+  int rc = xfold_fill(p, x, cls, qp, gamma, beta, K, B, N, C, H, cls_src, tok_src, scale, eps, p_drop, seed_dev, site);
+  if (rc) return rc;
+  p.zhat = zhat; p.z = reinterpret_cast<bf16*>(z); p.probs = probs; p.mean = mean; p.rstd = rstd; p.scratch = scratch;
+  return xfold_dispatch(false, p, as_stream(stream));
+}
+
+int cavit_xfold_bwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* zhat,
+                    const float* probs, const float* mean, const float* rstd, const float* gz, float* scratch, float* dx,
+                    float* dqp, float* dgamma, float* dbeta, int32_t K, int32_t B, int32_t N, int32_t C, int32_t H,
+                    const int32_t* cls_src, const int32_t* tok_src, float scale, float p_drop, const uint64_t* seed_dev,
+                    uint32_t site, void* stream) {
+  if (!x || !cls || !qp || !gamma || !zhat || !probs || !mean || !rstd || !gz || !scratch || !dx || !dqp || !dgamma ||
+      !dbeta || !cls_src || !tok_src)
+    return fail(CAVIT_E_BADARG, "cavit_xfold_bwd: null pointer");
+  XfoldParams p = {};
+  int rc = xfold_fill(p, x, cls, qp, gamma, gamma, K, B, N, C, H, cls_src, tok_src, scale, 0.f, p_drop, seed_dev, site);
+  if (rc) return rc;
+  p.zhat = const_cast<float*>(zhat); p.probs = const_cast<float*>(probs);
+  p.mean = const_cast<float*>(mean); p.rstd = const_cast<float*>(rstd);
+  p.gz = gz; p.scratch = scratch; p.dx = dx; p.dqp = dqp; p.dgamma = dgamma; p.dbeta = dbeta;
+  return xfold_dispatch(true, p, as_stream(stream));
+}
+
+int cavit_expand_heads(const void* W, void* E, int32_t groups, int32_t C, int32_t H, void* stream) {
+  if (!W || !E || groups <= 0 || C != H * 64) return fail(CAVIT_E_BADARG, "cavit_expand_heads: bad args");
+  const long long total = (long long)groups * C * H * C;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  expand_heads_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(W), reinterpret_cast<bf16*>(E), C, H,
+                                                                  total);
+  count_launch();
+  return check_launch("cavit_expand_heads");
+}
+
+int cavit_fold_heads(const float* dE, float* dW, int32_t groups, int32_t C, int32_t H, void* stream) {
+  if (!dE || !dW || groups <= 0 || C != H * 64) return fail(CAVIT_E_BADARG, "cavit_fold_heads: bad args");
+  const long long total = (long long)groups * C * C;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  fold_heads_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(dE, dW, C, H, total);
+  count_launch();
+  return check_launch("cavit_fold_heads");
+}
+
+}  // extern "C"

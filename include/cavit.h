@@ -158,6 +158,35 @@ int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const fl
                     const uint64_t* seed_dev, uint32_t site, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Folded single-query cross attention (csrc/xfold.cu). Replaces, for the engine's fusion path,
+ * LayerNorm(cat(cls_i, patches_j)) + wk / wv projections of all N tokens + matmul / softmax / matmul of
+ * CrossAttention.forward (/root/reference/model_cross.py:88-99, 111-112) and their autograd, by one pass over
+ * the fp32 token streams:  q'_h = Wk_h^T q_h is projected on the host side by a GEMM against the head-expanded
+ * weight (cavit_expand_heads), z_h = gamma o (sum_n p_n xhat_n) + beta comes back and o = Wv z + bv is again a GEMM.
+ *   x: fp32 [M][B*N][C] token streams; cls: fp32 [K][B][C] (row 0 of each fused sequence);
+ *   qp / gz / zhat / dqp: fp32 [K][B][H][C]; z: bf16 [K][B][H][C]; probs: fp32 [K][B][H][N];
+ *   mean / rstd: fp32 [K][B][N]; scratch: cavit_xfold_scratch_floats(K, B, N, H) floats;
+ *   cls_src / tok_src: HOST arrays of K stream indices.
+ * Backward accumulates atomically into dx (rows n >= 1 of stream tok_src[k]; row 0 of stream cls_src[k]),
+ * dgamma and dbeta ([K][C]) and stores dqp. p_drop must be 0: with attention dropout the probabilities no longer sum
+ * to one and the fold is not exact (CAVIT_E_UNSUPPORTED_SHAPE; use cavit_xattn_* then).
+ * ------------------------------------------------------------------------------------------- */
+int64_t cavit_xfold_scratch_floats(int32_t K, int32_t B, int32_t N, int32_t H);
+int cavit_xfold_fwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* beta,
+                    float* zhat, void* z, float* probs, float* mean, float* rstd, float* scratch, int32_t K,
+                    int32_t B, int32_t N, int32_t C, int32_t H, const int32_t* cls_src, const int32_t* tok_src,
+                    float scale, float eps, float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream);
+int cavit_xfold_bwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* zhat,
+                    const float* probs, const float* mean, const float* rstd, const float* gz, float* scratch,
+                    float* dx, float* dqp, float* dgamma, float* dbeta, int32_t K, int32_t B,
+                    int32_t N, int32_t C, int32_t H, const int32_t* cls_src, const int32_t* tok_src, float scale,
+                    float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream);
+/* E[g][c_out][h*C + c_in] = W[g][c_out][c_in] if c_out is a row of head h (c_out / 64 == h) else 0   (bf16)
+ * dW[g][c_out][c_in] = dE[g][c_out][(c_out / 64)*C + c_in]                                          (fp32) */
+int cavit_expand_heads(const void* W, void* E, int32_t groups, int32_t C, int32_t H, void* stream);
+int cavit_fold_heads(const float* dE, float* dW, int32_t groups, int32_t C, int32_t H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Patch extraction: 'b c (d p1)(h p2)(w p3) -> b (h w d)(p1 p2 p3 c)' gather of one [B, M, 1, D, H, W]
  * fp32 batch into bf16 patch rows [M][B*Np][P] (bit-exact index map).
  * Replaces: einops.rearrange at /root/reference/model_cross.py:193, modelv3.py:129.

@@ -428,3 +428,111 @@ def test_single_query_cross_attention(K, B, N, H):
     assert rel(dq, qd.grad) < 1e-4
     assert rel(dkv, kvd.grad) < 5e-3
     status_ok()
+
+
+# ------------------------------------------------------------------------------------------------ folded cross attention
+def _xfold_reference(X, cls_src, tok_src, lnw, lnb, Wq, bq, Wk, bk, Wv, bv, H, dm=None):
+    """fp64 restatement of LayerNorm(cat(cls_i, patches_j)) -> wq/wk/wv -> single-query attention, UNFOLDED
+    (/root/reference/model_cross.py:88-99, 111-112; oracle/functional.py::cross_attention). Returns o [K][B][C]."""
+    Kf = len(cls_src)
+    M, B, N, C = X.shape
+    outs = []
+    for k in range(Kf):
+        seq = torch.cat((X[cls_src[k]][:, 0:1], X[tok_src[k]][:, 1:]), dim=1)
+        xn = torch.nn.functional.layer_norm(seq, (C,), lnw[k], lnb[k], 1e-5)
+        q = (xn[:, 0:1] @ Wq[k].T + bq[k]).reshape(B, 1, H, 64).permute(0, 2, 1, 3)
+        kk = (xn @ Wk[k].T + bk[k]).reshape(B, N, H, 64).permute(0, 2, 1, 3)
+        v = (xn @ Wv[k].T + bv[k]).reshape(B, N, H, 64).permute(0, 2, 1, 3)
+        attn = torch.softmax((q @ kk.transpose(-2, -1)) * 64 ** -0.5, dim=-1)
+        if dm is not None:
+            attn = attn * dm[k]
+        outs.append((attn @ v).transpose(1, 2).reshape(B, C))
+    return torch.stack(outs)
+
+
+@pytest.mark.parametrize("M,B,N,H,cls_src,tok_src,p_drop", [
+    (2, 3, 9, 1, [0], [1], 0.0), (3, 2, 37, 2, [0, 1], [1, 2], 0.0), (4, 5, 197, 6, [0, 1, 2, 3], [1, 2, 3, 0], 0.0),
+    (2, 2, 65, 3, [0, 1], [1, 1], 0.0),      # two fusions reading the SAME token stream (atomic scatter)
+    (2, 2, 130, 12, [1], [0], 0.0), (2, 1, 40, 16, [0], [1], 0.0)])
+def test_folded_cross_attention_fwd_bwd(M, B, N, H, cls_src, tok_src, p_drop):
+    from cavit import ops
+    torch.manual_seed(21)
+    C, Kf = H * 64, len(cls_src)
+    f32 = dict(device=DEV, dtype=torch.float32)
+    X = torch.randn(M, B, N, C, **f32) * 3.0 + 1.5
+    lnw, lnb = 1.0 + 0.2 * torch.randn(Kf, C, **f32), 0.2 * torch.randn(Kf, C, **f32)
+    Wq, Wk, Wv = (torch.randn(Kf, C, C, **f32) / math.sqrt(C) for _ in range(3))
+    bq, bk, bv = (0.1 * torch.randn(Kf, C, **f32) for _ in range(3))
+    cls = torch.stack([X[cls_src[k]][:, 0] for k in range(Kf)]).contiguous()      # [K][B][C]
+    # host-side projections in fp32 torch (the engine does them with the tcgen05 GEMM): q, q' = Wk_h^T q_h
+    xn0 = torch.stack([torch.nn.functional.layer_norm(cls[k], (C,), lnw[k], lnb[k], 1e-5) for k in range(Kf)])
+    q = torch.einsum("kbc,kdc->kbd", xn0, Wq) + bq[:, None]
+    qp = torch.einsum("kbhd,khdc->kbhc", q.view(Kf, B, H, 64), Wk.view(Kf, H, 64, C)).contiguous()
+    zhat = torch.empty(Kf, B, H, C, **f32)
+    z = torch.empty(Kf, B, H, C, device=DEV, dtype=torch.bfloat16)
+    probs = torch.empty(Kf, B, H, N, **f32)
+    mean, rstd = torch.empty(Kf, B, N, **f32), torch.empty(Kf, B, N, **f32)
+    scratch = ops.xfold_scratch(Kf, B, N, H, DEV)
+    seed = torch.tensor([77], dtype=torch.int64, device=DEV)
+    kw = dict(K=Kf, B=B, N=N, C_=C, H=H, cls_src=cls_src, tok_src=tok_src, scale=64 ** -0.5, p_drop=p_drop, seed=seed, site=5)
+    ops.xfold_fwd(X, cls, qp, lnw, lnb, zhat, z, probs, mean, rstd, scratch, **kw)
+    status_ok()
+    o = torch.einsum("kbhc,khdc->kbhd", (lnw[:, None, None] * zhat + lnb[:, None, None]), Wv.view(Kf, H, 64, C)).reshape(Kf, B, C) + bv[:, None]
+    dm = None
+    if p_drop > 0:
+        mk = torch.empty(Kf * B * H * N, dtype=torch.uint8, device=DEV)
+        ops.dropout(ops.DROP_MASK, None, None, mk, n=mk.numel(), p=p_drop, seed=seed, site=5)
+        dm = (mk.view(Kf, B, H, 1, N).double() / (1.0 - p_drop))
+    leaves = [t.double().requires_grad_(True) for t in (X, lnw, lnb, Wq, bq, Wk, bk, Wv, bv)]
+    ref = _xfold_reference(leaves[0], cls_src, tok_src, *leaves[1:], H, dm=dm)
+    assert rel(o, ref) < 2e-5
+    assert rel(z.float(), lnw[:, None, None] * zhat + lnb[:, None, None]) < 5e-3
+    # ---- backward: upstream gradient do [K][B][C]
+    do = torch.randn(Kf, B, C, **f32)
+    ref.backward(do.double())
+    gz = torch.einsum("kbhd,khdc->kbhc", do.view(Kf, B, H, 64), Wv.view(Kf, H, 64, C)).contiguous()
+    dX = torch.zeros_like(X)
+    dqp = torch.empty(Kf, B, H, C, **f32)
+    dgam, dbet = torch.zeros(Kf, C, **f32), torch.zeros(Kf, C, **f32)
+    ops.xfold_bwd(X, cls, qp, lnw, zhat, probs, mean, rstd, gz, scratch, dX, dqp, dgam, dbet, **kw)
+    status_ok()
+    # remaining (host-side) pieces of the chain: q path through LayerNorm of the CLS rows, weight gradients
+    dq = torch.einsum("kbhc,khdc->kbhd", dqp, Wk.view(Kf, H, 64, C)).reshape(Kf, B, C)
+    xn0_leaf = xn0.detach().clone()
+    cls_leaf = cls.double().requires_grad_(True)
+    lw, lb = lnw.double().requires_grad_(True), lnb.double().requires_grad_(True)
+    xn0_d = torch.stack([torch.nn.functional.layer_norm(cls_leaf[k], (C,), lw[k], lb[k], 1e-5) for k in range(Kf)])
+    xn0_d.backward(torch.einsum("kbd,kdc->kbc", dq.double(), Wq.double()))
+    want_dX = leaves[0].grad
+    got = dX.double().clone()
+    for k in range(Kf):
+        got[cls_src[k]][:, 0] += cls_leaf.grad[k]
+    assert rel(got, want_dX) < 1e-4
+    assert rel(dgam.double() + lw.grad, leaves[1].grad) < 1e-4
+    assert rel(dbet.double() + lb.grad, leaves[2].grad) < 1e-4
+    assert rel(torch.einsum("kbd,kbc->kdc", dq, xn0_leaf), leaves[3].grad) < 1e-4            # dWq
+    assert rel(torch.einsum("kbhd,kbhc->khdc", q.view(Kf, B, H, 64), dqp).reshape(Kf, C, C), leaves[5].grad) < 1e-4  # dWk
+    assert float(leaves[6].grad.abs().max()) < 1e-9                                           # dbk == 0 analytically
+    zz = lnw[:, None, None] * zhat + lnb[:, None, None]
+    assert rel(torch.einsum("kbhd,kbhc->khdc", do.view(Kf, B, H, 64), zz).reshape(Kf, C, C), leaves[7].grad) < 1e-4  # dWv
+    assert rel(do.sum(1), leaves[8].grad) < 1e-5                                              # dbv
+
+
+def test_expand_and_fold_heads():
+    from cavit import ops
+    torch.manual_seed(22)
+    G, H = 3, 3
+    C = H * 64
+    W = bf(torch.randn(G, C, C, device=DEV))
+    E = torch.empty(G, C, H * C, device=DEV, dtype=torch.bfloat16)
+    ops.expand_heads(W, E, groups=G, C_=C, H=H)
+    want = torch.zeros(G, C, H, C, device=DEV, dtype=torch.bfloat16)
+    for h in range(H):
+        want[:, h * 64:(h + 1) * 64, h] = W[:, h * 64:(h + 1) * 64]
+    assert torch.equal(E.view(G, C, H, C), want)
+    dE = torch.randn(G, C, H * C, device=DEV)
+    dW = torch.empty(G, C, C, device=DEV)
+    ops.fold_heads(dE, dW, groups=G, C_=C, H=H)
+    ref = torch.stack([torch.cat([dE.view(G, C, H, C)[g, h * 64:(h + 1) * 64, h] for h in range(H)]) for g in range(G)])
+    assert torch.equal(dW, ref)
+    status_ok()

@@ -120,6 +120,26 @@ def main():
         src = rnd(G * T * C)
         dst = torch.empty(G * T * C, device=DEV, dtype=BF)
         mem_line("cast fp32->bf16", lambda: ops.cast_bf16(src, dst), G * T * C * 6)
+    if not a.only or "xfold" in a.only:
+        Kf = 4
+        f32 = dict(device=DEV, dtype=torch.float32)
+        X = torch.randn(G, B * N, C, **f32)
+        cls = torch.randn(Kf, B, C, **f32)
+        qp = torch.randn(Kf, B, H * C, **f32) * 0.05
+        lnw, lnb = torch.ones(Kf, C, **f32), torch.zeros(Kf, C, **f32)
+        zhat = torch.empty(Kf, B, H * C, **f32)
+        z = torch.empty(Kf, B, H * C, device=DEV, dtype=BF)
+        probs = torch.empty(Kf, B, H, N, **f32)
+        mean, rstd = torch.empty(Kf, B, N, **f32), torch.empty(Kf, B, N, **f32)
+        scratch = ops.xfold_scratch(Kf, B, N, H, DEV)
+        kw = dict(K=Kf, B=B, N=N, C_=C, H=H, cls_src=[0, 1, 2, 3], tok_src=[1, 2, 3, 0], scale=0.125)
+        mem_line("xfold fwd", lambda: ops.xfold_fwd(X, cls, qp, lnw, lnb, zhat, z, probs, mean, rstd, scratch, **kw), Kf * B * N * C * 4)
+        gz = torch.randn(Kf, B, H * C, **f32) * 0.05
+        dX = torch.zeros(G, B * N, C, **f32)
+        dqp = torch.empty(Kf, B, H * C, **f32)
+        dg, db = torch.zeros(Kf, C, **f32), torch.zeros(Kf, C, **f32)
+        mem_line("xfold bwd", lambda: ops.xfold_bwd(X, cls, qp, lnw, zhat, probs, mean, rstd, gz, scratch, dX, dqp, dg, db, **kw),
+                 Kf * B * N * C * 12)
     print("status", _abi.device_status())
 
 
