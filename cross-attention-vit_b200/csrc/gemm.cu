@@ -21,7 +21,6 @@ namespace cavit {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 
 struct GemmDev {
   int M, N, K, groups;
@@ -39,14 +38,22 @@ struct GemmDev {
 // 256 x BN tile; each CTA stages its own 128 rows of A and HALF of the B tile, so the L2 -> SM traffic per FLOP drops
 // by a third at BN = 256 (the K = 384 GEMMs of cfg2 run into the L2 fabric limit with 128 x 256 tiles) and the
 // shared-memory ring gets deeper for the same footprint.
-template <int BN, int CTAS>
+// EW = epilogue warps per TMEM lane quadrant. With two (each taking half of the tile's columns) the bias / GELU epilogues
+// of the 256-wide pair tiles are bounded by the dependent-instruction latency of 2 warps per scheduler (ncu: 52 % issue
+// utilisation at 31 % tensor activity); four warps per quadrant (64 columns each, no register prefetch) double the
+// latency hiding for the two math-heavy epilogues (GELU forward / backward; measured gain is small, a few per cent).
+// All other epilogues keep two warps per quadrant and a deeper operand ring.
+template <int BN, int CTAS, int EPI>
 struct GemmCfg {
+  static constexpr int EW = (CTAS == 2 && BN == 256 && (EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_GELU_BWD)) ? 4 : 2;
+  static constexpr int EPI_WARPS = 4 * EW;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, epilogue warps
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (CTAS == 2) ? ((BN == 128) ? 8 : 6) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int STAGES = (CTAS == 2) ? ((BN == 128) ? 8 : (EW == 4 ? 5 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue transpose stages*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 4096 /*epilogue transpose stages*/;
 };
 
 // ---------------------------------------------------------------------------------------- epilogue
@@ -214,12 +221,13 @@ __device__ __noinline__ void epi_chunk_slow(const GemmDev* pp, int g, long long 
 }
 
 // Body of one epilogue warp: q = TMEM lane quadrant (rows q*32..), half = which half of the tile's columns.
-template <int BN, int EPI, int OUT, int CTAS>
+template <int BN, int EPI, int OUT, int CTAS, int EW>
 __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               float* stage, volatile int* abort_flag, int q, int half, int lane,
                                               int total_tiles, int splits, int tiles_per_group, int unit, int num_units,
                                               int cta_rank) {
-  constexpr int CH = BN / 64;  // 32-column chunks per warp
+  constexpr int CH = BN / EW / 32;  // 32-column chunks per warp (`half` = which 1/EW of the tile's columns)
+  constexpr bool kPrefetch = (EW == 2);
   const int c4 = lane & 7, rsub = lane >> 3;
   const bool fast_kind = p.vec_ok && EPI != CAVIT_EPI_EMBED;
   constexpr int osz = (OUT == OUT_BF16) ? 2 : 4;
@@ -230,7 +238,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
     const int g = tile / tiles_per_group;
     const int rem = tile - g * tiles_per_group;
     const int m0 = (rem / p.tiles_n) * (GEMM_BM * CTAS) + cta_rank * GEMM_BM;
-    const int n0 = (rem % p.tiles_n) * BN + half * (BN / 2);
+    const int n0 = (rem % p.tiles_n) * BN + half * (BN / EW);
     const long long row0 = (long long)m0 + q * 32;
     EpiLane L;
     {
@@ -246,10 +254,10 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
       L.rows_left = left > 32 ? 32 : (left < 0 ? 0 : (int)left);
     }
     EpiPre<EPI> pre;
-    if (fast_kind && n0 + 32 <= p.N) epi_prefetch<EPI>(L, n0 + c4 * 4, pre);  // overlaps the tile's mainloop
+    if (kPrefetch && fast_kind && n0 + 32 <= p.N) epi_prefetch<EPI>(L, n0 + c4 * 4, pre);  // overlaps the tile's mainloop
     mbar_wait(tfull0 + 8u * as, aphase, abort_flag, p.status, ERR_TIMEOUT_TMEM_FULL);
     tc_fence_after();
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * (BN / 2);
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * (BN / EW);
 #pragma unroll 1
     for (int c = 0; c < CH; ++c) {
       const int col0 = n0 + c * 32;
@@ -264,8 +272,9 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
                                            __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
       __syncwarp();
       if (fast_kind && (col0 + 32 <= p.N)) {  // warp-uniform
+        if (!kPrefetch) epi_prefetch<EPI>(L, col0 + c4 * 4, pre);  // many warps: latency is hidden by the other warps
         const EpiPre<EPI> cur = pre;
-        if (c + 1 < CH && col0 + 64 <= p.N) epi_prefetch<EPI>(L, col0 + 32 + c4 * 4, pre);
+        if (kPrefetch && c + 1 < CH && col0 + 64 <= p.N) epi_prefetch<EPI>(L, col0 + 32 + c4 * 4, pre);
         epi_chunk_fast<EPI, OUT>(L, col0 + c4 * 4, stage, lane, cur);
       } else {
         epi_chunk_slow<EPI>(&p, g, row0, col0, stage, lane);
@@ -284,10 +293,10 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
 }
 
 template <int BN, int EPI, int OUT, int CTAS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((GemmCfg<BN, CTAS, EPI>::THREADS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmDev p) {
-  using Cfg = GemmCfg<BN, CTAS>;
+  using Cfg = GemmCfg<BN, CTAS, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -316,7 +325,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8 * CTAS);
+      mbar_init(tempty_bar(s), Cfg::EPI_WARPS * CTAS);
     }
     fence_barrier_init();
     prefetch_tmap(&tmA);
@@ -434,9 +443,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else {
     // ------------------------------------------------------------------ epilogue warps (2..9)
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;   // column half of the tile
+    const int half = (warp - 2) >> 2;   // which 1/EW of the tile's columns
     float* stage = epi_stage + (warp - 2) * 1024;
-    epilogue_role<BN, EPI, OUT, CTAS>(p, tmem_base, tfull_bar(0), tempty_bar(0), stage, abort_flag, q, half, lane, total_tiles,
+    epilogue_role<BN, EPI, OUT, CTAS, Cfg::EW>(p, tmem_base, tfull_bar(0), tempty_bar(0), stage, abort_flag, q, half, lane, total_tiles,
                                       splits, tiles_per_group, unit, num_units, cta_rank);
   }
 
@@ -451,7 +460,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
 template <int BN, int EPI, int OUT, int CTAS>
 static int launch_gemm_epi(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CTAS>;
+  using Cfg = GemmCfg<BN, CTAS, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, OUT, CTAS>,
@@ -464,7 +473,7 @@ static int launch_gemm_epi(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev
   const int units = (int)(total < max_units ? total : max_units);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * CTAS, 1, 1);
-  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
