@@ -41,7 +41,7 @@ _SIGS = {
     "cavit_ln_fwd": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "cavit_ln_bwd_workspace_floats": (C.c_size_t, [c_i32, c_i32]),
     "cavit_ln_bwd": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64,
-                             c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+                             c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cavit_ln_fusion_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32),
                                     c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "cavit_ln_fusion_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,

@@ -669,6 +669,7 @@ class Engine:
                    dx_row_stride=N * C, dx_gs=T * C)
         done("head")
         need_cast = True  # dXb must mirror dX before the first layer's GEMMs
+        b2_done = False   # fc2 bias gradient of this layer already produced by the LayerNorm backward above it
         for l in reversed(range(self.L)):
             tag = f"L{l}"
             if self.kind == "cross" and K and (l + 1) % cfg.num_self_blocks == 0:
@@ -686,13 +687,16 @@ class Engine:
             if drop:
                 self._dropout(ops.DROP_BF16, a["dbig"], None, a["dbig"], self.site_layer(l, "gelu"))
             self._wgrad(dXb, a["h"][l], self.g(f"{tag}.w2"), G=G, T=T, N=C, K=F)
-            self._colsum(dXb, self.g(f"{tag}.b2"), G=G, T=T, N=C)
+            if not b2_done:
+                self._colsum(dXb, self.g(f"{tag}.b2"), G=G, T=T, N=C)
             self._dgrad(a["dbig"], self.wb(f"{tag}.w1"), a["dmid"], G=G, T=T, N=F, K=C)
             self._wgrad(a["dbig"], a["xn2"][l], self.g(f"{tag}.w1"), G=G, T=T, N=F, K=C)
             self._colsum(a["dbig"], self.g(f"{tag}.b1"), G=G, T=T, N=F)
+            # the column sums of this LayerNorm backward's output are the out-proj bias gradient (no pass over dXb)
+            bo_fused = (H != 1) and not drop
             ops.ln_bwd(a["dmid"], x_mid, a["mean2"][l], a["rstd2"][l], self.w(f"{tag}.ln2.w"), dX, self.g(f"{tag}.ln2.w"),
                        self.g(f"{tag}.ln2.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX,
-                       dx_bf16=None if drop else dXb)
+                       dx_bf16=None if drop else dXb, dcol=self.g(f"{tag}.bo") if bo_fused else None)
             if drop:
                 if H != 1:
                     self._dropout(ops.DROP_CAST, dX, None, dXb, self.site_layer(l, "out"))
@@ -702,7 +706,8 @@ class Engine:
             if H != 1:
                 self._dgrad(dXb, self.wb(f"{tag}.wo"), a["dmid"], G=G, T=T, N=C, K=C)
                 self._wgrad(dXb, a["ao"][l], self.g(f"{tag}.wo"), G=G, T=T, N=C, K=C)
-                self._colsum(dXb, self.g(f"{tag}.bo"), G=G, T=T, N=C)
+                if not bo_fused:
+                    self._colsum(dXb, self.g(f"{tag}.bo"), G=G, T=T, N=C)
                 dao = a["dmid"]
             else:
                 dao = dXb
@@ -710,9 +715,12 @@ class Engine:
                          H=H, scale=self.scale)
             self._dgrad(a["dqkv"], self.wb(f"{tag}.wqkv"), a["dmid"], G=G, T=T, N=3 * C, K=C)
             self._wgrad(a["dqkv"], a["xn1"][l], self.g(f"{tag}.wqkv"), G=G, T=T, N=3 * C, K=C)
+            # ... and of the layer below's fc2 bias, unless a fusion backward rewrites dX in between
+            fusion_next = self.kind == "cross" and K and l % cfg.num_self_blocks == 0
+            b2_done = l >= 1 and not drop and not fusion_next
             ops.ln_bwd(a["dmid"], x_in, a["mean1"][l], a["rstd1"][l], self.w(f"{tag}.ln1.w"), dX, self.g(f"{tag}.ln1.w"),
                        self.g(f"{tag}.ln1.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX,
-                       dx_bf16=None if drop else dXb)
+                       dx_bf16=None if drop else dXb, dcol=self.g(f"L{l - 1}.b2") if b2_done else None)
             done(tag)
         # ---- embedding: d(pos), d(cls), dW = dY^T unfold(x), db
         if drop:   # through the embedding dropout; the bf16 copy is rebuilt from the masked gradient

@@ -80,18 +80,19 @@ def ln_fwd(x, gamma, beta, y, mean, rstd, *, rows_per_group, groups, C, x_row_st
 
 
 def ln_bwd_workspace(groups: int, C: int, device) -> torch.Tensor:
-    return torch.empty(lib().cavit_ln_bwd_workspace_floats(groups, C), dtype=F32, device=device)
+    """Zero-initialised (the ticket counters at its end must start at 0; every launch leaves them at 0)."""
+    return torch.zeros(lib().cavit_ln_bwd_workspace_floats(groups, C), dtype=F32, device=device)
 
 
 def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, partials, *, rows_per_group, groups, C, dresid=None,
-           dx_bf16=None, x_row_stride=None, x_gs=None, dx_row_stride=None, dx_gs=None):
+           dx_bf16=None, x_row_stride=None, x_gs=None, dx_row_stride=None, dx_gs=None, dcol=None):
     x_row_stride = C if x_row_stride is None else x_row_stride
     x_gs = rows_per_group * x_row_stride if x_gs is None else x_gs
     dx_row_stride = C if dx_row_stride is None else dx_row_stride
     dx_gs = rows_per_group * dx_row_stride if dx_gs is None else dx_gs
     check(lib().cavit_ln_bwd(dy.data_ptr(), x.data_ptr(), x_row_stride, x_gs, mean.data_ptr(), rstd.data_ptr(),
                              gamma.data_ptr(), rows_per_group, groups, C, _p(dresid), dx.data_ptr(), dx_row_stride,
-                             dx_gs, _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(), partials.data_ptr(),
+                             dx_gs, _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(), _p(dcol), partials.data_ptr(),
                              _stream()), "cavit_ln_bwd")
 
 

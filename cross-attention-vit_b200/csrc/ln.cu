@@ -105,18 +105,22 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
   }
 }
 
-// grid = (blocks_per_group, groups). partials: [groups][blocks_per_group][2][C]
-template <int NV>
-__global__ void __launch_bounds__(LN_THREADS)
+// grid = (blocks_per_group, groups). partials: [groups][blocks_per_group][3][C] followed by one ticket counter per group.
+// COL: also accumulate the column sums of the OUTPUT gradient (dx incl. the residual term): that is the bias gradient
+// of the Linear layer that produced this LayerNorm's input (out-proj / fc2), so no separate pass over dx is needed.
+// The block that takes the last ticket of its group reduces the partial rows (no separate finalize launch).
+template <int NV, bool COL>
+__global__ void __launch_bounds__(LN_THREADS, 2)
 ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long long row_stride, long long gs,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               int rows_per_group, int C, const float* dresid, float* dx, long long dx_row_stride, long long dx_gs,
-              bf16* __restrict__ dx_bf16, float* __restrict__ partials, const RowMap rm) {
+              bf16* __restrict__ dx_bf16, float* __restrict__ partials, unsigned int* __restrict__ tickets,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcol, const RowMap rm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.y;
   const int C4 = C >> 2;
   const float inv_c = 1.0f / (float)C;
-  float4 gm[NV], dg[NV], db[NV];
+  float4 gm[NV], dg[NV], db[NV], dc[COL ? NV : 1];
   const float4* g4 = reinterpret_cast<const float4*>(gamma + (long long)g * C);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -124,6 +128,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
     gm[i] = (c4 < C4) ? __ldg(g4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (COL) dc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows_per_group; r += (long long)gridDim.x * LN_WARPS) {
     const long long row = (long long)g * rows_per_group + r;
@@ -184,6 +189,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
         } else {
           o.x += dr[i].x; o.y += dr[i].y; o.z += dr[i].z; o.w += dr[i].w;
           *(reinterpret_cast<float4*>(dx + doff) + c4) = o;
+          if (COL) { dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w; }
           if (dx_bf16) {
             uint2 q;
             q.x = pack_bf16(o.x, o.y);
@@ -194,9 +200,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
       }
     }
   }
-  // d(gamma), d(beta): combine the block's 8 warps in shared memory, then one partial row per block
-  __shared__ float s_part[2 * 1024];
-  for (int i = threadIdx.x; i < 2 * C; i += LN_THREADS) s_part[i] = 0.f;
+  // d(gamma), d(beta) (, column sums): combine the block's 8 warps in shared memory, then one partial row per block
+  constexpr int NP = COL ? 3 : 2;
+  __shared__ float s_part[NP * 1024];
+  __shared__ unsigned int s_ticket;
+  for (int i = threadIdx.x; i < NP * C; i += LN_THREADS) s_part[i] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -206,44 +214,47 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
       float* pb = s_part + C + c4 * 4;
       atomicAdd(pg + 0, dg[i].x); atomicAdd(pg + 1, dg[i].y); atomicAdd(pg + 2, dg[i].z); atomicAdd(pg + 3, dg[i].w);
       atomicAdd(pb + 0, db[i].x); atomicAdd(pb + 1, db[i].y); atomicAdd(pb + 2, db[i].z); atomicAdd(pb + 3, db[i].w);
+      if (COL) {
+        float* pc = s_part + 2 * C + c4 * 4;
+        atomicAdd(pc + 0, dc[i].x); atomicAdd(pc + 1, dc[i].y); atomicAdd(pc + 2, dc[i].z); atomicAdd(pc + 3, dc[i].w);
+      }
     }
   }
   __syncthreads();
   const long long prow = (long long)g * gridDim.x + blockIdx.x;
-  float* po = partials + prow * 2 * C;
-  for (int i = threadIdx.x; i < 2 * C; i += LN_THREADS) po[i] = s_part[i];
-}
-
-// grid = (ceil(C/32), groups); block = (32, 8)
-__global__ void ln_param_grad_finalize(const float* __restrict__ partials, int prow_per_group, int C,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float sg[8][33], sb[8][33];
-  const int g = blockIdx.y;
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  float ag = 0.f, ab = 0.f;
-  if (c < C) {
-    for (int r = threadIdx.y; r < prow_per_group; r += 8) {
-      const float* p = partials + ((long long)g * prow_per_group + r) * 2 * C;
-      ag += p[c];
-      ab += p[C + c];
-    }
-  }
-  sg[threadIdx.y][threadIdx.x] = ag;
-  sb[threadIdx.y][threadIdx.x] = ab;
+  float* po = partials + prow * 3 * C;
+  for (int i = threadIdx.x; i < NP * C; i += LN_THREADS) po[i] = s_part[i];
+  // last block of the group reduces the partial rows
+  __threadfence();
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int r = 1; r < 8; ++r) {
-      ag += sg[r][threadIdx.x];
-      ab += sb[r][threadIdx.x];
+  if (threadIdx.x == 0) s_ticket = atomicAdd(tickets + g, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  const float* pbase = partials + (long long)g * gridDim.x * 3 * C;
+  for (int i = threadIdx.x; i < NP * C; i += LN_THREADS) {
+    float acc = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // fixed summation order: deterministic
+    unsigned int r = 0;
+    for (; r + 4 <= gridDim.x; r += 4) {
+      acc += __ldcg(pbase + (long long)r * 3 * C + i);
+      acc1 += __ldcg(pbase + (long long)(r + 1) * 3 * C + i);
+      acc2 += __ldcg(pbase + (long long)(r + 2) * 3 * C + i);
+      acc3 += __ldcg(pbase + (long long)(r + 3) * 3 * C + i);
     }
-    dgamma[(long long)g * C + c] = ag;
-    dbeta[(long long)g * C + c] = ab;
+    for (; r < gridDim.x; ++r) acc += __ldcg(pbase + (long long)r * 3 * C + i);
+    acc = (acc + acc1) + (acc2 + acc3);
+    const int which = i / C, c = i - which * C;
+    float* out = which == 0 ? dgamma : (which == 1 ? dbeta : dcol);
+    out[(long long)g * C + c] = acc;
   }
+  if (threadIdx.x == 0) tickets[g] = 0;   // ready for the next launch (stream order)
 }
 
 static int blocks_per_group(long long rows, int groups) {
   long long b = (rows + LN_WARPS - 1) / LN_WARPS;
-  long long want = ((long long)sm_count() * 8 + groups - 1) / groups;  // ~8 resident blocks (64 warps) per SM in total
+  // two resident blocks per SM (128 registers / thread): one grid-stride wave, and few partial rows for the
+  // in-kernel reduction of the parameter gradients
+  long long want = ((long long)sm_count() * 2 + groups - 1) / groups;
   if (want > LN_MAX_BLOCKS_PER_GROUP) want = LN_MAX_BLOCKS_PER_GROUP;
   if (b > want) b = want;
   if (b < 1) b = 1;
@@ -278,7 +289,7 @@ static int ln_fwd_launch(const float* x, long long row_stride, long long gs, int
 static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, long long gs, const float* mean,
                          const float* rstd, const float* gamma, int rpg, int groups, int C, const float* dresid,
                          float* dx, long long dx_rs, long long dx_gs, void* dx_bf16, float* dgamma, float* dbeta,
-                         float* partials, const RowMap& rm, cudaStream_t st) {
+                         float* dcol, float* partials, const RowMap& rm, cudaStream_t st) {
   if (C % 4 || C <= 0 || C > 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: C=%d", C);
   if ((row_stride % 4) || (gs % 4) || (dx_rs % 4) || (dx_gs % 4))
     return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: strides must be multiples of 4");
@@ -286,11 +297,20 @@ static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, l
   const int bpg = blocks_per_group(rpg, groups);
   dim3 grid(bpg, groups);
   const int nv = (C / 4 + 31) / 32;
-#define LN_BWD_CASE(NVV)                                                                                       \
-  case NVV:                                                                                                    \
-    ln_bwd_kernel<NVV><<<grid, LN_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dy), x, row_stride, gs, mean, \
-                                                    rstd, gamma, rpg, C, dresid, dx, dx_rs, dx_gs,             \
-                                                    reinterpret_cast<bf16*>(dx_bf16), partials, rm);           \
+  if (dcol && rm.fusion) return fail(CAVIT_E_BADARG, "layernorm bwd: dcol is not available on the fusion row map");
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(partials + (size_t)groups * LN_MAX_BLOCKS_PER_GROUP * 3 * C);
+#define LN_BWD_CASE(NVV)                                                                                             \
+  case NVV:                                                                                                          \
+    if (dcol)                                                                                                        \
+      ln_bwd_kernel<NVV, true><<<grid, LN_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dy), x, row_stride, gs, mean, rstd, \
+                                                            gamma, rpg, C, dresid, dx, dx_rs, dx_gs,                 \
+                                                            reinterpret_cast<bf16*>(dx_bf16), partials, tickets, dgamma, \
+                                                            dbeta, dcol, rm);                                        \
+    else                                                                                                             \
+      ln_bwd_kernel<NVV, false><<<grid, LN_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dy), x, row_stride, gs, mean, rstd, \
+                                                             gamma, rpg, C, dresid, dx, dx_rs, dx_gs,                \
+                                                             reinterpret_cast<bf16*>(dx_bf16), partials, tickets, dgamma, \
+                                                             dbeta, dcol, rm);                                       \
     break;
   switch (nv) {
     LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4) LN_BWD_CASE(5) LN_BWD_CASE(6) LN_BWD_CASE(7) LN_BWD_CASE(8)
@@ -298,12 +318,7 @@ static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, l
   }
 #undef LN_BWD_CASE
   count_launch();
-  int rc = check_launch("cavit_ln_bwd");
-  if (rc) return rc;
-  dim3 fgrid((C + 31) / 32, groups), fblock(32, 8);
-  ln_param_grad_finalize<<<fgrid, fblock, 0, st>>>(partials, bpg, C, dgamma, dbeta);
-  count_launch();
-  return check_launch("cavit_ln_bwd(finalize)");
+  return check_launch("cavit_ln_bwd");
 }
 
 }  // namespace cavit
@@ -323,18 +338,18 @@ int cavit_ln_fwd(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t row
 }
 
 size_t cavit_ln_bwd_workspace_floats(int32_t groups, int32_t C) {
-  return (size_t)groups * LN_MAX_BLOCKS_PER_GROUP * 2 * (size_t)C;
+  return (size_t)groups * LN_MAX_BLOCKS_PER_GROUP * 3 * (size_t)C + (size_t)groups;   // partial rows + ticket counters
 }
 
 int cavit_ln_bwd(const void* dy, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,
                  const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
                  const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_bf16, float* dgamma,
-                 float* dbeta, float* partials, void* stream) {
+                 float* dbeta, float* dcol, float* partials, void* stream) {
   if (!dy || !x || !mean || !rstd || !gamma || !dx) return fail(CAVIT_E_BADARG, "cavit_ln_bwd: null pointer");
   RowMap rm{};
   rm.fusion = 0;
   return ln_bwd_launch(dy, x, x_row_stride, x_gs, mean, rstd, gamma, rows_per_group, groups, C, dresid, dx,
-                       dx_row_stride, dx_gs, dx_bf16, dgamma, dbeta, partials, rm, as_stream(stream));
+                       dx_row_stride, dx_gs, dx_bf16, dgamma, dbeta, dcol, partials, rm, as_stream(stream));
 }
 
 int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, const float* x_cls, int32_t B, int32_t N, int32_t C,
@@ -365,7 +380,7 @@ int cavit_ln_fusion_bwd(const void* dy, const float* dy_cls, const float* stream
   rm.dy_cls = dy_cls;
   for (int k = 0; k < K; ++k) { rm.cls_src[k] = cls_src[k]; rm.tok_src[k] = tok_src[k]; }
   return ln_bwd_launch(dy, streams, C, stream_gs, mean, rstd, gamma, B * N, K, C, nullptr, dstreams, C, stream_gs,
-                       nullptr, dgamma, dbeta, partials, rm, as_stream(stream));
+                       nullptr, dgamma, dbeta, nullptr, partials, rm, as_stream(stream));
 }
 
 }  // extern "C"

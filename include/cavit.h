@@ -101,13 +101,17 @@ int cavit_ln_fwd(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t row
                  int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16, float* mean,
                  float* rstd, void* stream);
 /* dx[row] = (dresid ? dresid[row] : 0) + LN'(dy)[row]; optionally also written as bf16 (dx_bf16).
- * dgamma/dbeta [groups][C] are fully reduced (two-stage, deterministic) using `partials`, a fp32
- * workspace of cavit_ln_bwd_workspace_floats(groups, C) elements. dx may alias dresid.            */
+ * dgamma/dbeta [groups][C] are fully reduced inside the launch (per-block partial rows in `partials`, the last
+ * block of a group sums them in a fixed order: deterministic). `partials` is a fp32 workspace of
+ * cavit_ln_bwd_workspace_floats(groups, C) elements that must be ZERO-INITIALISED once (ticket counters live at
+ * its end and are left at zero by every launch). dcol (nullable) [groups][C] receives the column sums of dx,
+ * i.e. the bias gradient of the Linear layer whose output this LayerNorm normalised (out-proj / fc2 bias of
+ * model_cross.py:45,26). dx may alias dresid.                                                                  */
 size_t cavit_ln_bwd_workspace_floats(int32_t groups, int32_t C);
 int cavit_ln_bwd(const void* dy_bf16, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,
                  const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
                  const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_bf16,
-                 float* dgamma, float* dbeta, float* partials, void* stream);
+                 float* dgamma, float* dbeta, float* dcol, float* partials, void* stream);
 
 /* Fused gather + LayerNorm for the cross-modal fusion input `cat(cls_i, patches_j)`
  * (/root/reference/model_cross.py:140, 109): row 0 of every sample is read from x_cls[k][b]

@@ -170,6 +170,24 @@ def test_layernorm_fwd_bwd(C):
     assert rel(dxb, xd.grad + dres.double()) < 4e-3
     assert rel(dg, gd.grad) < 1e-4
     assert rel(db, bd.grad) < 1e-4
+    # fused column sums of the output gradient (bias gradient of the producing Linear), repeated launches on the
+    # same workspace (ticket counters return to zero), more rows than one block per group
+    R2 = 5000
+    x2 = torch.randn(G, R2, C, device=DEV)
+    mean2, rstd2 = torch.empty(G, R2, device=DEV), torch.empty(G, R2, device=DEV)
+    y2 = torch.empty(G, R2, C, device=DEV, dtype=torch.bfloat16)
+    ops.ln_fwd(x2, gamma, beta, y2, mean2, rstd2, rows_per_group=R2, groups=G, C=C)
+    dy2 = bf(torch.randn(G, R2, C, device=DEV))
+    dres2 = torch.randn(G, R2, C, device=DEV)
+    dx2 = torch.empty_like(x2)
+    dcol = torch.full((G, C), float("nan"), device=DEV)
+    for _ in range(3):
+        ops.ln_bwd(dy2, x2, mean2, rstd2, gamma, dx2, dg, db, ws, rows_per_group=R2, groups=G, C=C, dresid=dres2, dcol=dcol)
+        assert rel(dcol, dx2.double().sum(1)) < 1e-5
+    x2d = x2.double().requires_grad_(True)
+    torch.nn.functional.layer_norm(x2d, (C,)).mul(gamma.double()[:, None]).backward(dy2.double())
+    assert rel(dx2, x2d.grad + dres2.double()) < 1e-4
+    assert rel(dg, (dy2.double() * torch.nn.functional.layer_norm(x2.double(), (C,))).sum(1)) < 1e-4
     status_ok()
 
 
