@@ -305,8 +305,18 @@ def main():
         gm = agg.get("gemm", {"ms": 0.0, "n": 0, "flops": 0.0})
         achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
+        traffic = None   # mean DRAM bytes per GEMM launch of one step, from the committed ncu launch list of this workload
+        try:
+            if args.workload == "cfg2" and B == wl["batch"]:
+                with open(os.path.join(ROOT, "profiles", "step_summary_r01.json")) as f:
+                    traffic = json.load(f)["kernels"]["gemm_bf16_tcgen05_kernel"]["traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
         roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "profiles/step_summary_r01.json (ncu dram__bytes_read+write per GEMM launch, mean over one step)"
+                    if traffic else None,
+                    "peak_source": peaks["source"] + " (sustained)",
                     "launches_per_step": gm["n"], "share_of_step": gm["ms"] / tot if tot else None}
         breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"],
                          **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} if v["flops"] and v["ms"] > 0 else {})}

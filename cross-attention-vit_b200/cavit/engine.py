@@ -380,10 +380,25 @@ class Engine:
 
     # ------------------------------------------------------------------ GEMM helpers
     def _split_for(self, G, N_out, K_in, T):
-        tiles = G * ((N_out + 127) // 128) * ((K_in + 127) // 128)
-        want = (2 * 148 + tiles - 1) // tiles
+        """Split-K factor of a wgrad GEMM dW[N_out, K_in] = dY^T X (reduction over T tokens): the (group, tile, split)
+        work items should fill whole waves of the 148 persistent CTAs (a 2.2-wave launch wastes 27 % of the last
+        wave) while every split keeps >= 8 k-blocks of 64 tokens."""
+        bn = 256 if (K_in >= 256 and (K_in % 256 == 0 or K_in > 1024)) else 128     # mirrors cavit_gemm's N tile
+        tiles = G * ((N_out + 127) // 128) * ((K_in + bn - 1) // bn)
         kb = (T + 63) // 64
-        return max(1, min(want, kb // 4 if kb >= 8 else 1, 64))
+        sms = 148
+        best, best_score = 1, -1.0
+        for s_ in range(1, 65):
+            if s_ > 1 and kb // s_ < 8:
+                break
+            items = tiles * s_
+            waves = -(-items // sms)
+            eff = items / (waves * sms)
+            # prefer >= 2 waves of work (tail effects), then the best wave efficiency, then the smaller split
+            score = eff - (0.15 if items < 1.9 * sms else 0.0) - 0.004 * s_
+            if score > best_score:
+                best, best_score = s_, score
+        return best
 
     def _fwd(self, x, w, out, *, G, T, N, K, epi=EPI_NONE, bias=None, resid=None, aux=None, lda=None, a_gs=None):
         lda = K if lda is None else lda

@@ -102,6 +102,13 @@ struct EpiLane {
   const float* bias;  // &bias[g][0]
   long long out_step, resid_step, aux_step;  // byte strides for 4 rows
   int rows_left;      // rows of this lane's 8 that are inside M: iteration `it` is valid iff it*4 < rows_left
+  // EPI_EMBED: GEMM row r = (sequence s, patch t) is written to token row s*(np+1) + 1 + t (row 0 of every sequence is
+  // the CLS token, written by cavit_cls_rows) and gets positional row 1 + t added (model_cross.py:194-197)
+  long long embed_row;   // first GEMM row of this lane (row0 + rsub)
+  int embed_np;
+  char* out_base;        // &out[g][0][0]
+  const char* pos_base;  // &pos[0][0]
+  long long ldo_bytes, ldr_bytes;
 };
 
 template <int EPI>
@@ -133,7 +140,8 @@ __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const 
     t[it] = reinterpret_cast<const float4*>(stage + r * 32)[c4 ^ (r & 7)];
   }
   float2 b01 = make_float2(0.f, 0.f), b23 = make_float2(0.f, 0.f);
-  constexpr bool kBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID);
+  constexpr bool kBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID ||
+                          EPI == CAVIT_EPI_EMBED);
   if (kBias) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(L.bias + col));
     b01 = make_float2(b.x, b.y);
@@ -160,6 +168,15 @@ __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const 
       } else if (EPI == CAVIT_EPI_BIAS_RESID) {
         v01 = add2(v01, make_float2(pre.r[it].x, pre.r[it].y));
         v23 = add2(v23, make_float2(pre.r[it].z, pre.r[it].w));
+      } else if (EPI == CAVIT_EPI_EMBED) {
+        const long long r = L.embed_row + 4 * it;
+        const long long sq = r / L.embed_np;
+        const int t = (int)(r - sq * L.embed_np);
+        const float4 pe = ldg_v4f(L.pos_base + (long long)(1 + t) * L.ldr_bytes + col * 4);
+        v01 = add2(v01, make_float2(pe.x, pe.y));
+        v23 = add2(v23, make_float2(pe.z, pe.w));
+        stg_v4f(L.out_base + (sq * (L.embed_np + 1) + 1 + t) * L.ldo_bytes + col * 4, v01.x, v01.y, v23.x, v23.y);
+        continue;
       }
       if (OUT == OUT_RED) {
         float* of = reinterpret_cast<float*>(o);
@@ -229,7 +246,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
   constexpr int CH = BN / EW / 32;  // 32-column chunks per warp (`half` = which 1/EW of the tile's columns)
   constexpr bool kPrefetch = (EW == 2);
   const int c4 = lane & 7, rsub = lane >> 3;
-  const bool fast_kind = p.vec_ok && EPI != CAVIT_EPI_EMBED;
+  const bool fast_kind = p.vec_ok;
   constexpr int osz = (OUT == OUT_BF16) ? 2 : 4;
   int as = 0;
   uint32_t aphase = 0;
@@ -252,6 +269,12 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
       L.bias = p.bias + (long long)g * p.bias_gs;
       const long long left = (long long)p.M - r;
       L.rows_left = left > 32 ? 32 : (left < 0 ? 0 : (int)left);
+      L.embed_row = r;
+      L.embed_np = p.embed_np > 0 ? p.embed_np : 1;
+      L.out_base = reinterpret_cast<char*>(p.out) + (long long)g * p.out_gs * osz;
+      L.pos_base = reinterpret_cast<const char*>(p.resid);
+      L.ldo_bytes = p.ldo * osz;
+      L.ldr_bytes = p.ldr * 4;
     }
     EpiPre<EPI> pre;
     if (kPrefetch && fast_kind && n0 + 32 <= p.N) epi_prefetch<EPI>(L, n0 + c4 * 4, pre);  // overlaps the tile's mainloop
