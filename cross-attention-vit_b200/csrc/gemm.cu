@@ -41,11 +41,11 @@ struct GemmDev {
 // EW = epilogue warps per TMEM lane quadrant. With two (each taking half of the tile's columns) the bias / GELU epilogues
 // of the 256-wide pair tiles are bounded by the dependent-instruction latency of 2 warps per scheduler (ncu: 52 % issue
 // utilisation at 31 % tensor activity); four warps per quadrant (64 columns each, no register prefetch) double the
-// latency hiding for the two math-heavy epilogues (GELU forward / backward; measured gain is small, a few per cent).
-// All other epilogues keep two warps per quadrant and a deeper operand ring.
+// latency hiding, but measured no gain once the bias vector is prefetched ahead of the accumulator wait, and it costs
+// an operand stage (shared memory) and registers (96 / thread at 576 threads): all epilogues use two.
 template <int BN, int CTAS, int EPI>
 struct GemmCfg {
-  static constexpr int EW = (CTAS == 2 && BN == 256 && (EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_GELU_BWD)) ? 4 : 2;
+  static constexpr int EW = 2;
   static constexpr int EPI_WARPS = 4 * EW;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, epilogue warps
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -131,7 +131,8 @@ __device__ __forceinline__ void epi_prefetch(const EpiLane& L, int col, EpiPre<E
 
 // Fast path: all pointers / leading dimensions vector-aligned and the chunk's 32 columns inside N.
 template <int EPI, int OUT>
-__device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const float* stage, int lane, const EpiPre<EPI>& pre) {
+__device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const float* stage, int lane, const EpiPre<EPI>& pre,
+                                               const float4 bias4) {
   const int c4 = lane & 7, rsub = lane >> 3;
   float4 t[8];
 #pragma unroll
@@ -142,10 +143,9 @@ __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const 
   float2 b01 = make_float2(0.f, 0.f), b23 = make_float2(0.f, 0.f);
   constexpr bool kBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID ||
                           EPI == CAVIT_EPI_EMBED);
-  if (kBias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(L.bias + col));
-    b01 = make_float2(b.x, b.y);
-    b23 = make_float2(b.z, b.w);
+  if (kBias) {   // loaded by the caller before the accumulator wait (an L2 round trip per chunk otherwise)
+    b01 = make_float2(bias4.x, bias4.y);
+    b23 = make_float2(bias4.z, bias4.w);
   }
   // running row pointers (4 rows per step) instead of 64-bit it * stride products in every iteration
   char* o = L.out + col * ((OUT == OUT_BF16) ? 2 : 4);
@@ -278,10 +278,18 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
     }
     EpiPre<EPI> pre;
     if (kPrefetch && fast_kind && n0 + 32 <= p.N) epi_prefetch<EPI>(L, n0 + c4 * 4, pre);  // overlaps the tile's mainloop
+    constexpr bool kHasBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID ||
+                               EPI == CAVIT_EPI_EMBED);
+    float4 bias4[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      bias4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kHasBias && fast_kind && n0 + c * 32 + 32 <= p.N) bias4[c] = __ldg(reinterpret_cast<const float4*>(L.bias + n0 + c * 32 + c4 * 4));
+    }
     mbar_wait(tfull0 + 8u * as, aphase, abort_flag, p.status, ERR_TIMEOUT_TMEM_FULL);
     tc_fence_after();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * (BN / EW);
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;  // warp-uniform
@@ -298,7 +306,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
         if (!kPrefetch) epi_prefetch<EPI>(L, col0 + c4 * 4, pre);  // many warps: latency is hidden by the other warps
         const EpiPre<EPI> cur = pre;
         if (kPrefetch && c + 1 < CH && col0 + 64 <= p.N) epi_prefetch<EPI>(L, col0 + 32 + c4 * 4, pre);
-        epi_chunk_fast<EPI, OUT>(L, col0 + c4 * 4, stage, lane, cur);
+        epi_chunk_fast<EPI, OUT>(L, col0 + c4 * 4, stage, lane, cur, bias4[c]);
       } else {
         epi_chunk_slow<EPI>(&p, g, row0, col0, stage, lane);
       }
