@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libcavit_sm100a.so")
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_GELU_BWD, EPI_EMBED = range(6)
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_GELU_BWD, EPI_EMBED, EPI_BIAS_RELU, EPI_RELU_BWD = range(8)
 
 
 class CavitError(RuntimeError):
@@ -42,6 +42,16 @@ _SIGS = {
     "cavit_ln_bwd_workspace_floats": (C.c_size_t, [c_i32, c_i32]),
     "cavit_ln_bwd": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64,
                              c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_ln_fwd_dual": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_ln_bwd_f32": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64,
+                                 c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_tokens_from_channels": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_tokens_to_channels": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_conv_patch_rows": (c_i32, [c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
+    "cavit_conv_patch_rows_bwd": (c_i32, [c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
+    "cavit_bce_head_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "cavit_bce_head_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "cavit_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp]),
     "cavit_ln_fusion_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32),
                                     c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "cavit_ln_fusion_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,

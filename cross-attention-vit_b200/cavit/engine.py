@@ -26,7 +26,8 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _abi, ops
-from ._abi import EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_EMBED, EPI_GELU_BWD, EPI_NONE
+from ._abi import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_EMBED, EPI_GELU_BWD, EPI_NONE,
+                   EPI_RELU_BWD)
 
 BF16, F32 = torch.bfloat16, torch.float32
 _ALIGN = 64  # elements; keeps every segment 16-byte aligned in bf16 and 256-byte aligned in fp32
@@ -61,7 +62,81 @@ class ParamLayout:
         return off
 
 
+def build_layout_encoder(kind: str, cfg) -> ParamLayout:
+    """Flat packing for the transformer cores of `ViT` (kind 'cnnvit', /root/reference/model.py:79-286: pre-norm,
+    separate biased q/k/v Linears packed here as one [3C, C] operand, eps 1e-6, final encoder norm, single-logit
+    head) and `ViT3D` (kind 'vit3d', /root/reference/modelv2.py:61-87,187-241: nn.TransformerEncoderLayer,
+    post-norm, packed biased in-proj, ReLU FFN; head LN, Linear(C, C/8), Linear(C/8, classes)). The CNN stems'
+    parameters are not in this buffer (they stay with torch)."""
+    C, F = cfg.hidden_dim, cfg.mlp_dim
+    lay = ParamLayout()
+    start = lay.total
+    if kind == "cnnvit":
+        Np, P = cfg.patches_per_modality, cfg.patch_dim
+        lay.add("pos", (Np + 1, C), [("embeddings.positional_embedding", 0, (1, Np + 1, C))])
+        lay.add("cls", (C,), [("embeddings.class_token", 0, (1, 1, C))])
+        lay.add("embed.w", (C, P), [("embeddings.patch_embed.weight", 0, (C, cfg.in_channels) + tuple(cfg.grid))])
+        lay.add("embed.b", (C,), [("embeddings.patch_embed.bias", 0, (C,))])
+    else:
+        N = cfg.num_tokens
+        lay.add("pos", (N, C), [("pos_embed", 0, (1, N, C))])
+        lay.add("cls", (C,), [("cls_token", 0, (1, 1, C))])
+    lay.layer_ranges.append(("embed", start, lay.total))
+    for l in range(cfg.num_layers):
+        start = lay.total
+        tag = f"L{l}"
+        if kind == "cnnvit":
+            p = f"encoder.layers.{l}."
+            lay.add(f"{tag}.ln1.w", (1, C), [(p + "attention_norm.weight", 0, (C,))])
+            lay.add(f"{tag}.ln1.b", (1, C), [(p + "attention_norm.bias", 0, (C,))])
+            lay.add(f"{tag}.wqkv", (1, 3 * C, C), [(p + f"multi_head.{nm}.weight", i * C * C, (C, C))
+                                                   for i, nm in enumerate(("query", "key", "value"))])
+            lay.add(f"{tag}.bqkv", (1, 3 * C), [(p + f"multi_head.{nm}.bias", i * C, (C,))
+                                                for i, nm in enumerate(("query", "key", "value"))])
+            lay.add(f"{tag}.wo", (1, C, C), [(p + "multi_head.out.weight", 0, (C, C))])
+            lay.add(f"{tag}.bo", (1, C), [(p + "multi_head.out.bias", 0, (C,))])
+            lay.add(f"{tag}.ln2.w", (1, C), [(p + "ffn_norm.weight", 0, (C,))])
+            lay.add(f"{tag}.ln2.b", (1, C), [(p + "ffn_norm.bias", 0, (C,))])
+            lay.add(f"{tag}.w1", (1, F, C), [(p + "ffn.fc1.weight", 0, (F, C))])
+            lay.add(f"{tag}.b1", (1, F), [(p + "ffn.fc1.bias", 0, (F,))])
+            lay.add(f"{tag}.w2", (1, C, F), [(p + "ffn.fc2.weight", 0, (C, F))])
+            lay.add(f"{tag}.b2", (1, C), [(p + "ffn.fc2.bias", 0, (C,))])
+        else:
+            p = f"transformer.transformer.layers.{l}."
+            lay.add(f"{tag}.wqkv", (1, 3 * C, C), [(p + "self_attn.in_proj_weight", 0, (3 * C, C))])
+            lay.add(f"{tag}.bqkv", (1, 3 * C), [(p + "self_attn.in_proj_bias", 0, (3 * C,))])
+            lay.add(f"{tag}.wo", (1, C, C), [(p + "self_attn.out_proj.weight", 0, (C, C))])
+            lay.add(f"{tag}.bo", (1, C), [(p + "self_attn.out_proj.bias", 0, (C,))])
+            lay.add(f"{tag}.ln1.w", (1, C), [(p + "norm1.weight", 0, (C,))])
+            lay.add(f"{tag}.ln1.b", (1, C), [(p + "norm1.bias", 0, (C,))])
+            lay.add(f"{tag}.w1", (1, F, C), [(p + "linear1.weight", 0, (F, C))])
+            lay.add(f"{tag}.b1", (1, F), [(p + "linear1.bias", 0, (F,))])
+            lay.add(f"{tag}.w2", (1, C, F), [(p + "linear2.weight", 0, (C, F))])
+            lay.add(f"{tag}.b2", (1, C), [(p + "linear2.bias", 0, (C,))])
+            lay.add(f"{tag}.ln2.w", (1, C), [(p + "norm2.weight", 0, (C,))])
+            lay.add(f"{tag}.ln2.b", (1, C), [(p + "norm2.bias", 0, (C,))])
+        lay.layer_ranges.append((tag, start, lay.total))
+    start = lay.total
+    if kind == "cnnvit":
+        lay.add("fin.ln.w", (1, C), [("encoder.encoder_norm.weight", 0, (C,))])
+        lay.add("fin.ln.b", (1, C), [("encoder.encoder_norm.bias", 0, (C,))])
+        lay.add("head.w", (C,), [("final.weight", 0, (1, C))])
+        lay.add("head.b", (1,), [("final.bias", 0, (1,))])
+    else:
+        Fh = cfg.head_dim_hidden
+        lay.add("fin.ln.w", (1, C), [("mlp_head.0.weight", 0, (C,))])
+        lay.add("fin.ln.b", (1, C), [("mlp_head.0.bias", 0, (C,))])
+        lay.add("head.w1", (1, Fh, C), [("mlp_head.1.weight", 0, (Fh, C))])
+        lay.add("head.b1", (1, Fh), [("mlp_head.1.bias", 0, (Fh,))])
+        lay.add("head.w2", (1, cfg.num_classes, Fh), [("mlp_head.2.weight", 0, (cfg.num_classes, Fh))])
+        lay.add("head.b2", (1, cfg.num_classes), [("mlp_head.2.bias", 0, (cfg.num_classes,))])
+    lay.layer_ranges.append(("head", start, lay.total))
+    return lay
+
+
 def build_layout(kind: str, cfg) -> ParamLayout:
+    if kind in ("cnnvit", "vit3d"):
+        return build_layout_encoder(kind, cfg)
     C, F, H = cfg.hidden_dim, cfg.mlp_dim, cfg.num_heads
     M = cfg.num_modalities
     Np = _num_patches(cfg)
@@ -160,7 +235,7 @@ class Engine:
     """Executes one model (kind = 'cross' | 'vit') on one device. Not thread-safe."""
 
     def __init__(self, kind: str, cfg, named_params: "OrderedDict[str, torch.nn.Parameter]", device):
-        assert kind in ("cross", "vit")
+        assert kind in ("cross", "vit", "cnnvit", "vit3d")
         _abi.require_device(torch.device(device).index or 0)
         self.kind, self.cfg, self.device = kind, cfg, torch.device(device)
         self.C, self.F, self.H = cfg.hidden_dim, cfg.mlp_dim, cfg.num_heads
@@ -169,12 +244,32 @@ class Engine:
         if self.C % 64 or self.F % 8:
             raise _abi.CavitError("hidden_dim must be a multiple of 64 and mlp_dim a multiple of 8")
         self.Mimg = cfg.num_modalities
-        self.Np = _num_patches(cfg)
-        self.P = cfg.patch_size[0] * cfg.patch_size[1] * cfg.patch_size[2]
+        self.classes = cfg.num_classes
+        # per-kind block structure: pre-norm + bias-free QKV + GELU (model_cross.py / modelv3.py), pre-norm + biased
+        # q/k/v + eps 1e-6 (model.py:107-214), post-norm + biased in-proj + ReLU (nn.TransformerEncoderLayer, modelv2.py:72-78)
+        self.encoder = kind in ("cnnvit", "vit3d")
+        self.qkv_bias = self.encoder
+        self.post_norm = kind == "vit3d"
+        self.eps = 1e-6 if kind == "cnnvit" else 1e-5
+        if kind == "cnnvit":
+            self.Np, self.P = cfg.patches_per_modality, cfg.patch_dim
+        elif kind == "vit3d":
+            self.Np, self.P = cfg.tokens_per_modality, 8
+            if cfg.head_dim_hidden % 8:
+                raise _abi.CavitError("ViT3D: hidden_dim // 8 must be a multiple of 8")
+        else:
+            self.Np = _num_patches(cfg)
+            self.P = cfg.patch_size[0] * cfg.patch_size[1] * cfg.patch_size[2]
         if self.P % 8:
             raise _abi.CavitError("patch_dim must be a multiple of 8")
-        self.classes = cfg.num_classes
-        if kind == "cross":
+        if self.encoder:
+            if float(cfg.dropout) != 0.0:
+                raise _abi.CavitError("cavit encoder cores (ViT / ViT3D) support dropout = 0 only")
+            self.G, self.N = 1, self.Np * self.Mimg + 1
+            self.L = cfg.num_layers
+            self.cls_src, self.tok_src = [], []
+            self.smoothing = float(getattr(cfg, "label_smoothing", 0.0))
+        elif kind == "cross":
             self.G, self.N = self.Mimg, self.Np + 1
             self.L = cfg.num_multi_blocks * cfg.num_self_blocks
             order = sorted((int(i), int(j)) for i, j in dict(cfg.attn_order).items() if int(i) < self.Mimg)
@@ -309,6 +404,15 @@ class Engine:
             return torch.empty(shape, dtype=dt, device=dev)
 
         a: Dict[str, torch.Tensor] = {}
+        if self.post_norm:
+            self._plan_post(a, B, train)
+            self.a = a
+            self._plan_key = key
+            self.B, self.T = B, T
+            self.saved_valid = False
+            self._fwd_graphs.clear()
+            self._bwd_graphs.clear()
+            return
         # Folded single-query cross attention (csrc/xfold.cu): no K/V projection of the fused sequence, no materialised
         # LayerNorm of it. Attention dropout breaks the fold (probabilities stop summing to one): unfolded path then.
         self.fold = bool(K) and not drop and self.fold_ok
@@ -345,6 +449,13 @@ class Engine:
         a["meanc"], a["rstdc"] = e((G, B)), e((G, B))
         a["uh"], a["hh"] = e((G, B, F), BF16), e((G, B, F), BF16)
         a["logits"], a["loss"] = e((B, self.classes)), e((1,))
+        if self.kind == "cnnvit":
+            a["logits"] = e((B,))
+            a["pos_exp"], a["clsn32"] = torch.zeros((N, C), dtype=F32, device=dev), e((B, C))
+            if train:
+                a["dpos_exp"], a["dclsn32"] = e((N, C)), e((B, C))
+                a["drows"] = e((self.Mimg * B * self.Np, self.P), BF16)
+                a["dfeat"] = e((self.Mimg * B, self.cfg.in_channels) + tuple(self.cfg.feat_dims))
         if train:
             a["dX"], a["dXb"] = e((G, T, C)), e((G, T, C), BF16)
             a["dbig"] = e((G, T, F), BF16)
@@ -406,10 +517,11 @@ class Engine:
         ops.gemm(x, w, out, M=T, N=N, K=K, groups=G, lda=lda, ldb=K, ldo=N, a_gs=a_gs, b_gs=N * K, out_gs=T * N,
                  epi=epi, bias=bias, bias_gs=N, resid=resid, ldr=N, resid_gs=T * N, aux=aux, ldaux=N, aux_gs=T * N)
 
-    def _dgrad(self, dy, w, out, *, G, T, N, K, epi=EPI_NONE, aux=None):
-        """dX[T,K] = dY[T,N] W[N,K]."""
+    def _dgrad(self, dy, w, out, *, G, T, N, K, epi=EPI_NONE, aux=None, bias=None, resid=None):
+        """dX[T,K] = dY[T,N] W[N,K] (+ epilogue: EPI_BIAS_RESID adds an fp32 gradient stream, `bias` then is a zero vector)."""
         ops.gemm(dy, w, out, M=T, N=K, K=N, groups=G, a_mn=False, b_mn=True, lda=N, ldb=K, ldo=K, a_gs=T * N,
-                 b_gs=N * K, out_gs=T * K, epi=epi, aux=aux, ldaux=K, aux_gs=T * K)
+                 b_gs=N * K, out_gs=T * K, epi=epi, aux=aux, ldaux=K, aux_gs=T * K, bias=bias, bias_gs=K, resid=resid,
+                 ldr=K, resid_gs=T * K)
 
     def _wgrad(self, dy, x, dw, *, G, T, N, K, ldx=None, x_gs=None):
         """dW[N,K] = dY[T,N]^T X[T,K] (fp32, written into the flat gradient buffer)."""
@@ -426,13 +538,27 @@ class Engine:
         """Validates inputs, then runs the forward kernel sequence (eagerly, or by replaying its CUDA graph).
         drop: apply the configured dropout (module in training mode with dropout > 0)."""
         cfg = self.cfg
-        if img.dim() != 6 or img.shape[1] != self.Mimg or tuple(img.shape[3:]) != tuple(cfg.img_size) or img.shape[2] != 1:
-            raise _abi.CavitError(f"img must be [B, {self.Mimg}, 1, {tuple(cfg.img_size)}], got {tuple(img.shape)}")
         if img.dtype != F32 or not img.is_cuda:
             raise _abi.CavitError("img must be a float32 CUDA tensor")
+        if self.kind == "cnnvit":     # stem feature maps [M*B, Cin, A, Bd, Cd] (modality-major), float targets
+            want = (cfg.in_channels,) + tuple(cfg.feat_dims)
+            if img.dim() != 5 or tuple(img.shape[1:]) != want or img.shape[0] % self.Mimg:
+                raise _abi.CavitError(f"feature maps must be [{self.Mimg}*B, {want}], got {tuple(img.shape)}")
+            B = img.shape[0] // self.Mimg
+            labels = labels.to(device=self.device, dtype=F32).contiguous()
+        elif self.kind == "vit3d":    # stem features of all modalities on the token axis, channel-major [B, C, M*S]
+            if img.dim() != 3 or img.shape[1] != self.C or img.shape[2] != self.N - 1:
+                raise _abi.CavitError(f"features must be [B, {self.C}, {self.N - 1}], got {tuple(img.shape)}")
+            B = img.shape[0]
+            labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
+        else:
+            if img.dim() != 6 or img.shape[1] != self.Mimg or tuple(img.shape[3:]) != tuple(cfg.img_size) or img.shape[2] != 1:
+                raise _abi.CavitError(f"img must be [B, {self.Mimg}, 1, {tuple(cfg.img_size)}], got {tuple(img.shape)}")
+            B = img.shape[0]
+            labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
         img = img.contiguous()
-        labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
-        B = img.shape[0]
+        if labels.numel() != B:
+            raise _abi.CavitError(f"labels must have {B} entries, got {labels.numel()}")
         drop = bool(drop and self.p_drop > 0.0)
         self._plan(B, train, drop)
         self.drop = drop
@@ -467,18 +593,30 @@ class Engine:
 
     def _forward_impl(self, img: torch.Tensor, labels: torch.Tensor, train: bool, force_cast: bool = False):
         cfg = self.cfg
-        B = img.shape[0]
+        B = self.B       # (the leading axis of `img` is modality x sample for the CNN-stem ViT)
         if force_cast:   # inside a graph the operand refresh is unconditional
             ops.cast_bf16(self.flat, self.flat_bf16)
         else:
             self.refresh_operands()
         a, G, N, C, F, H, T, K = self.a, self.G, self.N, self.C, self.F, self.H, self.T, self.K
+        if self.post_norm:
+            return self._forward_post(img, labels, train)
         # ---- tokenisation: unfold -> embedding GEMM (+bias +pos, CLS-skipping row map) -> CLS rows
-        ops.patchify(img, a["patches"], patch_size=cfg.patch_size, sample_major=(self.kind == "vit"))
         np_seq = self.N - 1
         X0 = a["X"][0]
+        if self.kind == "cnnvit":
+            # Conv3d(k = stride) patch embedding of the stem's feature maps (model.py:84,95-105,258): every modality gets
+            # the SAME positional rows 1.., the CLS row exists once -> positional table expanded to the token axis
+            ops.conv_patch_rows(img, a["patches"], M=self.Mimg, B=B, Cin=cfg.in_channels, dims=cfg.feat_dims, grid=cfg.grid)
+            pos = a["pos_exp"]
+            for m in range(self.Mimg):
+                ops.gather_rows_f32(self.w("pos")[1:], pos[1 + m * self.Np:], rows=self.Np, C_=C, groups=1,
+                                    src_row_stride=C, src_gs=0, dst_row_stride=C, dst_gs=0)
+        else:
+            ops.patchify(img, a["patches"], patch_size=cfg.patch_size, sample_major=(self.kind == "vit"))
+            pos = self.w("pos")
         ops.gemm(a["patches"], self.wb("embed.w"), X0, M=self.Mimg * B * self.Np, N=C, K=self.P, lda=self.P,
-                 ldb=self.P, ldo=C, epi=EPI_EMBED, bias=self.w("embed.b"), resid=self.w("pos"), ldr=C, embed_np=np_seq)
+                 ldb=self.P, ldo=C, epi=EPI_EMBED, bias=self.w("embed.b"), resid=pos, ldr=C, embed_np=np_seq)
         ops.cls_rows(self.w("cls"), self.w("pos"), X0, M=G, B=B, N=N, C_=C)
         drop = self.drop
         if drop:   # x = dropout(x) after the positional add (model_cross.py:198)
@@ -493,8 +631,12 @@ class Engine:
                 xi = (xi + 2) % 3
             tag = f"L{l}"
             ops.ln_fwd(x_in, self.w(f"{tag}.ln1.w"), self.w(f"{tag}.ln1.b"), a["xn1"][s], a["mean1"][s], a["rstd1"][s],
-                       rows_per_group=T, groups=G, C=C)
-            self._fwd(a["xn1"][s], self.wb(f"{tag}.wqkv"), a["qkv"][s], G=G, T=T, N=3 * C, K=C)
+                       rows_per_group=T, groups=G, C=C, eps=self.eps)
+            if self.qkv_bias:   # model.py:118-120: query / key / value are biased Linears
+                self._fwd(a["xn1"][s], self.wb(f"{tag}.wqkv"), a["qkv"][s], G=G, T=T, N=3 * C, K=C, epi=EPI_BIAS,
+                          bias=self.w(f"{tag}.bqkv"))
+            else:
+                self._fwd(a["xn1"][s], self.wb(f"{tag}.wqkv"), a["qkv"][s], G=G, T=T, N=3 * C, K=C)
             ops.attn_fwd(a["qkv"][s], a["ao"][s], a["lse"][s], G=G, B=B, N=N, H=H, scale=self.scale)
             if H != 1 and drop:   # to_out = Linear, Dropout: x_mid = x_in + D(ao Wo^T + bo)
                 self._fwd(a["ao"][s], self.wb(f"{tag}.wo"), a["br"], G=G, T=T, N=C, K=C, epi=EPI_BIAS, bias=self.w(f"{tag}.bo"))
@@ -505,7 +647,7 @@ class Engine:
             else:  # to_out = nn.Identity() when heads == 1 (model_cross.py:37,44-48): no projection, no dropout
                 ops.add_bf16_f32(x_in, a["ao"][s], x_mid)
             ops.ln_fwd(x_mid, self.w(f"{tag}.ln2.w"), self.w(f"{tag}.ln2.b"), a["xn2"][s], a["mean2"][s], a["rstd2"][s],
-                       rows_per_group=T, groups=G, C=C)
+                       rows_per_group=T, groups=G, C=C, eps=self.eps)
             self._fwd(a["xn2"][s], self.wb(f"{tag}.w1"), a["h"][s], G=G, T=T, N=F, K=C, epi=EPI_BIAS_GELU,
                       bias=self.w(f"{tag}.b1"), aux=a["u"][s])
             if drop:
@@ -519,6 +661,14 @@ class Engine:
                 self._fusion_fwd(l // cfg.num_self_blocks, x_out, train)
         x_fin = a["X"][2 * self.L] if train else a["X"][xi]
         self._x_fin = x_fin
+        if self.kind == "cnnvit":
+            # encoder_norm (eps 1e-6) on the CLS rows, final Linear(C, 1), BCEWithLogits (model.py:202-206,224,273-286)
+            ops.ln_fwd(x_fin, self.w("fin.ln.w"), self.w("fin.ln.b"), None, a["meanc"], a["rstdc"], rows_per_group=B, groups=1,
+                       C=C, x_row_stride=N * C, x_gs=T * C, eps=self.eps, y_f32=a["clsn32"])
+            ops.bce_head_fwd(a["clsn32"], self.w("head.w"), self.w("head.b"), labels, a["logits"], a["loss"], B=B, C_=C)
+            self._labels = labels
+            self.saved_valid = train
+            return a["logits"], a["loss"]
         # ---- final norm on the CLS rows only (row 0 is all the reference consumes), heads, loss
         ops.ln_fwd(x_fin, self.w("fin.ln.w"), self.w("fin.ln.b"), a["clsn"], a["meanc"], a["rstdc"], rows_per_group=B,
                    groups=G, C=C, x_row_stride=N * C, x_gs=T * C)
@@ -664,7 +814,11 @@ class Engine:
                 s, e_ = ranges[tag]
                 on_range_done(tag, s, e_)
 
+        if self.post_norm:
+            return self._backward_post(loss_scale, done, loss_scale_dev)
         ws = a["ln_ws"]
+        if self.kind == "cnnvit":
+            return self._backward_cnnvit(loss_scale, done, loss_scale_dev)
         # ---- loss, heads, final norm
         ops.head_loss_bwd(a["hh"], self.w("head.w2"), self._labels, a["logits"], a["dhh"], self.g("head.w2"),
                           self.g("head.b2"), M=G, B=B, F=F, classes=self.classes, smoothing=self.smoothing,
@@ -683,6 +837,27 @@ class Engine:
                    self.g("fin.ln.b"), ws, rows_per_group=B, groups=G, C=C, x_row_stride=N * C, x_gs=T * C,
                    dx_row_stride=N * C, dx_gs=T * C)
         done("head")
+        self._backward_layers(dX, dXb, done)
+        # ---- embedding: d(pos), d(cls), dW = dY^T unfold(x), db
+        if drop:   # through the embedding dropout; the bf16 copy is rebuilt from the masked gradient
+            self._dropout(ops.DROP_F32, dX, None, dX, self.SITE_EMBED)
+            ops.cast_bf16(dX, dXb)
+        ops.embed_param_grads(dX, self.g("pos"), self.g("cls"), M=G, B=B, N=N, C_=C)
+        np_seq = self.N - 1
+        ops.compact_patch_rows_bf16(dXb, a["dcomp"], S=G * B, Np=np_seq, C_=C)
+        R = self.Mimg * B * self.Np
+        self._wgrad(a["dcomp"], a["patches"], self.g("embed.w"), G=1, T=R, N=C, K=self.P)
+        self._colsum(a["dcomp"], self.g("embed.b"), G=1, T=R, N=C)
+        done("embed")
+        return self.grad
+
+    def _backward_layers(self, dX, dXb, done):
+        """Backward through the pre-norm blocks L-1 .. 0 (and the fusions between them); on return dX / dXb hold the
+        gradient of the token streams after the embedding."""
+        cfg = self.cfg
+        a, G, N, C, F, H, T, K, B = self.a, self.G, self.N, self.C, self.F, self.H, self.T, self.K, self.B
+        ws = a["ln_ws"]
+        drop = self.drop
         need_cast = True  # dXb must mirror dX before the first layer's GEMMs
         b2_done = False   # fc2 bias gradient of this layer already produced by the LayerNorm backward above it
         for l in reversed(range(self.L)):
@@ -730,6 +905,8 @@ class Engine:
                          H=H, scale=self.scale)
             self._dgrad(a["dqkv"], self.wb(f"{tag}.wqkv"), a["dmid"], G=G, T=T, N=3 * C, K=C)
             self._wgrad(a["dqkv"], a["xn1"][l], self.g(f"{tag}.wqkv"), G=G, T=T, N=3 * C, K=C)
+            if self.qkv_bias:
+                self._colsum(a["dqkv"], self.g(f"{tag}.bqkv"), G=G, T=T, N=3 * C)
             # ... and of the layer below's fc2 bias, unless a fusion backward rewrites dX in between
             fusion_next = self.kind == "cross" and K and l % cfg.num_self_blocks == 0
             b2_done = l >= 1 and not drop and not fusion_next
@@ -737,16 +914,151 @@ class Engine:
                        self.g(f"{tag}.ln1.b"), ws, rows_per_group=T, groups=G, C=C, dresid=dX,
                        dx_bf16=None if drop else dXb, dcol=self.g(f"L{l - 1}.b2") if b2_done else None)
             done(tag)
-        # ---- embedding: d(pos), d(cls), dW = dY^T unfold(x), db
-        if drop:   # through the embedding dropout; the bf16 copy is rebuilt from the masked gradient
-            self._dropout(ops.DROP_F32, dX, None, dX, self.SITE_EMBED)
-            ops.cast_bf16(dX, dXb)
-        ops.embed_param_grads(dX, self.g("pos"), self.g("cls"), M=G, B=B, N=N, C_=C)
-        np_seq = self.N - 1
-        ops.compact_patch_rows_bf16(dXb, a["dcomp"], S=G * B, Np=np_seq, C_=C)
-        R = self.Mimg * B * self.Np
+
+    # ------------------------------------------------------------------ ViT (model.py) tail / embedding adjoint
+    def _backward_cnnvit(self, loss_scale, done, loss_scale_dev):
+        """Backward of the `ViT` core (/root/reference/model.py:253-286): BCE tail, encoder_norm on the CLS rows,
+        the pre-norm blocks, the Conv3d(k = stride) patch embedding down to d(stem feature maps)."""
+        cfg = self.cfg
+        a, N, C, T, B = self.a, self.N, self.C, self.T, self.B
+        ws = a["ln_ws"]
+        ops.bce_head_bwd(a["clsn32"], self.w("head.w"), self._labels, a["logits"], a["dclsn32"], self.g("head.w"),
+                         self.g("head.b"), B=B, C_=C, loss_scale=loss_scale, loss_scale_dev=loss_scale_dev)
+        dX, dXb = a["dX"], a["dXb"]
+        dX.zero_()
+        ops.ln_bwd(a["dclsn32"], self._x_fin, a["meanc"], a["rstdc"], self.w("fin.ln.w"), dX, self.g("fin.ln.w"),
+                   self.g("fin.ln.b"), ws, rows_per_group=B, groups=1, C=C, x_row_stride=N * C, x_gs=T * C,
+                   dx_row_stride=N * C, dx_gs=T * C)
+        done("head")
+        self._backward_layers(dX, dXb, done)
+        # positional table: row 0 once, rows 1.. summed over the modalities that shared them (model.py:89,103,258)
+        Np, M = self.Np, self.Mimg
+        ops.embed_param_grads(dX, a["dpos_exp"], self.g("cls"), M=1, B=B, N=N, C_=C)
+        gpos = self.g("pos")
+        ops.gather_rows_f32(a["dpos_exp"], gpos, rows=Np + 1, C_=C, groups=1, src_row_stride=C, src_gs=0, dst_row_stride=C,
+                            dst_gs=0)
+        for m in range(1, M):
+            ops.gather_rows_f32(a["dpos_exp"][1 + m * Np:], gpos[1:], rows=Np, C_=C, groups=1, src_row_stride=C, src_gs=0,
+                                dst_row_stride=C, dst_gs=0, accumulate=True)
+        ops.compact_patch_rows_bf16(dXb, a["dcomp"], S=B, Np=N - 1, C_=C)
+        R = M * B * Np
         self._wgrad(a["dcomp"], a["patches"], self.g("embed.w"), G=1, T=R, N=C, K=self.P)
         self._colsum(a["dcomp"], self.g("embed.b"), G=1, T=R, N=C)
+        # d(feature maps) = unpatchify(dY W): the stem is trainable, so the path does not end at the embedding
+        self._dgrad(a["dcomp"], self.wb("embed.w"), a["drows"], G=1, T=R, N=C, K=self.P)
+        ops.conv_patch_rows_bwd(a["drows"], a["dfeat"], M=M, B=B, Cin=cfg.in_channels, dims=cfg.feat_dims, grid=cfg.grid)
+        self.dinput = a["dfeat"]
+        done("embed")
+        return self.grad
+
+    # ------------------------------------------------------------------ ViT3D (modelv2.py): post-norm encoder
+    def _plan_post(self, a, B, train):
+        dev = self.device
+        N, C, F, H, L = self.N, self.C, self.F, self.H, self.L
+        T = B * N
+        Fh = self.cfg.head_dim_hidden
+
+        def e(shape, dt=F32):
+            return torch.empty(shape, dtype=dt, device=dev)
+
+        nL = L if train else 1
+        a["x0"], a["xa"], a["xb"] = e((1, T, C)), e((1, T, C)), e((1, T, C))
+        a["xin_b"] = [e((1, T, C), BF16) for _ in range(nL + 1 if train else 2)]   # bf16 layer inputs (wgrad operands)
+        for nm, shp, dt in [("qkv", (1, T, 3 * C), BF16), ("ao", (1, T, C), BF16), ("lse", (1, B, H, N), F32),
+                            ("s1", (1, T, C), F32), ("mean1", (1, T), F32), ("rstd1", (1, T), F32), ("x1b", (1, T, C), BF16),
+                            ("h", (1, T, F), BF16), ("s2", (1, T, C), F32), ("mean2", (1, T), F32), ("rstd2", (1, T), F32)]:
+            a[nm] = [e(shp, dt) for _ in range(nL)]
+        a["zeros"] = torch.zeros(max(3 * C, F), dtype=F32, device=dev)
+        a["clsn"], a["meanc"], a["rstdc"] = e((1, B, C), BF16), e((1, B)), e((1, B))
+        a["hh"] = e((1, B, Fh), BF16)
+        a["logits"], a["loss"] = e((B, self.classes)), e((1,))
+        if train:
+            a["dA"], a["dB"], a["dXb"] = e((1, T, C)), e((1, T, C)), e((1, T, C), BF16)
+            a["dbig"], a["dmid"], a["dqkv"] = e((1, T, F), BF16), e((1, T, C), BF16), e((1, T, 3 * C), BF16)
+            a["delta"], a["dq_acc"] = e((1, B, H, N)), e((1, T, C))
+            a["ln_ws"] = ops.ln_bwd_workspace(1, C, dev)
+            a["dhh"], a["dclsn"] = e((1, B, Fh), BF16), e((1, B, C), BF16)
+            a["dfeat"] = e((B, C, N - 1))
+
+    def _forward_post(self, feat, labels, train):
+        """`ViT3D.forward` from the stem features on (/root/reference/modelv2.py:203-241): token assembly, L post-norm
+        nn.TransformerEncoderLayer blocks  x = LN1(x + SA(x)); x = LN2(x + W2 relu(W1 x + b1) + b2), head on the CLS row."""
+        a, N, C, F, H, T, B = self.a, self.N, self.C, self.F, self.H, self.T, self.B
+        ops.tokens_from_channels(feat, self.w("cls"), self.w("pos"), a["x0"], B=B, C_=C, S=N - 1, has_cls=True)
+        ops.cast_bf16(a["x0"], a["xin_b"][0])
+        x_in = a["x0"]
+        for l in range(self.L):
+            s = l if train else 0
+            tag = f"L{l}"
+            xin_b = a["xin_b"][l if train else l % 2]
+            xout_b = a["xin_b"][l + 1 if train else (l + 1) % 2]
+            self._fwd(xin_b, self.wb(f"{tag}.wqkv"), a["qkv"][s], G=1, T=T, N=3 * C, K=C, epi=EPI_BIAS,
+                      bias=self.w(f"{tag}.bqkv"))
+            ops.attn_fwd(a["qkv"][s], a["ao"][s], a["lse"][s], G=1, B=B, N=N, H=H, scale=self.scale)
+            self._fwd(a["ao"][s], self.wb(f"{tag}.wo"), a["s1"][s], G=1, T=T, N=C, K=C, epi=EPI_BIAS_RESID,
+                      bias=self.w(f"{tag}.bo"), resid=x_in)
+            ops.ln_fwd(a["s1"][s], self.w(f"{tag}.ln1.w"), self.w(f"{tag}.ln1.b"), a["x1b"][s], a["mean1"][s], a["rstd1"][s],
+                       rows_per_group=T, groups=1, C=C, eps=self.eps, y_f32=a["xa"])
+            self._fwd(a["x1b"][s], self.wb(f"{tag}.w1"), a["h"][s], G=1, T=T, N=F, K=C, epi=EPI_BIAS_RELU,
+                      bias=self.w(f"{tag}.b1"))
+            self._fwd(a["h"][s], self.wb(f"{tag}.w2"), a["s2"][s], G=1, T=T, N=C, K=F, epi=EPI_BIAS_RESID,
+                      bias=self.w(f"{tag}.b2"), resid=a["xa"])
+            ops.ln_fwd(a["s2"][s], self.w(f"{tag}.ln2.w"), self.w(f"{tag}.ln2.b"), xout_b, a["mean2"][s], a["rstd2"][s],
+                       rows_per_group=T, groups=1, C=C, eps=self.eps, y_f32=a["xb"])
+            x_in = a["xb"]
+        self._x_fin = x_in
+        Fh = self.cfg.head_dim_hidden
+        ops.ln_fwd(x_in, self.w("fin.ln.w"), self.w("fin.ln.b"), a["clsn"], a["meanc"], a["rstdc"], rows_per_group=B, groups=1,
+                   C=C, x_row_stride=N * C, x_gs=T * C, eps=1e-5)
+        self._fwd(a["clsn"], self.wb("head.w1"), a["hh"], G=1, T=B, N=Fh, K=C, epi=EPI_BIAS, bias=self.w("head.b1"))
+        ops.head_loss_fwd(a["hh"], self.w("head.w2"), self.w("head.b2"), labels, a["logits"], a["loss"], M=1, B=B, F=Fh,
+                          classes=self.classes, smoothing=self.smoothing)
+        self._labels = labels
+        self.saved_valid = train
+        return a["logits"], a["loss"]
+
+    def _backward_post(self, loss_scale, done, loss_scale_dev):
+        a, N, C, F, H, T, B = self.a, self.N, self.C, self.F, self.H, self.T, self.B
+        ws, zeros = a["ln_ws"], a["zeros"]
+        Fh = self.cfg.head_dim_hidden
+        ops.head_loss_bwd(a["hh"], self.w("head.w2"), self._labels, a["logits"], a["dhh"], self.g("head.w2"),
+                          self.g("head.b2"), M=1, B=B, F=Fh, classes=self.classes, smoothing=self.smoothing,
+                          loss_scale=loss_scale, loss_scale_dev=loss_scale_dev)
+        self._dgrad(a["dhh"], self.wb("head.w1"), a["dclsn"], G=1, T=B, N=Fh, K=C)
+        self._wgrad(a["dhh"], a["clsn"], self.g("head.w1"), G=1, T=B, N=Fh, K=C)
+        self._colsum(a["dhh"], self.g("head.b1"), G=1, T=B, N=Fh)
+        dA, dB, dXb = a["dA"], a["dB"], a["dXb"]
+        dA.zero_()
+        ops.ln_bwd(a["dclsn"], self._x_fin, a["meanc"], a["rstdc"], self.w("fin.ln.w"), dA, self.g("fin.ln.w"),
+                   self.g("fin.ln.b"), ws, rows_per_group=B, groups=1, C=C, x_row_stride=N * C, x_gs=T * C,
+                   dx_row_stride=N * C, dx_gs=T * C)
+        done("head")
+        for l in reversed(range(self.L)):
+            tag = f"L{l}"
+            # x2 = LN2(s2): dA = d(x2) (fp32) -> dB = d(s2), dXb its bf16 copy, column sums = d(b2)
+            ops.ln_bwd(dA, a["s2"][l], a["mean2"][l], a["rstd2"][l], self.w(f"{tag}.ln2.w"), dB, self.g(f"{tag}.ln2.w"),
+                       self.g(f"{tag}.ln2.b"), ws, rows_per_group=T, groups=1, C=C, dx_bf16=dXb, dcol=self.g(f"{tag}.b2"))
+            self._dgrad(dXb, self.wb(f"{tag}.w2"), a["dbig"], G=1, T=T, N=C, K=F, epi=EPI_RELU_BWD, aux=a["h"][l])
+            self._wgrad(dXb, a["h"][l], self.g(f"{tag}.w2"), G=1, T=T, N=C, K=F)
+            # d(x1) = d(s2) + d(u) W1  (residual add fused into the dgrad epilogue, fp32)
+            self._dgrad(a["dbig"], self.wb(f"{tag}.w1"), dA, G=1, T=T, N=F, K=C, epi=EPI_BIAS_RESID, bias=zeros, resid=dB)
+            self._wgrad(a["dbig"], a["x1b"][l], self.g(f"{tag}.w1"), G=1, T=T, N=F, K=C)
+            self._colsum(a["dbig"], self.g(f"{tag}.b1"), G=1, T=T, N=F)
+            # x1 = LN1(s1): dA = d(x1) -> dB = d(s1), column sums = d(out_proj.bias)
+            ops.ln_bwd(dA, a["s1"][l], a["mean1"][l], a["rstd1"][l], self.w(f"{tag}.ln1.w"), dB, self.g(f"{tag}.ln1.w"),
+                       self.g(f"{tag}.ln1.b"), ws, rows_per_group=T, groups=1, C=C, dx_bf16=dXb, dcol=self.g(f"{tag}.bo"))
+            self._dgrad(dXb, self.wb(f"{tag}.wo"), a["dmid"], G=1, T=T, N=C, K=C)
+            self._wgrad(dXb, a["ao"][l], self.g(f"{tag}.wo"), G=1, T=T, N=C, K=C)
+            ops.attn_bwd(a["qkv"][l], a["ao"][l], a["dmid"], a["lse"][l], a["dqkv"], a["delta"], a["dq_acc"], G=1, B=B, N=N,
+                         H=H, scale=self.scale)
+            self._wgrad(a["dqkv"], a["xin_b"][l], self.g(f"{tag}.wqkv"), G=1, T=T, N=3 * C, K=C)
+            self._colsum(a["dqkv"], self.g(f"{tag}.bqkv"), G=1, T=T, N=3 * C)
+            # d(x_in) = d(s1) + d(qkv) Wqkv
+            self._dgrad(a["dqkv"], self.wb(f"{tag}.wqkv"), dA, G=1, T=T, N=3 * C, K=C, epi=EPI_BIAS_RESID, bias=zeros, resid=dB)
+            done(tag)
+        ops.embed_param_grads(dA, self.g("pos"), self.g("cls"), M=1, B=B, N=N, C_=C)
+        ops.tokens_to_channels(dA, a["dfeat"], B=B, C_=C, S=N - 1, has_cls=True)
+        self.dinput = a["dfeat"]
         done("embed")
         return self.grad
 

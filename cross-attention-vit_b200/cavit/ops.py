@@ -9,8 +9,8 @@ from typing import Optional
 import torch
 
 from . import _abi
-from ._abi import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_EMBED, EPI_GELU_BWD, EPI_NONE, GemmArgs,
-                   check, lib)
+from ._abi import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_EMBED, EPI_GELU_BWD, EPI_NONE,
+                   EPI_RELU_BWD, GemmArgs, check, lib)
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -71,9 +71,16 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulat
                 b_gs=T * K, out_gs=N * K, accumulate=accumulate, split_k=split_k)
 
 
-def ln_fwd(x, gamma, beta, y, mean, rstd, *, rows_per_group, groups, C, x_row_stride=None, x_gs=None, eps=1e-5):
+def ln_fwd(x, gamma, beta, y, mean, rstd, *, rows_per_group, groups, C, x_row_stride=None, x_gs=None, eps=1e-5,
+           y_f32=None):
+    """y: bf16 rows (may be None when y_f32 is given); y_f32: optional fp32 copy (cavit_ln_fwd_dual)."""
     x_row_stride = C if x_row_stride is None else x_row_stride
     x_gs = rows_per_group * x_row_stride if x_gs is None else x_gs
+    if y_f32 is not None or y is None:
+        check(lib().cavit_ln_fwd_dual(x.data_ptr(), x_row_stride, x_gs, rows_per_group, groups, C, gamma.data_ptr(),
+                                      beta.data_ptr(), eps, _p(y), _p(y_f32), mean.data_ptr(), rstd.data_ptr(), _stream()),
+              "cavit_ln_fwd_dual")
+        return
     check(lib().cavit_ln_fwd(x.data_ptr(), x_row_stride, x_gs, rows_per_group, groups, C, gamma.data_ptr(),
                              beta.data_ptr(), eps, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _stream()),
           "cavit_ln_fwd")
@@ -90,7 +97,8 @@ def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, partials, *, rows_per_gr
     x_gs = rows_per_group * x_row_stride if x_gs is None else x_gs
     dx_row_stride = C if dx_row_stride is None else dx_row_stride
     dx_gs = rows_per_group * dx_row_stride if dx_gs is None else dx_gs
-    check(lib().cavit_ln_bwd(dy.data_ptr(), x.data_ptr(), x_row_stride, x_gs, mean.data_ptr(), rstd.data_ptr(),
+    fn = lib().cavit_ln_bwd_f32 if dy.dtype == F32 else lib().cavit_ln_bwd   # fp32 dy: post-norm residual-stream gradient
+    check(fn(dy.data_ptr(), x.data_ptr(), x_row_stride, x_gs, mean.data_ptr(), rstd.data_ptr(),
                              gamma.data_ptr(), rows_per_group, groups, C, _p(dresid), dx.data_ptr(), dx_row_stride,
                              dx_gs, _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(), _p(dcol), partials.data_ptr(),
                              _stream()), "cavit_ln_bwd")
@@ -227,6 +235,45 @@ def compact_patch_rows_bf16(src, dst, *, S, Np, C_):
           "cavit_compact_patch_rows_bf16")
 
 
+def tokens_from_channels(feat, cls, pos, tokens, *, B, C_, S, has_cls=True):
+    check(lib().cavit_tokens_from_channels(feat.data_ptr(), _p(cls), pos.data_ptr(), tokens.data_ptr(), B, C_, S,
+                                           int(has_cls), _stream()), "cavit_tokens_from_channels")
+
+
+def tokens_to_channels(dtokens, dfeat, *, B, C_, S, has_cls=True):
+    check(lib().cavit_tokens_to_channels(dtokens.data_ptr(), dfeat.data_ptr(), B, C_, S, int(has_cls), _stream()),
+          "cavit_tokens_to_channels")
+
+
+def conv_patch_rows(feat, rows, *, M, B, Cin, dims, grid):
+    check(lib().cavit_conv_patch_rows(feat.data_ptr(), rows.data_ptr(), M, B, Cin, dims[0], dims[1], dims[2], grid[0],
+                                      grid[1], grid[2], _stream()), "cavit_conv_patch_rows")
+
+
+def conv_patch_rows_bwd(drows, dfeat, *, M, B, Cin, dims, grid):
+    check(lib().cavit_conv_patch_rows_bwd(drows.data_ptr(), dfeat.data_ptr(), M, B, Cin, dims[0], dims[1], dims[2],
+                                          grid[0], grid[1], grid[2], _stream()), "cavit_conv_patch_rows_bwd")
+
+
+def bce_head_fwd(x, w, b0, targets, logits, loss, *, B, C_):
+    check(lib().cavit_bce_head_fwd(x.data_ptr(), w.data_ptr(), b0.data_ptr(), _p(targets), logits.data_ptr(), _p(loss),
+                                   B, C_, _stream()), "cavit_bce_head_fwd")
+
+
+def bce_head_bwd(x, w, targets, logits, dx, dw, db, *, B, C_, loss_scale=1.0, loss_scale_dev=None):
+    check(lib().cavit_bce_head_bwd(x.data_ptr(), w.data_ptr(), targets.data_ptr(), logits.data_ptr(), loss_scale,
+                                   _p(loss_scale_dev), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), B, C_, _stream()),
+          "cavit_bce_head_bwd")
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, params_bf16, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+              step, grad_scale=1.0):
+    """Fused Adam over flat fp32 slabs (include/cavit.h: cavit_adam_step)."""
+    check(lib().cavit_adam_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                _p(params_bf16), params.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                                _stream()), "cavit_adam_step")
+
+
 def head_loss_fwd(h, W2, b2, labels, logits, loss, *, M, B, F, classes, smoothing, p_drop=0.0, seed=None, site=0):
     check(lib().cavit_head_loss_fwd(h.data_ptr(), W2.data_ptr(), b2.data_ptr(), labels.data_ptr(), logits.data_ptr(),
                                     loss.data_ptr(), M, B, F, classes, smoothing, p_drop, _p(seed), site, _stream()),
@@ -272,5 +319,6 @@ def _instrument(name, fn):
 for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_fwd", "attn_bwd", "xattn_fwd", "xattn_bwd",
            "patchify", "cls_rows", "embed_param_grads", "cast_bf16", "colsum_bf16", "gather_rows_f32", "add_bf16_f32",
            "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout", "xfold_fwd", "xfold_bwd",
-           "expand_heads", "fold_heads"):
+           "expand_heads", "fold_heads", "tokens_from_channels", "tokens_to_channels", "conv_patch_rows",
+           "conv_patch_rows_bwd", "bce_head_fwd", "bce_head_bwd", "adam_step"):
     globals()[_n] = _instrument(_n, globals()[_n])

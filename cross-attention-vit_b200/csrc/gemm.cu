@@ -114,12 +114,12 @@ struct EpiLane {
 template <int EPI>
 struct EpiPre {
   float4 r[(EPI == CAVIT_EPI_BIAS_RESID) ? 8 : 1];
-  uint2 a[(EPI == CAVIT_EPI_GELU_BWD) ? 8 : 1];
+  uint2 a[(EPI == CAVIT_EPI_GELU_BWD || EPI == CAVIT_EPI_RELU_BWD) ? 8 : 1];
 };
 
 template <int EPI>
 __device__ __forceinline__ void epi_prefetch(const EpiLane& L, int col, EpiPre<EPI>& pre) {
-  if (EPI != CAVIT_EPI_BIAS_RESID && EPI != CAVIT_EPI_GELU_BWD) return;
+  if (EPI != CAVIT_EPI_BIAS_RESID && EPI != CAVIT_EPI_GELU_BWD && EPI != CAVIT_EPI_RELU_BWD) return;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     if (it * 4 < L.rows_left) {
@@ -142,7 +142,7 @@ __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const 
   }
   float2 b01 = make_float2(0.f, 0.f), b23 = make_float2(0.f, 0.f);
   constexpr bool kBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID ||
-                          EPI == CAVIT_EPI_EMBED);
+                          EPI == CAVIT_EPI_EMBED || EPI == CAVIT_EPI_BIAS_RELU);
   if (kBias) {   // loaded by the caller before the accumulator wait (an L2 round trip per chunk otherwise)
     b01 = make_float2(bias4.x, bias4.y);
     b23 = make_float2(bias4.z, bias4.w);
@@ -165,6 +165,13 @@ __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const 
       } else if (EPI == CAVIT_EPI_GELU_BWD) {
         v01 = mul2(v01, gelu_grad_pair(unpack_bf16_fast(pre.a[it].x)));
         v23 = mul2(v23, gelu_grad_pair(unpack_bf16_fast(pre.a[it].y)));
+      } else if (EPI == CAVIT_EPI_BIAS_RELU) {   // nn.TransformerEncoderLayer's default activation (modelv2.py:72-78)
+        v01 = make_float2(fmaxf(v01.x, 0.f), fmaxf(v01.y, 0.f));
+        v23 = make_float2(fmaxf(v23.x, 0.f), fmaxf(v23.y, 0.f));
+      } else if (EPI == CAVIT_EPI_RELU_BWD) {    // dY * [h > 0] with h = relu(u) as stored by the forward
+        const float2 h01 = unpack_bf16_fast(pre.a[it].x), h23 = unpack_bf16_fast(pre.a[it].y);
+        v01 = make_float2(h01.x > 0.f ? v01.x : 0.f, h01.y > 0.f ? v01.y : 0.f);
+        v23 = make_float2(h23.x > 0.f ? v23.x : 0.f, h23.y > 0.f ? v23.y : 0.f);
       } else if (EPI == CAVIT_EPI_BIAS_RESID) {
         v01 = add2(v01, make_float2(pre.r[it].x, pre.r[it].y));
         v23 = add2(v23, make_float2(pre.r[it].z, pre.r[it].w));
@@ -219,6 +226,11 @@ __device__ __noinline__ void epi_chunk_slow(const GemmDev* pp, int g, long long 
     } else if (EPI == CAVIT_EPI_GELU_BWD) {
       const bf16* aux = reinterpret_cast<const bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col;
       for (int i = 0; i < ncols; ++i) v[i] *= gelu_erf_grad(__bfloat162float(aux[i]));
+    } else if (EPI == CAVIT_EPI_BIAS_RELU) {
+      for (int i = 0; i < ncols; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (EPI == CAVIT_EPI_RELU_BWD) {
+      const bf16* aux = reinterpret_cast<const bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col;
+      for (int i = 0; i < ncols; ++i) v[i] = __bfloat162float(aux[i]) > 0.f ? v[i] : 0.f;
     } else if (EPI == CAVIT_EPI_BIAS_RESID || EPI == CAVIT_EPI_EMBED) {
       const float* rp = (EPI == CAVIT_EPI_BIAS_RESID) ? p.resid + (long long)g * p.resid_gs + row * p.ldr + col
                                                       : p.resid + (1 + row % p.embed_np) * p.ldr + col;
@@ -279,7 +291,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
     EpiPre<EPI> pre;
     if (kPrefetch && fast_kind && n0 + 32 <= p.N) epi_prefetch<EPI>(L, n0 + c4 * 4, pre);  // overlaps the tile's mainloop
     constexpr bool kHasBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID ||
-                               EPI == CAVIT_EPI_EMBED);
+                               EPI == CAVIT_EPI_EMBED || EPI == CAVIT_EPI_BIAS_RELU);
     float4 bias4[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -542,6 +554,8 @@ static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d,
   CAVIT_GEMM_CASE(CAVIT_EPI_BIAS_RESID, OUT_F32)
   CAVIT_GEMM_CASE(CAVIT_EPI_GELU_BWD, OUT_BF16)
   CAVIT_GEMM_CASE(CAVIT_EPI_EMBED, OUT_F32)
+  CAVIT_GEMM_CASE(CAVIT_EPI_BIAS_RELU, OUT_BF16)
+  CAVIT_GEMM_CASE(CAVIT_EPI_RELU_BWD, OUT_BF16)
 #undef CAVIT_GEMM_CASE
   return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_gemm: epilogue %d with output mode %d is not instantiated", d.epi, out);
 }
@@ -562,13 +576,14 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   const int a_inner = a->a_mn ? a->M : a->K, b_inner = a->b_mn ? a->N : a->K;
   if ((a_inner % 8) || (b_inner % 8))
     return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_gemm: contiguous extent must be a multiple of 8 (A %d, B %d)", a_inner, b_inner);
-  if (a->epi < CAVIT_EPI_NONE || a->epi > CAVIT_EPI_EMBED) return fail(CAVIT_E_BADARG, "cavit_gemm: bad epilogue %d", a->epi);
-  if ((a->epi == CAVIT_EPI_BIAS_GELU || a->epi == CAVIT_EPI_GELU_BWD) && !a->aux)
+  if (a->epi < CAVIT_EPI_NONE || a->epi > CAVIT_EPI_RELU_BWD) return fail(CAVIT_E_BADARG, "cavit_gemm: bad epilogue %d", a->epi);
+  if ((a->epi == CAVIT_EPI_BIAS_GELU || a->epi == CAVIT_EPI_GELU_BWD || a->epi == CAVIT_EPI_RELU_BWD) && !a->aux)
     return fail(CAVIT_E_BADARG, "cavit_gemm: epilogue %d needs aux", a->epi);
   if ((a->epi == CAVIT_EPI_BIAS_RESID || a->epi == CAVIT_EPI_EMBED) && (!a->resid || !a->out_fp32))
     return fail(CAVIT_E_BADARG, "cavit_gemm: residual epilogues need resid and fp32 out");
   if (a->epi == CAVIT_EPI_EMBED && a->embed_np <= 0) return fail(CAVIT_E_BADARG, "cavit_gemm: embed_np");
-  if ((a->epi == CAVIT_EPI_BIAS || a->epi == CAVIT_EPI_BIAS_GELU || a->epi == CAVIT_EPI_BIAS_RESID || a->epi == CAVIT_EPI_EMBED) && !a->bias)
+  if ((a->epi == CAVIT_EPI_BIAS || a->epi == CAVIT_EPI_BIAS_GELU || a->epi == CAVIT_EPI_BIAS_RESID || a->epi == CAVIT_EPI_EMBED ||
+       a->epi == CAVIT_EPI_BIAS_RELU) && !a->bias)
     return fail(CAVIT_E_BADARG, "cavit_gemm: epilogue %d needs bias", a->epi);
   if (a->accumulate && !a->out_fp32) return fail(CAVIT_E_BADARG, "cavit_gemm: accumulate needs fp32 out");
   if (a->split_k > 1 && (!a->out_fp32 || a->epi != CAVIT_EPI_NONE))

@@ -52,7 +52,7 @@ template <int NV>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, int rows_per_group, int groups, int C,
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, bf16* __restrict__ y,
-              float* __restrict__ mean, float* __restrict__ rstd, const RowMap rm) {
+              float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd, const RowMap rm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)rows_per_group * groups;
   const int C4 = C >> 2;
@@ -92,10 +92,16 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
       const int c4 = lane + 32 * i;
       if (c4 < C4) {
         const float4 gm = __ldg(g4 + c4), bt = __ldg(b4 + c4);
-        uint2 o;
-        o.x = pack_bf16((v[i].x - mu) * rs * gm.x + bt.x, (v[i].y - mu) * rs * gm.y + bt.y);
-        o.y = pack_bf16((v[i].z - mu) * rs * gm.z + bt.z, (v[i].w - mu) * rs * gm.w + bt.w);
-        yr[c4] = o;
+        const float4 f = make_float4((v[i].x - mu) * rs * gm.x + bt.x, (v[i].y - mu) * rs * gm.y + bt.y,
+                                     (v[i].z - mu) * rs * gm.z + bt.z, (v[i].w - mu) * rs * gm.w + bt.w);
+        if (y) {
+          uint2 o;
+          o.x = pack_bf16(f.x, f.y);
+          o.y = pack_bf16(f.z, f.w);
+          yr[c4] = o;
+        }
+        // post-norm encoders (modelv2.py:72-78): the normalised row IS the next residual stream, kept in fp32
+        if (y32) reinterpret_cast<float4*>(y32 + row * C)[c4] = f;
       }
     }
     if (lane == 0) {
@@ -109,9 +115,9 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
 // COL: also accumulate the column sums of the OUTPUT gradient (dx incl. the residual term): that is the bias gradient
 // of the Linear layer that produced this LayerNorm's input (out-proj / fc2), so no separate pass over dx is needed.
 // The block that takes the last ticket of its group reduces the partial rows (no separate finalize launch).
-template <int NV, bool COL>
+template <int NV, bool COL, bool DYF>
 __global__ void __launch_bounds__(LN_THREADS, 2)
-ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long long row_stride, long long gs,
+ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long long row_stride, long long gs,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               int rows_per_group, int C, const float* dresid, float* dx, long long dx_row_stride, long long dx_gs,
               bf16* __restrict__ dx_bf16, float* __restrict__ partials, unsigned int* __restrict__ tickets,
@@ -133,7 +139,9 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
   for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows_per_group; r += (long long)gridDim.x * LN_WARPS) {
     const long long row = (long long)g * rows_per_group + r;
     const float4* xr = reinterpret_cast<const float4*>(src_row(rm, x, g, r, row_stride, gs, C));
-    const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * C);
+    // DYF: the incoming gradient is the fp32 residual-stream gradient itself (post-norm encoders), else a bf16 dgrad output
+    const uint2* dyr = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + row * C);
+    const float4* dyf = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * C);
     const float4* dyc = nullptr;  // extra fp32 gradient on the CLS row of a fusion
     if (rm.fusion && rm.dy_cls && (r % rm.N) == 0)
       dyc = reinterpret_cast<const float4*>(rm.dy_cls + ((long long)g * rm.B + r / rm.N) * C);
@@ -141,14 +149,15 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
     if (rm.fusion) doff = fusion_dst_offset(rm, g, r, row_stride, gs);  // scatter back into the donor stream
     else doff = (long long)g * dx_gs + r * dx_row_stride;
     // issue every load of the row up front (x, dy, residual gradient) before the reductions
-    float4 xv[NV], dr[NV];
-    uint2 d2[NV];
+    float4 xv[NV], dr[NV], d4[DYF ? NV : 1];
+    uint2 d2[DYF ? 1 : NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
       if (c4 < C4) {
         xv[i] = __ldg(xr + c4);
-        d2[i] = __ldg(dyr + c4);
+        if (DYF) d4[DYF ? i : 0] = __ldg(dyf + c4);
+        else d2[DYF ? 0 : i] = __ldg(dyr + c4);
         if (!rm.fusion && dresid) dr[i] = *(reinterpret_cast<const float4*>(dresid + doff) + c4);
         else dr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -160,7 +169,9 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, long lon
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
       if (c4 < C4) {
-        float2 d01 = unpack_bf16(d2[i].x), d23 = unpack_bf16(d2[i].y);
+        float2 d01, d23;
+        if (DYF) { d01 = make_float2(d4[DYF ? i : 0].x, d4[DYF ? i : 0].y); d23 = make_float2(d4[DYF ? i : 0].z, d4[DYF ? i : 0].w); }
+        else { d01 = unpack_bf16(d2[DYF ? 0 : i].x); d23 = unpack_bf16(d2[DYF ? 0 : i].y); }
         if (dyc) {
           const float4 e = __ldg(dyc + c4);
           d01.x += e.x; d01.y += e.y; d23.x += e.z; d23.y += e.w;
@@ -262,7 +273,7 @@ static int blocks_per_group(long long rows, int groups) {
 }
 
 static int ln_fwd_launch(const float* x, long long row_stride, long long gs, int rpg, int groups, int C,
-                         const float* gamma, const float* beta, float eps, void* y, float* mean, float* rstd,
+                         const float* gamma, const float* beta, float eps, void* y, float* y32, float* mean, float* rstd,
                          const RowMap& rm, cudaStream_t st) {
   if (C % 4 || C <= 0 || C > 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm: C=%d (need C %% 4 == 0, C <= 1024)", C);
   if ((row_stride % 4) || (gs % 4)) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm: strides must be multiples of 4");
@@ -275,7 +286,7 @@ static int ln_fwd_launch(const float* x, long long row_stride, long long gs, int
 #define LN_FWD_CASE(NVV)                                                                                      \
   case NVV:                                                                                                   \
     ln_fwd_kernel<NVV><<<(int)blocks, LN_THREADS, 0, st>>>(x, row_stride, gs, rpg, groups, C, gamma, beta, eps, \
-                                                           reinterpret_cast<bf16*>(y), mean, rstd, rm);       \
+                                                           reinterpret_cast<bf16*>(y), y32, mean, rstd, rm);  \
     break;
   switch (nv) {
     LN_FWD_CASE(1) LN_FWD_CASE(2) LN_FWD_CASE(3) LN_FWD_CASE(4) LN_FWD_CASE(5) LN_FWD_CASE(6) LN_FWD_CASE(7) LN_FWD_CASE(8)
@@ -289,7 +300,7 @@ static int ln_fwd_launch(const float* x, long long row_stride, long long gs, int
 static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, long long gs, const float* mean,
                          const float* rstd, const float* gamma, int rpg, int groups, int C, const float* dresid,
                          float* dx, long long dx_rs, long long dx_gs, void* dx_bf16, float* dgamma, float* dbeta,
-                         float* dcol, float* partials, const RowMap& rm, cudaStream_t st) {
+                         float* dcol, float* partials, const RowMap& rm, cudaStream_t st, bool dy_f32 = false) {
   if (C % 4 || C <= 0 || C > 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: C=%d", C);
   if ((row_stride % 4) || (gs % 4) || (dx_rs % 4) || (dx_gs % 4))
     return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: strides must be multiples of 4");
@@ -299,24 +310,21 @@ static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, l
   const int nv = (C / 4 + 31) / 32;
   if (dcol && rm.fusion) return fail(CAVIT_E_BADARG, "layernorm bwd: dcol is not available on the fusion row map");
   unsigned int* tickets = reinterpret_cast<unsigned int*>(partials + (size_t)groups * LN_MAX_BLOCKS_PER_GROUP * 3 * C);
-#define LN_BWD_CASE(NVV)                                                                                             \
-  case NVV:                                                                                                          \
-    if (dcol)                                                                                                        \
-      ln_bwd_kernel<NVV, true><<<grid, LN_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dy), x, row_stride, gs, mean, rstd, \
-                                                            gamma, rpg, C, dresid, dx, dx_rs, dx_gs,                 \
-                                                            reinterpret_cast<bf16*>(dx_bf16), partials, tickets, dgamma, \
-                                                            dbeta, dcol, rm);                                        \
-    else                                                                                                             \
-      ln_bwd_kernel<NVV, false><<<grid, LN_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(dy), x, row_stride, gs, mean, rstd, \
-                                                             gamma, rpg, C, dresid, dx, dx_rs, dx_gs,                \
-                                                             reinterpret_cast<bf16*>(dx_bf16), partials, tickets, dgamma, \
-                                                             dbeta, dcol, rm);                                       \
+#define LN_BWD_LAUNCH(NVV, COLV, DYFV)                                                                              \
+  ln_bwd_kernel<NVV, COLV, DYFV><<<grid, LN_THREADS, 0, st>>>(dy, x, row_stride, gs, mean, rstd, gamma, rpg, C, dresid, dx, \
+                                                              dx_rs, dx_gs, reinterpret_cast<bf16*>(dx_bf16), partials,   \
+                                                              tickets, dgamma, dbeta, dcol, rm)
+#define LN_BWD_CASE(NVV)                                                    \
+  case NVV:                                                                 \
+    if (dy_f32) { if (dcol) LN_BWD_LAUNCH(NVV, true, true); else LN_BWD_LAUNCH(NVV, false, true); }   \
+    else { if (dcol) LN_BWD_LAUNCH(NVV, true, false); else LN_BWD_LAUNCH(NVV, false, false); }        \
     break;
   switch (nv) {
     LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4) LN_BWD_CASE(5) LN_BWD_CASE(6) LN_BWD_CASE(7) LN_BWD_CASE(8)
     default: return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: C=%d", C);
   }
 #undef LN_BWD_CASE
+#undef LN_BWD_LAUNCH
   count_launch();
   return check_launch("cavit_ln_bwd");
 }
@@ -333,7 +341,17 @@ int cavit_ln_fwd(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t row
   if (!x || !gamma || !beta || !y || !mean || !rstd) return fail(CAVIT_E_BADARG, "cavit_ln_fwd: null pointer");
   RowMap rm{};
   rm.fusion = 0;
-  return ln_fwd_launch(x, x_row_stride, x_gs, rows_per_group, groups, C, gamma, beta, eps, y, mean, rstd, rm,
+  return ln_fwd_launch(x, x_row_stride, x_gs, rows_per_group, groups, C, gamma, beta, eps, y, nullptr, mean, rstd, rm,
+                       as_stream(stream));
+}
+
+int cavit_ln_fwd_dual(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t rows_per_group, int32_t groups,
+                      int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16, float* y_f32, float* mean,
+                      float* rstd, void* stream) {
+  if (!x || !gamma || !beta || (!y_bf16 && !y_f32) || !mean || !rstd) return fail(CAVIT_E_BADARG, "cavit_ln_fwd_dual: null pointer");
+  RowMap rm{};
+  rm.fusion = 0;
+  return ln_fwd_launch(x, x_row_stride, x_gs, rows_per_group, groups, C, gamma, beta, eps, y_bf16, y_f32, mean, rstd, rm,
                        as_stream(stream));
 }
 
@@ -352,6 +370,17 @@ int cavit_ln_bwd(const void* dy, const float* x, int64_t x_row_stride, int64_t x
                        dx_row_stride, dx_gs, dx_bf16, dgamma, dbeta, dcol, partials, rm, as_stream(stream));
 }
 
+int cavit_ln_bwd_f32(const float* dy_f32, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,
+                     const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
+                     const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_bf16, float* dgamma,
+                     float* dbeta, float* dcol, float* partials, void* stream) {
+  if (!dy_f32 || !x || !mean || !rstd || !gamma || !dx) return fail(CAVIT_E_BADARG, "cavit_ln_bwd_f32: null pointer");
+  RowMap rm{};
+  rm.fusion = 0;
+  return ln_bwd_launch(dy_f32, x, x_row_stride, x_gs, mean, rstd, gamma, rows_per_group, groups, C, dresid, dx,
+                       dx_row_stride, dx_gs, dx_bf16, dgamma, dbeta, dcol, partials, rm, as_stream(stream), true);
+}
+
 int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, const float* x_cls, int32_t B, int32_t N, int32_t C,
                         int32_t K, const int32_t* cls_src, const int32_t* tok_src, const float* gamma, const float* beta,
                         float eps, void* y, float* mean, float* rstd, void* stream) {
@@ -363,7 +392,7 @@ int cavit_ln_fusion_fwd(const float* streams, int64_t stream_gs, const float* x_
   rm.B = B;
   rm.x_cls = x_cls;
   for (int k = 0; k < K; ++k) { rm.cls_src[k] = cls_src[k]; rm.tok_src[k] = tok_src[k]; }
-  return ln_fwd_launch(streams, C, stream_gs, B * N, K, C, gamma, beta, eps, y, mean, rstd, rm, as_stream(stream));
+  return ln_fwd_launch(streams, C, stream_gs, B * N, K, C, gamma, beta, eps, y, nullptr, mean, rstd, rm, as_stream(stream));
 }
 
 int cavit_ln_fusion_bwd(const void* dy, const float* dy_cls, const float* streams, int64_t stream_gs, const float* x_cls,

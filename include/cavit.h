@@ -44,7 +44,9 @@ enum {
   CAVIT_EPI_BIAS_GELU = 2,     /* aux = u = acc + bias (bf16, pre-activation); out = GELU_erf(u) */
   CAVIT_EPI_BIAS_RESID = 3,    /* out = acc + bias[n] + resid[m][n]   (fp32 residual stream) */
   CAVIT_EPI_GELU_BWD = 4,      /* out = acc * GELU'(aux[m][n])        (fc2 dgrad)        */
-  CAVIT_EPI_EMBED = 5          /* out[row_map(m)][n] = acc + bias[n] + pos[1 + m % Np][n] (patch embedding) */
+  CAVIT_EPI_EMBED = 5,         /* out[row_map(m)][n] = acc + bias[n] + pos[1 + m % Np][n] (patch embedding) */
+  CAVIT_EPI_BIAS_RELU = 6,     /* out = max(acc + bias[n], 0)   (nn.TransformerEncoderLayer linear1, modelv2.py:72-78) */
+  CAVIT_EPI_RELU_BWD = 7       /* out = acc * [aux[m][n] > 0]   (aux = the stored relu output; linear2 dgrad) */
 };
 
 int cavit_abi_version(void);
@@ -80,7 +82,7 @@ typedef struct cavit_gemm_args {
   void* out; int64_t ldo, out_gs;
   const float* bias; int64_t bias_gs;               /* [groups][N] fp32 (NULL allowed for EPI_NONE) */
   const float* resid; int64_t ldr, resid_gs;        /* EPI_BIAS_RESID: fp32 [M][N]; EPI_EMBED: pos [1+Np][N] */
-  void* aux; int64_t ldaux, aux_gs;                 /* EPI_BIAS_GELU: bf16 out u; EPI_GELU_BWD: bf16 in u */
+  void* aux; int64_t ldaux, aux_gs;                 /* EPI_BIAS_GELU: bf16 out u; EPI_GELU_BWD: bf16 in u; EPI_RELU_BWD: bf16 in h */
   int32_t accumulate;  /* 1: out (fp32 only) += result */
   int32_t split_k;     /* >1: the K range is split over that many CTAs whose partial tiles are combined with
                           fp32 atomics into `out` (fp32, EPI_NONE only; zeroed by the call unless accumulate).
@@ -112,6 +114,19 @@ int cavit_ln_bwd(const void* dy_bf16, const float* x, int64_t x_row_stride, int6
                  const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
                  const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_bf16,
                  float* dgamma, float* dbeta, float* dcol, float* partials, void* stream);
+
+/* Same as cavit_ln_fwd with an additional (or only) fp32 copy of the normalised rows: in the post-norm
+ * nn.TransformerEncoderLayer of `ViT3D` (/root/reference/modelv2.py:72-78) the LayerNorm output IS the next
+ * residual stream, which stays fp32. Either of y_bf16 / y_f32 may be NULL, not both. Also the eps = 1e-6 norms of
+ * /root/reference/model.py:179-180,202 whose CLS rows feed the fp32 BCE tail. */
+int cavit_ln_fwd_dual(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t rows_per_group, int32_t groups,
+                      int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16, float* y_f32,
+                      float* mean, float* rstd, void* stream);
+/* cavit_ln_bwd whose incoming gradient is fp32 (the gradient of the post-norm residual stream itself). */
+int cavit_ln_bwd_f32(const float* dy_f32, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,
+                     const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
+                     const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_bf16,
+                     float* dgamma, float* dbeta, float* dcol, float* partials, void* stream);
 
 /* Fused gather + LayerNorm for the cross-modal fusion input `cat(cls_i, patches_j)`
  * (/root/reference/model_cross.py:140, 109): row 0 of every sample is read from x_cls[k][b]
@@ -207,6 +222,36 @@ int cavit_embed_param_grads(const float* dtokens, float* dpos, float* dcls, int3
                             int32_t C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Token assembly and tails of the CNN-stem encoders (csrc/enc.cu).
+ * ------------------------------------------------------------------------------------------- */
+/* tokens[b][off + s][c] = feat[b][c][s] + pos[off + s][c], off = has_cls; row 0 = cls + pos[0] when has_cls.
+ * Replaces flatten / cat / transpose / cls cat / `x + self.pos_embed` of ViT3D.forward
+ * (/root/reference/modelv2.py:203-224). feat: fp32 [B][C][S] (the per-modality stem outputs concatenated on the
+ * token axis); pos: fp32 [off + S][C]; tokens: fp32 [B][off + S][C]. */
+int cavit_tokens_from_channels(const float* feat, const float* cls, const float* pos, float* tokens, int32_t B,
+                               int32_t C, int32_t S, int32_t has_cls, void* stream);
+/* Adjoint: dfeat[b][c][s] = dtokens[b][off + s][c] (d(pos), d(cls) come from cavit_embed_param_grads). */
+int cavit_tokens_to_channels(const float* dtokens, float* dfeat, int32_t B, int32_t C, int32_t S, int32_t has_cls,
+                             void* stream);
+/* Conv3d(kernel = stride = grid) patch embedding as a permutation into GEMM rows
+ * (/root/reference/model.py:84,95-100: `patch_embed`, `flatten(-3)`, `transpose(-2,-1)`, modality concat of :258).
+ * feat: fp32 [M*B][Cin][A][Bd][Cd], sample index m*B + b; rows: bf16 [(b*M + m)*Np + t][P] with
+ * t = (a'*Bn + b')*Cn + c' (conv output order) and P index ((cin*g0 + i0)*g1 + i1)*g2 + i2 (= Conv3d weight
+ * flattened over its last four axes). Voxels beyond the last full patch are ignored (zero gradient). */
+int cavit_conv_patch_rows(const float* feat, void* rows_bf16, int32_t M, int32_t B, int32_t Cin, int32_t A, int32_t Bd,
+                          int32_t Cd, int32_t g0, int32_t g1, int32_t g2, void* stream);
+int cavit_conv_patch_rows_bwd(const void* drows_bf16, float* dfeat, int32_t M, int32_t B, int32_t Cin, int32_t A,
+                              int32_t Bd, int32_t Cd, int32_t g0, int32_t g1, int32_t g2, void* stream);
+/* Single-logit tail of `ViT` (/root/reference/model.py:224,279-286): logits[b] = x[b].w + b0,
+ * loss = BCEWithLogitsLoss(mean)(logits, targets). x: fp32 [B][C]; targets fp32 [B] (NULL: logits only).
+ * Backward: dx fp32 [B][C], dw [C], db [1]; upstream gradient as in cavit_head_loss_bwd. */
+int cavit_bce_head_fwd(const float* x, const float* w, const float* b0, const float* targets, float* logits,
+                       float* loss, int32_t B, int32_t C, void* stream);
+int cavit_bce_head_bwd(const float* x, const float* w, const float* targets, const float* logits, float loss_scale,
+                       const float* loss_scale_dev, float* dx, float* dw, float* db, int32_t B, int32_t C,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Small utilities.
  * ------------------------------------------------------------------------------------------- */
 /* dst_bf16[i] = (bf16) src[i] */
@@ -241,6 +286,17 @@ int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, c
                         float loss_scale, const float* loss_scale_dev, void* dh, float* dW2, float* db2, int32_t M,
                         int32_t B, int32_t F, int32_t classes, float smoothing, float p_drop,
                         const uint64_t* seed_dev, uint32_t site, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused Adam step over the flat parameter / gradient slabs (the same slabs the data-parallel all-reduce uses).
+ * Replaces: torch.optim.Adam(self.parameters(), lr, weight_decay).step() of configure_optimizers
+ * (/root/reference/model_cross.py:276-279, modelv3.py:211-214, modelv2.py:280-281, model.py:322-323):
+ *   g = grad_scale * grad + weight_decay * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)
+ * params_bf16 (nullable) receives the refreshed bf16 operand copy in the same pass. n % 4 == 0, step >= 1. */
+int cavit_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dropout (nn.Dropout on the path: model_cross.py:25,27,47,84,86,170,180,182). Masks are counter-based:

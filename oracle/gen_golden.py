@@ -67,5 +67,50 @@ def main():
               f"|logits|={float(l64.norm()):.6f} -> {path} ({os.path.getsize(path)} B)")
 
 
+def build_reference_encoder(name):
+    """Construct the reference's ViT / ViT3D for an encoder case -> (model, state) with the seeded 'test' state loaded."""
+    from oracle import encoders as E
+    kind, _, ctor, B, M, sseed, _ = E.ENC_CASES[name]
+    cfg = E.enc_config(name)
+    rc = ref_loader.ConfigDict()
+    for k, v in vars(cfg).items():
+        setattr(rc, k, dict(vars(v)) if hasattr(v, "__dict__") else v)
+    if kind == "cnnvit":
+        model = ref_loader.load("model").ViT(rc)
+    else:
+        model = ref_loader.load("modelv2").ViT3D({}, 1e-4, 0.0, M, rc, **ctor)
+    schema = {k: (tuple(v.shape), v.dtype) for k, v in model.state_dict().items()}
+    state = E.make_state_generic(schema, sseed)
+    model.load_state_dict(state, strict=True)
+    return model, state
+
+
+def main_encoders():
+    """Golden vectors of the CNN-stem models (model.py ViT, modelv2.py ViT3D), train mode (BatchNorm batch statistics)."""
+    from oracle import encoders as E
+    for name, (kind, *_rest) in E.ENC_CASES.items():
+        x, labels = E.enc_inputs(name)
+        rec = {"case": name, "torch": torch.__version__, "img_checksum": float(x.double().sum())}
+        for dt, tag in ((torch.float64, "64"), (torch.float32, "32")):
+            model, state = build_reference_encoder(name)
+            model = model.to(dt).train()
+            logits, loss = model(x.to(dt), labels.to(dt) if kind == "cnnvit" else labels)
+            loss.backward()
+            rec["logits" + tag], rec["loss" + tag] = logits.detach(), loss.detach()
+            if dt == torch.float64:
+                rec["state_checksum"] = state_checksum({k: v for k, v in state.items() if v.is_floating_point()})
+                rec["schema"] = {k: (tuple(v.shape), v.dtype) for k, v in state.items()}
+                rec["grad_probes"] = {k: grad_probes(k, p.grad, i) for i, (k, p) in enumerate(model.named_parameters())}
+        path = os.path.join(OUT, name + ".pt")
+        torch.save(rec, path)
+        print(f"{name}: loss64={float(rec['loss64']):.12f} loss32={float(rec['loss32']):.8f} -> {path} "
+              f"({os.path.getsize(path)} B)")
+
+
 if __name__ == "__main__":
+    if "--encoders-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        main_encoders()
+        sys.exit(0)
     main()
+    main_encoders()

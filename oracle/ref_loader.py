@@ -66,6 +66,25 @@ def _install_stubs():
         sys.modules["torchmetrics.classification"] = tmc
 
 
+def _install_encoder_stubs():
+    """Extra stubs for model.py / modelv2.py: MONAI's DenseNet121 (only used with
+    pretrained_cnn=True) and the import-time dataset construction of model.py:15,338-344."""
+    if "monai" not in sys.modules:
+        mo, mn, mnn = types.ModuleType("monai"), types.ModuleType("monai.networks"), types.ModuleType("monai.networks.nets")
+        mnn.DenseNet121 = object
+        mo.networks, mn.nets = mn, mnn
+        sys.modules.update({"monai": mo, "monai.networks": mn, "monai.networks.nets": mnn})
+    if "dataset_ucsf" not in sys.modules:
+        ds = types.ModuleType("dataset_ucsf")
+
+        class BrainDataset:
+            def __init__(self, *a, **k):
+                pass
+
+        ds.BrainDataset = BrainDataset
+        sys.modules["dataset_ucsf"] = ds
+
+
 def load(module_name: str):
     """Import `module_name` (e.g. 'model_cross', 'modelv3') from the reference tree."""
     d = reference_dir()
@@ -74,6 +93,15 @@ def load(module_name: str):
     _install_stubs()
     if d not in sys.path:
         sys.path.insert(0, d)
+    if module_name in ("model", "modelv2"):
+        _install_encoder_stubs()
+    if module_name == "model":   # model.py:338 reads labels.csv relative to the working directory at import time
+        cwd = os.getcwd()
+        os.chdir(d)
+        try:
+            return importlib.import_module(module_name)
+        finally:
+            os.chdir(cwd)
     return importlib.import_module(module_name)
 
 

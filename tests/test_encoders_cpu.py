@@ -1,0 +1,106 @@
+"""CPU: the CNN-stem models (`ViT`, model.py; `ViT3D`, modelv2.py) — oracle restatement against the golden vectors frozen
+from the reference, drop-in module schema / init parity, flat layout coverage."""
+import os
+
+import pytest
+import torch
+
+from oracle import encoders as E
+from oracle.cases import grad_probes
+from oracle.weights import state_checksum
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _golden(name):
+    return torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+
+
+def _module(name):
+    from cavit.encoders import ViT, ViT3D
+    kind, _, ctor, B, M, *_ = E.ENC_CASES[name]
+    cfg = E.enc_config(name)
+    return ViT(cfg) if kind == "cnnvit" else ViT3D({}, 1e-4, 0.0, M, cfg, **ctor)
+
+
+@pytest.mark.parametrize("name", list(E.ENC_CASES))
+def test_oracle_matches_reference_golden(name):
+    rec = _golden(name)
+    state = E.make_state_generic(rec["schema"], E.ENC_CASES[name][5])
+    assert abs(state_checksum({k: v for k, v in state.items() if v.is_floating_point()}) - rec["state_checksum"]) < 1e-9
+    x, labels = E.enc_inputs(name)
+    assert abs(float(x.double().sum()) - rec["img_checksum"]) < 1e-9
+    logits, loss, grads = E.enc_forward_backward(name, state, x, labels, torch.float64)
+    assert float((logits - rec["logits64"]).abs().max()) < 1e-11
+    assert abs(float(loss) - float(rec["loss64"])) < 1e-12
+    for i, (k, probe) in enumerate(rec["grad_probes"].items()):
+        mine = grad_probes(k, grads[k], i)
+        assert float((mine - probe).abs().max()) < 1e-9 * max(1.0, float(probe.abs().max())), k
+    # the fp32 reference run sits within the stated fp32 tolerance of the fp64 one
+    assert float((rec["logits32"].double() - rec["logits64"]).abs().max()) < 1e-3 * max(1.0, float(rec["logits64"].abs().max()))
+
+
+@pytest.mark.parametrize("name", list(E.ENC_CASES))
+def test_dropin_schema_and_layout(name):
+    from cavit.engine import build_layout
+    rec = _golden(name)
+    model = _module(name)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(rec["schema"].keys())
+    for k, v in sd.items():
+        assert (tuple(v.shape), v.dtype) == rec["schema"][k], k
+    kind, _, _, _, M, *_ = E.ENC_CASES[name]
+    lay = build_layout(kind, model._engine_cfg(M))
+    owned = {k for k, _ in model.named_parameters() if not k.startswith(model._stem_prefix)}
+    assert set(lay.slots) == owned
+    spans = sorted((off, off + int(torch.tensor(shp).prod())) for off, shp in lay.slots.values())
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    rs = sorted((s, e) for _, s, e in lay.layer_ranges)
+    assert rs[0][0] == 0 and rs[-1][1] == lay.total and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+
+
+def test_same_seed_gives_reference_init_and_outputs():
+    from oracle import ref_loader
+    if ref_loader.reference_dir() is None:
+        pytest.skip("reference tree not present")
+    from oracle.gen_golden import build_reference_encoder
+    for name, (kind, _, ctor, B, M, *_r) in E.ENC_CASES.items():
+        cfg = E.enc_config(name)
+        rc = ref_loader.ConfigDict()
+        for k, v in vars(cfg).items():
+            setattr(rc, k, dict(vars(v)) if hasattr(v, "__dict__") else v)
+        torch.manual_seed(99)
+        ref = ref_loader.load("model").ViT(rc) if kind == "cnnvit" else ref_loader.load("modelv2").ViT3D({}, 1e-4, 0.0, M, rc, **ctor)
+        torch.manual_seed(99)
+        ours = _module(name)
+        rsd, osd = ref.state_dict(), ours.state_dict()
+        assert list(rsd) == list(osd)
+        for k in rsd:
+            assert torch.equal(rsd[k], osd[k]), k
+        # fresh seed: restatement vs the imported reference module
+        model, state = build_reference_encoder(name)
+        x, labels = E.enc_inputs(name)
+        model = model.double().train()
+        lg, ls = model(x.double(), labels.double() if kind == "cnnvit" else labels)
+        l2, s2, _ = E.enc_forward_backward(name, state, x, labels)
+        assert float((lg - l2).abs().max()) < 1e-11 and abs(float(ls) - float(s2)) < 1e-12
+
+
+def test_cpu_forward_fails_loudly():
+    from cavit import CavitError
+    for name in E.ENC_CASES:
+        model = _module(name)
+        x, labels = E.enc_inputs(name)
+        with pytest.raises(CavitError):
+            model(x, labels)
+
+
+def test_unsupported_options_fail_loudly():
+    from cavit import CavitError
+    from cavit.encoders import ViT3D
+    cfg = E.enc_config("vit3d_small")
+    with pytest.raises(CavitError):
+        ViT3D({}, 1e-4, 0.0, 2, cfg, add_cls_token=False)
+    with pytest.raises(CavitError):
+        ViT3D({}, 1e-4, 0.0, 2, cfg, pretrained_cnn=True)
