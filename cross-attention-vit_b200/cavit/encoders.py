@@ -61,6 +61,13 @@ class _EncoderModel(_Base):
     _kind = ""
     _stem_prefix = ""
 
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        eng = self.__dict__.get("_engine_obj")
+        if eng is not None:      # values changed in place: the bf16 operand copy must be re-derived
+            eng._bf16_version = -1
+        return out
+
     def _engine_cfg(self, num_modalities: int) -> SimpleNamespace:
         raise NotImplementedError
 

@@ -302,6 +302,8 @@ class Engine:
         self._grad_idx = 0
         self._bf16_version = -1
         self._frozen = False
+        self.operands_external = False   # cavit.optim.FusedAdam rewrites flat_bf16 itself: no per-forward cast then
+        self.grad = None
         self.adopt_parameters()
         self._plan_key = None
         self.saved_valid = False
@@ -342,6 +344,8 @@ class Engine:
         the caller froze the weights with `freeze_operands()` (inference)."""
         if not self._params_in_place():
             self.adopt_parameters()
+        if self.operands_external and self._bf16_version >= 0:
+            return
         if not self._frozen or self._bf16_version < 0:
             ops.cast_bf16(self.flat, self.flat_bf16)
             self._bf16_version = 1
@@ -566,9 +570,12 @@ class Engine:
             self._new_seed()
         if not self._params_in_place():
             self.adopt_parameters()
+        if self.operands_external and self._bf16_version < 0:   # parameters were (re)loaded behind the optimizer's back
+            ops.cast_bf16(self.flat, self.flat_bf16)
+            self._bf16_version = 1
         if not (self.use_graphs and ops.PROFILE is None):
             return self._forward_impl(img, labels, train)
-        st = self._fwd_graphs.setdefault((B, train, drop), {"runs": 0, "graph": None})
+        st = self._fwd_graphs.setdefault((B, train, drop, self.operands_external), {"runs": 0, "graph": None})
         if st["graph"] is None:
             st["runs"] += 1
             if st["runs"] <= 2:   # eager warm-up: sets kernel attributes, fills the TMA descriptor cache
@@ -594,8 +601,9 @@ class Engine:
     def _forward_impl(self, img: torch.Tensor, labels: torch.Tensor, train: bool, force_cast: bool = False):
         cfg = self.cfg
         B = self.B       # (the leading axis of `img` is modality x sample for the CNN-stem ViT)
-        if force_cast:   # inside a graph the operand refresh is unconditional
-            ops.cast_bf16(self.flat, self.flat_bf16)
+        if force_cast:   # inside a graph the operand refresh is unconditional (unless an optimizer owns the bf16 copy)
+            if not self.operands_external:
+                ops.cast_bf16(self.flat, self.flat_bf16)
         else:
             self.refresh_operands()
         a, G, N, C, F, H, T, K = self.a, self.G, self.N, self.C, self.F, self.H, self.T, self.K

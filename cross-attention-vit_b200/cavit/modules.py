@@ -157,6 +157,13 @@ class _CavitFn(torch.autograd.Function):
 class _CavitModel(_Base):
     _kind = "cross"
 
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        eng = self.__dict__.get("_engine_obj")
+        if eng is not None:      # values changed in place: the bf16 operand copy must be re-derived
+            eng._bf16_version = -1
+        return out
+
     def _post_init(self, config):
         self.config = config
         self.patch_size = config.patch_size

@@ -53,6 +53,42 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
   }
 }
 
+// Vector variant: when the run of features that is contiguous in BOTH the patch row and the volume (wp, times hp when the
+// patch spans the whole W axis, times dp when it also spans H) is a multiple of 4, one thread moves 4 features: one index
+// decode, one 16-byte load (when aligned), one 8-byte store. cfg2 (224x224x1 slices, 16x16x1 patches): runs of 16 floats.
+__global__ void patchify_vec4_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int M, int D, int H,
+                                     int W, int dp, int hp, int wp, int sample_major) {
+  const int Dn = D / dp, Hn = H / hp, Wn = W / wp;
+  const long long Np = (long long)Dn * Hn * Wn;
+  const int P = dp * hp * wp;
+  const long long quads = (long long)M * B * Np * P / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += stride) {
+    long long e = i * 4;
+    const int f = (int)(e % P);
+    e /= P;
+    const long long t = e % Np;
+    e /= Np;
+    int b, m;
+    if (sample_major) { m = (int)(e % M); b = (int)(e / M); }
+    else { b = (int)(e % B); m = (int)(e / B); }
+    const int di = (int)(t % Dn), wi = (int)((t / Dn) % Wn), hi = (int)(t / ((long long)Dn * Wn));
+    const int c = f % wp, bb = (f / wp) % hp, a = f / (wp * hp);
+    const float* src = img + ((long long)b * M + m) * ((long long)D * H * W) +
+                       ((long long)(di * dp + a) * H + (hi * hp + bb)) * W + (wi * wp + c);
+    float4 v;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      v = __ldg(reinterpret_cast<const float4*>(src));
+    } else {
+      v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+    }
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+}
+
 // tokens[m][b*N][c] = cls[c] + pos[0][c]
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ tokens,
                                 int MB, int N, int C) {
@@ -433,6 +469,14 @@ int cavit_patchify(const float* img, void* patches, int32_t B, int32_t M, int32_
   const long long P = (long long)dp * hp * wp;
   if (P % 2) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_patchify: patch_dim must be even");
   const long long pairs = (long long)M * B * (D / dp) * (H / hp) * (W / wp) * P / 2;
+  long long run = wp;          // features contiguous in both the patch row and the volume
+  if (wp == W) { run *= hp; if (hp == H) run *= dp; }
+  if (run % 4 == 0) {
+    patchify_vec4_kernel<<<grid_for(pairs / 2, 256), 256, 0, as_stream(stream)>>>(img, reinterpret_cast<bf16*>(patches), B, M, D,
+                                                                                  H, W, dp, hp, wp, sample_major);
+    count_launch();
+    return check_launch("cavit_patchify");
+  }
   patchify_kernel<<<grid_for(pairs, 256), 256, 0, as_stream(stream)>>>(img, reinterpret_cast<bf16*>(patches), B, M, D, H, W,
                                                                         dp, hp, wp, sample_major);
   count_launch();

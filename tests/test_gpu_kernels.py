@@ -241,7 +241,8 @@ def test_layernorm_fusion_gather_and_scatter():
     status_ok()
 
 
-@pytest.mark.parametrize("img_size,patch", [((16, 24, 8), (8, 8, 4)), ((32, 32, 1), (16, 16, 1)), ((16, 16, 16), (16, 8, 2))])
+@pytest.mark.parametrize("img_size,patch", [((16, 24, 8), (8, 8, 4)), ((32, 32, 1), (16, 16, 1)), ((16, 16, 16), (16, 8, 2)),
+                                            ((16, 8, 4), (8, 8, 4)), ((8, 6, 2), (4, 2, 2)), ((224, 224, 1), (16, 16, 1))])
 def test_patchify_bit_exact(img_size, patch):
     from cavit import ops
     from oracle.functional import patchify

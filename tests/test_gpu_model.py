@@ -165,3 +165,48 @@ def test_eager_mode_sees_in_place_weight_updates():
     ref_state = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
     ref_logits, _ = OF.model_cross_forward(ref_state, img.double(), labels, cfg)
     assert rel(l1, ref_logits) < 2e-2
+
+
+def test_fused_adam_tracks_torch_adam_over_steps():
+    """cavit.optim.FusedAdam (one launch over the flat slabs, bf16 operand copy refreshed in the same pass) against
+    torch.optim.Adam — the reference's optimiser, model_cross.py:277 — fed with the same gradients."""
+    from cavit.modules import ModelCross
+    from cavit.optim import CosineAnnealing, FusedAdam
+    kind, cfg, state, img, labels = build_case("cross_chain3")
+    a, b = ModelCross(cfg), ModelCross(cfg)
+    a.load_state_dict(state)
+    b.load_state_dict(state)
+    a, b = a.cuda().train(), b.cuda().train()
+    a.engine()
+    fa = FusedAdam(a, lr=1e-3, weight_decay=5e-4)
+    sa = CosineAnnealing(fa, T_max=4, eta_min=1e-5)
+    tb = torch.optim.Adam(b.parameters(), lr=1e-3, weight_decay=5e-4)
+    sb = torch.optim.lr_scheduler.CosineAnnealingLR(tb, T_max=4, eta_min=1e-5)
+    for step in range(5):
+        la = a(img.cuda(), labels.cuda())[1]
+        la.backward()
+        fa.step()
+        fa.zero_grad()
+        lb = b(img.cuda(), labels.cuda())[1]
+        lb.backward()
+        tb.step()
+        tb.zero_grad()
+        assert abs(float(la) - float(lb)) < 1e-4 * max(1.0, abs(float(lb))), step
+        sa.step()
+        sb.step()
+        assert abs(fa.lr - sb.get_last_lr()[0]) < 1e-12
+    # Same update rule (bit-level check with identical gradients: tests/test_gpu_encoders.py::test_fused_adam_matches_torch_adam).
+    # Here the two models' gradients differ in the last bits (atomic split-K / fusion reductions), and Adam's first steps
+    # move every element by ~lr * sign(g): elements with noise-level gradients may step the other way, so the comparison is
+    # on the parameter displacement as a whole.
+    num = den = 0.0
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        num += float((pa - pb).double().norm()) ** 2
+        den += float((pb.detach().cpu().double() - state[k].double()).norm()) ** 2
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
+    # reloading weights behind the optimizer's back re-derives the bf16 operands
+    a.load_state_dict(state)
+    b2 = ModelCross(cfg)
+    b2.load_state_dict(state)
+    b2 = b2.cuda().train()
+    assert abs(float(a(img.cuda(), labels.cuda())[1]) - float(b2(img.cuda(), labels.cuda())[1])) < 1e-6
