@@ -75,6 +75,8 @@ _SIGS = {
     "cavit_cast_bf16": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "cavit_colsum_bf16": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "cavit_gather_rows_f32": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_gather_rows_f32_indexed": (c_i32, [c_vp, c_i64, c_i64, C.POINTER(c_i32), c_vp, c_i64, c_i64, C.POINTER(c_i32),
+                                              c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cavit_add_bf16_f32": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "cavit_gelu_bwd_bf16": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "cavit_compact_patch_rows_bf16": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),

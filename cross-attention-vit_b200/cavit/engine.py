@@ -698,9 +698,9 @@ class Engine:
         s = mb if train else 0
         tag = f"X{mb}"
         f_cls = a["f_cls"][s]
-        for k in range(K):  # save the CLS rows the fusions read (they are overwritten below)
-            ops.gather_rows_f32(X[self.cls_src[k]], f_cls[k], rows=B, C_=C, groups=1, src_row_stride=N * C, src_gs=0,
-                                dst_row_stride=C, dst_gs=0)
+        # save the CLS rows the fusions read (they are overwritten below): one launch over the K donor streams
+        ops.gather_rows_f32_indexed(X, f_cls, rows=B, C_=C, src_row_stride=N * C, src_gs=T * C, src_groups=self.cls_src,
+                                    dst_row_stride=C, dst_gs=B * C)
         drop = self.drop
         if self.fold:
             HC = H * C
@@ -748,9 +748,8 @@ class Engine:
         else:
             self._fwd(a["f_h"][s], self.wb(f"{tag}.w2"), a["f_z"][s], G=K, T=B, N=C, K=F, epi=EPI_BIAS_RESID,
                       bias=self.w(f"{tag}.b2"), resid=a["f_y"][s])
-        for k in range(K):
-            ops.gather_rows_f32(a["f_z"][s][k], X[self.cls_src[k]], rows=B, C_=C, groups=1, src_row_stride=C, src_gs=0,
-                                dst_row_stride=N * C, dst_gs=0)
+        ops.gather_rows_f32_indexed(a["f_z"][s], X, rows=B, C_=C, src_row_stride=C, src_gs=B * C, dst_row_stride=N * C,
+                                    dst_gs=T * C, dst_groups=self.cls_src)
 
     # ------------------------------------------------------------------ backward
     def _next_grad_buffer(self):
@@ -1077,9 +1076,8 @@ class Engine:
         s = mb
         d_z = a["d_z"]
         # gradient of the new CLS rows; the old CLS rows of receiving streams get no pass-through gradient
-        for k in range(K):
-            ops.gather_rows_f32(dX[self.cls_src[k]], d_z[k], rows=B, C_=C, groups=1, src_row_stride=N * C, src_gs=0,
-                                dst_row_stride=C, dst_gs=0, zero_src=True)
+        ops.gather_rows_f32_indexed(dX, d_z, rows=B, C_=C, src_row_stride=N * C, src_gs=T * C, src_groups=self.cls_src,
+                                    dst_row_stride=C, dst_gs=B * C, zero_src=True)
         drop = self.drop
         if drop:
             self._dropout(ops.DROP_CAST, d_z, None, a["d_zb"], self.site_fusion(mb, "fc2"))
@@ -1123,9 +1121,8 @@ class Engine:
                               self.w(f"{tag}.lnA.w"), dX, self.g(f"{tag}.lnA.w"), self.g(f"{tag}.lnA.b"), ws, B=B, N=N, C_=C,
                               cls_src=self.cls_src, tok_src=self.tok_src, dy_cls=a["d_xncls"])
         # residual path of the CLS token: y = ... + cls_in
-        for k in range(K):
-            ops.gather_rows_f32(a["d_y"][k], dX[self.cls_src[k]], rows=B, C_=C, groups=1, src_row_stride=C, src_gs=0,
-                                dst_row_stride=N * C, dst_gs=0, accumulate=True)
+        ops.gather_rows_f32_indexed(a["d_y"], dX, rows=B, C_=C, src_row_stride=C, src_gs=B * C, dst_row_stride=N * C,
+                                    dst_gs=T * C, dst_groups=self.cls_src, accumulate=True)
 
     def _fusion_bwd_folded(self, mb: int, dX: torch.Tensor):
         """Adjoint of the folded forward (see csrc/xfold.cu): everything left of the token streams is a [B, .] problem."""
@@ -1168,9 +1165,8 @@ class Engine:
                             dst_row_stride=C, dst_gs=0, accumulate=True)
         ops.gather_rows_f32(a["d_lnA"][1], self.g(f"{tag}.lnA.b"), rows=K, C_=C, groups=1, src_row_stride=C, src_gs=0,
                             dst_row_stride=C, dst_gs=0, accumulate=True)
-        for k in range(K):
-            ops.gather_rows_f32(a["d_clsq"][k], dX[self.cls_src[k]], rows=B, C_=C, groups=1, src_row_stride=C, src_gs=0,
-                                dst_row_stride=N * C, dst_gs=0, accumulate=True)
+        ops.gather_rows_f32_indexed(a["d_clsq"], dX, rows=B, C_=C, src_row_stride=C, src_gs=B * C, dst_row_stride=N * C,
+                                    dst_gs=self.T * C, dst_groups=self.cls_src, accumulate=True)
 
     def _x_for_fusion(self, mb: int) -> torch.Tensor:
         # streams as the fusion saw them (patch rows are untouched by the in-place CLS rewrite)

@@ -220,6 +220,18 @@ def gather_rows_f32(src, dst, *, rows, C_, groups, src_row_stride, src_gs, dst_r
           "cavit_gather_rows_f32")
 
 
+def gather_rows_f32_indexed(src, dst, *, rows, C_, src_row_stride, src_gs, dst_row_stride, dst_gs, src_groups=None,
+                            dst_groups=None, accumulate=False, zero_src=False):
+    """One launch for several row blocks that live in different groups (streams): group g copies
+    src + src_groups[g] * src_gs -> dst + dst_groups[g] * dst_gs (None = identity)."""
+    n = len(src_groups if src_groups is not None else dst_groups)
+    check(lib().cavit_gather_rows_f32_indexed(src.data_ptr(), src_row_stride, src_gs,
+                                              None if src_groups is None else _i32arr(src_groups), dst.data_ptr(),
+                                              dst_row_stride, dst_gs, None if dst_groups is None else _i32arr(dst_groups),
+                                              rows, C_, n, int(accumulate), int(zero_src), _stream()),
+          "cavit_gather_rows_f32_indexed")
+
+
 def add_bf16_f32(a, b_bf16, out):
     check(lib().cavit_add_bf16_f32(a.data_ptr(), b_bf16.data_ptr(), out.data_ptr(), a.numel(), _stream()),
           "cavit_add_bf16_f32")
@@ -320,5 +332,5 @@ for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_f
            "patchify", "cls_rows", "embed_param_grads", "cast_bf16", "colsum_bf16", "gather_rows_f32", "add_bf16_f32",
            "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout", "xfold_fwd", "xfold_bwd",
            "expand_heads", "fold_heads", "tokens_from_channels", "tokens_to_channels", "conv_patch_rows",
-           "conv_patch_rows_bwd", "bce_head_fwd", "bce_head_bwd", "adam_step"):
+           "conv_patch_rows_bwd", "bce_head_fwd", "bce_head_bwd", "adam_step", "gather_rows_f32_indexed"):
     globals()[_n] = _instrument(_n, globals()[_n])

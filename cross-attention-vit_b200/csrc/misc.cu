@@ -160,9 +160,13 @@ colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, long long gs, int 
 }
 
 // ------------------------------------------------------------------------------------------ gather rows
+struct GatherIdx {
+  int use;            // 0: group g uses group strides directly
+  int src[16], dst[16];   // else: group g reads from src group src[g] and writes dst group dst[g]
+};
 __global__ void gather_rows_f32_kernel(float* __restrict__ src, long long srs, long long sgs, float* __restrict__ dst,
                                        long long drs, long long dgs, int rows, int C, int groups, int accumulate,
-                                       int zero_src) {
+                                       int zero_src, const GatherIdx gi) {
   const int C4 = C >> 2;
   const long long total = (long long)groups * rows * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -170,10 +174,11 @@ __global__ void gather_rows_f32_kernel(float* __restrict__ src, long long srs, l
     long long e = i / C4;
     const int r = (int)(e % rows);
     const int g = (int)(e / rows);
-    float4* sp = reinterpret_cast<float4*>(src + (long long)g * sgs + (long long)r * srs) + c4;
+    const int gs_ = gi.use ? gi.src[g] : g, gd = gi.use ? gi.dst[g] : g;
+    float4* sp = reinterpret_cast<float4*>(src + (long long)gs_ * sgs + (long long)r * srs) + c4;
     const float4 v = *sp;
     if (zero_src) *sp = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4* d = reinterpret_cast<float4*>(dst + (long long)g * dgs + (long long)r * drs) + c4;
+    float4* d = reinterpret_cast<float4*>(dst + (long long)gd * dgs + (long long)r * drs) + c4;
     if (accumulate) {
       float4 o = *d;
       o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
@@ -524,10 +529,34 @@ int cavit_gather_rows_f32(float* src, int64_t srs, int64_t sgs, float* dst, int6
                           int32_t C, int32_t groups, int32_t accumulate, int32_t zero_src, void* stream) {
   if (!src || !dst || (C % 4) || (srs % 4) || (sgs % 4) || (drs % 4) || (dgs % 4))
     return fail(CAVIT_E_BADARG, "cavit_gather_rows_f32: bad args");
+  GatherIdx gi{};
   gather_rows_f32_kernel<<<grid_for((long long)groups * rows * C / 4, 256), 256, 0, as_stream(stream)>>>(
-      src, srs, sgs, dst, drs, dgs, rows, C, groups, accumulate, zero_src);
+      src, srs, sgs, dst, drs, dgs, rows, C, groups, accumulate, zero_src, gi);
   count_launch();
   return check_launch("cavit_gather_rows_f32");
+}
+
+int cavit_gather_rows_f32_indexed(float* src, int64_t srs, int64_t sgs, const int32_t* src_group, float* dst, int64_t drs,
+                                  int64_t dgs, const int32_t* dst_group, int32_t rows, int32_t C, int32_t groups,
+                                  int32_t accumulate, int32_t zero_src, void* stream) {
+  if (!src || !dst || (C % 4) || (srs % 4) || (sgs % 4) || (drs % 4) || (dgs % 4))
+    return fail(CAVIT_E_BADARG, "cavit_gather_rows_f32_indexed: bad args");
+  if (groups < 1 || groups > 16) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_gather_rows_f32_indexed: groups=%d (max 16)", groups);
+  GatherIdx gi{};
+  gi.use = 1;
+  for (int g = 0; g < groups; ++g) {
+    gi.src[g] = src_group ? src_group[g] : g;
+    gi.dst[g] = dst_group ? dst_group[g] : g;
+    if (gi.src[g] < 0 || gi.dst[g] < 0) return fail(CAVIT_E_BADARG, "cavit_gather_rows_f32_indexed: negative group index");
+  }
+  for (int g = 0; g < groups; ++g)      // read-modify-write / move needs distinct targets inside one launch
+    for (int h = g + 1; h < groups; ++h)
+      if (gi.dst[g] == gi.dst[h] || (zero_src && gi.src[g] == gi.src[h]))
+        return fail(CAVIT_E_BADARG, "cavit_gather_rows_f32_indexed: duplicate group index");
+  gather_rows_f32_kernel<<<grid_for((long long)groups * rows * C / 4, 256), 256, 0, as_stream(stream)>>>(
+      src, srs, sgs, dst, drs, dgs, rows, C, groups, accumulate, zero_src, gi);
+  count_launch();
+  return check_launch("cavit_gather_rows_f32_indexed");
 }
 
 int cavit_add_bf16_f32(const float* a, const void* b, float* out, int64_t n, void* stream) {

@@ -264,6 +264,13 @@ int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, in
 int cavit_gather_rows_f32(float* src, int64_t src_row_stride, int64_t src_gs, float* dst,
                           int64_t dst_row_stride, int64_t dst_gs, int32_t rows, int32_t C, int32_t groups,
                           int32_t accumulate, int32_t zero_src, void* stream);
+/* Same with HOST index arrays (length `groups` <= 16, NULL = identity): group g reads source group src_group[g] and
+ * writes destination group dst_group[g] — the CLS rows of the K fusions live in K different token streams
+ * (/root/reference/model_cross.py:136-142), one launch moves all of them. Destination groups must be distinct. */
+int cavit_gather_rows_f32_indexed(float* src, int64_t src_row_stride, int64_t src_gs, const int32_t* src_group,
+                                  float* dst, int64_t dst_row_stride, int64_t dst_gs, const int32_t* dst_group,
+                                  int32_t rows, int32_t C, int32_t groups, int32_t accumulate, int32_t zero_src,
+                                  void* stream);
 /* out[i] = a[i] + (float) b_bf16[i]   (residual add for the heads == 1 case where the reference's
  * attention has no output projection, /root/reference/model_cross.py:37,44-48). out may alias a. */
 int cavit_add_bf16_f32(const float* a, const void* b_bf16, float* out, int64_t n, void* stream);

@@ -555,3 +555,32 @@ def test_expand_and_fold_heads():
     ref = torch.stack([torch.cat([dE.view(G, C, H, C)[g, h * 64:(h + 1) * 64, h] for h in range(H)]) for g in range(G)])
     assert torch.equal(dW, ref)
     status_ok()
+
+
+def test_gather_rows_indexed_moves_cls_rows_of_several_streams():
+    from cavit import ops
+    torch.manual_seed(12)
+    M, B, N, C = 4, 5, 9, 128
+    X = torch.randn(M, B * N, C, device=DEV)
+    idx = [2, 0, 3]
+    buf = torch.zeros(len(idx), B, C, device=DEV)
+    ops.gather_rows_f32_indexed(X, buf, rows=B, C_=C, src_row_stride=N * C, src_gs=B * N * C, src_groups=idx,
+                                dst_row_stride=C, dst_gs=B * C)
+    for k, m in enumerate(idx):
+        assert torch.equal(buf[k], X[m].view(B, N, C)[:, 0])
+    X2 = X.clone()
+    add = torch.randn(len(idx), B, C, device=DEV)
+    ops.gather_rows_f32_indexed(add, X2, rows=B, C_=C, src_row_stride=C, src_gs=B * C, dst_row_stride=N * C,
+                                dst_gs=B * N * C, dst_groups=idx, accumulate=True)
+    want = X.clone().view(M, B, N, C)
+    for k, m in enumerate(idx):
+        want[m, :, 0] += add[k]
+    assert torch.equal(X2.view(M, B, N, C), want)
+    # "move": source rows are cleared
+    X3 = X.clone()
+    ops.gather_rows_f32_indexed(X3, buf, rows=B, C_=C, src_row_stride=N * C, src_gs=B * N * C, src_groups=idx,
+                                dst_row_stride=C, dst_gs=B * C, zero_src=True)
+    for k, m in enumerate(idx):
+        assert float(X3[m].view(B, N, C)[:, 0].abs().max()) == 0.0
+    assert torch.equal(X3[1], X[1])
+    status_ok()
