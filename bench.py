@@ -294,14 +294,19 @@ def main():
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
+        peaks = measured_peaks()
+        gemm_bound_ms, gemm_bytes = 0.0, 0.0
         for name, a, b, info in prof:
             t = a.elapsed_time(b)
             d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
             d["ms"] += t
             d["n"] += 1
             d["flops"] += info.get("flops", 0.0)
+            if name == "gemm":   # per launch: the slower of its tensor-pipe time and its HBM time at the measured peaks
+                gemm_bytes += info.get("bytes", 0.0)
+                gemm_bound_ms += max(info["flops"] / (peaks["bf16_tflops_sustained"] * 1e12),
+                                     info.get("bytes", 0.0) / (peaks["hbm_gbs"] * 1e9)) * 1e3
         tot = sum(d["ms"] for d in agg.values())
-        peaks = measured_peaks()
         gm = agg.get("gemm", {"ms": 0.0, "n": 0, "flops": 0.0})
         achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
@@ -317,7 +322,15 @@ def main():
                     "traffic_source": "profiles/step_summary_r01.json (ncu dram__bytes_read+write per GEMM launch, mean over one step)"
                     if traffic else None,
                     "peak_source": peaks["source"] + " (sustained)",
-                    "launches_per_step": gm["n"], "share_of_step": gm["ms"] / tot if tot else None}
+                    "launches_per_step": gm["n"], "share_of_step": gm["ms"] / tot if tot else None,
+                    # K = 384 GEMMs with bf16 I/O sit at ~170 FLOP/B against a machine balance of ~210: several of them are
+                    # bounded by HBM, not by the tensor pipe. Both limits per launch:
+                    "two_limit": {"algorithmic_bytes_per_step": gemm_bytes,
+                                  "hbm_gbs_achieved": gemm_bytes / (gm["ms"] * 1e-3) / 1e9 if gm["ms"] > 0 else None,
+                                  "bound_ms_per_step": gemm_bound_ms,
+                                  "frac_of_bound": gemm_bound_ms / gm["ms"] if gm["ms"] > 0 else None,
+                                  "how": "sum over launches of max(flops / measured sustained bf16 peak, algorithmic bytes / "
+                                         "measured HBM peak) divided by the summed measured durations"}}
         breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"],
                          **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} if v["flops"] and v["ms"] > 0 else {})}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}

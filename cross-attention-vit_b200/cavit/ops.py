@@ -316,8 +316,18 @@ def _instrument(name, fn):
         e1.record(torch.cuda.current_stream())
         info = {}
         if name == "gemm":
-            info = {"flops": 2.0 * kw["M"] * kw["N"] * kw["K"] * kw.get("groups", 1),
-                    "shape": (kw["M"], kw["N"], kw["K"], kw.get("groups", 1), int(kw.get("a_mn", False)), int(kw.get("b_mn", False)))}
+            g_, m_, n_, k_ = kw.get("groups", 1), kw["M"], kw["N"], kw["K"]
+            out_t = args[2] if len(args) > 2 else kw["out"]
+            epi = kw.get("epi", EPI_NONE)
+            # algorithmic HBM bytes: operands once, output once, plus what the epilogue streams (fp32 residual in,
+            # bf16 pre-activation out / in)
+            nbytes = g_ * (2.0 * m_ * k_ + 2.0 * n_ * k_ + m_ * n_ * out_t.element_size())
+            if epi == EPI_BIAS_RESID:
+                nbytes += 4.0 * g_ * m_ * n_
+            if epi in (EPI_BIAS_GELU, EPI_GELU_BWD, EPI_RELU_BWD):
+                nbytes += 2.0 * g_ * m_ * n_
+            info = {"flops": 2.0 * m_ * n_ * k_ * g_, "bytes": nbytes,
+                    "shape": (m_, n_, k_, g_, int(kw.get("a_mn", False)), int(kw.get("b_mn", False)))}
         elif name in ("attn_fwd", "attn_bwd"):
             mult = 4.0 if name == "attn_fwd" else 10.0   # QK^T + PV ; S, dP, dV, dK, dQ
             info = {"flops": mult * kw["G"] * kw["B"] * kw["H"] * kw["N"] * kw["N"] * 64}

@@ -101,19 +101,28 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
 }
 
 // dpos[n][c] = sum over (m,b) of dtokens[(m*B+b)*N + n][c]; dcls = dpos[0] (cls and pos[0] feed the same row).
+// grid = (column chunks, slices of the (m, b) axis): every slice adds its partial sum atomically into the zeroed outputs, so
+// the 310 MB read at cfg2 is spread over the whole GPU instead of 148 blocks that each walk 1024 rows serially.
 __global__ void embed_param_grads_kernel(const float* __restrict__ dtok, float* __restrict__ dpos, float* __restrict__ dcls,
                                          int MB, int N, int C) {
   const int C4 = C >> 2;
   const long long total = (long long)N * C4;
+  const int per = (MB + gridDim.y - 1) / gridDim.y;
+  const int mb0 = blockIdx.y * per, mb1 = min(MB, mb0 + per);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* p = reinterpret_cast<const float4*>(dtok) + i;
-    for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll 4
+    for (int mb = mb0; mb < mb1; ++mb) {
       const float4 v = __ldg(p + (long long)mb * total);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    reinterpret_cast<float4*>(dpos)[i] = acc;
-    if (i < C4) reinterpret_cast<float4*>(dcls)[i] = acc;
+    float* o = dpos + i * 4;
+    atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+    if (i < C4) {
+      float* q = dcls + i * 4;
+      atomicAdd(q + 0, acc.x); atomicAdd(q + 1, acc.y); atomicAdd(q + 2, acc.z); atomicAdd(q + 3, acc.w);
+    }
   }
 }
 
@@ -393,17 +402,28 @@ __global__ void head_dw_kernel(const bf16* __restrict__ h, const long long* __re
   float acc[HEAD_MAX_CLASSES], accb[HEAD_MAX_CLASSES];
 #pragma unroll
   for (int k = 0; k < HEAD_MAX_CLASSES; ++k) acc[k] = accb[k] = 0.f;
-  for (int b = 0; b < B; ++b) {
+  // d(logits) of every sample is the same for all columns f: the block computes the B rows once into shared memory
+  // (each thread used to redo the softmax of every sample: B dependent exp chains per thread, 0.24 ms for a [256, 2] problem)
+  extern __shared__ float s_dz[];   // [B][classes]
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
     float dz[HEAD_MAX_CLASSES];
     dlogits_row(logits + b * classes, labels[b], classes, smoothing, scale / ((float)B * (float)M), dz);
-    if (use_drop)
-      for (int k = 0; k < classes; ++k) dz[k] *= drop_mult(d, seed, ((uint64_t)m * B + b) * classes + k);
+    for (int k = 0; k < classes; ++k) {
+      float v = dz[k];
+      if (use_drop) v *= drop_mult(d, seed, ((uint64_t)m * B + b) * classes + k);
+      s_dz[b * classes + k] = v;
+    }
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int b = 0; b < B; ++b) {
     const float hv = (f < F) ? __bfloat162float(h[((long long)m * B + b) * F + f]) : 0.f;
 #pragma unroll
     for (int k = 0; k < HEAD_MAX_CLASSES; ++k)
       if (k < classes) {
-        acc[k] += dz[k] * hv;
-        accb[k] += dz[k];
+        const float dzk = s_dz[b * classes + k];
+        acc[k] += dzk * hv;
+        accb[k] += dzk;
       }
   }
   if (f < F)
@@ -499,7 +519,14 @@ int cavit_cls_rows(const float* cls, const float* pos, float* tokens, int32_t M,
 int cavit_embed_param_grads(const float* dtokens, float* dpos, float* dcls, int32_t M, int32_t B, int32_t N, int32_t C,
                             void* stream) {
   if (!dtokens || !dpos || !dcls || (C % 4)) return fail(CAVIT_E_BADARG, "cavit_embed_param_grads: bad args");
-  embed_param_grads_kernel<<<grid_for((long long)N * C / 4, 128), 128, 0, as_stream(stream)>>>(dtokens, dpos, dcls, M * B, N, C);
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(dpos, 0, sizeof(float) * (size_t)N * C, st);
+  cudaMemsetAsync(dcls, 0, sizeof(float) * (size_t)C, st);
+  const int gx = grid_for((long long)N * C / 4, 128);
+  int gy = (sm_count() * 8 + gx - 1) / gx;     // ~8 blocks per SM in total
+  if (gy > M * B) gy = M * B;
+  if (gy < 1) gy = 1;
+  embed_param_grads_kernel<<<dim3(gx, gy), 128, 0, st>>>(dtokens, dpos, dcls, M * B, N, C);
   count_launch();
   return check_launch("cavit_embed_param_grads");
 }
@@ -649,7 +676,13 @@ int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, c
   if (use < 0) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: bad dropout arguments");
   head_dh_kernel<<<dim3(B, M), 256, 0, st>>>(W2, lab, logits, loss_scale, loss_scale_dev, reinterpret_cast<bf16*>(dh), M, B, F, classes,
                                              smoothing, d, use);
-  head_dw_kernel<<<dim3((F + 255) / 256, M), 256, 0, st>>>(reinterpret_cast<const bf16*>(h), lab, logits, loss_scale,
+  if ((size_t)B * classes * sizeof(float) > 96 * 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_head_loss_bwd: batch %d too large", B);
+  static bool dw_attr = false;
+  if (!dw_attr) {
+    cudaFuncSetAttribute(head_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    dw_attr = true;
+  }
+  head_dw_kernel<<<dim3((F + 255) / 256, M), 256, (size_t)B * classes * sizeof(float), st>>>(reinterpret_cast<const bf16*>(h), lab, logits, loss_scale,
                                                            loss_scale_dev, dW2, db2, M, B, F, classes, smoothing, d, use);
   count_launch(2);
   return check_launch("cavit_head_loss_bwd");
