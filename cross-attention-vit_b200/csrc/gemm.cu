@@ -596,7 +596,8 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   // wgrad (MN-major A: few, short tiles with a long split-K reduction) keeps single-CTA tiles. With pairs and a K-major
   // B operand, N tiles of 192 remove the 10-25 % padding of N = 1152 (QKV) and N = 384 (out-proj, fc2).
   static const bool force_1cta = [] { const char* e = getenv("CAVIT_GEMM_1CTA"); return e && e[0] == '1'; }();
-  const int CTAS = (!force_1cta && a->M > GEMM_BM && !a->a_mn) ? 2 : 1;
+  static const bool wgrad_pair = [] { const char* e = getenv("CAVIT_WGRAD_PAIR"); return e && e[0] == '1'; }();
+  const int CTAS = (!force_1cta && a->M > GEMM_BM && (!a->a_mn || wgrad_pair)) ? 2 : 1;
   int BN = (a->N >= 256 && (a->N % 256 == 0 || a->N > 1024)) ? 256 : 128;
   if (CTAS == 2 && !a->b_mn && a->N % 192 == 0 && a->N % 256 != 0) BN = 192;
   const CUtensorMap *ta, *tb;

@@ -80,13 +80,14 @@ def main():
         dw2 = torch.empty(G, C, F, device=DEV)
         dwq = torch.empty(G, 3 * C, C, device=DEV)
         dwo = torch.empty(G, C, C, device=DEV)
-        for sk in (1, 2, 4, 8):
+        sweep = [int(v) for v in os.environ.get("CAVIT_KB_SPLITS", "").split(",") if v]
+        for sk in sweep or (1, 2, 4, 8):
             gemm_line(f"wgrad fc1 dW[F,C] split_k={sk}", lambda: ops.linear_wgrad(xf, x, dw1, split_k=sk), 2 * G * T * F * C)
-        for sk in (1, 2, 4):
+        for sk in sweep or (1, 2, 4):
             gemm_line(f"wgrad fc2 dW[C,F] split_k={sk}", lambda: ops.linear_wgrad(x, xf, dw2, split_k=sk), 2 * G * T * F * C)
-        for sk in (1, 2, 4):
+        for sk in sweep or (1, 2, 4):
             gemm_line(f"wgrad qkv dW[3C,C] split_k={sk}", lambda: ops.linear_wgrad(qkv, x, dwq, split_k=sk), 2 * G * T * 3 * C * C)
-        for sk in (1, 4, 8, 16):
+        for sk in sweep or (1, 4, 8, 16):
             gemm_line(f"wgrad out dW[C,C] split_k={sk}", lambda: ops.linear_wgrad(x, x, dwo, split_k=sk), 2 * G * T * C * C)
     if not a.only or "attn" in a.only:
         qkv = rnd(G, T, 3 * C).to(BF)
