@@ -67,6 +67,36 @@ class SlabReducer:
                 flat[start:end].div_(world)
 
 
+class TensorGradReducer:
+    """Averages the gradients of ordinary (non-flat) parameters across ranks as autograd produces them: the CNN stems
+    of `cavit.encoders.ViT` / `ViT3D` live outside the engine's flat buffer (torch modules); their
+    gradients appear after the engine's backward, while autograd walks the stem. One all-reduce per parameter from a
+    post-accumulate hook (a handful of small tensors); backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, params, group=None):
+        self.group = group
+        self.params = [p for p in params if p.requires_grad]
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        self.reduced = 0
+
+    def _hook(self, p: torch.Tensor):
+        world = dist.get_world_size(self.group)
+        if p.grad.is_cuda and dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
+            p.grad.div_(world)
+        self.reduced += 1
+
+    def broadcast(self, tensors, src: int = 0):
+        for t in tensors:
+            dist.broadcast(t.data if isinstance(t, torch.nn.Parameter) else t, src=src, group=self.group)
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
 class DataParallel:
     """Wraps a cavit model: `dp = DataParallel(model); logits, loss = dp(img, labels); loss.backward()`."""
 
@@ -80,7 +110,16 @@ class DataParallel:
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.model, self.group = model, group
-        self.engine = model.engine()
+        self.stem = None
+        if hasattr(model, "_stem_prefix"):     # cavit.encoders.ViT / ViT3D: engine exists after the first forward
+            self.engine = model.__dict__.get("_engine_obj")
+            if self.engine is None:
+                raise RuntimeError("DataParallel(ViT / ViT3D): run one forward first so that the encoder engine exists")
+            named = [(k, p) for k, p in model.named_parameters() if k.startswith(model._stem_prefix)]
+            self.stem = TensorGradReducer([p for _, p in named], group)
+            self.stem.broadcast([p for _, p in named] + [b for k, b in model.named_buffers() if k.startswith(model._stem_prefix)])
+        else:
+            self.engine = model.engine()
         self.comm_stream = torch.cuda.Stream(device=self.engine.device)
         self.min_slab_elems = min_slab_elems
         self._reducer: Optional[SlabReducer] = None

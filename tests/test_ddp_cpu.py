@@ -59,3 +59,41 @@ def test_slab_reducer_covers_flat_buffer_and_averages():
         assert ok
         assert 2 <= n_slabs <= 6
         assert lo == hi == 1.5      # mean of 1 and 2 everywhere: every element reduced exactly once
+
+
+def _stem_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cavit.ddp import TensorGradReducer
+    from cavit.encoders import CNN3DEncoder
+    torch.manual_seed(100 + rank)                       # different replicas before the broadcast
+    stem = CNN3DEncoder(hidden_dim=16)
+    red = TensorGradReducer(list(stem.parameters()))
+    red.broadcast(list(stem.parameters()) + list(stem.buffers()))
+    w0 = float(stem.conv1.weight.double().sum())
+    x = torch.randn(2, 1, 32, 32, 32, generator=torch.Generator().manual_seed(7 + rank))  # different shards
+    stem(x).square().mean().backward()
+    g = stem.conv4.weight.grad.clone()
+    gs = [torch.zeros_like(g) for _ in range(world)]
+    dist.all_gather(gs, g)
+    same = all(torch.equal(gs[0], t) for t in gs)
+    q.put((rank, w0, bool(same), red.reduced, len(red.params)))
+    dist.destroy_process_group()
+
+
+def test_stem_gradients_are_averaged_across_ranks():
+    """The CNN stems of ViT / ViT3D are outside the flat buffer: their parameters are broadcast and their gradients
+    all-reduced per tensor (cavit.ddp.TensorGradReducer) — world_size 2 over gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stem_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1]                        # same weights after the broadcast
+    for rank, w0, same, reduced, n in res:
+        assert same and reduced == n
