@@ -419,7 +419,10 @@ class Engine:
             return
         # Folded single-query cross attention (csrc/xfold.cu): no K/V projection of the fused sequence, no materialised
         # LayerNorm of it. Attention dropout breaks the fold (probabilities stop summing to one): unfolded path then.
-        self.fold = bool(K) and not drop and self.fold_ok
+        # ... and the folded kernels run one CTA per (fusion, sample): below ~2 CTAs per SM (small batches of long sequences,
+        # cfg1 / cfg3 / cfg5) the token-parallel unfolded path is faster (cfg3: 26 ms vs 3 ms per step for the fusion backward)
+        min_ctas = int(os.environ.get("CAVIT_XFOLD_MIN_CTAS", "296"))
+        self.fold = bool(K) and not drop and self.fold_ok and K * B >= min_ctas
         fold = self.fold
         a["patches"] = e((self.Mimg * B * self.Np, self.P), BF16)
         nL = self.L if train else 1

@@ -115,8 +115,11 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
 // COL: also accumulate the column sums of the OUTPUT gradient (dx incl. the residual term): that is the bias gradient
 // of the Linear layer that produced this LayerNorm's input (out-proj / fc2), so no separate pass over dx is needed.
 // The block that takes the last ticket of its group reduces the partial rows (no separate finalize launch).
+// Two resident blocks per SM up to C = 384 (NV <= 3: fits 128 registers); wider rows keep every load of the row in registers
+// (up to 5 float4 arrays of NV entries), which spills under a 128-register cap (C = 1024: 1.4 KB of spills per thread and a
+// 2.8x slower kernel), so they run one block per SM with the full register file.
 template <int NV, bool COL, bool DYF>
-__global__ void __launch_bounds__(LN_THREADS, 2)
+__global__ void __launch_bounds__(LN_THREADS, (NV <= 3 ? 2 : 1))
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long long row_stride, long long gs,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               int rows_per_group, int C, const float* dresid, float* dx, long long dx_row_stride, long long dx_gs,

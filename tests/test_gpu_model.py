@@ -36,10 +36,17 @@ def _run_ours(kind, cfg, state, img, labels):
     return model, logits.detach(), loss.detach(), grads
 
 
+@pytest.mark.parametrize("fold", [True, False])
 @pytest.mark.parametrize("name", list(CASES))
-def test_model_matches_oracle_and_golden(name):
+def test_model_matches_oracle_and_golden(name, fold, monkeypatch):
+    # the folded single-query cross attention is only chosen when (fusions x batch) fills the GPU; force both routes here
+    monkeypatch.setenv("CAVIT_XFOLD_MIN_CTAS", "0" if fold else "1000000")
     kind, cfg, state, img, labels = build_case(name)
+    if not fold and (kind != "cross" or not cfg.attn_order):
+        pytest.skip("no fusion blocks")
     model, logits, loss, grads = _run_ours(kind, cfg, state, img, labels)
+    if kind == "cross" and cfg.attn_order:
+        assert model.engine().fold == (fold and model.engine().fold_ok)
     ref_logits, ref_loss, ref_grads = OF.forward_backward(state, img, labels, cfg, kind, torch.float64)
     rec = torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
     assert rel(logits, ref_logits) < 2e-2
