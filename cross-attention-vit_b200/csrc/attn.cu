@@ -264,6 +264,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         float m_part = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          // a 32-column chunk entirely beyond the last key (ragged last tile, e.g. N = 197: 59 of its 128 columns) holds no
+          // scores: skip its TMEM read and, below, its exponentials (warp-uniform; only the straddling chunk is masked)
+          if (cbase + c * 32 >= kv_valid) continue;
           uint32_t r[32];
           tmem_ld32(tS + t_lane + cbase + c * 32, r);
           tmem_ld_wait();
@@ -296,10 +299,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         float l_part = 0.f;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          float pv[32];
+          if (cbase + c * 32 >= kv_valid) {   // no keys here: P = 0 (the P.V MMA still reads these columns)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pv[i] = 0.f;
+            store_row_chunk_sw128(myP, row, cbase + c * 32, pv);
+            continue;
+          }
           uint32_t r[32];
           tmem_ld32(tS + t_lane + cbase + c * 32, r);
           tmem_ld_wait();
-          float pv[32];
           if (cbase + c * 32 + 32 <= kv_valid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
