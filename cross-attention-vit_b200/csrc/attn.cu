@@ -18,6 +18,7 @@
 //   dQ_i = dS K                             (A = dS^T tile viewed MN-major) -> fp32 red.global.add
 //
 // Ragged tails (N = tile + 1): out-of-range keys get P = 0; out-of-range query rows are not stored.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -72,6 +73,22 @@ __device__ __forceinline__ void store_row_16_sw128(uint8_t* tile, int r, int c0,
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// Optional timeline trace (build with NVCC_EXTRA=-DCAVIT_FWD_TRACE): CTA 0 records clock64() at protocol points of the
+// TMA producer (role 0), the MMA issuer (1) and lane 0 of the first softmax warp of each slot (2, 3).
+#ifdef CAVIT_FWD_TRACE
+__device__ unsigned long long g_fwd_trace[4][2048];
+__device__ __forceinline__ void fwd_trace(int role, uint32_t& n, int tag) {
+  if (blockIdx.x == 0 && n < 1024) {
+    g_fwd_trace[role][2 * n] = clock64();
+    g_fwd_trace[role][2 * n + 1] = tag;
+    ++n;
+  }
+}
+#define FWD_TRACE(role, n, tag) fwd_trace(role, n, tag)
+#else
+#define FWD_TRACE(role, n, tag)
+#endif
 
 struct AttnFwdParams {
   bf16* out;
@@ -158,18 +175,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       int st = 0;
       uint32_t ph = 0;
       int it = 0;
+      uint32_t ntr = 0;
+      (void)ntr;
       for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int qp = (int)(item % nqp);
         const long long gbh = item / nqp;
         const int bh = (int)(gbh % BH), g = (int)(gbh / BH);
         const int b = bh / p.H, h = bh % p.H;
         const int row_base = b * p.N;
+        FWD_TRACE(0, ntr, 0);
+        {   // L2 prefetch of the NEXT item's Q and first key / value tiles: one whole item ahead of their smem loads
+          const long long nitem = item + gridDim.x;
+          if (nitem < items) {
+            const int nqp_i = (int)(nitem % nqp);
+            const long long ngbh = nitem / nqp;
+            const int nbh = (int)(ngbh % BH), ng = (int)(ngbh / BH);
+            const int nrow = (nbh / p.H) * p.N, nh = nbh % p.H;
+            tma_prefetch_3d(&tmQKV, nh * ATT_D, nrow + nqp_i * 2 * ATT_TILE, ng);
+            tma_prefetch_3d(&tmQKV, nh * ATT_D, nrow + nqp_i * 2 * ATT_TILE + ATT_TILE, ng);
+            const int npf = nkv < 3 ? nkv : 3;
+            for (int j = 0; j < npf; ++j) {
+              tma_prefetch_3d(&tmQKV, p.C + nh * ATT_D, nrow + j * ATT_TILE, ng);
+              tma_prefetch_3d(&tmQKV, 2 * p.C + nh * ATT_D, nrow + j * ATT_TILE, ng);
+            }
+          }
+        }
         mbar_wait(bar_qempty, (it & 1) ^ 1u, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        FWD_TRACE(0, ntr, 1);
         mbar_arrive_expect_tx(bar_qfull, 2 * ATT_TILE_BYTES);
         tma_load_3d(&tmQKV, bar_qfull, sQ, h * ATT_D, row_base + qp * 2 * ATT_TILE, g);
         tma_load_3d(&tmQKV, bar_qfull, sQ + ATT_TILE_BYTES, h * ATT_D, row_base + qp * 2 * ATT_TILE + ATT_TILE, g);
         for (int j = 0; j < nkv; ++j) {
           mbar_wait(bar_kvempty(st), ph ^ 1u, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          FWD_TRACE(0, ntr, 2);
           mbar_arrive_expect_tx(bar_kvfull(st), 2 * ATT_TILE_BYTES);
           tma_load_3d(&tmQKV, bar_kvfull(st), sKV + st * 2 * ATT_TILE_BYTES, p.C + h * ATT_D, row_base + j * ATT_TILE, g);
           tma_load_3d(&tmQKV, bar_kvfull(st), sKV + st * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, 2 * p.C + h * ATT_D,
@@ -183,54 +221,79 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);
+      const uint64_t dQ[2] = {umma_desc_sw128(sQ, 16, 1024), umma_desc_sw128(sQ + ATT_TILE_BYTES, 16, 1024)};
+      const uint64_t dP[2] = {umma_desc_sw128(sP, 16, 1024), umma_desc_sw128(sP + 2 * ATT_TILE_BYTES, 16, 1024)};
+      const uint64_t dK0 = umma_desc_sw128(sKV, 16, 1024);
+      const uint64_t dV0 = umma_desc_sw128(sKV + ATT_TILE_BYTES, ATT_TILE_BYTES, 1024);
       int st = 0;
       uint32_t ph = 0;
       uint32_t t = 0;  // global tile counter of this CTA (same for both slots)
       int it = 0;
+      uint32_t ntr = 0;
+      (void)ntr;
       auto issue_s = [&](int sl, int stage) {
         // S[sl] may be overwritten once the slot's softmax warps have read the previous tile
         mbar_wait(bar_sfree(sl), (t & 1) ^ 1u, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        FWD_TRACE(1, ntr, 10 + sl);
         tc_fence_after();
+        // descriptors advance by constant adds on the 16-byte-granular start-address field (all of shared memory fits it)
+        const uint64_t ad0 = dQ[sl], bd0 = dK0 + static_cast<uint32_t>(stage * (2 * ATT_TILE_BYTES >> 4));
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(sQ + sl * ATT_TILE_BYTES + k * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(sKV + stage * 2 * ATT_TILE_BYTES + k * 32, 16, 1024);
-          umma_bf16_ss(tmem + sl * 128, ad, bd, idesc_s, k != 0);
-        }
+        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + sl * 128, ad0 + 2 * k, bd0 + 2 * k, idesc_s, k != 0);
         umma_commit(bar_sfull(sl));
       };
       auto issue_pv = [&](int sl, int stage, uint32_t tt) {
         mbar_wait(bar_pfull(sl), tt & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        FWD_TRACE(1, ntr, 12 + sl);
         tc_fence_after();
+        const uint64_t ad0 = dP[sl], bd0 = dV0 + static_cast<uint32_t>(stage * (2 * ATT_TILE_BYTES >> 4));
 #pragma unroll
-        for (int k = 0; k < ATT_TILE / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(sP + sl * 2 * ATT_TILE_BYTES + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
-          umma_bf16_ss(tmem + 256 + sl * 64, ad, bd, idesc_o, k != 0);
-        }
+        for (int k = 0; k < ATT_TILE / 16; ++k)
+          umma_bf16_ss(tmem + 256 + sl * 64, ad0 + ((k >> 2) * (ATT_TILE_BYTES >> 4) + (k & 3) * 2), bd0 + k * (2048 >> 4), idesc_o,
+                       k != 0);
         umma_commit(bar_ofull(sl));
       };
+      // The schedule is software-pipelined ACROSS work items: after the P.V of a slot's last key tile the next item's first
+      // S for that slot is issued at once (its Q arrived while this item was running), so a slot never waits for the other
+      // slot's last tile at an item boundary and the two slots stay half a period apart.
+      bool first = true;
       for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        mbar_wait(bar_qfull, it & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-        mbar_wait(bar_kvfull(st), ph, abort_flag, p.status, ERR_TIMEOUT_ATTN);
-        issue_s(0, st);
-        issue_s(1, st);
+        const bool has_next = item + gridDim.x < items;
+        FWD_TRACE(1, ntr, 14);
+        if (first) {
+          mbar_wait(bar_qfull, it & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          mbar_wait(bar_kvfull(st), ph, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          issue_s(0, st);
+          issue_s(1, st);
+          // Q is only read by the S MMAs: it is released as soon as the item's LAST S MMAs are issued, so that the producer
+          // loads the next item's Q (and runs ahead on its K/V) while this item's softmax / P.V still run.
+          if (nkv == 1) umma_commit(bar_qempty);
+          first = false;
+        }
         for (int j = 0; j < nkv; ++j) {
           int nst = st + 1;
           uint32_t nph = ph;
           if (nst == ATT_FWD_KV_STAGES) { nst = 0; nph ^= 1u; }
           const bool more = (j + 1 < nkv);
+          const bool nxt = more || has_next;   // the next S of each slot: next key tile, or tile 0 of the next item
           if (more) mbar_wait(bar_kvfull(nst), nph, abort_flag, p.status, ERR_TIMEOUT_ATTN);
           issue_pv(0, st, t);
-          if (more) { ++t; issue_s(0, nst); --t; }
+          if (!more && has_next) {
+            mbar_wait(bar_qfull, (it + 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+            FWD_TRACE(1, ntr, 15);
+            mbar_wait(bar_kvfull(nst), nph, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+            FWD_TRACE(1, ntr, 16);
+          }
+          if (nxt) { ++t; issue_s(0, nst); --t; }
           issue_pv(1, st, t);
-          if (more) { ++t; issue_s(1, nst); --t; }
+          if (nxt) { ++t; issue_s(1, nst); --t; }
+          if (more && j + 2 == nkv) umma_commit(bar_qempty);          // this item's last S MMAs are out
+          if (!more && has_next && nkv == 1) umma_commit(bar_qempty);  // single-tile items: the next item's only S MMAs are out
           umma_commit(bar_kvempty(st));  // K_j / V_j no longer needed once everything issued so far retires
           ++t;
           st = nst;
           ph = nph;
         }
-        umma_commit(bar_qempty);  // all S MMAs of this item have been issued: Q buffers free when they retire
       }
     }
   } else {
@@ -246,10 +309,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     const int bar_id = 1 + sl * 4 + quad;           // the two warps (parts) of this slot's lane quadrant
     const int cbase = part * 64;
     uint32_t t = 0;
+    uint32_t ntr = 0;
+    (void)ntr;
+    const bool tracer = (quad == 0 && part == 0 && lane == 0);
+    (void)tracer;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-      const int qp = (int)(item % nqp);
-      const long long gbh = item / nqp;
-      const int bh = (int)(gbh % BH), g = (int)(gbh / BH);
+      // 32-bit index math (the launcher rejects problems with >= 2^31 items): 64-bit div / mod cost hundreds of instructions
+      // per item on the softmax warps' critical path
+      const unsigned item_u = (unsigned)item;
+      const int qp = (int)(item_u % (unsigned)nqp);
+      const unsigned gbh = item_u / (unsigned)nqp;
+      const int bh = (int)(gbh % (unsigned)BH), g = (int)(gbh / (unsigned)BH);
       const int b = bh / p.H, h = bh % p.H;
       const int row_base = b * p.N;
       float o[32];
@@ -257,7 +327,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       for (int i = 0; i < 32; ++i) o[i] = 0.f;
       float m_run = -INFINITY, l_run = 0.f, alpha = 0.f;
       for (int j = 0; j < nkv; ++j, ++t) {
+        if (tracer) FWD_TRACE(2 + sl, ntr, 20);
         mbar_wait(bar_sfull(sl), t & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        if (tracer) FWD_TRACE(2 + sl, ntr, 21);
         tc_fence_after();
         const int kv_valid = min(ATT_TILE, p.N - j * ATT_TILE);
         // pass 1: row maximum of this warp's 64 columns
@@ -280,13 +352,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
           }
         }
         x_max[part * ATT_TILE + row] = m_part;
+        if (tracer) FWD_TRACE(2 + sl, ntr, 22);
         named_bar_sync(bar_id, 64);
+        if (tracer) FWD_TRACE(2 + sl, ntr, 23);
         const float m_tile = fmaxf(m_part, x_max[(part ^ 1) * ATT_TILE + row]);
         const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
         // fold the previous tile's O into the accumulators (its P.V finished long ago; this also
         // guarantees that the MMA no longer reads the P buffer we are about to overwrite)
         if (j > 0) {
           mbar_wait(bar_ofull(sl), (t - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+          if (tracer) FWD_TRACE(2 + sl, ntr, 24);
           tc_fence_after();
           uint32_t r[32];
           tmem_ld32(tO + t_lane + part * 32, r);
@@ -325,6 +400,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
           }
           store_row_chunk_sw128(myP, row, cbase + c * 32, pv);
         }
+        if (tracer) FWD_TRACE(2 + sl, ntr, 25);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sfree(sl));   // S[sl] fully read by this warp
@@ -338,7 +414,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         alpha = alpha_new;
       }
       // last tile's O
+      if (tracer) FWD_TRACE(2 + sl, ntr, 26);
       mbar_wait(bar_ofull(sl), (t - 1) & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+      if (tracer) FWD_TRACE(2 + sl, ntr, 27);
       tc_fence_after();
       {
         uint32_t r[32];
@@ -348,10 +426,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(r[i]);
       }
       tc_fence_before();
-      const int q = qp * 2 * ATT_TILE + sl * ATT_TILE + row;
-      if (q < p.N) {
+      // Output rows go through the slot's P buffer (free: the last P.V has retired) so that the global stores are whole
+      // 128-byte rows (8 lanes x 16 B) instead of 32 scattered 16-byte pieces per warp instruction, which kept the LSU busy
+      // for ~2000 cycles per item. Staging layout: [128 rows][8 x 16 B], 16-byte chunk index XOR (row & 7).
+      {
         const float inv_l = 1.0f / l_run;
-        bf16* orow = p.out + (long long)g * p.out_gs + (long long)(row_base + q) * p.C + h * ATT_D + part * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 w;
@@ -359,10 +438,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
           w.y = pack_bf16(o[i + 2] * inv_l, o[i + 3] * inv_l);
           w.z = pack_bf16(o[i + 4] * inv_l, o[i + 5] * inv_l);
           w.w = pack_bf16(o[i + 6] * inv_l, o[i + 7] * inv_l);
-          *reinterpret_cast<uint4*>(orow + i) = w;
+          *reinterpret_cast<uint4*>(myP + row * 128 + (((part * 4 + (i >> 3)) ^ (row & 7)) << 4)) = w;
         }
-        if (part == 0)
+        const int q = qp * 2 * ATT_TILE + sl * ATT_TILE + row;
+        if (part == 0 && q < p.N)
           p.lse[(((long long)g * p.B + b) * p.H + h) * p.N + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+        named_bar_sync(bar_id, 64);   // both column halves of this quadrant's 32 rows are staged
+        // the two warps of the quadrant store 16 rows each; the next use of this P region (pass 2 of the next item) comes
+        // after the max-exchange barrier of the same two warps, so the staged rows are not overwritten while being read
+        const int c16 = lane & 7;
+#pragma unroll
+        for (int it2 = 0; it2 < 4; ++it2) {
+          const int r = quad * 32 + part * 16 + it2 * 4 + (lane >> 3);
+          const int qr = qp * 2 * ATT_TILE + sl * ATT_TILE + r;
+          if (qr < p.N) {
+            const uint4 v = *reinterpret_cast<const uint4*>(myP + r * 128 + ((c16 ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(p.out + (long long)g * p.out_gs + (long long)(row_base + qr) * p.C + h * ATT_D + c16 * 8) = v;
+          }
+        }
       }
     }
   }
@@ -706,8 +799,22 @@ int cavit_attn_fwd(const void* qkv, void* out, float* lse, int32_t G, int32_t B,
   p.status = status_word();
   if (!p.status) return fail(CAVIT_E_DEVICE, "no status word");
   const long long items = (long long)G * B * H * ((N + 2 * ATT_TILE - 1) / (2 * ATT_TILE));
+  if (items >= (1ll << 31)) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_attn_fwd: too many work items");
   const int grid = (int)(items < sm_count() ? items : sm_count());
   attn_fwd_kernel<<<grid, ATT_FWD_THREADS, ATT_FWD_SMEM, as_stream(stream)>>>(*tm, p);
+#ifdef CAVIT_FWD_TRACE
+  {
+    static int calls = 0;
+    if (++calls == 3) {
+      cudaDeviceSynchronize();
+      static unsigned long long h[4][2048];
+      cudaMemcpyFromSymbol(h, g_fwd_trace, sizeof(h));
+      for (int role = 0; role < 4; ++role)
+        for (int i = 0; i < 400; ++i)
+          if (h[role][2 * i]) fprintf(stderr, "FWDTRACE %d %d %llu %llu\n", role, i, h[role][2 * i] - h[1][0], h[role][2 * i + 1]);
+    }
+  }
+#endif
   count_launch();
   return check_launch("cavit_attn_fwd");
 }
