@@ -519,7 +519,7 @@ struct AttnBwdParams {
 // shared memory and accumulated with 16-byte vector reductions (red.global.add.v4.f32).
 // smem: K | V | Q0 | Q1 | dO0 | dO1 | PT(2 chunks) | dST(2 chunks) | dQ stages 16 x 2 KB | lse/delta [3][128] x2 | barriers
 constexpr int ATT_BWD_COMPUTE_WARPS = 16;
-constexpr int ATT_BWD_THREADS = (ATT_BWD_COMPUTE_WARPS + 1) * 32;
+constexpr int ATT_BWD_THREADS = (ATT_BWD_COMPUTE_WARPS + 3) * 32;   // + control warp + two more MMA issuers (dV, dK)
 constexpr int ATT_BWD_SMEM = 10 * ATT_TILE_BYTES + 16 * 2048 + 3072 + 1024 + 128;
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -566,7 +566,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(bar_s, 1);
     mbar_init(bar_sfree, ATT_BWD_COMPUTE_WARPS);
     mbar_init(bar_p, ATT_BWD_COMPUTE_WARPS);
-    mbar_init(bar_d, 1);
+    mbar_init(bar_d, 3);   // three issuers commit per tile: control warp (dQ), warp 17 (dV), warp 18 (dK)
     fence_barrier_init();
     prefetch_tmap(&tmQKV);
     prefetch_tmap(&tmDO);
@@ -590,7 +590,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // ================================================================= control warp
     if (lane == 0) {
       const uint32_t idesc_kk = umma_idesc_bf16(128, 0, 0);   // S^T, dP^T : both operands K-major, N = 128
-      const uint32_t idesc_kmn = umma_idesc_bf16(64, 0, 1);   // dV, dK    : A K-major (smem P^T/dS^T), B MN-major, N = 64
       const uint32_t idesc_mnmn = umma_idesc_bf16(64, 1, 1);  // dQ        : A = dS^T viewed MN-major, B = K MN-major
       auto load_q = [&](int i) {
         const uint32_t bar = bar_q0 + 8 * (i & 1);
@@ -598,20 +597,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tma_load_3d(&tmQKV, bar, sQ + (i & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + i * ATT_TILE, g);
         tma_load_3d(&tmDO, bar, sDO + (i & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + i * ATT_TILE, g);
       };
+      // One thread issues 32 MMAs per query tile, 24 of them only 32 tensor-pipe cycles long (N = 64): the issue path must
+      // not rebuild descriptors. All of them are constant adds on these bases (16-byte units of the start-address field).
+      const uint64_t dK_k = umma_desc_sw128(sK, 16, 1024), dV_k = umma_desc_sw128(sV, 16, 1024);
+      // (second Q / dO buffer = + one tile; selected arithmetically: indexing a local array would go through local memory)
+      const uint64_t dQ_k0 = umma_desc_sw128(sQ, 16, 1024), dDO_k0 = umma_desc_sw128(sDO, 16, 1024);
+      const uint64_t dDST_mn = umma_desc_sw128(sDST, ATT_TILE_BYTES, 1024), dK_mn = umma_desc_sw128(sK, ATT_TILE_BYTES, 1024);
       auto issue_s = [&](int i) {  // S^T = K Q_i^T ; dP^T = V dO_i^T
-        const int buf = i & 1;
+        const uint32_t boff = static_cast<uint32_t>(i & 1) * (ATT_TILE_BYTES >> 4);
+        const uint64_t qd = dQ_k0 + boff, dd = dDO_k0 + boff;
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) {
-          const uint64_t kd = umma_desc_sw128(sK + k * 32, 16, 1024);
-          const uint64_t qd = umma_desc_sw128(sQ + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
-          umma_bf16_ss(tST, kd, qd, idesc_kk, k != 0);
-        }
+        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tST, dK_k + 2 * k, qd + 2 * k, idesc_kk, k != 0);
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) {
-          const uint64_t vd = umma_desc_sw128(sV + k * 32, 16, 1024);
-          const uint64_t dd = umma_desc_sw128(sDO + buf * ATT_TILE_BYTES + k * 32, 16, 1024);
-          umma_bf16_ss(tDPT, vd, dd, idesc_kk, k != 0);
-        }
+        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tDPT, dV_k + 2 * k, dd + 2 * k, idesc_kk, k != 0);
         umma_commit(bar_s);
       };
       mbar_arrive_expect_tx(bar_kv, 2 * ATT_TILE_BYTES);
@@ -636,28 +634,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(bar_p, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < ATT_TILE / 16; ++k) {  // dV[kv][d] += P^T[kv][q] dO[q][d]
-          const uint64_t ad = umma_desc_sw128(sPT + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(sDO + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
-          umma_bf16_ss(tDV, ad, bd, idesc_kmn, (i | k) != 0);
-        }
-#pragma unroll
-        for (int k = 0; k < ATT_TILE / 16; ++k) {  // dK[kv][d] += dS^T[kv][q] Q[q][d]
-          const uint64_t ad = umma_desc_sw128(sDST + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(sQ + buf * ATT_TILE_BYTES + k * 2048, ATT_TILE_BYTES, 1024);
-          umma_bf16_ss(tDK, ad, bd, idesc_kmn, (i | k) != 0);
-        }
-#pragma unroll
-        for (int k = 0; k < ATT_TILE / 16; ++k) {  // dQ[q][d] = dS[q][kv] K[kv][d]  (A = dS^T viewed MN-major)
-          const uint64_t ad = umma_desc_sw128(sDST + k * 2048, ATT_TILE_BYTES, 1024);
-          const uint64_t bd = umma_desc_sw128(sK + k * 2048, ATT_TILE_BYTES, 1024);
-          umma_bf16_ss(tDQ, ad, bd, idesc_mnmn, k != 0);
-        }
-        umma_commit(bar_d);
+        for (int k = 0; k < ATT_TILE / 16; ++k)   // dQ[q][d] = dS[q][kv] K[kv][d]  (A = dS^T viewed MN-major)
+          umma_bf16_ss(tDQ, dDST_mn + k * 128, dK_mn + k * 128, idesc_mnmn, k != 0);
+        umma_commit(bar_d);   // (dV / dK of this tile are issued and committed by the second issuer warp)
         if (i + 2 < nq) {  // refill this Q/dO buffer once the MMAs that read it have retired
           mbar_wait(bar_d, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
           load_q(i + 2);
         }
+      }
+    }
+  } else if (warp > ATT_BWD_COMPUTE_WARPS) {
+    // ================================================================= MMA issuers for dV (warp 17) and dK (warp 18)
+    // A single thread needs ~75 cycles per tcgen05.mma (descriptor arithmetic, R2UR, election), i.e. ~2400 cycles for the
+    // 32 MMAs of a query tile whose tensor-pipe time is 1280 cycles: the issue stream is split over three warps
+    // (control: S^T, dP^T of tile i+1 and dQ of tile i; these two: dV and dK, which accumulate in their own TMEM columns).
+    if (lane == 0) {
+      const bool is_dk = (warp == ATT_BWD_COMPUTE_WARPS + 2);
+      const uint32_t idesc_kmn = umma_idesc_bf16(64, 0, 1);
+      const uint64_t a0 = umma_desc_sw128(is_dk ? sDST : sPT, 16, 1024);                   // dS^T (dK) or P^T (dV), K-major
+      const uint64_t b0 = umma_desc_sw128(is_dk ? sQ : sDO, ATT_TILE_BYTES, 1024);          // Q (dK) or dO (dV), MN-major
+      const uint32_t acc = is_dk ? tDK : tDV;
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(bar_p, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
+        tc_fence_after();
+        const uint64_t b = b0 + static_cast<uint32_t>(i & 1) * (ATT_TILE_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < ATT_TILE / 16; ++k)   // dV[kv][d] += P^T[kv][q] dO[q][d]   /   dK[kv][d] += dS^T[kv][q] Q[q][d]
+          umma_bf16_ss(acc, a0 + ((k >> 2) * (ATT_TILE_BYTES >> 4) + (k & 3) * 2), b + k * 128, idesc_kmn, (i | k) != 0);
+        umma_commit(bar_d);
       }
     }
   } else {
@@ -681,7 +685,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int rr = it * 8 + (lane >> 2);
         const float4 v = reinterpret_cast<const float4*>(my_stage + rr * 16)[j ^ ((rr >> 1) & 3)];
         const int q = qi * ATT_TILE + quad * 32 + rr;
+#ifdef CAVIT_BWD_NO_DQ   // timing experiment only: how much of the kernel is the fp32 dQ reduction traffic?
+        if (q < 0)
+#else
         if (q < p.N)
+#endif
           red_add_v4(p.dq_acc + (long long)g * p.acc_gs + (long long)(row_base + q) * p.C + h * ATT_D + part * 16 + j * 4, v.x, v.y,
                      v.z, v.w);
       }

@@ -57,43 +57,22 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
   const long long total = (long long)rows_per_group * groups;
   const int C4 = C >> 2;
   const float inv_c = 1.0f / (float)C;
-  // gamma / beta of the current group stay in registers (re-read only when a warp's rows cross into the next group): they
-  // were 2 NV extra loads per row in a kernel that ncu shows at 60 % issue-slot utilisation, i.e. instruction-bound
-  float4 gm[NV], bt[NV];
-  int g_cached = -1;
-  const long long stride = (long long)gridDim.x * LN_WARPS;
-  long long row = (long long)blockIdx.x * LN_WARPS + warp;
-  // software prefetch: the next row's loads are in flight while this row is reduced and written
-  float4 v[NV], vn[NV];
-  auto load_row = [&](long long rw, float4 (&dst)[NV]) {
-    const int g = (int)(rw / rows_per_group);
-    const long long r = rw - (long long)g * rows_per_group;
+  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < total; row += (long long)gridDim.x * LN_WARPS) {
+    const int g = (int)(row / rows_per_group);
+    const long long r = row - (long long)g * rows_per_group;
     const float4* xr = reinterpret_cast<const float4*>(src_row(rm, x, g, r, row_stride, gs, C));
+    float4 v[NV];
+    float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
-      dst[i] = (c4 < C4) ? __ldg(xr + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  if (row < total) load_row(row, v);
-  for (; row < total; row += stride) {
-    const bool has_next = row + stride < total;
-    if (has_next) load_row(row + stride, vn);
-    const int g = (int)(row / rows_per_group);
-    if (g != g_cached) {
-      const float4* g4 = reinterpret_cast<const float4*>(gamma + (long long)g * C);
-      const float4* b4 = reinterpret_cast<const float4*>(beta + (long long)g * C);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c4 = lane + 32 * i;
-        gm[i] = (c4 < C4) ? __ldg(g4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bt[i] = (c4 < C4) ? __ldg(b4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < C4) {
+        v[i] = __ldg(xr + c4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      } else {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      g_cached = g;
     }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);   // padded lanes hold zeros
     const float mu = warp_sum(s) * inv_c;
     float ss = 0.f;
 #pragma unroll
@@ -105,13 +84,16 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
       }
     }
     const float rs = rsqrtf(warp_sum(ss) * inv_c + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma + (long long)g * C);
+    const float4* b4 = reinterpret_cast<const float4*>(beta + (long long)g * C);
     uint2* yr = reinterpret_cast<uint2*>(y + row * C);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
       if (c4 < C4) {
-        const float4 f = make_float4((v[i].x - mu) * rs * gm[i].x + bt[i].x, (v[i].y - mu) * rs * gm[i].y + bt[i].y,
-                                     (v[i].z - mu) * rs * gm[i].z + bt[i].z, (v[i].w - mu) * rs * gm[i].w + bt[i].w);
+        const float4 gm = __ldg(g4 + c4), bt = __ldg(b4 + c4);
+        const float4 f = make_float4((v[i].x - mu) * rs * gm.x + bt.x, (v[i].y - mu) * rs * gm.y + bt.y,
+                                     (v[i].z - mu) * rs * gm.z + bt.z, (v[i].w - mu) * rs * gm.w + bt.w);
         if (y) {
           uint2 o;
           o.x = pack_bf16(f.x, f.y);
@@ -125,10 +107,6 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
     if (lane == 0) {
       mean[row] = mu;
       rstd[row] = rs;
-    }
-    if (has_next) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = vn[i];
     }
   }
 }
