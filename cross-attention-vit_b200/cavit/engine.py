@@ -502,6 +502,8 @@ class Engine:
         work items should fill whole waves of the 148 persistent CTAs (a 2.2-wave launch wastes 27 % of the last
         wave) while every split keeps >= 8 k-blocks of 64 tokens."""
         bn = 256 if (K_in >= 256 and (K_in % 256 == 0 or K_in > 1024)) else 128     # mirrors cavit_gemm's N tile
+        if K_in % 192 == 0 and K_in % 256 != 0 and os.environ.get("CAVIT_WGRAD_BN192", "1") != "0":
+            bn = 192
         tiles = G * ((N_out + 127) // 128) * ((K_in + bn - 1) // bn)
         kb = (T + 63) // 64
         sms = 148
@@ -512,8 +514,9 @@ class Engine:
             items = tiles * s_
             waves = -(-items // sms)
             eff = items / (waves * sms)
-            # prefer >= 2 waves of work (tail effects), then the best wave efficiency, then the smaller split
-            score = eff - (0.15 if items < 1.9 * sms else 0.0) - 0.004 * s_
+            # best wave efficiency, then the smaller split (a single full wave measured as good as two: wgrad out 144 items
+            # 0.078 ms vs 288 items 0.110 ms, wgrad qkv 144 items 0.190 vs 288 items 0.196)
+            score = eff - 0.004 * s_
             if score > best_score:
                 best, best_score = s_, score
         return best

@@ -51,7 +51,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (CTAS == 2) ? ((BN == 128) ? 8 : (EW == 4 ? 5 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int STAGES = (CTAS == 2) ? ((BN == 128) ? 8 : (EW == 4 ? 5 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 4));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 4096 /*epilogue transpose stages*/;
 };
@@ -600,6 +600,11 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   const int CTAS = (!force_1cta && a->M > GEMM_BM && (!a->a_mn || wgrad_pair)) ? 2 : 1;
   int BN = (a->N >= 256 && (a->N % 256 == 0 || a->N > 1024)) ? 256 : 128;
   if (CTAS == 2 && !a->b_mn && a->N % 192 == 0 && a->N % 256 != 0) BN = 192;
+  // wgrad with N = 384 (dW[., C = 384]): two 192-wide tiles instead of three 128-wide ones. A single issuing thread needs
+  // ~40-75 cycles per tcgen05.mma while a 128x128x16 MMA occupies the tensor pipe for only 32: wider MMAs (48 cycles) are
+  // what keeps the split-K wgrad loop from being issue-bound.
+  static const bool wgrad192 = [] { const char* e = getenv("CAVIT_WGRAD_BN192"); return !(e && e[0] == '0'); }();
+  if (wgrad192 && CTAS == 1 && a->a_mn && a->b_mn && a->N % 192 == 0 && a->N % 256 != 0) BN = 192;
   const CUtensorMap *ta, *tb;
   if (!a->a_mn)
     ta = tensor_map_bf16_3d(a->A, a->K, a->M, a->groups, a->lda, a->a_gs, 64, GEMM_BM);
@@ -647,5 +652,6 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
     return launch_gemm<128, 2>(ta, tb, d, as_stream(stream));
   }
   if (BN == 256) return launch_gemm<256, 1>(ta, tb, d, as_stream(stream));
+  if (BN == 192) return launch_gemm<192, 1>(ta, tb, d, as_stream(stream));
   return launch_gemm<128, 1>(ta, tb, d, as_stream(stream));
 }
