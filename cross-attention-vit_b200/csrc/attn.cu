@@ -218,7 +218,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     }
   } else if (warp == 17) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the schedule converged (every lane executes the waits); one elected lane issues, so that the
+    // compiler emits ELECT + back-to-back predicated UTCHMMA instead of re-deriving a single active thread per instruction.
+    {
       const uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);
       const uint64_t dQ[2] = {umma_desc_sw128(sQ, 16, 1024), umma_desc_sw128(sQ + ATT_TILE_BYTES, 16, 1024)};
@@ -229,7 +231,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       uint32_t ph = 0;
       uint32_t t = 0;  // global tile counter of this CTA (same for both slots)
       int it = 0;
-      uint32_t ntr = 0;
+      uint32_t ntr = (lane == 0) ? 0u : 4096u;   // trace: lane 0 only
       (void)ntr;
       auto issue_s = [&](int sl, int stage) {
         // S[sl] may be overwritten once the slot's softmax warps have read the previous tile
@@ -238,20 +240,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         tc_fence_after();
         // descriptors advance by constant adds on the 16-byte-granular start-address field (all of shared memory fits it)
         const uint64_t ad0 = dQ[sl], bd0 = dK0 + static_cast<uint32_t>(stage * (2 * ATT_TILE_BYTES >> 4));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + sl * 128, ad0 + 2 * k, bd0 + 2 * k, idesc_s, k != 0);
-        umma_commit(bar_sfull(sl));
+          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + sl * 128, ad0 + 2 * k, bd0 + 2 * k, idesc_s, k != 0);
+          umma_commit(bar_sfull(sl));
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int sl, int stage, uint32_t tt) {
         mbar_wait(bar_pfull(sl), tt & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
         FWD_TRACE(1, ntr, 12 + sl);
         tc_fence_after();
         const uint64_t ad0 = dP[sl], bd0 = dV0 + static_cast<uint32_t>(stage * (2 * ATT_TILE_BYTES >> 4));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_TILE / 16; ++k)
-          umma_bf16_ss(tmem + 256 + sl * 64, ad0 + ((k >> 2) * (ATT_TILE_BYTES >> 4) + (k & 3) * 2), bd0 + k * (2048 >> 4), idesc_o,
-                       k != 0);
-        umma_commit(bar_ofull(sl));
+          for (int k = 0; k < ATT_TILE / 16; ++k)
+            umma_bf16_ss(tmem + 256 + sl * 64, ad0 + ((k >> 2) * (ATT_TILE_BYTES >> 4) + (k & 3) * 2), bd0 + k * (2048 >> 4),
+                         idesc_o, k != 0);
+          umma_commit(bar_ofull(sl));
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint32_t bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
       };
       // The schedule is software-pipelined ACROSS work items: after the P.V of a slot's last key tile the next item's first
       // S for that slot is issued at once (its Q arrived while this item was running), so a slot never waits for the other
@@ -267,7 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
           issue_s(1, st);
           // Q is only read by the S MMAs: it is released as soon as the item's LAST S MMAs are issued, so that the producer
           // loads the next item's Q (and runs ahead on its K/V) while this item's softmax / P.V still run.
-          if (nkv == 1) umma_commit(bar_qempty);
+          if (nkv == 1) commit(bar_qempty);
           first = false;
         }
         for (int j = 0; j < nkv; ++j) {
@@ -298,9 +310,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
             issue_pv(1, st, t);
             if (nxt) { ++t; issue_s(1, nst); --t; }
           }
-          if (more && j + 2 == nkv) umma_commit(bar_qempty);          // this item's last S MMAs are out
-          if (!more && has_next && nkv == 1) umma_commit(bar_qempty);  // single-tile items: the next item's only S MMAs are out
-          umma_commit(bar_kvempty(st));  // K_j / V_j no longer needed once everything issued so far retires
+          if (more && j + 2 == nkv) commit(bar_qempty);          // this item's last S MMAs are out
+          if (!more && has_next && nkv == 1) commit(bar_qempty);  // single-tile items: the next item's only S MMAs are out
+          commit(bar_kvempty(st));  // K_j / V_j no longer needed once everything issued so far retires
           ++t;
           st = nst;
           ph = nph;
