@@ -600,14 +600,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   if (warp == ATT_BWD_COMPUTE_WARPS) {
     // ================================================================= control warp
-    if (lane == 0) {
+    // (runs converged: every lane executes the waits, one elected lane issues the TMA loads and the MMAs back to back)
+    {
       const uint32_t idesc_kk = umma_idesc_bf16(128, 0, 0);   // S^T, dP^T : both operands K-major, N = 128
       const uint32_t idesc_mnmn = umma_idesc_bf16(64, 1, 1);  // dQ        : A = dS^T viewed MN-major, B = K MN-major
       auto load_q = [&](int i) {
-        const uint32_t bar = bar_q0 + 8 * (i & 1);
-        mbar_arrive_expect_tx(bar, 2 * ATT_TILE_BYTES);
-        tma_load_3d(&tmQKV, bar, sQ + (i & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + i * ATT_TILE, g);
-        tma_load_3d(&tmDO, bar, sDO + (i & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + i * ATT_TILE, g);
+        if (elect_one()) {
+          const uint32_t bar = bar_q0 + 8 * (i & 1);
+          mbar_arrive_expect_tx(bar, 2 * ATT_TILE_BYTES);
+          tma_load_3d(&tmQKV, bar, sQ + (i & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + i * ATT_TILE, g);
+          tma_load_3d(&tmDO, bar, sDO + (i & 1) * ATT_TILE_BYTES, h * ATT_D, row_base + i * ATT_TILE, g);
+        }
+        __syncwarp();
       };
       // One thread issues 32 MMAs per query tile, 24 of them only 32 tensor-pipe cycles long (N = 64): the issue path must
       // not rebuild descriptors. All of them are constant adds on these bases (16-byte units of the start-address field).
@@ -618,15 +622,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       auto issue_s = [&](int i) {  // S^T = K Q_i^T ; dP^T = V dO_i^T
         const uint32_t boff = static_cast<uint32_t>(i & 1) * (ATT_TILE_BYTES >> 4);
         const uint64_t qd = dQ_k0 + boff, dd = dDO_k0 + boff;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tST, dK_k + 2 * k, qd + 2 * k, idesc_kk, k != 0);
+          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tST, dK_k + 2 * k, qd + 2 * k, idesc_kk, k != 0);
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tDPT, dV_k + 2 * k, dd + 2 * k, idesc_kk, k != 0);
-        umma_commit(bar_s);
+          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tDPT, dV_k + 2 * k, dd + 2 * k, idesc_kk, k != 0);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
       };
-      mbar_arrive_expect_tx(bar_kv, 2 * ATT_TILE_BYTES);
-      tma_load_3d(&tmQKV, bar_kv, sK, p.C + h * ATT_D, row_base + kv0, g);
-      tma_load_3d(&tmQKV, bar_kv, sV, 2 * p.C + h * ATT_D, row_base + kv0, g);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_kv, 2 * ATT_TILE_BYTES);
+        tma_load_3d(&tmQKV, bar_kv, sK, p.C + h * ATT_D, row_base + kv0, g);
+        tma_load_3d(&tmQKV, bar_kv, sV, 2 * p.C + h * ATT_D, row_base + kv0, g);
+      }
+      __syncwarp();
       load_q(0);
       if (nq > 1) load_q(1);
       mbar_wait(bar_kv, 0, abort_flag, p.status, ERR_TIMEOUT_ATTN);
@@ -645,10 +655,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // P^T,dS^T(i) are in shared memory (and dQ(i-1) has been drained) -> dV, dK, dQ of tile i
         mbar_wait(bar_p, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_TILE / 16; ++k)   // dQ[q][d] = dS[q][kv] K[kv][d]  (A = dS^T viewed MN-major)
-          umma_bf16_ss(tDQ, dDST_mn + k * 128, dK_mn + k * 128, idesc_mnmn, k != 0);
-        umma_commit(bar_d);   // (dV / dK of this tile are issued and committed by the second issuer warp)
+          for (int k = 0; k < ATT_TILE / 16; ++k)   // dQ[q][d] = dS[q][kv] K[kv][d]  (A = dS^T viewed MN-major)
+            umma_bf16_ss(tDQ, dDST_mn + k * 128, dK_mn + k * 128, idesc_mnmn, k != 0);
+          umma_commit(bar_d);   // (dV / dK of this tile are issued and committed by the two other issuer warps)
+        }
+        __syncwarp();
         if (i + 2 < nq) {  // refill this Q/dO buffer once the MMAs that read it have retired
           mbar_wait(bar_d, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
           load_q(i + 2);
@@ -660,7 +673,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // A single thread needs ~75 cycles per tcgen05.mma (descriptor arithmetic, R2UR, election), i.e. ~2400 cycles for the
     // 32 MMAs of a query tile whose tensor-pipe time is 1280 cycles: the issue stream is split over three warps
     // (control: S^T, dP^T of tile i+1 and dQ of tile i; these two: dV and dK, which accumulate in their own TMEM columns).
-    if (lane == 0) {
+    {
       const bool is_dk = (warp == ATT_BWD_COMPUTE_WARPS + 2);
       const uint32_t idesc_kmn = umma_idesc_bf16(64, 0, 1);
       const uint64_t a0 = umma_desc_sw128(is_dk ? sDST : sPT, 16, 1024);                   // dS^T (dK) or P^T (dV), K-major
@@ -670,10 +683,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(bar_p, i & 1, abort_flag, p.status, ERR_TIMEOUT_ATTN);
         tc_fence_after();
         const uint64_t b = b0 + static_cast<uint32_t>(i & 1) * (ATT_TILE_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_TILE / 16; ++k)   // dV[kv][d] += P^T[kv][q] dO[q][d]   /   dK[kv][d] += dS^T[kv][q] Q[q][d]
-          umma_bf16_ss(acc, a0 + ((k >> 2) * (ATT_TILE_BYTES >> 4) + (k & 3) * 2), b + k * 128, idesc_kmn, (i | k) != 0);
-        umma_commit(bar_d);
+          for (int k = 0; k < ATT_TILE / 16; ++k)   // dV[kv][d] += P^T[kv][q] dO[q][d]   /   dK[kv][d] += dS^T[kv][q] Q[q][d]
+            umma_bf16_ss(acc, a0 + ((k >> 2) * (ATT_TILE_BYTES >> 4) + (k & 3) * 2), b + k * 128, idesc_kmn, (i | k) != 0);
+          umma_commit(bar_d);
+        }
+        __syncwarp();
       }
     }
   } else {
