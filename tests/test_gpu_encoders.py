@@ -231,3 +231,48 @@ def test_encoder_inference_paths():
     p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in state.items()}
     ref_logits, ref_loss = E.vit3d_forward(p64, x.double(), labels, E.enc_config(name), 0.1, training=False)
     assert rel(logits, ref_logits) < 2e-2 and abs(float(loss) - float(ref_loss)) < 2e-2
+
+
+def test_vit3d_long_token_axis_uses_generic_attention_kernels():
+    """ViT3D with 4 modalities x 64 tokens + CLS = 257 tokens (> 256: the tiled attention kernels with the three-warp MMA
+    issue of the backward), hidden 256 / 4 heads, against the fp64 oracle with the ReLU pattern replayed."""
+    from types import SimpleNamespace
+    from cavit import _abi
+    from cavit.encoders import ViT3D
+    cfg = SimpleNamespace(hidden_dim=256, transformer=SimpleNamespace(num_heads=4, num_layers=2), img_size=(64, 64, 64))
+    M, B = 4, 2
+    torch.manual_seed(5)
+    model = ViT3D({}, 1e-4, 0.0, M, cfg, num_classes=2, label_smoothing=0.0)
+    schema = {k: (tuple(v.shape), v.dtype) for k, v in model.state_dict().items()}
+    state = E.make_state_generic(schema, 41)
+    model.load_state_dict(state)
+    model = model.cuda().train()
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(B, M, 1, 64, 64, 64, generator=g)
+    labels = torch.tensor([0, 1])
+    logits, loss = model(x.cuda(), labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _abi.device_status() == 0
+    eng = model._engine_obj
+    assert eng.N == 257
+    masks = [(eng.a["h"][l][0] > 0).view(B, eng.N, -1).cpu() for l in range(eng.L)]
+    lp = {}
+    for k, v in state.items():
+        if not v.is_floating_point():
+            lp[k] = v
+        elif k.endswith(("running_mean", "running_var")):
+            lp[k] = v.double()
+        else:
+            lp[k] = v.double().clone().requires_grad_(True)
+    report = []
+    ref_logits, ref_loss = E.vit3d_forward(lp, x.double(), labels, cfg, 0.0, training=True, relu_masks=masks, mask_report=report)
+    ref_loss.backward()
+    assert all(frac < 0.03 for frac, _ in report), report
+    assert rel(logits, ref_logits) < 2e-2 and abs(float(loss) - float(ref_loss)) < 2e-2
+    tot_err = tot_ref = 0.0
+    for k, p in model.named_parameters():
+        gref = lp[k].grad
+        tot_err += float((p.grad.double().cpu() - gref).norm()) ** 2
+        tot_ref += float(gref.norm()) ** 2
+    assert (tot_err / tot_ref) ** 0.5 < 4e-2, (tot_err / tot_ref) ** 0.5
