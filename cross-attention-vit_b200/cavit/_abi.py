@@ -49,6 +49,8 @@ _SIGS = {
     "cavit_tokens_to_channels": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cavit_conv_patch_rows": (c_i32, [c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
     "cavit_conv_patch_rows_bwd": (c_i32, [c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
+    "cavit_token_mean_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_token_mean_bwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cavit_bce_head_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "cavit_bce_head_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "cavit_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp]),

@@ -312,15 +312,13 @@ class ViT3D(_EncoderModel):
         self.label_smoothing = label_smoothing
         if pretrained_cnn:
             raise _abi.CavitError("ViT3D(pretrained_cnn=True) needs MONAI's DenseNet121, which is outside this path")
-        if not add_cls_token:
-            raise _abi.CavitError("ViT3D(add_cls_token=False) (mean-pooled head) is not built; use the CLS head")
         self.config, self.num_modalities, self.num_classes, self._dropout_p = config, num_modalities, num_classes, float(dropout)
         self.encoder_3d = CNN3DEncoder(hidden_dim=config.hidden_dim)
         self.add_cls_token = add_cls_token
-        self.cls_token = nn.Parameter(torch.zeros(1, 1, config.hidden_dim))
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, config.hidden_dim)) if add_cls_token else None
         D, H, W = config.img_size
         num_tokens = (D // 16) * (H // 16) * (W // 16) * num_modalities
-        self.pos_embed = nn.Parameter(torch.zeros(1, num_tokens + 1, config.hidden_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_tokens + int(add_cls_token), config.hidden_dim))
         self.transformer = TransformerEncoder(embed_dim=config.hidden_dim, num_heads=config.transformer.num_heads,
                                               num_layers=config.transformer.num_layers, dropout=dropout)
         self.mlp_head = nn.Sequential(nn.LayerNorm(config.hidden_dim), nn.Linear(config.hidden_dim, config.hidden_dim // 8),
@@ -329,7 +327,8 @@ class ViT3D(_EncoderModel):
 
     def _init_weights(self):
         nn.init.normal_(self.pos_embed, std=0.02)
-        nn.init.normal_(self.cls_token, std=0.02)
+        if self.cls_token is not None:
+            nn.init.normal_(self.cls_token, std=0.02)
         for m in self.modules():
             if isinstance(m, nn.Linear):
                 nn.init.xavier_uniform_(m.weight)
@@ -341,13 +340,15 @@ class ViT3D(_EncoderModel):
 
     def _engine_cfg(self, num_modalities):
         c = self.config
-        S = (self.pos_embed.shape[1] - 1) // num_modalities
-        if S * num_modalities + 1 != self.pos_embed.shape[1]:
+        hc = int(self.add_cls_token)
+        S = (self.pos_embed.shape[1] - hc) // num_modalities
+        if S * num_modalities + hc != self.pos_embed.shape[1]:
             raise _abi.CavitError("ViT3D: pos_embed does not match the number of modalities")
         return SimpleNamespace(hidden_dim=c.hidden_dim, mlp_dim=4 * c.hidden_dim, num_heads=c.transformer.num_heads,
                                num_layers=c.transformer.num_layers, num_modalities=num_modalities,
                                num_classes=self.num_classes, dropout=0.0, label_smoothing=float(self.label_smoothing),
-                               tokens_per_modality=S, num_tokens=self.pos_embed.shape[1], head_dim_hidden=c.hidden_dim // 8)
+                               tokens_per_modality=S, num_tokens=self.pos_embed.shape[1], head_dim_hidden=c.hidden_dim // 8,
+                               has_cls=bool(self.add_cls_token))
 
     def forward(self, x, labels):
         if self.training and self._dropout_p > 0:

@@ -80,7 +80,8 @@ def build_layout_encoder(kind: str, cfg) -> ParamLayout:
     else:
         N = cfg.num_tokens
         lay.add("pos", (N, C), [("pos_embed", 0, (1, N, C))])
-        lay.add("cls", (C,), [("cls_token", 0, (1, 1, C))])
+        if getattr(cfg, "has_cls", True):
+            lay.add("cls", (C,), [("cls_token", 0, (1, 1, C))])
     lay.layer_ranges.append(("embed", start, lay.total))
     for l in range(cfg.num_layers):
         start = lay.total
@@ -262,10 +263,11 @@ class Engine:
             self.P = cfg.patch_size[0] * cfg.patch_size[1] * cfg.patch_size[2]
         if self.P % 8:
             raise _abi.CavitError("patch_dim must be a multiple of 8")
+        self.has_cls = bool(getattr(cfg, "has_cls", True))   # ViT3D(add_cls_token=False): mean-pooled head, no CLS row
         if self.encoder:
             if float(cfg.dropout) != 0.0:
                 raise _abi.CavitError("cavit encoder cores (ViT / ViT3D) support dropout = 0 only")
-            self.G, self.N = 1, self.Np * self.Mimg + 1
+            self.G, self.N = 1, self.Np * self.Mimg + int(self.has_cls)
             self.L = cfg.num_layers
             self.cls_src, self.tok_src = [], []
             self.smoothing = float(getattr(cfg, "label_smoothing", 0.0))
@@ -557,8 +559,8 @@ class Engine:
             B = img.shape[0] // self.Mimg
             labels = labels.to(device=self.device, dtype=F32).contiguous()
         elif self.kind == "vit3d":    # stem features of all modalities on the token axis, channel-major [B, C, M*S]
-            if img.dim() != 3 or img.shape[1] != self.C or img.shape[2] != self.N - 1:
-                raise _abi.CavitError(f"features must be [B, {self.C}, {self.N - 1}], got {tuple(img.shape)}")
+            if img.dim() != 3 or img.shape[1] != self.C or img.shape[2] != self.N - int(self.has_cls):
+                raise _abi.CavitError(f"features must be [B, {self.C}, {self.N - int(self.has_cls)}], got {tuple(img.shape)}")
             B = img.shape[0]
             labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
         else:
@@ -983,6 +985,11 @@ class Engine:
             a[nm] = [e(shp, dt) for _ in range(nL)]
         a["zeros"] = torch.zeros(max(3 * C, F), dtype=F32, device=dev)
         a["clsn"], a["meanc"], a["rstdc"] = e((1, B, C), BF16), e((1, B)), e((1, B))
+        if not self.has_cls:
+            a["pool"] = e((1, B, C))
+            a["dcls_dummy"] = e((C,))
+            if train:
+                a["dpool"] = e((1, B, C))
         a["hh"] = e((1, B, Fh), BF16)
         a["logits"], a["loss"] = e((B, self.classes)), e((1,))
         if train:
@@ -991,13 +998,14 @@ class Engine:
             a["delta"], a["dq_acc"] = e((1, B, H, N)), e((1, T, C))
             a["ln_ws"] = ops.ln_bwd_workspace(1, C, dev)
             a["dhh"], a["dclsn"] = e((1, B, Fh), BF16), e((1, B, C), BF16)
-            a["dfeat"] = e((B, C, N - 1))
+            a["dfeat"] = e((B, C, N - int(self.has_cls)))
 
     def _forward_post(self, feat, labels, train):
         """`ViT3D.forward` from the stem features on (/root/reference/modelv2.py:203-241): token assembly, L post-norm
         nn.TransformerEncoderLayer blocks  x = LN1(x + SA(x)); x = LN2(x + W2 relu(W1 x + b1) + b2), head on the CLS row."""
         a, N, C, F, H, T, B = self.a, self.N, self.C, self.F, self.H, self.T, self.B
-        ops.tokens_from_channels(feat, self.w("cls"), self.w("pos"), a["x0"], B=B, C_=C, S=N - 1, has_cls=True)
+        hc = self.has_cls
+        ops.tokens_from_channels(feat, self.w("cls") if hc else None, self.w("pos"), a["x0"], B=B, C_=C, S=N - int(hc), has_cls=hc)
         ops.cast_bf16(a["x0"], a["xin_b"][0])
         x_in = a["x0"]
         for l in range(self.L):
@@ -1021,8 +1029,13 @@ class Engine:
             x_in = a["xb"]
         self._x_fin = x_in
         Fh = self.cfg.head_dim_hidden
-        ops.ln_fwd(x_in, self.w("fin.ln.w"), self.w("fin.ln.b"), a["clsn"], a["meanc"], a["rstdc"], rows_per_group=B, groups=1,
-                   C=C, x_row_stride=N * C, x_gs=T * C, eps=1e-5)
+        if hc:   # head on the CLS row (row 0 of every sample)
+            ops.ln_fwd(x_in, self.w("fin.ln.w"), self.w("fin.ln.b"), a["clsn"], a["meanc"], a["rstdc"], rows_per_group=B,
+                       groups=1, C=C, x_row_stride=N * C, x_gs=T * C, eps=1e-5)
+        else:    # add_cls_token=False: head on the mean over all tokens (modelv2.py:233-235)
+            ops.token_mean_fwd(x_in, a["pool"], B=B, N=N, C_=C)
+            ops.ln_fwd(a["pool"], self.w("fin.ln.w"), self.w("fin.ln.b"), a["clsn"], a["meanc"], a["rstdc"], rows_per_group=B,
+                       groups=1, C=C, eps=1e-5)
         self._fwd(a["clsn"], self.wb("head.w1"), a["hh"], G=1, T=B, N=Fh, K=C, epi=EPI_BIAS, bias=self.w("head.b1"))
         ops.head_loss_fwd(a["hh"], self.w("head.w2"), self.w("head.b2"), labels, a["logits"], a["loss"], M=1, B=B, F=Fh,
                           classes=self.classes, smoothing=self.smoothing)
@@ -1041,10 +1054,15 @@ class Engine:
         self._wgrad(a["dhh"], a["clsn"], self.g("head.w1"), G=1, T=B, N=Fh, K=C)
         self._colsum(a["dhh"], self.g("head.b1"), G=1, T=B, N=Fh)
         dA, dB, dXb = a["dA"], a["dB"], a["dXb"]
-        dA.zero_()
-        ops.ln_bwd(a["dclsn"], self._x_fin, a["meanc"], a["rstdc"], self.w("fin.ln.w"), dA, self.g("fin.ln.w"),
-                   self.g("fin.ln.b"), ws, rows_per_group=B, groups=1, C=C, x_row_stride=N * C, x_gs=T * C,
-                   dx_row_stride=N * C, dx_gs=T * C)
+        if self.has_cls:
+            dA.zero_()
+            ops.ln_bwd(a["dclsn"], self._x_fin, a["meanc"], a["rstdc"], self.w("fin.ln.w"), dA, self.g("fin.ln.w"),
+                       self.g("fin.ln.b"), ws, rows_per_group=B, groups=1, C=C, x_row_stride=N * C, x_gs=T * C,
+                       dx_row_stride=N * C, dx_gs=T * C)
+        else:
+            ops.ln_bwd(a["dclsn"], a["pool"], a["meanc"], a["rstdc"], self.w("fin.ln.w"), a["dpool"], self.g("fin.ln.w"),
+                       self.g("fin.ln.b"), ws, rows_per_group=B, groups=1, C=C)
+            ops.token_mean_bwd(a["dpool"], dA, B=B, N=N, C_=C)
         done("head")
         for l in reversed(range(self.L)):
             tag = f"L{l}"
@@ -1069,8 +1087,8 @@ class Engine:
             # d(x_in) = d(s1) + d(qkv) Wqkv
             self._dgrad(a["dqkv"], self.wb(f"{tag}.wqkv"), dA, G=1, T=T, N=3 * C, K=C, epi=EPI_BIAS_RESID, bias=zeros, resid=dB)
             done(tag)
-        ops.embed_param_grads(dA, self.g("pos"), self.g("cls"), M=1, B=B, N=N, C_=C)
-        ops.tokens_to_channels(dA, a["dfeat"], B=B, C_=C, S=N - 1, has_cls=True)
+        ops.embed_param_grads(dA, self.g("pos"), self.g("cls") if self.has_cls else a["dcls_dummy"], M=1, B=B, N=N, C_=C)
+        ops.tokens_to_channels(dA, a["dfeat"], B=B, C_=C, S=N - int(self.has_cls), has_cls=self.has_cls)
         self.dinput = a["dfeat"]
         done("embed")
         return self.grad

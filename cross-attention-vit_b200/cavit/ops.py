@@ -267,6 +267,14 @@ def conv_patch_rows_bwd(drows, dfeat, *, M, B, Cin, dims, grid):
                                           grid[0], grid[1], grid[2], _stream()), "cavit_conv_patch_rows_bwd")
 
 
+def token_mean_fwd(x, out, *, B, N, C_):
+    check(lib().cavit_token_mean_fwd(x.data_ptr(), out.data_ptr(), B, N, C_, _stream()), "cavit_token_mean_fwd")
+
+
+def token_mean_bwd(dmean, dx, *, B, N, C_):
+    check(lib().cavit_token_mean_bwd(dmean.data_ptr(), dx.data_ptr(), B, N, C_, _stream()), "cavit_token_mean_bwd")
+
+
 def bce_head_fwd(x, w, b0, targets, logits, loss, *, B, C_):
     check(lib().cavit_bce_head_fwd(x.data_ptr(), w.data_ptr(), b0.data_ptr(), _p(targets), logits.data_ptr(), _p(loss),
                                    B, C_, _stream()), "cavit_bce_head_fwd")
@@ -342,5 +350,5 @@ for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_f
            "patchify", "cls_rows", "embed_param_grads", "cast_bf16", "colsum_bf16", "gather_rows_f32", "add_bf16_f32",
            "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout", "xfold_fwd", "xfold_bwd",
            "expand_heads", "fold_heads", "tokens_from_channels", "tokens_to_channels", "conv_patch_rows",
-           "conv_patch_rows_bwd", "bce_head_fwd", "bce_head_bwd", "adam_step", "gather_rows_f32_indexed"):
+           "conv_patch_rows_bwd", "bce_head_fwd", "bce_head_bwd", "adam_step", "gather_rows_f32_indexed", "token_mean_fwd", "token_mean_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

@@ -60,6 +60,37 @@ __global__ void tokens_to_channels_kernel(const float* __restrict__ dX, float* _
   }
 }
 
+// ------------------------------------------------------------------------------ token mean (ViT3D without a CLS token)
+// out[b][c] = mean_n x[b][n][c]   (modelv2.py:233-235: `x.mean(dim=1)`).  grid = (ceil(C/128), B), block 128: thread = column.
+__global__ void token_mean_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* p = x + (long long)b * N * C + c;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int n = 0;
+  for (; n + 4 <= N; n += 4) {
+    a0 += __ldg(p + (long long)n * C);
+    a1 += __ldg(p + (long long)(n + 1) * C);
+    a2 += __ldg(p + (long long)(n + 2) * C);
+    a3 += __ldg(p + (long long)(n + 3) * C);
+  }
+  for (; n < N; ++n) a0 += __ldg(p + (long long)n * C);
+  out[(long long)b * C + c] = ((a0 + a1) + (a2 + a3)) / (float)N;
+}
+// dx[b][n][c] = dmean[b][c] / N
+__global__ void token_mean_bwd_kernel(const float* __restrict__ dmean, float* __restrict__ dx, int B, int N, int C) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * N * C4;
+  const float inv = 1.0f / (float)N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const long long b = i / ((long long)N * C4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(dmean + b * C) + c4);
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    reinterpret_cast<float4*>(dx)[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------ Conv3d(k = stride) patch rows
 // feat: fp32 [M*B][Cin][A][Bd][Cd] (sample index m*B + b: the stem runs modality-major);
 // rows: bf16 [(b*M + m)*Np + t][f],  t = (a'*Bn + b')*Cn + c',  f = ((cin*g0 + i0)*g1 + i1)*g2 + i2.
@@ -218,6 +249,20 @@ int cavit_conv_patch_rows_bwd(const void* drows_bf16, float* dfeat, int32_t M, i
       dfeat, reinterpret_cast<bf16*>(const_cast<void*>(drows_bf16)), q);
   count_launch();
   return check_launch("cavit_conv_patch_rows_bwd");
+}
+
+int cavit_token_mean_fwd(const float* x, float* out, int32_t B, int32_t N, int32_t C, void* stream) {
+  if (!x || !out || B <= 0 || N <= 0 || C <= 0 || B > 65535) return fail(CAVIT_E_BADARG, "cavit_token_mean_fwd: bad args");
+  token_mean_fwd_kernel<<<dim3((C + 127) / 128, B), 128, 0, as_stream(stream)>>>(x, out, N, C);
+  count_launch();
+  return check_launch("cavit_token_mean_fwd");
+}
+
+int cavit_token_mean_bwd(const float* dmean, float* dx, int32_t B, int32_t N, int32_t C, void* stream) {
+  if (!dmean || !dx || B <= 0 || N <= 0 || C <= 0 || (C % 4)) return fail(CAVIT_E_BADARG, "cavit_token_mean_bwd: bad args");
+  token_mean_bwd_kernel<<<grid_cap((long long)B * N * C / 4, 256), 256, 0, as_stream(stream)>>>(dmean, dx, B, N, C);
+  count_launch();
+  return check_launch("cavit_token_mean_bwd");
 }
 
 int cavit_bce_head_fwd(const float* x, const float* w, const float* b0, const float* targets, float* logits, float* loss,

@@ -242,6 +242,10 @@ int cavit_conv_patch_rows(const float* feat, void* rows_bf16, int32_t M, int32_t
                           int32_t Cd, int32_t g0, int32_t g1, int32_t g2, void* stream);
 int cavit_conv_patch_rows_bwd(const void* drows_bf16, float* dfeat, int32_t M, int32_t B, int32_t Cin, int32_t A,
                               int32_t Bd, int32_t Cd, int32_t g0, int32_t g1, int32_t g2, void* stream);
+/* Mean over the token axis and its adjoint: the head input of `ViT3D(add_cls_token=False)`
+ * (/root/reference/modelv2.py:233-235, `x.mean(dim=1)`). x / dx: fp32 [B][N][C]; out / dmean: fp32 [B][C]. */
+int cavit_token_mean_fwd(const float* x, float* out, int32_t B, int32_t N, int32_t C, void* stream);
+int cavit_token_mean_bwd(const float* dmean, float* dx, int32_t B, int32_t N, int32_t C, void* stream);
 /* Single-logit tail of `ViT` (/root/reference/model.py:224,279-286): logits[b] = x[b].w + b0,
  * loss = BCEWithLogitsLoss(mean)(logits, targets). x: fp32 [B][C]; targets fp32 [B] (NULL: logits only).
  * Backward: dx fp32 [B][C], dw [C], db [1]; upstream gradient as in cavit_head_loss_bwd. */

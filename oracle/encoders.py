@@ -137,7 +137,10 @@ def vit3d_core(p: Params, feat: Tensor, labels: Tensor, heads: int, layers: int,
     (fraction of units that differ from the oracle's own pattern, max |u| / std(u) over those units)."""
     B = feat.shape[0]
     h = feat.transpose(1, 2)
-    h = torch.cat((p["cls_token"].expand(B, -1, -1), h), dim=1) + p["pos_embed"]
+    has_cls = "cls_token" in p      # ViT3D(add_cls_token=False) registers no cls_token (modelv2.py:140-143)
+    if has_cls:
+        h = torch.cat((p["cls_token"].expand(B, -1, -1), h), dim=1)
+    h = h + p["pos_embed"]
     for l in range(layers):
         pre = f"transformer.transformer.layers.{l}."
         a = mha(h, p[pre + "self_attn.in_proj_weight"], p[pre + "self_attn.in_proj_bias"],
@@ -155,7 +158,8 @@ def vit3d_core(p: Params, feat: Tensor, labels: Tensor, heads: int, layers: int,
             act = u * mk.to(u.dtype)
         f = linear(act, p[pre + "linear2.weight"], p[pre + "linear2.bias"])
         h = layer_norm(h + f, p[pre + "norm2.weight"], p[pre + "norm2.bias"], 1e-5)
-    c = layer_norm(h[:, 0], p["mlp_head.0.weight"], p["mlp_head.0.bias"], 1e-5)
+    pooled = h[:, 0] if has_cls else h.mean(dim=1)     # modelv2.py:229-235
+    c = layer_norm(pooled, p["mlp_head.0.weight"], p["mlp_head.0.bias"], 1e-5)
     logits = linear(linear(c, p["mlp_head.1.weight"], p["mlp_head.1.bias"]), p["mlp_head.2.weight"], p["mlp_head.2.bias"])
     return logits, cross_entropy(logits, labels, label_smoothing)
 
@@ -201,6 +205,7 @@ ENC_CASES = {
     # name: (kind, config kwargs, ctor kwargs, batch, modalities, state seed, input seed)
     "cnnvit_small": ("cnnvit", dict(), dict(), 3, 2, 21, 31),
     "vit3d_small": ("vit3d", dict(), dict(num_classes=2, label_smoothing=0.1), 2, 3, 22, 33),
+    "vit3d_meanpool": ("vit3d", dict(), dict(num_classes=3, add_cls_token=False), 2, 2, 23, 34),
 }
 
 

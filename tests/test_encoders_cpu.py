@@ -101,6 +101,6 @@ def test_unsupported_options_fail_loudly():
     from cavit.encoders import ViT3D
     cfg = E.enc_config("vit3d_small")
     with pytest.raises(CavitError):
-        ViT3D({}, 1e-4, 0.0, 2, cfg, add_cls_token=False)
-    with pytest.raises(CavitError):
         ViT3D({}, 1e-4, 0.0, 2, cfg, pretrained_cnn=True)
+    m = ViT3D({}, 1e-4, 0.0, 2, cfg, add_cls_token=False)      # mean-pooled head: supported, registers no cls_token
+    assert m.cls_token is None and "cls_token" not in m.state_dict()
