@@ -221,11 +221,11 @@ def test_fused_adam_tracks_torch_adam_over_steps():
 
 def test_raw_mri_intensities_match_oracle():
     """The reference feeds RAW MRI intensities (O(10^3), no normalisation: dataset_ucsf.py:81-89), which is why the residual
-    stream, LayerNorm statistics and logits stay fp32 here. The large DC component of raw intensities
-    (mean ~2000 against a spread of ~1000) passes through the bf16 operands of the embedding GEMM and is only removed by the
-    first LayerNorm, so its rounding noise is ~2x that of zero-mean inputs: measured 2.8e-2 on logits of magnitude 0.1 where
-    the N(0,1) cases stay below 2e-2. Tolerance here: 3.5e-2 (logits), 4e-2 (gradient vector); a DC-centred embedding
-    (W x = W (x - c) + c W 1, the correction in fp32) is the known fix and is listed in DESIGN.md section 7."""
+    stream, LayerNorm statistics and logits stay fp32 here. With a mean of ~2000 against a spread of ~1000
+    every token carries the same large component 2000 (W 1), so the informative differences between tokens are about half of
+    the embedded magnitude and the bf16 operand rounding of the embedding GEMM weighs ~2x more than with zero-mean inputs:
+    measured 2.8e-2 on logits of magnitude 0.1 where the N(0,1) cases stay below 2e-2. Tolerance here: 3.5e-2 (logits),
+    4e-2 (gradient vector); see DESIGN.md section 7."""
     from oracle.cases import CASES
     from oracle.functional import make_config
     from oracle.weights import make_inputs, make_state, state_schema_cross
