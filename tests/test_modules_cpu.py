@@ -76,3 +76,20 @@ def test_cpu_forward_fails_loudly():
     img = torch.zeros(1, cfg.num_modalities, 1, *cfg.img_size)
     with pytest.raises(CavitError):
         model(img, torch.zeros(1, dtype=torch.long))
+
+
+def test_cosine_annealing_matches_torch_scheduler():
+    """cavit.optim.CosineAnnealing (closed form) against torch's CosineAnnealingLR stepped per epoch, the schedule of
+    configure_optimizers (/root/reference/model_cross.py:280-291)."""
+    from types import SimpleNamespace
+    from cavit.optim import CosineAnnealing
+    opt = SimpleNamespace(base_lr=1e-4, lr=1e-4)
+    sched = CosineAnnealing(opt, T_max=250, eta_min=1e-6)
+    p = torch.nn.Parameter(torch.zeros(1))
+    topt = torch.optim.Adam([p], lr=1e-4)
+    tsched = torch.optim.lr_scheduler.CosineAnnealingLR(topt, T_max=250, eta_min=1e-6)
+    for _ in range(300):       # past T_max too: torch's recursive form keeps following the cosine
+        topt.step()
+        tsched.step()
+        sched.step()
+        assert abs(opt.lr - tsched.get_last_lr()[0]) < 1e-12
