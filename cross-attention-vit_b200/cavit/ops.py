@@ -232,6 +232,13 @@ def gather_rows_f32_indexed(src, dst, *, rows, C_, src_row_stride, src_gs, dst_r
           "cavit_gather_rows_f32_indexed")
 
 
+def stage_volumes(raw, desc, out, *, volumes, D, H, W, pad_value=-1.0):
+    """Stored voxels (uint8 blob + 32-byte descriptors, both on the device) -> fp32 [volumes][D][H][W]
+    (include/cavit.h: cavit_stage_volumes)."""
+    check(lib().cavit_stage_volumes(raw.data_ptr(), desc.data_ptr(), out.data_ptr(), volumes, D, H, W, pad_value,
+                                    _stream()), "cavit_stage_volumes")
+
+
 def add_bf16_f32(a, b_bf16, out):
     check(lib().cavit_add_bf16_f32(a.data_ptr(), b_bf16.data_ptr(), out.data_ptr(), a.numel(), _stream()),
           "cavit_add_bf16_f32")
@@ -350,5 +357,6 @@ for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_f
            "patchify", "cls_rows", "embed_param_grads", "cast_bf16", "colsum_bf16", "gather_rows_f32", "add_bf16_f32",
            "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout", "xfold_fwd", "xfold_bwd",
            "expand_heads", "fold_heads", "tokens_from_channels", "tokens_to_channels", "conv_patch_rows",
-           "conv_patch_rows_bwd", "bce_head_fwd", "bce_head_bwd", "adam_step", "gather_rows_f32_indexed", "token_mean_fwd", "token_mean_bwd"):
+           "conv_patch_rows_bwd", "bce_head_fwd", "bce_head_bwd", "adam_step", "gather_rows_f32_indexed", "token_mean_fwd", "token_mean_bwd",
+           "stage_volumes"):
     globals()[_n] = _instrument(_n, globals()[_n])

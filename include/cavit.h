@@ -324,6 +324,29 @@ int cavit_adam_step(float* params, const float* grads, float* exp_avg, float* ex
 int cavit_dropout(int32_t mode, const void* a, const void* b, void* out, int64_t n, float p,
                   const uint64_t* seed_dev, uint32_t site, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Input staging for stored volumes.
+ * Replaces, per batch, the host side of the deterministic transform chain of BrainDataset
+ * (/root/reference/dataset_ucsf.py:81-89 train without augmentation, :121-134 test, :157-158 .to(torch.float)):
+ * nibabel's read scaling (stored * scl_slope + scl_inter in float64), MONAI's ResizeWithPadOrCropd(img_size,
+ * constant_values = pad_value) and the conversion to a C-contiguous fp32 tensor.
+ *   raw   device copy of the stored voxel bytes of all volumes (native byte order, file order: axis 0 fastest);
+ *   desc  device array of `volumes` descriptors; byte_offset must be a multiple of the voxel size;
+ *   out   fp32 [volumes][D][H][W] (the [B][M][1][D][H][W] model input with volumes = B * M, sample-major).
+ * Axis a of the stored volume maps to axis a of (D, H, W): centre crop where dims[a] > target (start dims[a]/2 - target/2),
+ * symmetric pad where smaller (before = (target - dims[a]) / 2). slope == 1 and inter == 0 means "take stored values"
+ * (the caller maps nibabel's invalid-slope rule, slope 0 / NaN / inf, to that pair). */
+enum { CAVIT_VOX_U8 = 0, CAVIT_VOX_I16 = 1, CAVIT_VOX_I32 = 2, CAVIT_VOX_F32 = 3, CAVIT_VOX_F64 = 4, CAVIT_VOX_I8 = 5,
+       CAVIT_VOX_U16 = 6, CAVIT_VOX_U32 = 7 };
+typedef struct cavit_volume_desc {
+  int64_t byte_offset; /* of the volume's first voxel inside `raw` */
+  int32_t dims[3];     /* stored extents, axis 0 fastest */
+  int32_t dtype;       /* CAVIT_VOX_* */
+  float slope, inter;  /* scl_slope, scl_inter after the validity rule */
+} cavit_volume_desc;   /* 32 bytes */
+int cavit_stage_volumes(const void* raw, const cavit_volume_desc* desc, float* out, int32_t volumes, int32_t D, int32_t H,
+                        int32_t W, float pad_value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

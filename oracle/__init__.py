@@ -14,8 +14,12 @@ functional.py   independent torch restatement (fp32/fp64) of ``ModelCross.forwar
 weights.py      deterministic weight / input construction shared by fixtures and tests.
 ref_loader.py   imports the UNMODIFIED reference from /root/reference with stub modules
                 for its absent third-party imports (only usable in the build container).
+encoders.py     restatement of the CNN-stem models ``ViT`` (model.py) and ``ViT3D`` (modelv2.py).
 gen_golden.py   generates tests/golden/*.pt by running the real reference (committed
                 together with the vectors it made).
+
+staging.py      numpy restatement of the un-augmented input chain of dataset_ucsf.py (nibabel read
+                scaling + MONAI ResizeWithPadOrCrop); PARITY UNPINNED (both packages absent), see its header.
 
 Parity pinning: the reference ships no tests or golden vectors, so the
 oracle is pinned against outputs of the reference itself run in the build container
