@@ -232,6 +232,12 @@ def gather_rows_f32_indexed(src, dst, *, rows, C_, src_row_stride, src_gs, dst_r
           "cavit_gather_rows_f32_indexed")
 
 
+def batch_metrics(logits, labels, loss, accum, *, B, classes):
+    """accum (10 doubles) += this batch's weighted metrics (include/cavit.h: cavit_batch_metrics). loss: device scalar or None."""
+    check(lib().cavit_batch_metrics(logits.data_ptr(), labels.data_ptr(), _p(loss), accum.data_ptr(), B, classes, _stream()),
+          "cavit_batch_metrics")
+
+
 def stage_volumes(raw, desc, out, *, volumes, D, H, W, pad_value=-1.0):
     """Stored voxels (uint8 blob + 32-byte descriptors, both on the device) -> fp32 [volumes][D][H][W]
     (include/cavit.h: cavit_stage_volumes)."""
@@ -358,5 +364,5 @@ for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_f
            "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout", "xfold_fwd", "xfold_bwd",
            "expand_heads", "fold_heads", "tokens_from_channels", "tokens_to_channels", "conv_patch_rows",
            "conv_patch_rows_bwd", "bce_head_fwd", "bce_head_bwd", "adam_step", "gather_rows_f32_indexed", "token_mean_fwd", "token_mean_bwd",
-           "stage_volumes"):
+           "stage_volumes", "batch_metrics"):
     globals()[_n] = _instrument(_n, globals()[_n])

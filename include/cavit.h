@@ -347,6 +347,17 @@ typedef struct cavit_volume_desc {
 int cavit_stage_volumes(const void* raw, const cavit_volume_desc* desc, float* out, int32_t volumes, int32_t D, int32_t H,
                         int32_t W, float pad_value, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-step classification metrics, accumulated on the device.
+ * Replaces log_stats (/root/reference/model_cross.py:243-255: argmax, compute_metrics of /root/reference/utils.py:18-62,
+ * softmax + torchmetrics.functional.auroc) and the train_loss / val_loss logging of :262-273, which cost one host
+ * synchronisation per metric per step; Lightning's on_epoch mean weights each batch by its size.
+ *   accum[0..7] += B * (accuracy, precision, recall, specificity, F1, NPV, AUROC, *loss);  accum[8] += B;  accum[9] += 1
+ * logits fp32 [B][2], labels int64 [B] (non-zero = positive), loss nullable device scalar; 0 / 0 = 0; AUROC = 0 when the batch
+ * holds a single class (torchmetrics' convention). 1 <= B <= 8192. */
+int cavit_batch_metrics(const float* logits, const int64_t* labels, const float* loss, double* accum, int32_t B,
+                        int32_t classes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,8 @@ gen_golden.py   generates tests/golden/*.pt by running the real reference (commi
 
 staging.py      numpy restatement of the un-augmented input chain of dataset_ucsf.py (nibabel read
                 scaling + MONAI ResizeWithPadOrCrop); PARITY UNPINNED (both packages absent), see its header.
+metrics.py      restatement of log_stats / compute_metrics (utils.py, model_cross.py:243-255); pinned against
+                scikit-learn (torchmetrics absent: PARITY UNPINNED against it).
 
 Parity pinning: the reference ships no tests or golden vectors, so the
 oracle is pinned against outputs of the reference itself run in the build container

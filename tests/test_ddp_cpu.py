@@ -97,3 +97,37 @@ def test_stem_gradients_are_averaged_across_ranks():
     assert res[0][1] == res[1][1]                        # same weights after the broadcast
     for rank, w0, same, reduced, n in res:
         assert same and reduced == n
+
+
+def _metrics_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cavit.metrics import epoch_means
+    # rank 0 saw 3 batches (40 samples), rank 1 one batch (8 samples): weighted sums as cavit_batch_metrics leaves them
+    accum = torch.zeros(10, dtype=torch.float64)
+    if rank == 0:
+        accum[:8] = torch.arange(1, 9, dtype=torch.float64) * 40 * 0.1
+        accum[8], accum[9] = 40, 3
+    else:
+        accum[:8] = torch.arange(1, 9, dtype=torch.float64) * 8 * 0.05
+        accum[8], accum[9] = 8, 1
+    q.put((rank, epoch_means(accum).tolist()))
+    dist.destroy_process_group()
+
+
+def test_epoch_metrics_average_rank_means():
+    """Lightning's sync_dist reduction (/root/reference/model_cross.py:243-255): each rank's own weighted epoch mean,
+    then the plain mean over ranks — NOT the sample-weighted global mean."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_metrics_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, vals in res:
+        for k, v in enumerate(vals):
+            assert abs(v - (k + 1) * (0.1 + 0.05) / 2) < 1e-12
