@@ -222,10 +222,9 @@ def test_fused_adam_tracks_torch_adam_over_steps():
 def test_raw_mri_intensities_match_oracle():
     """The reference feeds RAW MRI intensities (O(10^3), no normalisation: dataset_ucsf.py:81-89), which is why the residual
     stream, LayerNorm statistics and logits stay fp32 here. With a mean of ~2000 against a spread of ~1000
-    every token carries the same large component 2000 (W 1), so the informative differences between tokens are about half of
-    the embedded magnitude and the bf16 operand rounding of the embedding GEMM weighs ~2x more than with zero-mean inputs:
-    measured 2.8e-2 on logits of magnitude 0.1 where the N(0,1) cases stay below 2e-2. Tolerance here: 3.5e-2 (logits),
-    4e-2 (gradient vector); see DESIGN.md section 7."""
+    every token carries the same large component 2000 (W 1) and the logits cancel down to ~0.08 (0.45 for N(0,1) volumes):
+    the absolute logit error (~2e-3) is smaller than in the N(0,1) cases, relative to the small logits it measures 2.8e-2.
+    Tolerance here: 3.5e-2 (logits), 4e-2 (gradient vector); see DESIGN.md section 7."""
     from oracle.cases import CASES
     from oracle.functional import make_config
     from oracle.weights import make_inputs, make_state, state_schema_cross
