@@ -129,3 +129,45 @@ def test_bad_arguments_fail_loudly():
         st.stage([[v, v], [v]])
     with pytest.raises(CavitError):
         st.stage([[v]], out=torch.empty(1, 1, 1, 4, 4, 5, device="cuda:0"))
+
+
+@pytest.mark.parametrize("name", ["cross_ring4", "cross_heads3"])
+def test_files_to_logits_and_gradients_match_oracle(tmp_path, name):
+    """The whole input side of a training step from FILES: .nii.gz -> read_nifti -> VolumeStager -> ModelCross forward +
+    backward, against the oracle chain (oracle/staging.py -> oracle/functional.py, fp64). Volumes are cropped along one axis
+    and padded along another; the staged batch is bit-exact, logits / gradients within the model tolerances."""
+    from oracle import functional as OF
+    from oracle.cases import build_case
+    from cavit.modules import ModelCross
+    from cavit.staging import VolumeStager, read_nifti
+    kind, cfg, state, img0, labels = build_case(name)
+    B, M = img0.shape[:2]
+    D, H, W = cfg.img_size
+    rng = np.random.default_rng(11)
+    samples, raws = [], []
+    for b in range(B):
+        vs, rs = [], []
+        for m in range(M):
+            dims = (D + 5 + m, max(H - 6, 1), W)                  # crop i, pad j, keep k
+            arr = rng.integers(-3000, 3000, size=dims).astype(np.int16)
+            p = str(tmp_path / f"s{b}_m{m}.nii.gz")
+            O.write_nifti(p, arr, slope=1.0 / 1024, inter=0.25 * m, extension_bytes=2896)
+            v = read_nifti(p)
+            vs.append(v)
+            rs.append((v.data, v.dims, v.slope, v.inter))
+        samples.append(vs)
+        raws.append(rs)
+    x = VolumeStager(cfg.img_size, "cuda:0").stage(samples)
+    want = torch.from_numpy(O.stage_batch(raws, cfg.img_size))
+    assert torch.equal(x.cpu(), want)
+    model = ModelCross(cfg)
+    model.load_state_dict(state)
+    model = model.cuda().train()
+    logits, loss = model(x, labels.cuda())
+    loss.backward()
+    ref_logits, ref_loss, ref_grads = OF.forward_backward(state, want, labels, cfg, kind, torch.float64)
+    err = float((logits.detach().double().cpu() - ref_logits).norm() / ref_logits.norm())
+    assert err < 2e-2, err
+    num = sum(float((p.grad.double().cpu() - ref_grads[k]).norm()) ** 2 for k, p in model.named_parameters())
+    den = sum(float(g.norm()) ** 2 for g in ref_grads.values())
+    assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
