@@ -14,7 +14,9 @@ There is no CPU path: staging needs the CUDA library and a B200, like everything
 from __future__ import annotations
 
 import gzip
+import os
 import struct
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -96,7 +98,7 @@ class VolumeStager:
     """Builds the ``[B, M, 1, D, H, W]`` fp32 device batch from stored volumes with one H2D copy of the stored bytes and
     one kernel launch. ``stage`` may be called every step: the pinned and device buffers are reused and grown on demand."""
 
-    def __init__(self, img_size: Sequence[int], device, pad_value: float = -1.0):
+    def __init__(self, img_size: Sequence[int], device, pad_value: float = -1.0, workers: Optional[int] = None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _abi.CavitError("VolumeStager needs a CUDA device (there is no CPU path)")
@@ -105,6 +107,8 @@ class VolumeStager:
         if len(self.img_size) != 3 or min(self.img_size) < 1:
             raise _abi.CavitError(f"img_size must be three positive extents, got {img_size}")
         self.pad_value = float(pad_value)
+        workers = min(8, os.cpu_count() or 1) if workers is None else int(workers)
+        self._pool = ThreadPoolExecutor(max_workers=workers) if workers > 1 else None   # packs the crop windows
         self._host: Optional[torch.Tensor] = None      # pinned uint8: descriptors, then the stored bytes
         self._dev: Optional[torch.Tensor] = None
         self._copied: Optional[torch.cuda.Event] = None
@@ -144,12 +148,19 @@ class VolumeStager:
         host, dev = self._buffers(off)
         hv = host.numpy()
         hv[:base] = desc.view(np.uint8)
-        for d, v, w in zip(desc, vols, wins):
+
+        def pack(i):
+            v, w = vols[i], wins[i]
             ext = tuple(n for _, n in w)
-            o = base + int(d["byte_offset"])
+            o = base + int(desc[i]["byte_offset"])
             dst = hv[o:o + int(np.prod(ext)) * v.data.itemsize].view(v.data.dtype).reshape(ext, order="F")
-            src = v.data.reshape(v.dims, order="F")[tuple(slice(a, a + n) for a, n in w)]
-            np.copyto(dst, src)
+            np.copyto(dst, v.data.reshape(v.dims, order="F")[tuple(slice(a, a + n) for a, n in w)])
+
+        if self._pool is not None and V > 1:     # numpy's strided copy releases the GIL
+            list(self._pool.map(pack, range(V)))
+        else:
+            for i in range(V):
+                pack(i)
         D, H, W = self.img_size
         if out is None:
             out = torch.empty(B, M, 1, D, H, W, dtype=torch.float32, device=self.device)
