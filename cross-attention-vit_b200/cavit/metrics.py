@@ -59,3 +59,27 @@ def epoch_means(accum: torch.Tensor, process_group=None) -> torch.Tensor:
         dist.all_reduce(means, op=dist.ReduceOp.SUM, group=process_group)
         means = means / dist.get_world_size(group=process_group)
     return means
+
+
+class TestOutputs:
+    """``test_step`` / ``on_test_epoch_end`` of the reference (/root/reference/model_cross.py:294-308) copy every batch's
+    logits and labels to the host as they are produced (``logits.cpu()`` blocks the host once per batch). Here the batches
+    stay on the device and ``finish()`` moves them with one concatenation and one device-to-host copy each."""
+    __test__ = False   # not a pytest class
+
+    def __init__(self):
+        self._logits, self._targets = [], []
+
+    def append(self, logits: torch.Tensor, labels: torch.Tensor) -> None:
+        if logits.device.type != "cuda":
+            raise _abi.CavitError("TestOutputs.append: device tensors expected (there is no CPU path)")
+        self._logits.append(logits.detach().clone())     # the engine reuses its logits buffer every step
+        self._targets.append(labels.detach().clone())
+
+    def finish(self):
+        """-> (test_logits [N, classes], test_targets [N]) on the host, as ``on_test_epoch_end`` leaves them."""
+        if not self._logits:
+            raise _abi.CavitError("TestOutputs.finish: no batches")
+        out = torch.cat(self._logits).cpu(), torch.cat(self._targets).cpu()
+        self._logits, self._targets = [], []
+        return out

@@ -102,3 +102,25 @@ def test_bad_arguments_fail_loudly():
         em.update(torch.zeros(4, 2, device="cuda"), torch.zeros(5, dtype=torch.long, device="cuda"))
     with pytest.raises(CavitError):
         em.update(torch.zeros(9000, 2, device="cuda"), torch.zeros(9000, dtype=torch.long, device="cuda"))
+
+
+def test_test_outputs_gather_once():
+    """test_step / on_test_epoch_end (model_cross.py:294-308): logits of every batch, in order, on the host at the end —
+    also when the model reuses its output buffer between steps."""
+    from oracle.cases import build_case
+    from cavit.metrics import TestOutputs
+    from cavit.modules import ModelCross
+    kind, cfg, state, img, labels = build_case("cross_chain3")
+    model = ModelCross(cfg)
+    model.load_state_dict(state)
+    model = model.cuda().eval()
+    outs, want = TestOutputs(), []
+    with torch.no_grad():
+        for step in range(3):
+            x = (img + 0.25 * step).cuda()
+            logits, _ = model(x, labels.cuda())
+            outs.append(logits, labels.cuda())
+            want.append(logits.cpu().clone())
+    got_logits, got_targets = outs.finish()
+    assert torch.equal(got_logits, torch.cat(want)) and torch.equal(got_targets, labels.repeat(3))
+    assert not torch.equal(want[0], want[1])
