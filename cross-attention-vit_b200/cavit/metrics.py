@@ -6,7 +6,7 @@ The reference's ``log_stats`` (/root/reference/model_cross.py:243-255) runs afte
 Lightning average the per-batch values over the epoch (weighted by batch size) and then over the ranks. ``EpochMetrics``
 keeps that definition — the epoch value of each metric is the batch-size-weighted mean of its PER-BATCH values, averaged
 over ranks — but a step costs one single-block kernel launch on the step's own stream (``cavit_batch_metrics``) and an
-epoch one 10-double all-reduce and one device-to-host copy.
+epoch one 8-double all-reduce and one device-to-host copy.
 """
 from __future__ import annotations
 
@@ -26,7 +26,7 @@ class EpochMetrics:
             raise _abi.CavitError("EpochMetrics needs a CUDA device (there is no CPU path)")
         _abi.require_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
         self.prefix = prefix
-        self.accum = torch.zeros(10, dtype=torch.float64, device=self.device)
+        self.accum = torch.zeros(16, dtype=torch.float64, device=self.device)   # 10 values + scratch (include/cavit.h)
 
     def reset(self) -> None:
         self.accum.zero_()
@@ -51,7 +51,7 @@ class EpochMetrics:
 
 
 def epoch_means(accum: torch.Tensor, process_group=None) -> torch.Tensor:
-    """The 10-double accumulator of ``cavit_batch_metrics`` -> 8 epoch values: this rank's batch-size-weighted means, then
+    """The accumulator of ``cavit_batch_metrics`` (first 10 doubles) -> 8 epoch values: this rank's batch-size-weighted means, then
     the mean over the ranks of ``process_group`` (one all-reduce of 8 doubles; skipped without torch.distributed)."""
     import torch.distributed as dist
     means = torch.where(accum[8] > 0, accum[:8] / accum[8].clamp_min(1.0), torch.zeros_like(accum[:8]))

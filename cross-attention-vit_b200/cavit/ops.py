@@ -233,7 +233,7 @@ def gather_rows_f32_indexed(src, dst, *, rows, C_, src_row_stride, src_gs, dst_r
 
 
 def batch_metrics(logits, labels, loss, accum, *, B, classes):
-    """accum (10 doubles) += this batch's weighted metrics (include/cavit.h: cavit_batch_metrics). loss: device scalar or None."""
+    """accum (16 doubles: 10 values + scratch) += this batch's weighted metrics (include/cavit.h: cavit_batch_metrics). loss: device scalar or None."""
     check(lib().cavit_batch_metrics(logits.data_ptr(), labels.data_ptr(), _p(loss), accum.data_ptr(), B, classes, _stream()),
           "cavit_batch_metrics")
 

@@ -353,6 +353,8 @@ int cavit_stage_volumes(const void* raw, const cavit_volume_desc* desc, float* o
  * softmax + torchmetrics.functional.auroc) and the train_loss / val_loss logging of :262-273, which cost one host
  * synchronisation per metric per step; Lightning's on_epoch mean weights each batch by its size.
  *   accum[0..7] += B * (accuracy, precision, recall, specificity, F1, NPV, AUROC, *loss);  accum[8] += B;  accum[9] += 1
+ * accum holds 16 doubles, zero-initialised by the caller: [10], [11] are scratch words the launch leaves at zero
+ * (cross-block pair count and ticket), [12..15] are reserved.
  * logits fp32 [B][2], labels int64 [B] (non-zero = positive), loss nullable device scalar; 0 / 0 = 0; AUROC = 0 when the batch
  * holds a single class (torchmetrics' convention). 1 <= B <= 8192. */
 int cavit_batch_metrics(const float* logits, const int64_t* labels, const float* loss, double* accum, int32_t B,

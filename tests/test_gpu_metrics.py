@@ -34,6 +34,7 @@ def test_single_batch_matches_oracle(B, scale, ties):
     for k in want:
         assert abs(got[k] - want[k]) < TOL, (k, got[k], want[k])
     assert em.accum[8].item() == B and em.accum[9].item() == 1
+    assert em.accum[10:].abs().sum().item() == 0            # scratch words are left at zero
 
 
 def test_degenerate_batches():
