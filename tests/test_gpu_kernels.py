@@ -300,6 +300,13 @@ def test_colsum_cast_gather():
     out = torch.empty(G, C, device=DEV)
     ops.colsum_bf16(x, out, rows=R, C_=C, groups=G)
     assert rel(out, x.float().sum(1)) < 1e-4
+    # both thread mappings (rows-per-pass for widths that leave a 256-column block partly empty, column blocks otherwise),
+    # ragged row counts, a single row
+    for G2, R2, C2 in [(1, 1, 384), (2, 777, 64), (1, 333, 200), (4, 2049, 512), (2, 1000, 1152), (1, 4100, 1536), (3, 50, 8)]:
+        x2 = bf(torch.randn(G2, R2, C2, device=DEV))
+        o2 = torch.full((G2, C2), 7.0, device=DEV)
+        ops.colsum_bf16(x2, o2, rows=R2, C_=C2, groups=G2)
+        assert rel(o2, x2.float().sum(1)) < 1e-4, (G2, R2, C2)
     src = torch.randn(1001, device=DEV)
     dst = torch.empty(1001, device=DEV, dtype=torch.bfloat16)
     ops.cast_bf16(src, dst)
