@@ -94,6 +94,44 @@ def read_nifti(path: str) -> RawVolume:
     return RawVolume(data, (dim[1], dim[2], dim[3]), slope, inter)
 
 
+def plan_batch(vols: Sequence[RawVolume], img_size: Sequence[int]):
+    """Layout of one batch's transfer: ``V`` descriptors, then each volume's centre-crop window (16-byte aligned).
+
+    Only the stored voxels inside the window cross PCIe (for 240 x 240 x 155 files and a 128 x 128 x 64 target that is 12 %
+    of the file); the descriptor carries the WINDOW's extents, for which the kernel's own crop is the identity and its pad
+    widths are those of the full volume. Returns (descriptors, per-volume [(start, length)] * 3, total bytes)."""
+    V = len(vols)
+    wins = [[(s // 2 - t // 2 if s > t else 0, min(s, t)) for s, t in zip(v.dims, img_size)] for v in vols]
+    desc = np.zeros(V, dtype=DESC_DTYPE)
+    base = V * DESC_DTYPE.itemsize
+    off = base
+    for i, (v, w) in enumerate(zip(vols, wins)):
+        off = (off + 15) & ~15
+        desc[i] = (off - base, [n for _, n in w], _VOX_CODE[v.data.dtype.str[1:]], v.slope, v.inter)
+        off += w[0][1] * w[1][1] * w[2][1] * v.data.itemsize
+    return desc, wins, off
+
+
+def pack_batch(vols: Sequence[RawVolume], desc: np.ndarray, wins, hv: np.ndarray, pool=None) -> None:
+    """Write the descriptors and the crop windows (file order kept: axis 0 fastest) into the byte buffer ``hv``."""
+    V = len(vols)
+    base = V * DESC_DTYPE.itemsize
+    hv[:base] = desc.view(np.uint8)
+
+    def pack(i):
+        v, w = vols[i], wins[i]
+        ext = tuple(n for _, n in w)
+        o = base + int(desc[i]["byte_offset"])
+        dst = hv[o:o + int(np.prod(ext)) * v.data.itemsize].view(v.data.dtype).reshape(ext, order="F")
+        np.copyto(dst, v.data.reshape(v.dims, order="F")[tuple(slice(a, a + n) for a, n in w)])
+
+    if pool is not None and V > 1:     # numpy's strided copy releases the GIL
+        list(pool.map(pack, range(V)))
+    else:
+        for i in range(V):
+            pack(i)
+
+
 class VolumeStager:
     """Builds the ``[B, M, 1, D, H, W]`` fp32 device batch from stored volumes with one H2D copy of the stored bytes and
     one kernel launch. ``stage`` may be called every step: the pinned and device buffers are reused and grown on demand."""
@@ -134,33 +172,10 @@ class VolumeStager:
             raise _abi.CavitError("VolumeStager.stage: every sample needs the same, non-zero number of volumes")
         vols = [v for s in samples for v in s]
         V = len(vols)
-        # Only the stored voxels inside the centre-crop window cross PCIe (for 240 x 240 x 155 files and a 128 x 128 x 64
-        # target that is 12 % of the file); the descriptor then carries the window's extents, for which the kernel's own
-        # crop is the identity and its pad widths are those of the full volume.
-        wins = [[(s // 2 - t // 2 if s > t else 0, min(s, t)) for s, t in zip(v.dims, self.img_size)] for v in vols]
-        desc = np.zeros(V, dtype=DESC_DTYPE)
+        desc, wins, off = plan_batch(vols, self.img_size)
         base = V * DESC_DTYPE.itemsize
-        off = base
-        for i, (v, w) in enumerate(zip(vols, wins)):
-            off = (off + 15) & ~15
-            desc[i] = (off - base, [n for _, n in w], _VOX_CODE[v.data.dtype.str[1:]], v.slope, v.inter)
-            off += w[0][1] * w[1][1] * w[2][1] * v.data.itemsize
         host, dev = self._buffers(off)
-        hv = host.numpy()
-        hv[:base] = desc.view(np.uint8)
-
-        def pack(i):
-            v, w = vols[i], wins[i]
-            ext = tuple(n for _, n in w)
-            o = base + int(desc[i]["byte_offset"])
-            dst = hv[o:o + int(np.prod(ext)) * v.data.itemsize].view(v.data.dtype).reshape(ext, order="F")
-            np.copyto(dst, v.data.reshape(v.dims, order="F")[tuple(slice(a, a + n) for a, n in w)])
-
-        if self._pool is not None and V > 1:     # numpy's strided copy releases the GIL
-            list(self._pool.map(pack, range(V)))
-        else:
-            for i in range(V):
-                pack(i)
+        pack_batch(vols, desc, wins, host.numpy(), self._pool)
         D, H, W = self.img_size
         if out is None:
             out = torch.empty(B, M, 1, D, H, W, dtype=torch.float32, device=self.device)

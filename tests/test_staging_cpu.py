@@ -108,3 +108,37 @@ def test_reader_on_the_reference_volumes():
         assert np.array_equal(out[0, :, 8:-8], O.read_scaling(stored, v.slope, v.inter).astype(np.float32))
         if not seg:
             assert out.min() >= -1.0 and out.max() > 100.0                       # intensities in scanner units
+
+
+def test_transfer_layout_carries_exactly_the_crop_windows():
+    """Host logic of VolumeStager (plan_batch / pack_batch): descriptors + 16-byte aligned crop windows in file order.
+    Decoding the packed windows with the oracle must give what the oracle gives for the whole volumes."""
+    from concurrent.futures import ThreadPoolExecutor
+    from cavit.staging import DESC_DTYPE, RawVolume, pack_batch, plan_batch
+    rng = np.random.default_rng(21)
+    img_size = (12, 20, 7)
+    specs = [((30, 9, 7), np.int16, 0.5, 3.0), ((12, 20, 7), np.uint8, 1.0, 0.0), ((5, 41, 16), np.float32, 0.0, 1.0),
+             ((13, 21, 8), np.float64, 2.0, -1.0), ((1, 1, 1), np.int32, 1.0, 2.0)]
+    vols = []
+    for dims, dt, s, i in specs:
+        arr = (rng.integers(-100, 100, size=dims) if np.issubdtype(dt, np.integer) and dt != np.uint8
+               else rng.integers(0, 200, size=dims)).astype(dt)
+        vols.append(RawVolume(np.asfortranarray(arr).ravel(order="F"), dims, s, i))
+    desc, wins, total = plan_batch(vols, img_size)
+    base = len(vols) * DESC_DTYPE.itemsize
+    assert [tuple(d["dims"]) for d in desc] == [(12, 9, 7), (12, 20, 7), (5, 20, 7), (12, 20, 7), (1, 1, 1)]
+    assert wins[0][0] == (30 // 2 - 12 // 2, 12) and wins[2][1] == (41 // 2 - 20 // 2, 20) and wins[3][2] == (8 // 2 - 7 // 2, 7)
+    assert all(int(d["byte_offset"]) % 16 == 0 for d in desc)
+    for pool in (None, ThreadPoolExecutor(max_workers=3)):
+        hv = np.full(total + 8, 0xAB, dtype=np.uint8)
+        pack_batch(vols, desc, wins, hv, pool)
+        assert np.all(hv[total:] == 0xAB)                         # nothing written past the planned size
+        got = np.frombuffer(hv[:base].tobytes(), dtype=DESC_DTYPE)
+        assert np.array_equal(got["dims"], desc["dims"]) and np.array_equal(got["byte_offset"], desc["byte_offset"])
+        for v, d in zip(vols, desc):
+            n = int(np.prod(d["dims"]))
+            o = base + int(d["byte_offset"])
+            win = np.frombuffer(hv[o:o + n * v.data.itemsize].tobytes(), dtype=v.data.dtype)
+            a = O.stage_volume(win, tuple(int(x) for x in d["dims"]), float(d["slope"]), float(d["inter"]), img_size)
+            b = O.stage_volume(v.data, v.dims, v.slope, v.inter, img_size)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
