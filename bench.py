@@ -119,7 +119,8 @@ class ClockSampler:
 
 
 def cpu_port_throughput(wl, steps: int, warmup: int):
-    """The reference's algorithm (oracle port) fwd+bwd on the host cores, bounded batch."""
+    """The reference's algorithm (oracle port) fwd+bwd on the host cores, bounded batch. Only used when neither
+    /root/reference nor oracle/_ref (oracle/make_ref.py) is present."""
     from oracle import functional as OF
     from oracle.weights import make_inputs, make_state, state_schema_cross
     cfg = OF.make_config(**wl["cfg"])   # oracle-side config: this leg IS the CPU checker being timed
@@ -144,21 +145,137 @@ def cpu_port_throughput(wl, steps: int, warmup: int):
             "s_per_step": med}
 
 
+def _reference_model(cfg_kw):
+    """The UNMODIFIED reference ModelCross (imported from /root/reference, or from its byte-for-byte copy in the
+    git-ignored oracle/_ref on the GPU box), weights from its own initialiser under torch.manual_seed(0)."""
+    from oracle import functional as OF, ref_loader
+    if ref_loader.reference_dir() is None:
+        return None, None, None
+    cfg = OF.make_config(**cfg_kw)
+    mod = ref_loader.load("model_cross")
+    torch.manual_seed(0)
+    model = mod.ModelCross(ref_loader.to_config_dict(cfg)).train()   # dropout 0.0: identity in train mode
+    return model, cfg, ref_loader.reference_dir()
+
+
+def cpu_reference_throughput(wl, steps: int, warmup: int):
+    """The reference's own CPU implementation of the path (model_cross.py:186-212 forward + loss.backward()), fp32 as
+    shipped, all host threads, on a bounded batch of the arm's workload."""
+    from oracle.weights import make_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, cfg, where = _reference_model(wl["cfg"])
+    if model is None:
+        return cpu_port_throughput(wl, steps, warmup)
+    B = wl["cpu_batch"]
+    img, labels = make_inputs(cfg, B, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        logits, loss = model(img, labels)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": B / med, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{len(times)} fwd+bwd steps of the unmodified reference ModelCross ({where}) on the same model "
+                      f"config at batch {B} (fp32 as shipped, synthetic N(0,1) volumes), median",
+            "s_per_step": med}
+
+
+def configs0_real_voxels(dev):
+    """BASELINE.json configs[0] / BASELINE.md section 5: the reference ModelCross (config2.py defaults, M = 4 ring) on the
+    six bundled UCSF-PDGM cases (T1, T1c, T2, FLAIR; centre window 128 x 128 x 64; raw intensities), 3 batches of 2,
+    on the host cores — and the same batches through the sm_100a path on `dev`, logits compared in the same run.
+    Needs oracle/_ref (oracle/make_ref.py); returns None without it."""
+    import numpy as np
+    from oracle import make_ref
+    path = os.path.join(ROOT, "oracle", "_ref", "ucsf_cfg1_int16.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    wl = WORKLOADS["cfg1"]
+    model, cfg, where = _reference_model(wl["cfg"])
+    if model is None:
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    img = make_ref.volumes_fp32(z["stored"], z["slope"], z["inter"], cfg.img_size)      # [6, 4, 1, 128, 128, 64] fp32
+    labels = torch.from_numpy(z["labels"])
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    times, ref_logits = [], []
+    for i in (0, 0, 1, 2):          # one warm-up pass over the first batch, then the three batches
+        x, y = img[2 * i:2 * i + 2], labels[2 * i:2 * i + 2]
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        logits, loss = model(x, y)
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+        ref_logits.append(logits.detach())
+    times, ref_logits = sorted(times[1:]), torch.cat(ref_logits[1:])
+    out = {"cpu": {"value": 2 / times[1], "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "reference",
+                   "sample": f"unmodified reference ModelCross ({where}), config2.py defaults, fp32, 3 batches of 2 real "
+                             "UCSF-PDGM cases (T1, T1c, T2, FLAIR), median step", "s_per_step": times[1]}}
+    if dev is not None:
+        from cavit.config import make_config
+        from cavit.modules import ModelCross
+        for prec in ("bf16", "fp32"):
+            ours = ModelCross(make_config(**wl["cfg"]))
+            ours.load_state_dict(state)
+            ours.set_precision(prec)
+            ours = ours.to(dev).train()
+            got, ms = [], []
+            for rep in range(3):    # repetitions 0, 1 warm up (eager runs + graph capture); the third is timed
+                got = []
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(3):
+                    logits, loss = ours(img[2 * i:2 * i + 2].to(dev), labels[2 * i:2 * i + 2].to(dev))
+                    loss.backward()
+                    for p in ours.parameters():
+                        p.grad = None
+                    got.append(logits.detach().float().cpu())
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1) / 3)
+            got = torch.cat(got)
+            out[prec] = {"value": 2 / (ms[-1] * 1e-3), "unit": "volumes/s", "ms_per_step": ms[-1],
+                         "logits_rel_vs_reference_fp32": float((got.double() - ref_logits.double()).norm() / ref_logits.double().norm()),
+                         "note": "same six cases, H2D copies inside the timed steps"}
+            del ours
+    return out
+
+
 def run_reference(args, wl, rank):
     if rank != 0:
         return
-    cfg_name = args.workload
-    res = cpu_port_throughput(wl, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    res = cpu_reference_throughput(wl, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
     line = {
         "impl": "reference", "metric": "MRI volumes/sec fwd+bwd", "value": res["value"], "unit": "volumes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["s_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg_name}: ModelCross {wl['cfg']['hidden_dim']}d, batch {wl['cpu_batch']} on CPU (bounded sample)"},
+        "config": workload_config(args.workload, wl, args.batch or wl["batch"], max(1, args.gpus), None, args.precision),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_config(name, wl, B, world, mode, precision="bf16"):
+    """The `config` object of the JSON line: the same for both arms (the reference arm runs a bounded sample of it,
+    described in its cpu_baseline.sample)."""
+    c = wl["cfg"]
+    prec = {"bf16": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LayerNorm / softmax statistics",
+            "fp32": "fp32-tolerance mode: bf16 hi+lo split operands (3 MMAs per product), fp32 accumulate, fp32 SIMT attention"}
+    return {"workload": f"{name}: ModelCross C={c['hidden_dim']} H={c['num_heads']} F={c['mlp_dim']} "
+                        f"{c['num_multi_blocks']}x{c['num_self_blocks']} blocks, img {tuple(c['img_size'])} patch {tuple(c['patch_size'])}, "
+                        f"M=4 ring cross-attention, per-GPU batch {B}",
+            "global_batch": B * world, "parallelism": f"dp{world}" + (f" ({mode} all-reduce)" if world > 1 and mode else ""),
+            "l2": "per-step working set (activations + weights, several GB) far exceeds the 126 MB L2; no explicit flush",
+            "precision": prec[precision]}
 
 
 def main():
@@ -169,7 +286,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: bf16 operands (headline); fp32: the fp32-tolerance mode (split operands)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs0", action="store_true", help="skip the configs[0] real-voxel leg (CPU reference + GPU)")
     ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -191,15 +311,18 @@ def main():
     _abi.require_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        if "CAVIT_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["CAVIT_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)   # the version banner would go to stdout next to the JSON line
+        # NCCL's log (version banner, ring / NVLS setup, rank count) goes to a per-rank file instead of stdout, where it
+        # would sit next to the JSON line: gpurun_out/nccl_<host>_<pid>.log when NCCL_DEBUG is set by the caller
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     cfg = make_config(**wl["cfg"])
     B = args.batch or wl["batch"]
     torch.manual_seed(0)
-    model = ModelCross(cfg).cuda().train()
+    model = ModelCross(cfg)
+    model.set_precision(args.precision)
+    model = model.cuda().train()
     runner = model
     if world > 1:
         from cavit.ddp import DataParallel
@@ -258,22 +381,28 @@ def main():
     # batch i+1 on a copy stream while step i runs; cavit.data.ScalarReadback delivers the loss one step late.
     from cavit.data import DevicePrefetcher, ScalarReadback
 
+    logits_host = torch.empty((4, B, cfg.num_classes), dtype=torch.float32).pin_memory()
+
     def run_e2e(nsteps):
         feed = DevicePrefetcher(((img_host, labels_host) for _ in range(nsteps)), dev)
         rb = ScalarReadback(dev)
-        losses = []
-        for x, y in feed:
+        losses, d2h_logits = [], 0
+        for i, (x, y) in enumerate(feed):
             logits, loss = runner(x, y)
             loss.backward()
             for p in model.parameters():
                 p.grad = None
+            # both results of forward() go back to the host every step: the [B, classes] logits into a pinned ring (their
+            # copy is ordered before the loss copy on the same stream, so popping step i's loss implies step i's logits)
+            logits_host[i % 4].copy_(logits.detach(), non_blocking=True)
+            d2h_logits += logits.numel() * 4
             rb.push(loss)
             if rb.pending() > 1:
                 losses.append(rb.pop())
         while rb.pending():
             losses.append(rb.pop())
         assert len(losses) == nsteps
-        return feed.h2d_bytes // nsteps, rb.d2h_bytes // nsteps, losses
+        return feed.h2d_bytes // nsteps, (rb.d2h_bytes + d2h_logits) // nsteps, losses
 
     run_e2e(2)
     barrier()
@@ -310,17 +439,22 @@ def main():
         gm = agg.get("gemm", {"ms": 0.0, "n": 0, "flops": 0.0})
         achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
-        traffic = None   # mean DRAM bytes per GEMM launch of one step, from the committed ncu launch list of this workload
-        try:
-            if args.workload == "cfg2" and B == wl["batch"]:
-                with open(os.path.join(ROOT, "profiles", "step_summary_r01.json")) as f:
-                    traffic = json.load(f)["kernels"]["gemm_bf16_tcgen05_kernel"]["traffic_bytes_per_launch"]
-        except Exception:
-            traffic = None
+        # `traffic` cannot be measured outside a profiler: it is a CITATION of the committed ncu launch list of this
+        # workload (mean dram__bytes_read + dram__bytes_write per GEMM launch of one step), newest round first
+        traffic, traffic_file = None, None
+        if args.workload == "cfg2" and B == wl["batch"] and args.precision == "bf16":
+            for name in ("step_summary_r02.json", "step_summary_r01.json"):
+                try:
+                    with open(os.path.join(ROOT, "profiles", name)) as f:
+                        traffic = json.load(f)["kernels"]["gemm_bf16_tcgen05_kernel"]["traffic_bytes_per_launch"]
+                    traffic_file = "profiles/" + name
+                    break
+                except Exception:
+                    continue
         roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "profiles/step_summary_r01.json (ncu dram__bytes_read+write per GEMM launch, mean over one step)"
-                    if traffic else None,
+                    "traffic_cited_from_committed_ncu_file": (f"{traffic_file}: ncu dram__bytes_read + dram__bytes_write per GEMM "
+                                                              "launch, mean over one step; not measured in this run") if traffic else None,
                     "peak_source": peaks["source"] + " (sustained)",
                     "launches_per_step": gm["n"], "share_of_step": gm["ms"] / tot if tot else None,
                     # K = 384 GEMMs with bf16 I/O sit at ~170 FLOP/B against a machine balance of ~210: several of them are
@@ -370,34 +504,39 @@ def main():
                      "note": "one launch over the flat fp32 slabs (p, g, m, v) that also rewrites the bf16 operand copy"}
 
     if rank == 0:
-        cpu = None
+        cpu, configs0 = None, None
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_port_throughput(wl, 3, 1)
+            r = cpu_reference_throughput(wl, 3, 1)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if not args.no_configs0:
+                del model, runner, img   # free the bench model before the cfg1 models of this leg are built
+                torch.cuda.empty_cache()
+                try:
+                    configs0 = configs0_real_voxels(dev)
+                except Exception as exc:   # a reported extra: never lose the bench line over it
+                    configs0 = {"error": repr(exc)}
         fpv = 3.0 * flops_per_volume(cfg)
         peaks = measured_peaks()
         line = {
             "metric": "MRI volumes/sec fwd+bwd", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: ModelCross C={cfg.hidden_dim} H={cfg.num_heads} F={cfg.mlp_dim} "
-                                   f"{cfg.num_multi_blocks}x{cfg.num_self_blocks} blocks, img {tuple(cfg.img_size)} patch {tuple(cfg.patch_size)}, "
-                                   f"M=4 ring cross-attention, per-GPU batch {B}",
-                       "global_batch": B * world, "parallelism": f"dp{world}" + (f" ({runner.mode} all-reduce)" if world > 1 else ""),
-                       "l2": "per-step working set (activations + weights, several GB) far exceeds the 126 MB L2; no explicit flush",
-                       "precision": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LayerNorm / softmax statistics"},
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (hi+lo split operands, fp32 accumulate)",
+            "data": "synthetic",
+            "config": workload_config(args.workload, wl, B, world, None, args.precision),
+            "ddp_mode": runner.mode if world > 1 else None,
             "model_tflops": value * fpv / 1e12,
             "model_flops_frac_of_peak": (value / world) * fpv / 1e12 / peaks["bf16_tflops_sustained"],
             "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps,
                     "how": "model(img, labels) + loss.backward() per step; pinned host batch -> device by cavit.data.DevicePrefetcher "
-                           "(copy of step i+1 overlaps step i), loss -> host by cavit.data.ScalarReadback (one step late)"},
+                           "(copy of step i+1 overlaps step i), logits and loss -> pinned host memory every step (read one step late)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernel_breakdown_ms": breakdown,
             "optimizer": optimizer,
+            "configs0_real_voxels": configs0,
             "loss": float(loss.detach()),
         }
         print(json.dumps(line), flush=True)

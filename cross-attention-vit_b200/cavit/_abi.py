@@ -10,6 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libcavit_sm100a.so")
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
+ABI_VERSION = 1
+
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_GELU_BWD, EPI_EMBED, EPI_BIAS_RELU, EPI_RELU_BWD = range(8)
 
 
@@ -107,7 +109,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.cavit_abi_version() != 1:
+        if L.cavit_abi_version() != ABI_VERSION:
             raise CavitError("libcavit_sm100a.so ABI version mismatch")
         _lib = L
     return _lib

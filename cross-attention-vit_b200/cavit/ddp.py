@@ -101,36 +101,51 @@ class DataParallel:
     """Wraps a cavit model: `dp = DataParallel(model); logits, loss = dp(img, labels); loss.backward()`."""
 
     def __init__(self, model, group=None, min_slab_elems: int = 8 << 20, mode: str = "auto"):
-        """mode = "overlap": backward runs eagerly and every finished gradient slab is all-reduced on a
-        communication stream while the remaining backward kernels run (best when the all-reduce is a
-        visible fraction of the step, i.e. large models / small per-GPU batches);
-        mode = "post": backward replays its CUDA graph and the flat gradient buffer is all-reduced
-        afterwards in one call (best when launch overhead would cost more than the un-overlapped
-        all-reduce); "auto" picks "post" below 512 MB of gradients."""
+        """mode = "overlap": every finished gradient slab (>= min_slab_elems, in backward-completion order) is
+        all-reduced on a communication stream while the remaining backward kernels run. The slab all-reduces are
+        recorded INTO the backward CUDA graph (NCCL collectives are capturable), so overlap costs no eager launches;
+        if this stack cannot capture them the engine falls back to eager launches and, for small models, this wrapper
+        to "post";
+        mode = "post": backward replays its CUDA graph and the flat gradient buffer is all-reduced afterwards in
+        one call; "auto" = "overlap"."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.model, self.group = model, group
         self.stem = None
+        self._stem_buffers = []
         if hasattr(model, "_stem_prefix"):     # cavit.encoders.ViT / ViT3D: engine exists after the first forward
             self.engine = model.__dict__.get("_engine_obj")
             if self.engine is None:
                 raise RuntimeError("DataParallel(ViT / ViT3D): run one forward first so that the encoder engine exists")
             named = [(k, p) for k, p in model.named_parameters() if k.startswith(model._stem_prefix)]
             self.stem = TensorGradReducer([p for _, p in named], group)
-            self.stem.broadcast([p for _, p in named] + [b for k, b in model.named_buffers() if k.startswith(model._stem_prefix)])
+            # BatchNorm running statistics of the ViT3D stem: torch / Lightning DDP (broadcast_buffers=True) re-broadcasts
+            # rank 0's buffers at every forward; so does __call__ below (a few small tensors)
+            self._stem_buffers = [b for k, b in model.named_buffers() if k.startswith(model._stem_prefix)]
+            self.stem.broadcast([p for _, p in named] + self._stem_buffers)
         else:
             self.engine = model.engine()
         self.comm_stream = torch.cuda.Stream(device=self.engine.device)
         self.min_slab_elems = min_slab_elems
         self._reducer: Optional[SlabReducer] = None
         if mode == "auto":
-            mode = "post" if self.engine.layout.total * 4 < (512 << 20) else "overlap"
+            mode = "overlap"
+        if mode not in ("overlap", "post"):
+            raise ValueError(f"mode must be 'auto', 'overlap' or 'post', got {mode!r}")
         self.mode = mode
-        if mode == "overlap":
-            self.engine.on_range_done = self._on_range_done
-        else:
-            self.engine.post_backward = self._post_backward
+        self._set_mode(mode)
         self.broadcast_parameters()
+
+    def _set_mode(self, mode: str):
+        eng = self.engine
+        eng.on_range_done = eng.post_backward = None
+        eng.hook_capturable = False
+        if mode == "overlap":
+            eng.on_range_done = self._on_range_done
+            eng.hook_capturable = True      # the hook only enqueues: event record, all-reduce on comm_stream, stream wait
+        else:
+            eng.post_backward = self._post_backward
+        self.mode = mode
 
     def broadcast_parameters(self, src: int = 0):
         dist.broadcast(self.engine.flat, src=src, group=self.group)
@@ -160,6 +175,11 @@ class DataParallel:
             self._reducer.reduce_(flat, start, end)
 
     def __call__(self, img, labels):
+        eng = self.engine
+        if self.mode == "overlap" and eng._hook_capture_failed and eng.layout.total * 4 < (512 << 20):
+            self._set_mode("post")          # eager launches would cost a small model more than the exposed all-reduce
+        if self._stem_buffers and self.model.training:
+            self.stem.broadcast(self._stem_buffers)
         return self.model(img, labels)
 
     def parameters(self):

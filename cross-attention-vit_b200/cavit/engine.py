@@ -235,10 +235,19 @@ def build_layout(kind: str, cfg) -> ParamLayout:
 class Engine:
     """Executes one model (kind = 'cross' | 'vit') on one device. Not thread-safe."""
 
-    def __init__(self, kind: str, cfg, named_params: "OrderedDict[str, torch.nn.Parameter]", device):
+    def __init__(self, kind: str, cfg, named_params: "OrderedDict[str, torch.nn.Parameter]", device, precision: str = "bf16"):
         assert kind in ("cross", "vit", "cnnvit", "vit3d")
-        _abi.require_device(torch.device(device).index or 0)
-        self.kind, self.cfg, self.device = kind, cfg, torch.device(device)
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:   # an index-less device means the CURRENT device, not cuda:0
+            device = torch.device("cuda", torch.cuda.current_device())
+        _abi.require_device(device.index)
+        self.kind, self.cfg, self.device = kind, cfg, device
+        if precision not in ("bf16", "fp32"):
+            raise _abi.CavitError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision == "fp32" and kind not in ("cross", "vit"):
+            raise _abi.CavitError("the fp32-tolerance mode covers ModelCross / ModelVIT (pre-norm blocks); ViT / ViT3D cores run in bf16 mode")
+        self.precision = precision
+        self.split = precision == "fp32"      # GEMM operands as bf16 hi + lo planes (3 MMAs per product), see engine_fp32.py
         self.C, self.F, self.H = cfg.hidden_dim, cfg.mlp_dim, cfg.num_heads
         if self.C != self.H * 64:
             raise _abi.CavitError(f"cavit attention kernels are specialised for head_dim 64 (hidden_dim {self.C}, heads {self.H})")
@@ -308,6 +317,10 @@ class Engine:
         self.grad = None
         self.adopt_parameters()
         self._plan_key = None
+        # (batch, train, drop) -> (buffers, forward graphs, backward graphs): a train <-> eval switch or a short last batch
+        # re-uses its plan (and its captured CUDA graphs) instead of re-allocating every activation buffer. Bounded LRU.
+        self._plans: "OrderedDict[Tuple, Tuple]" = OrderedDict()
+        self.max_plans = int(os.environ.get("CAVIT_MAX_PLANS", "3"))
         self.saved_valid = False
         # CUDA graphs: the forward / backward kernel sequences are static for a given (batch, mode), so after
         # two eager runs they are captured once and replayed (removes ~1.5k launch calls per step from the
@@ -316,6 +329,9 @@ class Engine:
         self._fwd_graphs: Dict = {}
         self._bwd_graphs: Dict = {}
         self.on_range_done = None
+        self.hook_capturable = False        # set by the owner of on_range_done when the hook only enqueues stream work
+        self._hook_capture_failed = False
+        self.hook_capture_error = None
         self.post_backward = None
         self.graph_launches = 0   # kernels executed through graph replays (the library counter only sees eager launches)
 
@@ -402,6 +418,24 @@ class Engine:
         key = (B, train, drop)
         if self._plan_key == key:
             return
+        if self._plan_key is not None:      # park the current plan (LRU order: most recent last)
+            self._plans[self._plan_key] = (self.a, self._fwd_graphs, self._bwd_graphs, self.fold)
+            self._plans.move_to_end(self._plan_key)
+            while len(self._plans) > self.max_plans:
+                self._plans.popitem(last=False)
+        self.saved_valid = False
+        if key in self._plans:
+            self.a, self._fwd_graphs, self._bwd_graphs, self.fold = self._plans.pop(key)
+            self._plan_key = key
+            self.B, self.T = B, B * self.N
+            return
+        self._fwd_graphs, self._bwd_graphs = {}, {}
+        if self.split:
+            from . import engine_fp32
+            self.a = engine_fp32.plan(self, B, train)
+            self._plan_key = key
+            self.B, self.T = B, B * self.N
+            return
         dev = self.device
         G, N, C, F, H, K = self.G, self.N, self.C, self.F, self.H, self.K
         T = B * N
@@ -415,9 +449,6 @@ class Engine:
             self.a = a
             self._plan_key = key
             self.B, self.T = B, T
-            self.saved_valid = False
-            self._fwd_graphs.clear()
-            self._bwd_graphs.clear()
             return
         # Folded single-query cross attention (csrc/xfold.cu): no K/V projection of the fused sequence, no materialised
         # LayerNorm of it. Attention dropout breaks the fold (probabilities stop summing to one): unfolded path then.
@@ -494,9 +525,6 @@ class Engine:
         self.a = a
         self._plan_key = key
         self.B, self.T = B, T
-        self.saved_valid = False
-        self._fwd_graphs.clear()   # captured graphs reference the previous plan's buffers
-        self._bwd_graphs.clear()
 
     # ------------------------------------------------------------------ GEMM helpers
     def _split_for(self, G, N_out, K_in, T):
@@ -548,10 +576,17 @@ class Engine:
     # ------------------------------------------------------------------ forward
     def forward(self, img: torch.Tensor, labels: torch.Tensor, train: bool, drop: bool = False):
         """Validates inputs, then runs the forward kernel sequence (eagerly, or by replaying its CUDA graph).
-        drop: apply the configured dropout (module in training mode with dropout > 0)."""
+        drop: apply the configured dropout (module in training mode with dropout > 0).
+        Every launch goes to the current stream of THIS engine's device, whatever the caller's current device is."""
+        with torch.cuda.device(self.device):
+            return self._forward_checked(img, labels, train, drop)
+
+    def _forward_checked(self, img: torch.Tensor, labels: torch.Tensor, train: bool, drop: bool = False):
         cfg = self.cfg
         if img.dtype != F32 or not img.is_cuda:
             raise _abi.CavitError("img must be a float32 CUDA tensor")
+        if img.device != self.device:
+            raise _abi.CavitError(f"img is on {img.device}, the model on {self.device}")
         if self.kind == "cnnvit":     # stem feature maps [M*B, Cin, A, Bd, Cd] (modality-major), float targets
             want = (cfg.in_channels,) + tuple(cfg.feat_dims)
             if img.dim() != 5 or tuple(img.shape[1:]) != want or img.shape[0] % self.Mimg:
@@ -784,27 +819,43 @@ class Engine:
         if not self.saved_valid:
             raise _abi.CavitError("backward() without a preceding training forward()")
         self.saved_valid = False
-        self.grad = self._next_grad_buffer()
-        out = self._backward_dispatch(loss_scale, on_range_done, loss_scale_dev)
-        if self.post_backward is not None:   # e.g. cavit.ddp's whole-buffer gradient all-reduce
-            self.post_backward(out)
+        with torch.cuda.device(self.device):
+            self.grad = self._next_grad_buffer()
+            out = self._backward_dispatch(loss_scale, on_range_done, loss_scale_dev)
+            if self.post_backward is not None:   # e.g. cavit.ddp's whole-buffer gradient all-reduce
+                self.post_backward(out)
         return out
 
     def _backward_dispatch(self, loss_scale, on_range_done, loss_scale_dev):
-        if not (self.use_graphs and ops.PROFILE is None and on_range_done is None):
+        # A range hook that only ENQUEUES stream work (cavit.ddp: event record, NCCL all-reduce on a side stream, stream
+        # wait) is recorded into the backward graph like the kernels around it (`hook_capturable`); any other hook
+        # forces eager launches.
+        hook_ok = on_range_done is None or (self.hook_capturable and not self._hook_capture_failed)
+        if not (self.use_graphs and ops.PROFILE is None and hook_ok):
             return self._backward_impl(loss_scale, on_range_done, loss_scale_dev)
-        st = self._bwd_graphs.setdefault((self.B, self._grad_idx, self.drop), {"runs": 0, "graph": None})
+        st = self._bwd_graphs.setdefault((self.B, self._grad_idx, self.drop, on_range_done is not None), {"runs": 0, "graph": None})
         if st["graph"] is None:
             st["runs"] += 1
             if st["runs"] <= 2:
-                return self._backward_impl(loss_scale, None, loss_scale_dev)
+                return self._backward_impl(loss_scale, on_range_done, loss_scale_dev)
             st["scale"] = torch.ones(1, dtype=F32, device=self.device)
             st["labels"] = self._labels
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             n0 = _abi.launch_count()
-            with torch.cuda.graph(graph):
-                self._backward_impl(1.0, None, st["scale"])
+            if on_range_done is None:
+                with torch.cuda.graph(graph):
+                    self._backward_impl(1.0, None, st["scale"])
+            else:
+                try:   # collectives inside the capture: thread-local capture mode keeps NCCL's watchdog thread out of it
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        self._backward_impl(1.0, on_range_done, st["scale"])
+                except Exception as exc:   # this stack cannot capture the hook's work: stay eager from now on (and say so)
+                    self._hook_capture_failed = True
+                    self.hook_capture_error = repr(exc)
+                    del self._bwd_graphs[(self.B, self._grad_idx, self.drop, True)]
+                    torch.cuda.synchronize(self.device)
+                    return self._backward_impl(loss_scale, on_range_done, loss_scale_dev)
             st["launches"] = _abi.launch_count() - n0
             st["graph"] = graph
         if st["labels"].data_ptr() != self._labels.data_ptr():

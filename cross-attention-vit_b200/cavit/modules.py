@@ -172,7 +172,21 @@ class _CavitModel(_Base):
         self.optim_params = config.optim_params
         self._dropout_p = float(config.dropout)
         self._engine_obj = None
+        self._precision = str(getattr(config, "precision", "bf16"))
+        self._epoch_metrics = {}
         self.initialize_model()
+
+    def set_precision(self, precision: str):
+        """"bf16" (default): bf16 GEMM / attention operands, fp32 accumulation — within ~2e-2 of the reference's fp32 path;
+        "fp32": the fp32-tolerance mode (the reference trains in fp32: `L.Trainer` without `precision=`,
+        /root/reference/main_mist.py:211-218) — every GEMM operand as a bf16 hi + lo pair (3 tensor-core MMAs per
+        product), fp32 attention — within ~1e-3. Returns self."""
+        if precision not in ("bf16", "fp32"):
+            raise _abi.CavitError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision != self._precision:
+            self._precision = precision
+            object.__setattr__(self, "_engine_obj", None)    # rebuilt (same parameters) on the next forward
+        return self
 
     @staticmethod
     def init_weights(module):
@@ -196,9 +210,11 @@ class _CavitModel(_Base):
             raise _abi.CavitError("cavit models run on a CUDA B200 only: move the model with .cuda() first "
                                   "(there is no CPU / eager fallback)")
         eng = self._engine_obj
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         if eng is None or eng.device != dev:
             named = OrderedDict(self.named_parameters())
-            eng = Engine(self._kind, self.config, named, dev)
+            eng = Engine(self._kind, self.config, named, dev, precision=self._precision)
             object.__setattr__(self, "_engine_obj", eng)
         return eng
 
@@ -211,16 +227,47 @@ class _CavitModel(_Base):
         return _CavitFn.apply(eng, train, drop, img, labels, *params)
 
     # ---------------------------------------------------------------- Lightning-style hooks
+    def log_stats(self, name, logits, labels):
+        """The reference's per-step `log_stats` (/root/reference/model_cross.py:243-255, utils.py:18-62: six torchmetrics
+        objects, six `.item()` read-backs and an AUROC sort per step, logged `on_epoch=True, sync_dist=True`). Here a step
+        adds its batch to a device-side accumulator with one launch (cavit.metrics.EpochMetrics, no host synchronisation);
+        the epoch values — the same batch-size-weighted means, averaged over ranks — are logged under the same keys from
+        `on_train_epoch_end` / `on_validation_epoch_end`."""
+        from .metrics import EpochMetrics
+        em = self._epoch_metrics.get(name)
+        if em is None or em.device != logits.device:
+            em = self._epoch_metrics[name] = EpochMetrics(logits.device, prefix=name)
+        em.update(logits, labels)
+
+    def _log_epoch_stats(self, name):
+        em = self._epoch_metrics.get(name)
+        if em is None:
+            return {}
+        vals = em.compute()
+        em.reset()
+        for k, v in vals.items():
+            if not k.endswith("_loss"):     # the loss is logged per step by training_step / validation_step, as in the reference
+                self.log(k, v, on_epoch=True, on_step=False, sync_dist=False)    # already reduced over ranks
+        return vals
+
+    def on_train_epoch_end(self):
+        self._log_epoch_stats("train")
+
+    def on_validation_epoch_end(self):
+        self._log_epoch_stats("val")
+
     def training_step(self, batch, batch_idx):
         x, labels = batch
         logits, loss = self(x, labels)
         self.log("train_loss", loss, on_epoch=True, on_step=False, sync_dist=True)
+        self.log_stats("train", logits, labels)
         return loss
 
     def validation_step(self, batch, batch_idx):
         x, labels = batch
         logits, loss = self(x, labels)
         self.log("val_loss", loss, on_epoch=True, on_step=False, sync_dist=True)
+        self.log_stats("val", logits, labels)
 
     def configure_optimizers(self):
         opt = torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)

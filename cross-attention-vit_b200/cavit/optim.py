@@ -36,24 +36,48 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(eng.flat)
         self.exp_avg_sq = torch.zeros_like(eng.flat)
         self.step_count = 0
+        self._acc = None       # flat gradient slab assembled from `.grad` tensors that do not alias the engine's buffer
         # the step rewrites the bf16 operand copy itself; the engine then skips its per-forward cast
         self.own_operands = bool(own_operands)
         if self.own_operands:
             eng.refresh_operands()
             eng.operands_external = True
 
+    def _gradient_slab(self) -> torch.Tensor:
+        """The flat gradient the update reads. Normally the engine's buffer of the last backward (every ``p.grad`` is a
+        view of it). Under gradient accumulation (several backward() calls without zero_grad) autograd keeps SUMMING into
+        the ``.grad`` tensors of the first backward while the engine writes each later backward into another buffer
+        (Engine._next_grad_buffer), so the accumulated gradient lives in ``p.grad`` only: it is gathered into a flat
+        scratch slab here (same offsets), so that the step never silently uses just the last micro-batch."""
+        eng = self.engine
+        base = eng.grad.data_ptr()
+        stray = [(key, p) for key, p in eng.params.items()
+                 if p.grad is not None and p.grad.data_ptr() != base + 4 * eng.layout.slots[key][0]]
+        if not stray:
+            return eng.grad
+        if self._acc is None:
+            self._acc = torch.empty_like(eng.flat)
+        self._acc.copy_(eng.grad)
+        for key, p in stray:
+            off, shp = eng.layout.slots[key]
+            self._acc[off:off + p.numel()].view(shp).copy_(p.grad)
+        return self._acc
+
     def step(self, grad_scale: float = 1.0):
-        """One update from the gradients of the last backward (``engine.grad``; after the data-parallel all-reduce when
-        cavit.ddp is attached). grad_scale multiplies the gradients (e.g. 1 / accumulation steps)."""
+        """One update from the parameters' gradients: the engine's flat buffer of the last backward (after the
+        data-parallel all-reduce when cavit.ddp is attached), or — when gradients were accumulated over several
+        backward() calls — the sums autograd left in ``p.grad``. grad_scale multiplies the gradients
+        (e.g. 1 / accumulation steps)."""
         eng = self.engine
         if getattr(eng, "grad", None) is None:
             raise _abi.CavitError("FusedAdam.step() before any backward()")
         if not eng._params_in_place():
             eng.adopt_parameters()
         self.step_count += 1
-        ops.adam_step(eng.flat, eng.grad, self.exp_avg, self.exp_avg_sq, eng.flat_bf16 if self.own_operands else None,
-                      lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
-                      step=self.step_count, grad_scale=grad_scale)
+        with torch.cuda.device(eng.device):
+            ops.adam_step(eng.flat, self._gradient_slab(), self.exp_avg, self.exp_avg_sq,
+                          eng.flat_bf16 if self.own_operands else None, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
+                          eps=self.eps, weight_decay=self.weight_decay, step=self.step_count, grad_scale=grad_scale)
 
     def zero_grad(self, set_to_none: bool = True):
         """Every backward overwrites the flat gradient buffer, so there is nothing to clear; `.grad` views are dropped

@@ -33,23 +33,33 @@ int check_launch(const char* what) {
 
 __device__ int g_status_word[4];
 
+// Both are properties of the CURRENT device (a __device__ symbol has one instance per device): cached per device id so
+// that a process driving several GPUs (model on cuda:1 while cuda:0 is also in use) never gets another device's address.
+constexpr int kMaxDevices = 64;
+
 int* status_word() {
-  static int* p = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static std::atomic<int*> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  int* p = cache[dev].load(std::memory_order_acquire);
+  if (!p) {
     void* q = nullptr;
-    if (cudaGetSymbolAddress(&q, g_status_word) == cudaSuccess) p = static_cast<int*>(q);
-  });
+    if (cudaGetSymbolAddress(&q, g_status_word) != cudaSuccess) return nullptr;
+    p = static_cast<int*>(q);
+    cache[dev].store(p, std::memory_order_release);
+  }
   return p;
 }
 
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }

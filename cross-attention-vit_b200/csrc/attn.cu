@@ -831,11 +831,11 @@ int cavit_attn_fwd(const void* qkv, void* out, float* lse, int32_t G, int32_t B,
   const long long T = (long long)B * N;
   const CUtensorMap* tm = tensor_map_bf16_3d(qkv, 3 * C, T, G, 3 * C, T * 3 * C, 64, ATT_TILE);
   if (!tm) return CAVIT_E_BADARG;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceFlag attr;
+  if (attr.unset()) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM);
     if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "attn fwd smem attribute: %s", cudaGetErrorString(e));
-    attr = true;
+    attr.set();
   }
   AttnFwdParams p;
   p.out = reinterpret_cast<bf16*>(out);
@@ -880,11 +880,11 @@ int cavit_attn_bwd(const void* qkv, const void* out, const void* dout, const flo
   const CUtensorMap* tq = tensor_map_bf16_3d(qkv, 3 * C, T, G, 3 * C, T * 3 * C, 64, ATT_TILE);
   const CUtensorMap* td = tensor_map_bf16_3d(dout, C, T, G, C, T * C, 64, ATT_TILE);
   if (!tq || !td) return CAVIT_E_BADARG;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceFlag attr;
+  if (attr.unset()) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
     if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "attn bwd smem attribute: %s", cudaGetErrorString(e));
-    attr = true;
+    attr.set();
   }
   {
     const long long warps = (long long)G * T * H;

@@ -481,11 +481,11 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
 template <int NKV, int NH>
 static int launch_short(const CUtensorMap* tkv, const CUtensorMap* tq, const CUtensorMap* td, const AttnBwdShortParams& p,
                         int grid, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceFlag attr;
+  if (attr.unset()) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_short_kernel<NKV, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM);
     if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "attn bwd (short) smem attribute: %s", cudaGetErrorString(e));
-    attr = true;
+    attr.set();
   }
   attn_bwd_short_kernel<NKV, NH><<<grid, SB_THREADS, SB_SMEM, stream>>>(*tkv, *tq, *td, p);
   return CAVIT_OK;

@@ -504,12 +504,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 template <int BN, int EPI, int OUT, int CTAS>
 static int launch_gemm_epi(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (attr_set.unset()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, OUT, CTAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "gemm smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.set();
   }
   const long long total = (long long)d.tiles_m * d.tiles_n * d.groups * d.split_k;
   const int max_units = sm_count() / CTAS;

@@ -10,7 +10,7 @@ namespace cavit {
 
 // thread-local last-error message; returns `code` so callers can `return fail(...)`.
 int fail(int code, const char* fmt, ...);
-// device status word (kernel-side time-outs). One per process (single device per process).
+// device status word (kernel-side time-outs) of the CURRENT device (one per device, cached per device id).
 int* status_word();
 void count_launch(int n = 1);
 // Checks cudaGetLastError() after a launch.
@@ -34,6 +34,21 @@ inline uint32_t drop_threshold(float p) {
   return (uint32_t)t;
 }
 int sm_count();
+
+// "done once" flag per CUDA device: kernel function attributes (dynamic shared memory limits) belong to a device, so a
+// process that uses a second GPU has to set them again there.
+struct PerDeviceFlag {
+  unsigned char f[64] = {};
+  static int dev() { int d = 0; return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : -1; }
+  bool unset() const { const int d = dev(); return d < 0 || !f[d]; }
+  void set() { const int d = dev(); if (d >= 0) f[d] = 1; }
+};
+// largest dynamic shared-memory size a kernel has been opted into on the current device
+struct PerDeviceMax {
+  size_t v[64] = {};
+  size_t get() const { const int d = PerDeviceFlag::dev(); return d < 0 ? 0 : v[d]; }
+  void set(size_t x) { const int d = PerDeviceFlag::dev(); if (d >= 0) v[d] = x; }
+};
 
 // Short-sequence (N <= 256) attention backward: one persistent CTA per SM walks whole heads (attn_short.cu).
 int launch_attn_bwd_short(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int G, int B,

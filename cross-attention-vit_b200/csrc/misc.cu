@@ -677,10 +677,10 @@ int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, c
   head_dh_kernel<<<dim3(B, M), 256, 0, st>>>(W2, lab, logits, loss_scale, loss_scale_dev, reinterpret_cast<bf16*>(dh), M, B, F, classes,
                                              smoothing, d, use);
   if ((size_t)B * classes * sizeof(float) > 96 * 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_head_loss_bwd: batch %d too large", B);
-  static bool dw_attr = false;
-  if (!dw_attr) {
+  static PerDeviceFlag dw_attr;
+  if (dw_attr.unset()) {
     cudaFuncSetAttribute(head_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    dw_attr = true;
+    dw_attr.set();
   }
   head_dw_kernel<<<dim3((F + 255) / 256, M), 256, (size_t)B * classes * sizeof(float), st>>>(reinterpret_cast<const bf16*>(h), lab, logits, loss_scale,
                                                            loss_scale_dev, dW2, db2, M, B, F, classes, smoothing, d, use);

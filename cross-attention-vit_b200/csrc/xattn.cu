@@ -207,10 +207,10 @@ int cavit_xattn_fwd(const float* q, const void* kv, float* out, float* probs, in
   if (K <= 0 || B <= 0 || N <= 0 || H <= 0) return fail(CAVIT_E_BADARG, "cavit_xattn_fwd: bad extents");
   const size_t smem = sizeof(float) * ((size_t)N + XA_D + 4 + 4 * XA_D);
   if (smem > 200 * 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_xattn_fwd: N=%d too long for one CTA", N);
-  static size_t cur = 48 * 1024;
-  if (smem > cur) {
+  static PerDeviceMax cur;
+  if (smem > 48 * 1024 && smem > cur.get()) {
     cudaFuncSetAttribute(xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cur = smem;
+    cur.set(smem);
   }
   DropCfg d;
   const int use = xa_drop(p_drop, seed_dev, site, &d);
@@ -228,10 +228,10 @@ int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const fl
   if (K <= 0 || B <= 0 || N <= 0 || H <= 0) return fail(CAVIT_E_BADARG, "cavit_xattn_bwd: bad extents");
   const size_t smem = sizeof(float) * ((size_t)N + 2 * XA_D + 4 + 4 * XA_D);
   if (smem > 200 * 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_xattn_bwd: N=%d too long for one CTA", N);
-  static size_t cur = 48 * 1024;
-  if (smem > cur) {
+  static PerDeviceMax cur;
+  if (smem > 48 * 1024 && smem > cur.get()) {
     cudaFuncSetAttribute(xattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cur = smem;
+    cur.set(smem);
   }
   DropCfg d;
   const int use = xa_drop(p_drop, seed_dev, site, &d);

@@ -509,19 +509,19 @@ static int xfold_launch(bool bwd, const XfoldParams& p, cudaStream_t st) {
   static const int pad_kb = [] { const char* e = getenv("CAVIT_XFOLD_PAD_KB"); return e ? atoi(e) : 0; }();
   if (pad_kb > 0 && smem < (size_t)pad_kb * 1024) smem = (size_t)pad_kb * 1024;
   if (bwd) {
-    static size_t cur = 0;
-    if (smem > cur) {
+    static PerDeviceMax cur;
+    if (smem > cur.get()) {
       if (cudaFuncSetAttribute(xfold_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return fail(CAVIT_E_LAUNCH, "xfold bwd smem attribute");
-      cur = smem;
+      cur.set(smem);
     }
     xfold_bwd_kernel<H><<<dim3(p.B, p.K), threads, smem, st>>>(p);
   } else {
-    static size_t cur = 0;
-    if (smem > cur) {
+    static PerDeviceMax cur;
+    if (smem > cur.get()) {
       if (cudaFuncSetAttribute(xfold_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return fail(CAVIT_E_LAUNCH, "xfold fwd smem attribute");
-      cur = smem;
+      cur.set(smem);
     }
     xfold_fwd_kernel<H><<<dim3(p.B, p.K), threads, smem, st>>>(p);
   }

@@ -3,8 +3,9 @@
 The reference's model files import third-party packages that are absent from this image
 (``lightning``, ``ml_collections``, ``torchmetrics``). This loader places
 minimal stub modules in ``sys.modules`` and imports ``model_cross`` / ``modelv3`` straight
-from the reference tree, which must be present (build container only; the GPU box has no
-/root/reference and must never call this).
+from the reference tree: /root/reference in the build container, or — on the GPU box, which has
+no /root/reference — the byte-for-byte copies that ``oracle/make_ref.py`` placed into the
+git-ignored ``oracle/_ref/`` (used there by the timed CPU-baseline legs of bench.py only).
 """
 from __future__ import annotations
 
@@ -15,7 +16,10 @@ import types
 
 import torch.nn as nn
 
-REFERENCE_DIRS = [os.environ.get("CAVIT_REFERENCE_DIR", ""), "/root/reference"]
+# /root/reference in the build container; on the GPU box the byte-for-byte copies that oracle/make_ref.py placed
+# into the git-ignored, gpurun-shipped oracle/_ref/ (test infrastructure: cpu_baseline / --impl reference only)
+REFERENCE_DIRS = [os.environ.get("CAVIT_REFERENCE_DIR", ""), "/root/reference",
+                  os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
 
 
 def reference_dir():

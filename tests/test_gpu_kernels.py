@@ -384,8 +384,14 @@ def _attn_ref(qkv, B, N, H):
     return x, o, lse
 
 
+# N = 785 (ModelVIT on cfg2 slices), 2251 (cfg3: 18 key tiles), 4097 (cfg5: 33 tiles) are the BASELINE.json sequence lengths
+# of the long-sequence kernels (cross-item pipelining, three-warp MMA issue); several heads per launch so that the
+# persistent CTAs walk more than one work item
+LONG_ATTN = [(1, 1, 785, 2), (1, 1, 2251, 2), (1, 1, 4097, 1), (2, 1, 1025, 3), (1, 2, 2251, 12)]
+
+
 @pytest.mark.parametrize("G,B,N,H", [(1, 1, 128, 1), (1, 2, 64, 2), (2, 2, 197, 3), (1, 1, 513, 2), (1, 3, 9, 2),
-                                     (1, 1, 257, 1)])
+                                     (1, 1, 257, 1)] + LONG_ATTN)
 def test_attention_fwd(G, B, N, H):
     from cavit import ops
     torch.manual_seed(10)
@@ -405,7 +411,7 @@ def test_attention_fwd(G, B, N, H):
                                      # ragged tails, and enough heads that every persistent CTA walks several of them
                                      (1, 2, 16, 1), (1, 2, 17, 2), (1, 1, 31, 1), (1, 2, 129, 2), (1, 1, 144, 1),
                                      (1, 1, 200, 2), (1, 2, 255, 1), (1, 1, 256, 2), (2, 40, 197, 6), (1, 50, 65, 4),
-                                     (1, 1, 257, 1)])
+                                     (1, 1, 257, 1)] + LONG_ATTN)
 def test_attention_bwd(G, B, N, H):
     from cavit import ops
     torch.manual_seed(11)

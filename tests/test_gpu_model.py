@@ -240,3 +240,58 @@ def test_raw_mri_intensities_match_oracle():
     num = sum(float((grads[k].double().cpu() - g).norm()) ** 2 for k, g in ref_grads.items())
     den = sum(float(g.norm()) ** 2 for g in ref_grads.values())
     assert (num / den) ** 0.5 < 4e-2, (num / den) ** 0.5
+
+
+def test_fused_adam_with_gradient_accumulation_matches_torch_adam():
+    """k micro-batches without zero_grad: autograd sums into `p.grad` while the engine's flat buffer holds only the last
+    micro-batch; FusedAdam must step on the SUM (scaled by 1/k), like torch.optim.Adam on `p.grad / k`."""
+    from cavit.modules import ModelCross
+    from cavit.optim import FusedAdam
+    from oracle.weights import make_inputs
+    kind, cfg, state, _, _ = build_case("cross_chain3")
+    img, labels = make_inputs(cfg, 6, seed=21)
+    a, b = ModelCross(cfg), ModelCross(cfg)
+    a.load_state_dict(state)
+    b.load_state_dict(state)
+    a, b = a.cuda().train(), b.cuda().train()
+    a.engine()
+    fa = FusedAdam(a, lr=1e-3, weight_decay=0.0)
+    tb = torch.optim.Adam(b.parameters(), lr=1e-3, weight_decay=0.0)
+    k = 3
+    for step in range(2):
+        for i in range(k):
+            sl = slice(2 * i, 2 * i + 2)
+            a(img[sl].cuda(), labels[sl].cuda())[1].backward()
+            (b(img[sl].cuda(), labels[sl].cuda())[1] / k).backward()
+        fa.step(grad_scale=1.0 / k)
+        fa.zero_grad()
+        tb.step()
+        tb.zero_grad()
+    num = den = 0.0
+    for (key, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        num += float((pa - pb).double().norm()) ** 2
+        den += float((pb.detach().cpu().double() - state[key].double()).norm()) ** 2
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
+
+
+def test_model_on_second_device_while_first_is_current():
+    """The engine launches on ITS device's current stream whatever the caller's current device is (per-device status word,
+    SM count and kernel attributes)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from cavit import _abi
+    from cavit.modules import ModelCross
+    kind, cfg, state, img, labels = build_case("cross_chain3")
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.cuda.set_device(0)
+        m = ModelCross(cfg)
+        m.load_state_dict(state)
+        m = m.to(dev).train()
+        logits, loss = m(img.to(dev), labels.to(dev))
+        loss.backward()
+        torch.cuda.synchronize(dev)
+        outs.append((logits.detach().cpu(), torch.cat([p.grad.flatten().cpu() for p in m.parameters()])))
+    with torch.cuda.device(1):
+        assert _abi.device_status() == 0
+    assert rel(outs[1][0], outs[0][0]) < 1e-5 and rel(outs[1][1], outs[0][1]) < 1e-3
