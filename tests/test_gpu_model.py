@@ -244,7 +244,8 @@ def test_raw_mri_intensities_match_oracle():
 
 def test_fused_adam_with_gradient_accumulation_matches_torch_adam():
     """k micro-batches without zero_grad: autograd sums into `p.grad` while the engine's flat buffer holds only the last
-    micro-batch; FusedAdam must step on the SUM (scaled by 1/k), like torch.optim.Adam on `p.grad / k`."""
+    micro-batch; FusedAdam must step on the SUM (scaled by 1/k), like torch.optim.Adam on `p.grad / k` (both models run
+    the same unscaled micro-batch backwards, so their gradients agree to the atomics' summation order)."""
     from cavit.modules import ModelCross
     from cavit.optim import FusedAdam
     from oracle.weights import make_inputs
@@ -262,9 +263,12 @@ def test_fused_adam_with_gradient_accumulation_matches_torch_adam():
         for i in range(k):
             sl = slice(2 * i, 2 * i + 2)
             a(img[sl].cuda(), labels[sl].cuda())[1].backward()
-            (b(img[sl].cuda(), labels[sl].cuda())[1] / k).backward()
+            b(img[sl].cuda(), labels[sl].cuda())[1].backward()
         fa.step(grad_scale=1.0 / k)
         fa.zero_grad()
+        with torch.no_grad():
+            for p in b.parameters():
+                p.grad.div_(k)
         tb.step()
         tb.zero_grad()
     num = den = 0.0
