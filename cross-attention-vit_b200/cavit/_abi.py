@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libcavit_sm100a.so")
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_GELU_BWD, EPI_EMBED, EPI_BIAS_RELU, EPI_RELU_BWD = range(8)
 
@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("resid", c_vp), ("ldr", c_i64), ("resid_gs", c_i64),
         ("aux", c_vp), ("ldaux", c_i64), ("aux_gs", c_i64),
         ("accumulate", c_i32), ("split_k", c_i32), ("embed_np", c_i32),
+        ("A_lo", c_vp), ("B_lo", c_vp),     # fp32-tolerance mode: lo planes of split operands (NULL = plain bf16)
     ]
 
 
@@ -68,7 +69,7 @@ _SIGS = {
     "cavit_xattn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp,
                                 C.c_uint32, c_vp]),
     "cavit_xfold_scratch_floats": (c_i64, [c_i32, c_i32, c_i32, c_i32]),
-    "cavit_xfold_fwd": (c_i32, [c_vp] * 11 + [c_i32] * 5 + [C.POINTER(c_i32), C.POINTER(c_i32), c_f32, c_f32, c_f32, c_vp,
+    "cavit_xfold_fwd": (c_i32, [c_vp] * 12 + [c_i32] * 5 + [C.POINTER(c_i32), C.POINTER(c_i32), c_f32, c_f32, c_f32, c_vp,
                                 C.c_uint32, c_vp]),
     "cavit_xfold_bwd": (c_i32, [c_vp] * 14 + [c_i32] * 5 + [C.POINTER(c_i32), C.POINTER(c_i32), c_f32, c_f32, c_vp,
                                 C.c_uint32, c_vp]),
@@ -90,6 +91,20 @@ _SIGS = {
                                     C.c_uint32, c_vp]),
     "cavit_head_loss_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
                                     c_f32, c_f32, c_vp, C.c_uint32, c_vp]),
+    # ---- fp32-tolerance mode (split bf16 hi + lo operands, fp32 attention / GELU / head)
+    "cavit_cast_split": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "cavit_gelu_split": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "cavit_gelu_bwd_split": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "cavit_ln_fwd_split": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_ln_bwd_split": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64,
+                                   c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cavit_colsum_split": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "cavit_patchify_split": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cavit_attn_fwd_f32": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_attn_bwd_f32": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_head_loss_fwd_f32": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "cavit_head_loss_bwd_f32": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
+                                        c_f32, c_vp]),
 }
 
 EXPORTS = tuple(_SIGS)

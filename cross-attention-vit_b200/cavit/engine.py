@@ -309,6 +309,8 @@ class Engine:
         self.params = named_params
         self.flat = torch.zeros(self.layout.total, dtype=F32, device=self.device)
         self.flat_bf16 = torch.zeros(self.layout.total, dtype=BF16, device=self.device)
+        # fp32-tolerance mode: second bf16 plane of the operand copy (w ~ flat_bf16 + flat_bf16_lo)
+        self.flat_bf16_lo = torch.zeros(self.layout.total, dtype=BF16, device=self.device) if self.split else None
         self.grad_bufs = [torch.zeros(self.layout.total, dtype=F32, device=self.device)]
         self._grad_idx = 0
         self._bf16_version = -1
@@ -365,8 +367,14 @@ class Engine:
         if self.operands_external and self._bf16_version >= 0:
             return
         if not self._frozen or self._bf16_version < 0:
-            ops.cast_bf16(self.flat, self.flat_bf16)
+            self._cast_operands()
             self._bf16_version = 1
+
+    def _cast_operands(self):
+        if self.split:
+            ops.cast_split(self.flat, ops.with_lo(self.flat_bf16, self.flat_bf16_lo))
+        else:
+            ops.cast_bf16(self.flat, self.flat_bf16)
 
     def freeze_operands(self, frozen: bool = True):
         """Inference helper: skip the per-forward fp32 -> bf16 weight cast until unfrozen."""
@@ -384,7 +392,10 @@ class Engine:
         return self._seg(self.flat, name)
 
     def wb(self, name):
-        return self._seg(self.flat_bf16, name)
+        t = self._seg(self.flat_bf16, name)
+        if self.split:     # the bf16 operand view carries its lo plane (see ops.lo_of)
+            t._lo = self._seg(self.flat_bf16_lo, name)
+        return t
 
     def g(self, name):
         return self._seg(self.grad, name)
@@ -607,6 +618,9 @@ class Engine:
         if labels.numel() != B:
             raise _abi.CavitError(f"labels must have {B} entries, got {labels.numel()}")
         drop = bool(drop and self.p_drop > 0.0)
+        if drop and self.split:
+            raise _abi.CavitError("the fp32-tolerance mode runs with dropout = 0 (the parity configuration); "
+                                  "use precision='bf16' to train with dropout")
         self._plan(B, train, drop)
         self.drop = drop
         if drop:
@@ -614,7 +628,7 @@ class Engine:
         if not self._params_in_place():
             self.adopt_parameters()
         if self.operands_external and self._bf16_version < 0:   # parameters were (re)loaded behind the optimizer's back
-            ops.cast_bf16(self.flat, self.flat_bf16)
+            self._cast_operands()
             self._bf16_version = 1
         if not (self.use_graphs and ops.PROFILE is None):
             return self._forward_impl(img, labels, train)
@@ -646,9 +660,12 @@ class Engine:
         B = self.B       # (the leading axis of `img` is modality x sample for the CNN-stem ViT)
         if force_cast:   # inside a graph the operand refresh is unconditional (unless an optimizer owns the bf16 copy)
             if not self.operands_external:
-                ops.cast_bf16(self.flat, self.flat_bf16)
+                self._cast_operands()
         else:
             self.refresh_operands()
+        if self.split:
+            from . import engine_fp32
+            return engine_fp32.forward_impl(self, img, labels, train)
         a, G, N, C, F, H, T, K = self.a, self.G, self.N, self.C, self.F, self.H, self.T, self.K
         if self.post_norm:
             return self._forward_post(img, labels, train)
@@ -880,6 +897,9 @@ class Engine:
                 s, e_ = ranges[tag]
                 on_range_done(tag, s, e_)
 
+        if self.split:
+            from . import engine_fp32
+            return engine_fp32.backward_impl(self, loss_scale, done, loss_scale_dev)
         if self.post_norm:
             return self._backward_post(loss_scale, done, loss_scale_dev)
         ws = a["ln_ws"]

@@ -24,6 +24,31 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# ---- fp32-tolerance mode: a "split" bf16 tensor is a hi plane that carries its lo plane as the attribute `_lo`
+# (x ~ hi + lo, 16 mantissa bits). The wrappers below pick the lo plane up from the operands they are given, so the
+# engine passes the same (hi) tensors in both precision modes.
+def split_pair(shape, device) -> torch.Tensor:
+    """Allocate a split bf16 tensor: returns the hi plane; `.lo` of it is reachable through `lo_of`."""
+    full = torch.empty((2,) + tuple(shape), dtype=BF16, device=device)
+    return with_lo(full[0], full[1])
+
+
+def with_lo(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
+    hi._lo = lo
+    return hi
+
+
+def lo_of(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else getattr(t, "_lo", None)
+
+
+def sub(t: torch.Tensor, idx) -> torch.Tensor:
+    """t[idx] that keeps the lo plane of a split tensor."""
+    v = t[idx]
+    lo = lo_of(t)
+    return v if lo is None else with_lo(v, lo[idx])
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, groups: int = 1,
          a_mn: bool = False, b_mn: bool = False, lda: int, ldb: int, ldo: int, a_gs: int = 0, b_gs: int = 0,
          out_gs: int = 0, epi: int = EPI_NONE, bias: Optional[torch.Tensor] = None, bias_gs: int = 0,
@@ -33,6 +58,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     """D[g][m][n] = sum_k A_g(m,k) B_g(n,k) (see include/cavit.h: cavit_gemm)."""
     assert A.dtype == BF16 and B.dtype == BF16 and out.dtype in (BF16, F32)
     a = GemmArgs()
+    a_lo, b_lo = lo_of(A), lo_of(B)
+    if (a_lo is None) != (b_lo is None):
+        raise _abi.CavitError("cavit gemm: either both operands are split (hi + lo planes) or neither")
+    a.A_lo, a.B_lo = _p(a_lo), _p(b_lo)
     a.M, a.N, a.K, a.groups = M, N, K, groups
     a.a_mn, a.b_mn, a.epi, a.out_fp32 = int(a_mn), int(b_mn), epi, int(out.dtype == F32)
     a.A, a.lda, a.a_gs = A.data_ptr(), lda, a_gs
@@ -84,6 +113,65 @@ def ln_fwd(x, gamma, beta, y, mean, rstd, *, rows_per_group, groups, C, x_row_st
     check(lib().cavit_ln_fwd(x.data_ptr(), x_row_stride, x_gs, rows_per_group, groups, C, gamma.data_ptr(),
                              beta.data_ptr(), eps, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _stream()),
           "cavit_ln_fwd")
+
+
+def ln_fwd_split(x, gamma, beta, y, mean, rstd, *, rows_per_group, groups, C, x_row_stride=None, x_gs=None, eps=1e-5):
+    """y: split bf16 tensor (hi plane carrying its lo plane)."""
+    x_row_stride = C if x_row_stride is None else x_row_stride
+    x_gs = rows_per_group * x_row_stride if x_gs is None else x_gs
+    check(lib().cavit_ln_fwd_split(x.data_ptr(), x_row_stride, x_gs, rows_per_group, groups, C, gamma.data_ptr(),
+                                   beta.data_ptr(), eps, y.data_ptr(), lo_of(y).data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                   _stream()), "cavit_ln_fwd_split")
+
+
+def ln_bwd_split(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, partials, *, rows_per_group, groups, C, dresid=None,
+                 dx_split=None, x_row_stride=None, x_gs=None, dx_row_stride=None, dx_gs=None, dcol=None):
+    """dy: fp32; dx_split: optional split bf16 copy of dx."""
+    assert dy.dtype == F32
+    x_row_stride = C if x_row_stride is None else x_row_stride
+    x_gs = rows_per_group * x_row_stride if x_gs is None else x_gs
+    dx_row_stride = C if dx_row_stride is None else dx_row_stride
+    dx_gs = rows_per_group * dx_row_stride if dx_gs is None else dx_gs
+    check(lib().cavit_ln_bwd_split(dy.data_ptr(), x.data_ptr(), x_row_stride, x_gs, mean.data_ptr(), rstd.data_ptr(),
+                                   gamma.data_ptr(), rows_per_group, groups, C, _p(dresid), dx.data_ptr(), dx_row_stride,
+                                   dx_gs, _p(dx_split), _p(lo_of(dx_split)), dgamma.data_ptr(), dbeta.data_ptr(), _p(dcol),
+                                   partials.data_ptr(), _stream()), "cavit_ln_bwd_split")
+
+
+def cast_split(src, dst):
+    """fp32 -> split bf16 (dst: hi plane carrying its lo plane)."""
+    assert src.dtype == F32 and dst.dtype == BF16 and src.numel() == dst.numel()
+    check(lib().cavit_cast_split(src.data_ptr(), dst.data_ptr(), lo_of(dst).data_ptr(), src.numel(), _stream()), "cavit_cast_split")
+
+
+def gelu_split(u, h=None, h32=None):
+    check(lib().cavit_gelu_split(u.data_ptr(), _p(h), _p(lo_of(h)), _p(h32), u.numel(), _stream()), "cavit_gelu_split")
+
+
+def gelu_bwd_split(dh, u, du):
+    check(lib().cavit_gelu_bwd_split(dh.data_ptr(), u.data_ptr(), du.data_ptr(), lo_of(du).data_ptr(), dh.numel(), _stream()),
+          "cavit_gelu_bwd_split")
+
+
+def attn_fwd_f32(qkv, out, lse, *, G, B, N, H, scale):
+    check(lib().cavit_attn_fwd_f32(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), G, B, N, H, scale, _stream()),
+          "cavit_attn_fwd_f32")
+
+
+def attn_bwd_f32(qkv, out, dout, lse, dqkv, delta, *, G, B, N, H, scale):
+    check(lib().cavit_attn_bwd_f32(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                   delta.data_ptr(), G, B, N, H, scale, _stream()), "cavit_attn_bwd_f32")
+
+
+def head_loss_fwd_f32(h, W2, b2, labels, logits, loss, *, M, B, F, classes, smoothing):
+    check(lib().cavit_head_loss_fwd_f32(h.data_ptr(), W2.data_ptr(), b2.data_ptr(), labels.data_ptr(), logits.data_ptr(),
+                                        loss.data_ptr(), M, B, F, classes, smoothing, _stream()), "cavit_head_loss_fwd_f32")
+
+
+def head_loss_bwd_f32(h, W2, labels, logits, dh, dW2, db2, *, M, B, F, classes, smoothing, loss_scale=1.0, loss_scale_dev=None):
+    check(lib().cavit_head_loss_bwd_f32(h.data_ptr(), W2.data_ptr(), labels.data_ptr(), logits.data_ptr(), loss_scale,
+                                        _p(loss_scale_dev), dh.data_ptr(), dW2.data_ptr(), db2.data_ptr(), M, B, F, classes,
+                                        smoothing, _stream()), "cavit_head_loss_bwd_f32")
 
 
 def ln_bwd_workspace(groups: int, C: int, device) -> torch.Tensor:
@@ -153,7 +241,7 @@ def xfold_fwd(x, cls, qp, gamma, beta, zhat, z, probs, mean, rstd, scratch, *, K
               eps=1e-5, p_drop=0.0, seed=None, site=0):
     """Folded single-query cross attention, forward (include/cavit.h: cavit_xfold_fwd)."""
     check(lib().cavit_xfold_fwd(x.data_ptr(), cls.data_ptr(), qp.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                zhat.data_ptr(), z.data_ptr(), probs.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                zhat.data_ptr(), z.data_ptr(), _p(lo_of(z)), probs.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                 scratch.data_ptr(), K, B, N, C_, H, _i32arr(cls_src), _i32arr(tok_src), scale, eps, p_drop,
                                 _p(seed), site, _stream()), "cavit_xfold_fwd")
 
@@ -169,6 +257,8 @@ def xfold_bwd(x, cls, qp, gamma, zhat, probs, mean, rstd, gz, scratch, dx, dqp, 
 
 def expand_heads(W, E, *, groups, C_, H):
     check(lib().cavit_expand_heads(W.data_ptr(), E.data_ptr(), groups, C_, H, _stream()), "cavit_expand_heads")
+    if lo_of(W) is not None:    # a pure permutation of the weight elements: the lo plane goes through the same map
+        check(lib().cavit_expand_heads(lo_of(W).data_ptr(), lo_of(E).data_ptr(), groups, C_, H, _stream()), "cavit_expand_heads")
 
 
 def fold_heads(dE, dW, *, groups, C_, H):
@@ -186,6 +276,11 @@ def dropout(mode, a, b, out, *, n, p, seed, site):
 def patchify(img, patches, *, patch_size, sample_major=False):
     B, M, _, D, H, W = img.shape
     dp, hp, wp = patch_size
+    lo = lo_of(patches)
+    if lo is not None:
+        check(lib().cavit_patchify_split(img.data_ptr(), patches.data_ptr(), lo.data_ptr(), B, M, D, H, W, dp, hp, wp,
+                                         int(sample_major), _stream()), "cavit_patchify_split")
+        return
     check(lib().cavit_patchify(img.data_ptr(), patches.data_ptr(), B, M, D, H, W, dp, hp, wp, int(sample_major),
                                _stream()),
           "cavit_patchify")
@@ -209,6 +304,11 @@ def colsum_bf16(x, out, *, rows, C_, groups, ldx=None, x_gs=None, out_gs=None):
     ldx = C_ if ldx is None else ldx
     x_gs = rows * ldx if x_gs is None else x_gs
     out_gs = C_ if out_gs is None else out_gs
+    lo = lo_of(x)
+    if lo is not None:
+        check(lib().cavit_colsum_split(x.data_ptr(), lo.data_ptr(), ldx, x_gs, rows, C_, groups, out.data_ptr(), out_gs,
+                                       _stream()), "cavit_colsum_split")
+        return
     check(lib().cavit_colsum_bf16(x.data_ptr(), ldx, x_gs, rows, C_, groups, out.data_ptr(), out_gs, _stream()),
           "cavit_colsum_bf16")
 
@@ -258,6 +358,9 @@ def gelu_bwd_bf16(dh, u, du):
 def compact_patch_rows_bf16(src, dst, *, S, Np, C_):
     check(lib().cavit_compact_patch_rows_bf16(src.data_ptr(), dst.data_ptr(), S, Np, C_, _stream()),
           "cavit_compact_patch_rows_bf16")
+    if lo_of(src) is not None:
+        check(lib().cavit_compact_patch_rows_bf16(lo_of(src).data_ptr(), lo_of(dst).data_ptr(), S, Np, C_, _stream()),
+              "cavit_compact_patch_rows_bf16")
 
 
 def tokens_from_channels(feat, cls, pos, tokens, *, B, C_, S, has_cls=True):
@@ -349,8 +452,10 @@ def _instrument(name, fn):
                 nbytes += 2.0 * g_ * m_ * n_
             info = {"flops": 2.0 * m_ * n_ * k_ * g_, "bytes": nbytes,
                     "shape": (m_, n_, k_, g_, int(kw.get("a_mn", False)), int(kw.get("b_mn", False)))}
-        elif name in ("attn_fwd", "attn_bwd"):
-            mult = 4.0 if name == "attn_fwd" else 10.0   # QK^T + PV ; S, dP, dV, dK, dQ
+            if lo_of(args[0]) is not None:      # split operands: three MMAs per product are EXECUTED
+                info["executed_flops"] = 3.0 * info["flops"]
+        elif name in ("attn_fwd", "attn_bwd", "attn_fwd_f32", "attn_bwd_f32"):
+            mult = 4.0 if name.startswith("attn_fwd") else 10.0   # QK^T + PV ; S, dP, dV, dK, dQ
             info = {"flops": mult * kw["G"] * kw["B"] * kw["H"] * kw["N"] * kw["N"] * 64}
         PROFILE.append((name, e0, e1, info))
         return out
@@ -359,6 +464,9 @@ def _instrument(name, fn):
     return wrapped
 
 
+for _n in ("ln_fwd_split", "ln_bwd_split", "cast_split", "gelu_split", "gelu_bwd_split", "attn_fwd_f32", "attn_bwd_f32",
+           "head_loss_fwd_f32", "head_loss_bwd_f32"):
+    globals()[_n] = _instrument(_n, globals()[_n])
 for _n in ("gemm", "ln_fwd", "ln_bwd", "ln_fusion_fwd", "ln_fusion_bwd", "attn_fwd", "attn_bwd", "xattn_fwd", "xattn_bwd",
            "patchify", "cls_rows", "embed_param_grads", "cast_bf16", "colsum_bf16", "gather_rows_f32", "add_bf16_f32",
            "gelu_bwd_bf16", "compact_patch_rows_bf16", "head_loss_fwd", "head_loss_bwd", "dropout", "xfold_fwd", "xfold_bwd",

@@ -38,7 +38,7 @@ class FusedAdam:
         self.step_count = 0
         self._acc = None       # flat gradient slab assembled from `.grad` tensors that do not alias the engine's buffer
         # the step rewrites the bf16 operand copy itself; the engine then skips its per-forward cast
-        self.own_operands = bool(own_operands)
+        self.own_operands = bool(own_operands) and not eng.split   # fp32 mode: the engine re-splits hi / lo planes itself
         if self.own_operands:
             eng.refresh_operands()
             eng.operands_external = True

@@ -25,6 +25,7 @@ constexpr int GEMM_BK = 64;
 struct GemmDev {
   int M, N, K, groups;
   int a_mn, b_mn, epi, out_fp32, accumulate, embed_np, split_k, kb_per_split;
+  int passes;   // 1: D = A B^T.  3 (fp32-tolerance mode): operands are bf16 hi + lo pairs, D = Ah Bh^T + Al Bh^T + Ah Bl^T
   void* out; long long ldo, out_gs;
   const float* bias; long long bias_gs;
   const float* resid; long long ldr, resid_gs;
@@ -338,6 +339,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
 template <int BN, int EPI, int OUT, int CTAS>
 __global__ void __launch_bounds__((GemmCfg<BN, CTAS, EPI>::THREADS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                          const GemmDev p) {
   using Cfg = GemmCfg<BN, CTAS, EPI>;
   constexpr int STAGES = Cfg::STAGES;
@@ -373,6 +375,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     fence_barrier_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.passes > 1) {
+      prefetch_tmap(&tmAlo);
+      prefetch_tmap(&tmBlo);
+    }
   }
   if (warp == 1) {
     if (CTAS == 2) {
@@ -407,6 +413,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int n0 = (rem % p.tiles_n) * BN + cta_rank * (BN / CTAS);  // this CTA's share of the B tile
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        // split-operand mode: the k range is walked three times with (A, B) = (hi, hi), (lo, hi), (hi, lo) — to the MMA
+        // issuer it is one three-times-longer accumulation, the missing lo x lo term is below 2^-16 relative
+        for (int ps = 0; ps < p.passes; ++ps) {
+        const CUtensorMap* mapA = (ps == 1) ? &tmAlo : &tmA;
+        const CUtensorMap* mapB = (ps == 2) ? &tmBlo : &tmB;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, abort_flag, p.status, ERR_TIMEOUT_EMPTY);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
@@ -419,18 +430,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             else tma_load_3d(m, full_bar(stage), dst, c0, c1, g);
           };
           if (!p.a_mn) {
-            load(&tmA, sA, k0, m0);
+            load(mapA, sA, k0, m0);
           } else {
 #pragma unroll
-            for (int c = 0; c < GEMM_BM / 64; ++c) load(&tmA, sA + c * (GEMM_BK * 128), m0 + c * 64, k0);
+            for (int c = 0; c < GEMM_BM / 64; ++c) load(mapA, sA + c * (GEMM_BK * 128), m0 + c * 64, k0);
           }
           if (!p.b_mn) {
-            load(&tmB, sB, k0, n0);
+            load(mapB, sB, k0, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / CTAS / 64; ++c) load(&tmB, sB + c * (GEMM_BK * 128), n0 + c * 64, k0);
+            for (int c = 0; c < BN / CTAS / 64; ++c) load(mapB, sB + c * (GEMM_BK * 128), n0 + c * 64, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
         }
       }
     }
@@ -453,7 +465,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int work = unit; work < total_tiles; work += num_units) {
         const int split = work % splits;
         const int kb0 = split * p.kb_per_split;
-        const int num_kb = min(num_kb_total, kb0 + p.kb_per_split) - kb0;
+        const int num_kb = (min(num_kb_total, kb0 + p.kb_per_split) - kb0) * p.passes;
         mbar_wait(tempty_bar(as), aphase ^ 1u, abort_flag, p.status, ERR_TIMEOUT_TMEM_EMPTY);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -502,7 +514,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 template <int BN, int EPI, int OUT, int CTAS>
-static int launch_gemm_epi(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
+static int launch_gemm_epi(const CUtensorMap* const* tm, GemmDev& d, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS, EPI>;
   static PerDeviceFlag attr_set;
   if (attr_set.unset()) {
@@ -526,14 +538,14 @@ static int launch_gemm_epi(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, OUT, CTAS>, *ta, *tb, d);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, OUT, CTAS>, *tm[0], *tm[1], *tm[2], *tm[3], d);
   if (e != cudaSuccess) return fail(CAVIT_E_LAUNCH, "cavit_gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("cavit_gemm");
 }
 
 template <int BN, int CTAS>
-static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap* const* tm, GemmDev& d, cudaStream_t stream) {
   d.tiles_m = (d.M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS);
   d.tiles_n = (d.N + BN - 1) / BN;
   const int num_kb = (d.K + GEMM_BK - 1) / GEMM_BK;
@@ -544,7 +556,7 @@ static int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, GemmDev& d,
   if (d.accumulate) d.vec_ok = 0;  // read-modify-write outputs take the generic path
   const int out = d.split_k > 1 ? OUT_RED : (d.out_fp32 ? OUT_F32 : OUT_BF16);
 #define CAVIT_GEMM_CASE(E, O) \
-  if (d.epi == E && out == O) return launch_gemm_epi<BN, E, O, CTAS>(ta, tb, d, stream);
+  if (d.epi == E && out == O) return launch_gemm_epi<BN, E, O, CTAS>(tm, d, stream);
   CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_BF16)
   CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_F32)
   CAVIT_GEMM_CASE(CAVIT_EPI_NONE, OUT_RED)
@@ -569,6 +581,10 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   if (a->M <= 0 || a->N <= 0 || a->K <= 0 || a->groups <= 0)
     return fail(CAVIT_E_BADARG, "cavit_gemm: non-positive extent M=%d N=%d K=%d groups=%d", a->M, a->N, a->K, a->groups);
   if (!a->A || !a->B || !a->out) return fail(CAVIT_E_BADARG, "cavit_gemm: null operand");
+  if ((a->A_lo == nullptr) != (a->B_lo == nullptr))
+    return fail(CAVIT_E_BADARG, "cavit_gemm: split operands need both A_lo and B_lo");
+  if (a->A_lo && ((reinterpret_cast<uintptr_t>(a->A_lo) & 15) || (reinterpret_cast<uintptr_t>(a->B_lo) & 15)))
+    return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_gemm: lo planes need 16-byte aligned bases");
   if ((a->lda % 8) || (a->ldb % 8) || (a->a_gs % 8) || (a->b_gs % 8) ||
       (reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15))
     return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_gemm: operands need 16-byte aligned rows (ld %% 8 == 0)");
@@ -611,17 +627,21 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
   static const bool wgrad192 = [] { const char* e = getenv("CAVIT_WGRAD_BN192"); return !(e && e[0] == '0'); }();
   if (wgrad192 && CTAS == 1 && a->a_mn && a->b_mn && a->N % 192 == 0 && a->N % 256 != 0) BN = 192;
   if (dgrad_single) BN = 192;
-  const CUtensorMap *ta, *tb;
-  if (!a->a_mn)
-    ta = tensor_map_bf16_3d(a->A, a->K, a->M, a->groups, a->lda, a->a_gs, 64, GEMM_BM);
-  else
-    ta = tensor_map_bf16_3d(a->A, a->M, a->K, a->groups, a->lda, a->a_gs, 64, GEMM_BK);
-  if (!ta) return CAVIT_E_BADARG;
-  if (!a->b_mn)
-    tb = tensor_map_bf16_3d(a->B, a->K, a->N, a->groups, a->ldb, a->b_gs, 64, BN / CTAS);
-  else
-    tb = tensor_map_bf16_3d(a->B, a->N, a->K, a->groups, a->ldb, a->b_gs, 64, GEMM_BK);
-  if (!tb) return CAVIT_E_BADARG;
+  const bool split_ops = a->A_lo != nullptr;
+  auto map_a = [&](const void* base) {
+    return !a->a_mn ? tensor_map_bf16_3d(base, a->K, a->M, a->groups, a->lda, a->a_gs, 64, GEMM_BM)
+                    : tensor_map_bf16_3d(base, a->M, a->K, a->groups, a->lda, a->a_gs, 64, GEMM_BK);
+  };
+  auto map_b = [&](const void* base) {
+    return !a->b_mn ? tensor_map_bf16_3d(base, a->K, a->N, a->groups, a->ldb, a->b_gs, 64, BN / CTAS)
+                    : tensor_map_bf16_3d(base, a->N, a->K, a->groups, a->ldb, a->b_gs, 64, GEMM_BK);
+  };
+  const CUtensorMap* tm[4];
+  tm[0] = map_a(a->A);
+  tm[1] = map_b(a->B);
+  tm[2] = split_ops ? map_a(a->A_lo) : tm[0];
+  tm[3] = split_ops ? map_b(a->B_lo) : tm[1];
+  if (!tm[0] || !tm[1] || !tm[2] || !tm[3]) return CAVIT_E_BADARG;
 
   GemmDev d;
   d.M = a->M; d.N = a->N; d.K = a->K; d.groups = a->groups;
@@ -640,6 +660,7 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
                a->resid_gs % 4 == 0 && al(a->aux, 8) && a->ldaux % 4 == 0 && a->aux_gs % 4 == 0;
   }
   d.split_k = a->split_k > 1 ? a->split_k : 1;
+  d.passes = split_ops ? 3 : 1;
   d.kb_per_split = 0;
   d.status = status;
   if (d.split_k > 1 && !a->accumulate) {  // atomics combine into a zeroed output
@@ -653,11 +674,11 @@ extern "C" int cavit_gemm(const cavit_gemm_args* a, void* stream) {
     }
   }
   if (CTAS == 2) {
-    if (BN == 256) return launch_gemm<256, 2>(ta, tb, d, as_stream(stream));
-    if (BN == 192) return launch_gemm<192, 2>(ta, tb, d, as_stream(stream));
-    return launch_gemm<128, 2>(ta, tb, d, as_stream(stream));
+    if (BN == 256) return launch_gemm<256, 2>(tm, d, as_stream(stream));
+    if (BN == 192) return launch_gemm<192, 2>(tm, d, as_stream(stream));
+    return launch_gemm<128, 2>(tm, d, as_stream(stream));
   }
-  if (BN == 256) return launch_gemm<256, 1>(ta, tb, d, as_stream(stream));
-  if (BN == 192) return launch_gemm<192, 1>(ta, tb, d, as_stream(stream));
-  return launch_gemm<128, 1>(ta, tb, d, as_stream(stream));
+  if (BN == 256) return launch_gemm<256, 1>(tm, d, as_stream(stream));
+  if (BN == 192) return launch_gemm<192, 1>(tm, d, as_stream(stream));
+  return launch_gemm<128, 1>(tm, d, as_stream(stream));
 }

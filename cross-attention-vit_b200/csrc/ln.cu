@@ -52,7 +52,8 @@ template <int NV>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, int rows_per_group, int groups, int C,
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, bf16* __restrict__ y,
-              float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd, const RowMap rm) {
+              bf16* __restrict__ y_lo, float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd,
+              const RowMap rm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)rows_per_group * groups;
   const int C4 = C >> 2;
@@ -99,6 +100,13 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
           o.x = pack_bf16(f.x, f.y);
           o.y = pack_bf16(f.z, f.w);
           yr[c4] = o;
+          if (y_lo) {   // fp32-tolerance mode: second bf16 plane with the rounding residual (split GEMM operand)
+            const float2 h01 = unpack_bf16_fast(o.x), h23 = unpack_bf16_fast(o.y);
+            uint2 l;
+            l.x = pack_bf16(f.x - h01.x, f.y - h01.y);
+            l.y = pack_bf16(f.z - h23.x, f.w - h23.y);
+            reinterpret_cast<uint2*>(y_lo + row * C)[c4] = l;
+          }
         }
         // post-norm encoders (modelv2.py:72-78): the normalised row IS the next residual stream, kept in fp32
         if (y32) reinterpret_cast<float4*>(y32 + row * C)[c4] = f;
@@ -123,7 +131,8 @@ __global__ void __launch_bounds__(LN_THREADS, (NV <= 3 ? 2 : 1))
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long long row_stride, long long gs,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               int rows_per_group, int C, const float* dresid, float* dx, long long dx_row_stride, long long dx_gs,
-              bf16* __restrict__ dx_bf16, float* __restrict__ partials, unsigned int* __restrict__ tickets,
+              bf16* __restrict__ dx_bf16, bf16* __restrict__ dx_lo, float* __restrict__ partials,
+              unsigned int* __restrict__ tickets,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcol, const RowMap rm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.y;
@@ -209,6 +218,13 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
             q.x = pack_bf16(o.x, o.y);
             q.y = pack_bf16(o.z, o.w);
             *(reinterpret_cast<uint2*>(dx_bf16 + row * C) + c4) = q;
+            if (dx_lo) {
+              const float2 h01 = unpack_bf16_fast(q.x), h23 = unpack_bf16_fast(q.y);
+              uint2 l;
+              l.x = pack_bf16(o.x - h01.x, o.y - h01.y);
+              l.y = pack_bf16(o.z - h23.x, o.w - h23.y);
+              *(reinterpret_cast<uint2*>(dx_lo + row * C) + c4) = l;
+            }
           }
         }
       }
@@ -277,7 +293,7 @@ static int blocks_per_group(long long rows, int groups) {
 
 static int ln_fwd_launch(const float* x, long long row_stride, long long gs, int rpg, int groups, int C,
                          const float* gamma, const float* beta, float eps, void* y, float* y32, float* mean, float* rstd,
-                         const RowMap& rm, cudaStream_t st) {
+                         const RowMap& rm, cudaStream_t st, void* y_lo = nullptr) {
   if (C % 4 || C <= 0 || C > 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm: C=%d (need C %% 4 == 0, C <= 1024)", C);
   if ((row_stride % 4) || (gs % 4)) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm: strides must be multiples of 4");
   const long long total = (long long)rpg * groups;
@@ -289,7 +305,7 @@ static int ln_fwd_launch(const float* x, long long row_stride, long long gs, int
 #define LN_FWD_CASE(NVV)                                                                                      \
   case NVV:                                                                                                   \
     ln_fwd_kernel<NVV><<<(int)blocks, LN_THREADS, 0, st>>>(x, row_stride, gs, rpg, groups, C, gamma, beta, eps, \
-                                                           reinterpret_cast<bf16*>(y), y32, mean, rstd, rm);  \
+                                                           reinterpret_cast<bf16*>(y), reinterpret_cast<bf16*>(y_lo), y32, mean, rstd, rm);  \
     break;
   switch (nv) {
     LN_FWD_CASE(1) LN_FWD_CASE(2) LN_FWD_CASE(3) LN_FWD_CASE(4) LN_FWD_CASE(5) LN_FWD_CASE(6) LN_FWD_CASE(7) LN_FWD_CASE(8)
@@ -303,7 +319,8 @@ static int ln_fwd_launch(const float* x, long long row_stride, long long gs, int
 static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, long long gs, const float* mean,
                          const float* rstd, const float* gamma, int rpg, int groups, int C, const float* dresid,
                          float* dx, long long dx_rs, long long dx_gs, void* dx_bf16, float* dgamma, float* dbeta,
-                         float* dcol, float* partials, const RowMap& rm, cudaStream_t st, bool dy_f32 = false) {
+                         float* dcol, float* partials, const RowMap& rm, cudaStream_t st, bool dy_f32 = false,
+                         void* dx_lo = nullptr) {
   if (C % 4 || C <= 0 || C > 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: C=%d", C);
   if ((row_stride % 4) || (gs % 4) || (dx_rs % 4) || (dx_gs % 4))
     return fail(CAVIT_E_UNSUPPORTED_SHAPE, "layernorm bwd: strides must be multiples of 4");
@@ -315,7 +332,8 @@ static int ln_bwd_launch(const void* dy, const float* x, long long row_stride, l
   unsigned int* tickets = reinterpret_cast<unsigned int*>(partials + (size_t)groups * LN_MAX_BLOCKS_PER_GROUP * 3 * C);
 #define LN_BWD_LAUNCH(NVV, COLV, DYFV)                                                                              \
   ln_bwd_kernel<NVV, COLV, DYFV><<<grid, LN_THREADS, 0, st>>>(dy, x, row_stride, gs, mean, rstd, gamma, rpg, C, dresid, dx, \
-                                                              dx_rs, dx_gs, reinterpret_cast<bf16*>(dx_bf16), partials,   \
+                                                              dx_rs, dx_gs, reinterpret_cast<bf16*>(dx_bf16),             \
+                                                              reinterpret_cast<bf16*>(dx_lo), partials,                   \
                                                               tickets, dgamma, dbeta, dcol, rm)
 #define LN_BWD_CASE(NVV)                                                    \
   case NVV:                                                                 \
@@ -356,6 +374,30 @@ int cavit_ln_fwd_dual(const float* x, int64_t x_row_stride, int64_t x_gs, int32_
   rm.fusion = 0;
   return ln_fwd_launch(x, x_row_stride, x_gs, rows_per_group, groups, C, gamma, beta, eps, y_bf16, y_f32, mean, rstd, rm,
                        as_stream(stream));
+}
+
+/* fp32-tolerance mode: the normalised rows as bf16 hi + lo planes (the split operand of the next GEMM) */
+int cavit_ln_fwd_split(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t rows_per_group, int32_t groups, int32_t C,
+                       const float* gamma, const float* beta, float eps, void* y_hi, void* y_lo, float* mean, float* rstd,
+                       void* stream) {
+  if (!x || !gamma || !beta || !y_hi || !y_lo || !mean || !rstd) return fail(CAVIT_E_BADARG, "cavit_ln_fwd_split: null pointer");
+  RowMap rm{};
+  rm.fusion = 0;
+  return ln_fwd_launch(x, x_row_stride, x_gs, rows_per_group, groups, C, gamma, beta, eps, y_hi, nullptr, mean, rstd, rm,
+                       as_stream(stream), y_lo);
+}
+
+/* fp32-tolerance mode: fp32 incoming gradient (an fp32 dgrad output), dx additionally as bf16 hi + lo planes (nullable pair) */
+int cavit_ln_bwd_split(const float* dy_f32, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,
+                       const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
+                       const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_hi, void* dx_lo,
+                       float* dgamma, float* dbeta, float* dcol, float* partials, void* stream) {
+  if (!dy_f32 || !x || !mean || !rstd || !gamma || !dx) return fail(CAVIT_E_BADARG, "cavit_ln_bwd_split: null pointer");
+  if ((dx_hi == nullptr) != (dx_lo == nullptr)) return fail(CAVIT_E_BADARG, "cavit_ln_bwd_split: dx_hi and dx_lo go together");
+  RowMap rm{};
+  rm.fusion = 0;
+  return ln_bwd_launch(dy_f32, x, x_row_stride, x_gs, mean, rstd, gamma, rows_per_group, groups, C, dresid, dx,
+                       dx_row_stride, dx_gs, dx_hi, dgamma, dbeta, dcol, partials, rm, as_stream(stream), true, dx_lo);
 }
 
 size_t cavit_ln_bwd_workspace_floats(int32_t groups, int32_t C) {

@@ -20,12 +20,76 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = __float2bfloat16(src[(n4 << 2) + threadIdx.x]);
 }
 
+// fp32-tolerance mode: x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits between them). The two planes are
+// what the tensor-core GEMM consumes as (A_hi, A_lo) / (B_hi, B_lo) in its 3-pass split-operand mode (gemm.cu).
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(a, b);
+  const float2 h = unpack_bf16_fast(hi);
+  lo = pack_bf16(a - h.x, b - h.y);
+}
+__global__ void cast_split_kernel(const float* __restrict__ src, bf16* __restrict__ hi, bf16* __restrict__ lo, long long n) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    uint2 h, l;
+    split_bf16x2(v.x, v.y, h.x, l.x);
+    split_bf16x2(v.z, v.w, h.y, l.y);
+    reinterpret_cast<uint2*>(hi)[i] = h;
+    reinterpret_cast<uint2*>(lo)[i] = l;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long j = (n4 << 2) + threadIdx.x;
+    const bf16 h = __float2bfloat16(src[j]);
+    hi[j] = h;
+    lo[j] = __float2bfloat16(src[j] - __bfloat162float(h));
+  }
+}
+
+// fp32-tolerance mode GELU (exact erf form, nn.GELU default, model_cross.py:24) on fp32 pre-activations:
+//   forward   h = gelu(u)          -> split planes (the fc2 / head operand) and, optionally, an fp32 copy
+//   backward  du = dh * gelu'(u)   -> split planes (the fc1 dgrad / wgrad operand)
+__global__ void gelu_split_kernel(const float* __restrict__ u, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                  float* __restrict__ h32, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(u) + i);
+    float4 g;
+    g.x = 0.5f * v.x * (1.0f + erff(v.x * 0.70710678118654752f));
+    g.y = 0.5f * v.y * (1.0f + erff(v.y * 0.70710678118654752f));
+    g.z = 0.5f * v.z * (1.0f + erff(v.z * 0.70710678118654752f));
+    g.w = 0.5f * v.w * (1.0f + erff(v.w * 0.70710678118654752f));
+    if (hi) {
+      uint2 h, l;
+      split_bf16x2(g.x, g.y, h.x, l.x);
+      split_bf16x2(g.z, g.w, h.y, l.y);
+      reinterpret_cast<uint2*>(hi)[i] = h;
+      reinterpret_cast<uint2*>(lo)[i] = l;
+    }
+    if (h32) reinterpret_cast<float4*>(h32)[i] = g;
+  }
+}
+__device__ __forceinline__ float gelu_grad_exact(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+__global__ void gelu_bwd_split_kernel(const float* __restrict__ dh, const float* __restrict__ u, bf16* __restrict__ hi,
+                                      bf16* __restrict__ lo, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dh) + i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(u) + i);
+    uint2 h, l;
+    split_bf16x2(d.x * gelu_grad_exact(v.x), d.y * gelu_grad_exact(v.y), h.x, l.x);
+    split_bf16x2(d.z * gelu_grad_exact(v.z), d.w * gelu_grad_exact(v.w), h.y, l.y);
+    reinterpret_cast<uint2*>(hi)[i] = h;
+    reinterpret_cast<uint2*>(lo)[i] = l;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ patchify
 // out[m][b*Np + t][f] = img[b][m][0][di*dp + a][hi*hp + bb][wi*wp + c]
 //   t = (hi*Wn + wi)*Dn + di   (d fastest),   f = (a*hp + bb)*wp + c      
 // One thread produces two consecutive features (one 4-byte bf16x2 store).
-__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int M, int D, int H,
-                                int W, int dp, int hp, int wp, int sample_major) {
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, bf16* __restrict__ out_lo, int B, int M,
+                                int D, int H, int W, int dp, int hp, int wp, int sample_major) {
   const int Dn = D / dp, Hn = H / hp, Wn = W / wp;
   const long long Np = (long long)Dn * Hn * Wn;
   const int P = dp * hp * wp;
@@ -49,15 +113,22 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
       const int c = ff % wp, bb = (ff / wp) % hp, a = ff / (wp * hp);
       v[j] = __ldg(vol + ((long long)(di * dp + a) * H + (hi * hp + bb)) * W + (wi * wp + c));
     }
-    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16(v[0], v[1]);
+    if (out_lo) {   // fp32-tolerance mode: hi + lo planes of the patch rows
+      uint32_t h, l;
+      split_bf16x2(v[0], v[1], h, l);
+      reinterpret_cast<uint32_t*>(out)[i] = h;
+      reinterpret_cast<uint32_t*>(out_lo)[i] = l;
+    } else {
+      reinterpret_cast<uint32_t*>(out)[i] = pack_bf16(v[0], v[1]);
+    }
   }
 }
 
 // Vector variant: when the run of features that is contiguous in BOTH the patch row and the volume (wp, times hp when the
 // patch spans the whole W axis, times dp when it also spans H) is a multiple of 4, one thread moves 4 features: one index
 // decode, one 16-byte load (when aligned), one 8-byte store. cfg2 (224x224x1 slices, 16x16x1 patches): runs of 16 floats.
-__global__ void patchify_vec4_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int M, int D, int H,
-                                     int W, int dp, int hp, int wp, int sample_major) {
+__global__ void patchify_vec4_kernel(const float* __restrict__ img, bf16* __restrict__ out, bf16* __restrict__ out_lo, int B,
+                                     int M, int D, int H, int W, int dp, int hp, int wp, int sample_major) {
   const int Dn = D / dp, Hn = H / hp, Wn = W / wp;
   const long long Np = (long long)Dn * Hn * Wn;
   const int P = dp * hp * wp;
@@ -83,8 +154,15 @@ __global__ void patchify_vec4_kernel(const float* __restrict__ img, bf16* __rest
       v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
     }
     uint2 o;
-    o.x = pack_bf16(v.x, v.y);
-    o.y = pack_bf16(v.z, v.w);
+    if (out_lo) {
+      uint2 l;
+      split_bf16x2(v.x, v.y, o.x, l.x);
+      split_bf16x2(v.z, v.w, o.y, l.y);
+      reinterpret_cast<uint2*>(out_lo)[i] = l;
+    } else {
+      o.x = pack_bf16(v.x, v.y);
+      o.y = pack_bf16(v.z, v.w);
+    }
     reinterpret_cast<uint2*>(out)[i] = o;
   }
 }
@@ -132,8 +210,8 @@ __global__ void embed_param_grads_kernel(const float* __restrict__ dtok, float* 
 // the 8 warps are combined through shared memory and the row slices with fp32 atomics into a
 // zero-initialised out.
 __global__ void __launch_bounds__(256)
-colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, long long gs, int rows, int C, float* __restrict__ out,
-                   long long out_gs) {
+colsum_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x_lo, long long ldx, long long gs, int rows, int C,
+                   float* __restrict__ out, long long out_gs) {
   __shared__ float sm[8][256 + 8];
   const int g = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,6 +232,13 @@ colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, long long gs, int 
       f = unpack_bf16(v.y); acc[2] += f.x; acc[3] += f.y;
       f = unpack_bf16(v.z); acc[4] += f.x; acc[5] += f.y;
       f = unpack_bf16(v.w); acc[6] += f.x; acc[7] += f.y;
+      if (x_lo) {   // fp32-tolerance mode: the rows are hi + lo pairs
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(x_lo + (long long)g * gs + c + (long long)r * ldx));
+        f = unpack_bf16(w.x); acc[0] += f.x; acc[1] += f.y;
+        f = unpack_bf16(w.y); acc[2] += f.x; acc[3] += f.y;
+        f = unpack_bf16(w.z); acc[4] += f.x; acc[5] += f.y;
+        f = unpack_bf16(w.w); acc[6] += f.x; acc[7] += f.y;
+      }
     }
   }
 #pragma unroll
@@ -290,7 +375,14 @@ constexpr int HEAD_MAX_CLASSES = 8;
 
 // grid = B, block = 256. logits[b][k] = (1/M) sum_m D_m( b2[m][k] + sum_f h[m][b][f] W2[m][k][f] ), where D_m is the
 // (optional) dropout the reference applies to every head's logits (model_cross.py:182) before the mean.
-__global__ void head_logits_kernel(const bf16* __restrict__ h, const float* __restrict__ W2, const float* __restrict__ b2,
+__device__ __forceinline__ float head_ld(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float head_ld(const float* p) { return *p; }
+__device__ __forceinline__ void head_st(bf16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void head_st(float* p, float v) { *p = v; }
+
+// T = bf16 (bf16 mode: the hidden activations are the bf16 output of the head GEMM) or float (fp32-tolerance mode)
+template <typename T>
+__global__ void head_logits_kernel(const T* __restrict__ h, const float* __restrict__ W2, const float* __restrict__ b2,
                                    float* __restrict__ logits, int M, int B, int F, int classes, DropCfg d, int use_drop) {
   __shared__ float red[HEAD_MAX_CLASSES][8];
   __shared__ float total[HEAD_MAX_CLASSES];
@@ -302,9 +394,9 @@ __global__ void head_logits_kernel(const bf16* __restrict__ h, const float* __re
     float acc[HEAD_MAX_CLASSES];
 #pragma unroll
     for (int k = 0; k < HEAD_MAX_CLASSES; ++k) acc[k] = 0.f;
-    const bf16* hr = h + ((long long)m * B + b) * F;
+    const T* hr = h + ((long long)m * B + b) * F;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
-      const float hv = __bfloat162float(hr[f]);
+      const float hv = head_ld(hr + f);
 #pragma unroll
       for (int k = 0; k < HEAD_MAX_CLASSES; ++k)
         if (k < classes) acc[k] += hv * __ldg(W2 + ((long long)m * classes + k) * F + f);
@@ -370,9 +462,10 @@ __device__ __forceinline__ void dlogits_row(const float* z, long long label, int
 }
 
 // grid = (B, M): dh[m][b][f] = sum_k dz[b][k] W2[m][k][f],  dz = dlogits / M
+template <typename T>
 __global__ void head_dh_kernel(const float* __restrict__ W2, const long long* __restrict__ labels,
                                const float* __restrict__ logits, float scale, const float* __restrict__ scale_dev,
-                               bf16* __restrict__ dh, int M, int B, int F, int classes, float smoothing, DropCfg d,
+                               T* __restrict__ dh, int M, int B, int F, int classes, float smoothing, DropCfg d,
                                int use_drop) {
   const int b = blockIdx.x, m = blockIdx.y;
   if (scale_dev) scale *= __ldg(scale_dev);
@@ -382,16 +475,17 @@ __global__ void head_dh_kernel(const float* __restrict__ W2, const long long* __
     const unsigned long long seed = *d.seed;
     for (int k = 0; k < classes; ++k) dz[k] *= drop_mult(d, seed, ((uint64_t)m * B + b) * classes + k);
   }
-  bf16* o = dh + ((long long)m * B + b) * F;
+  T* o = dh + ((long long)m * B + b) * F;
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < classes; ++k) s += dz[k] * __ldg(W2 + ((long long)m * classes + k) * F + f);
-    o[f] = __float2bfloat16(s);
+    head_st(o + f, s);
   }
 }
 
 // grid = (ceil(F/256), M): dW2[m][k][f] = sum_b dz[b][k] h[m][b][f];  block (0, m) also writes db2.
-__global__ void head_dw_kernel(const bf16* __restrict__ h, const long long* __restrict__ labels,
+template <typename T>
+__global__ void head_dw_kernel(const T* __restrict__ h, const long long* __restrict__ labels,
                                const float* __restrict__ logits, float scale, const float* __restrict__ scale_dev,
                                float* __restrict__ dW2, float* __restrict__ db2, int M, int B, int F, int classes,
                                float smoothing, DropCfg d, int use_drop) {
@@ -417,7 +511,7 @@ __global__ void head_dw_kernel(const bf16* __restrict__ h, const long long* __re
   __syncthreads();
 #pragma unroll 4
   for (int b = 0; b < B; ++b) {
-    const float hv = (f < F) ? __bfloat162float(h[((long long)m * B + b) * F + f]) : 0.f;
+    const float hv = (f < F) ? head_ld(h + ((long long)m * B + b) * F + f) : 0.f;
 #pragma unroll
     for (int k = 0; k < HEAD_MAX_CLASSES; ++k)
       if (k < classes) {
@@ -476,6 +570,59 @@ static int grid_for(long long work, int threads) {
 
 using namespace cavit;
 
+static int make_drop(float p, const uint64_t* seed_dev, uint32_t site, DropCfg* d) {
+  d->seed = reinterpret_cast<const unsigned long long*>(seed_dev);
+  d->site = site;
+  d->thresh = 0;
+  d->inv_keep = 1.f;
+  if (p <= 0.f) return 0;
+  if (p >= 1.f || !seed_dev) return -1;
+  d->thresh = drop_threshold(p);
+  d->inv_keep = 1.0f / (1.0f - p);
+  return 1;
+}
+
+template <typename T>
+static int head_fwd_launch(const T* h, const float* W2, const float* b2, const int64_t* labels, float* logits, float* loss,
+                           int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing, float p_drop,
+                           const uint64_t* seed_dev, uint32_t site, void* stream) {
+  if (!h || !W2 || !b2 || !labels || !logits || !loss) return fail(CAVIT_E_BADARG, "cavit_head_loss_fwd: null pointer");
+  if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d (max %d)", classes, HEAD_MAX_CLASSES);
+  cudaStream_t st = as_stream(stream);
+  DropCfg d;
+  const int use = make_drop(p_drop, seed_dev, site, &d);
+  if (use < 0) return fail(CAVIT_E_BADARG, "cavit_head_loss_fwd: bad dropout arguments");
+  head_logits_kernel<T><<<B, 256, 0, st>>>(h, W2, b2, logits, M, B, F, classes, d, use);
+  ce_loss_kernel<<<1, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), loss, B, classes, smoothing);
+  count_launch(2);
+  return check_launch("cavit_head_loss_fwd");
+}
+
+template <typename T>
+static int head_bwd_launch(const T* h, const float* W2, const int64_t* labels, const float* logits, float loss_scale,
+                           const float* loss_scale_dev, T* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F,
+                           int32_t classes, float smoothing, float p_drop, const uint64_t* seed_dev, uint32_t site,
+                           void* stream) {
+  if (!h || !W2 || !labels || !logits || !dh || !dW2 || !db2) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: null pointer");
+  if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d", classes);
+  cudaStream_t st = as_stream(stream);
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+  DropCfg d;
+  const int use = make_drop(p_drop, seed_dev, site, &d);
+  if (use < 0) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: bad dropout arguments");
+  head_dh_kernel<T><<<dim3(B, M), 256, 0, st>>>(W2, lab, logits, loss_scale, loss_scale_dev, dh, M, B, F, classes, smoothing, d, use);
+  if ((size_t)B * classes * sizeof(float) > 96 * 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_head_loss_bwd: batch %d too large", B);
+  static PerDeviceFlag dw_attr;
+  if (dw_attr.unset()) {
+    cudaFuncSetAttribute(head_dw_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    dw_attr.set();
+  }
+  head_dw_kernel<T><<<dim3((F + 255) / 256, M), 256, (size_t)B * classes * sizeof(float), st>>>(
+      h, lab, logits, loss_scale, loss_scale_dev, dW2, db2, M, B, F, classes, smoothing, d, use);
+  count_launch(2);
+  return check_launch("cavit_head_loss_bwd");
+}
+
 extern "C" {
 
 int cavit_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
@@ -486,8 +633,8 @@ int cavit_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   return check_launch("cavit_cast_bf16");
 }
 
-int cavit_patchify(const float* img, void* patches, int32_t B, int32_t M, int32_t D, int32_t H, int32_t W, int32_t dp,
-                   int32_t hp, int32_t wp, int32_t sample_major, void* stream) {
+static int patchify_launch(const float* img, void* patches, void* patches_lo, int32_t B, int32_t M, int32_t D, int32_t H,
+                           int32_t W, int32_t dp, int32_t hp, int32_t wp, int32_t sample_major, void* stream) {
   if (!img || !patches) return fail(CAVIT_E_BADARG, "cavit_patchify: null pointer");
   if (dp <= 0 || hp <= 0 || wp <= 0 || D % dp || H % hp || W % wp)
     return fail(CAVIT_E_BADARG, "image dimensions must be divisible by the patch size");
@@ -497,15 +644,54 @@ int cavit_patchify(const float* img, void* patches, int32_t B, int32_t M, int32_
   long long run = wp;          // features contiguous in both the patch row and the volume
   if (wp == W) { run *= hp; if (hp == H) run *= dp; }
   if (run % 4 == 0) {
-    patchify_vec4_kernel<<<grid_for(pairs / 2, 256), 256, 0, as_stream(stream)>>>(img, reinterpret_cast<bf16*>(patches), B, M, D,
-                                                                                  H, W, dp, hp, wp, sample_major);
+    patchify_vec4_kernel<<<grid_for(pairs / 2, 256), 256, 0, as_stream(stream)>>>(
+        img, reinterpret_cast<bf16*>(patches), reinterpret_cast<bf16*>(patches_lo), B, M, D, H, W, dp, hp, wp, sample_major);
     count_launch();
     return check_launch("cavit_patchify");
   }
-  patchify_kernel<<<grid_for(pairs, 256), 256, 0, as_stream(stream)>>>(img, reinterpret_cast<bf16*>(patches), B, M, D, H, W,
-                                                                        dp, hp, wp, sample_major);
+  patchify_kernel<<<grid_for(pairs, 256), 256, 0, as_stream(stream)>>>(
+      img, reinterpret_cast<bf16*>(patches), reinterpret_cast<bf16*>(patches_lo), B, M, D, H, W, dp, hp, wp, sample_major);
   count_launch();
   return check_launch("cavit_patchify");
+}
+
+int cavit_patchify(const float* img, void* patches, int32_t B, int32_t M, int32_t D, int32_t H, int32_t W, int32_t dp,
+                   int32_t hp, int32_t wp, int32_t sample_major, void* stream) {
+  return patchify_launch(img, patches, nullptr, B, M, D, H, W, dp, hp, wp, sample_major, stream);
+}
+
+int cavit_patchify_split(const float* img, void* patches_hi, void* patches_lo, int32_t B, int32_t M, int32_t D, int32_t H,
+                         int32_t W, int32_t dp, int32_t hp, int32_t wp, int32_t sample_major, void* stream) {
+  if (!patches_lo) return fail(CAVIT_E_BADARG, "cavit_patchify_split: null lo plane");
+  return patchify_launch(img, patches_hi, patches_lo, B, M, D, H, W, dp, hp, wp, sample_major, stream);
+}
+
+int cavit_cast_split(const float* src, void* hi, void* lo, int64_t n, void* stream) {
+  if (!src || !hi || !lo || n < 0) return fail(CAVIT_E_BADARG, "cavit_cast_split: bad args");
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(hi) & 7) || (reinterpret_cast<uintptr_t>(lo) & 7))
+    return fail(CAVIT_E_BADARG, "cavit_cast_split: misaligned buffer");
+  if (n == 0) return CAVIT_OK;
+  cast_split_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(src, reinterpret_cast<bf16*>(hi),
+                                                                              reinterpret_cast<bf16*>(lo), n);
+  count_launch();
+  return check_launch("cavit_cast_split");
+}
+
+int cavit_gelu_split(const float* u, void* h_hi, void* h_lo, float* h_f32, int64_t n, void* stream) {
+  if (!u || n <= 0 || (n % 4) || (!h_hi && !h_f32) || ((h_hi == nullptr) != (h_lo == nullptr)))
+    return fail(CAVIT_E_BADARG, "cavit_gelu_split: bad args (n % 4 == 0; hi and lo together, or h_f32)");
+  gelu_split_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(u, reinterpret_cast<bf16*>(h_hi),
+                                                                          reinterpret_cast<bf16*>(h_lo), h_f32, n / 4);
+  count_launch();
+  return check_launch("cavit_gelu_split");
+}
+
+int cavit_gelu_bwd_split(const float* dh, const float* u, void* du_hi, void* du_lo, int64_t n, void* stream) {
+  if (!dh || !u || !du_hi || !du_lo || n <= 0 || (n % 4)) return fail(CAVIT_E_BADARG, "cavit_gelu_bwd_split: bad args");
+  gelu_bwd_split_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(dh, u, reinterpret_cast<bf16*>(du_hi),
+                                                                              reinterpret_cast<bf16*>(du_lo), n / 4);
+  count_launch();
+  return check_launch("cavit_gelu_bwd_split");
 }
 
 int cavit_cls_rows(const float* cls, const float* pos, float* tokens, int32_t M, int32_t B, int32_t N, int32_t C,
@@ -531,9 +717,10 @@ int cavit_embed_param_grads(const float* dtokens, float* dpos, float* dcls, int3
   return check_launch("cavit_embed_param_grads");
 }
 
-int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C, int32_t groups, float* out,
-                      int64_t out_gs, void* stream) {
-  if (!x || !out || rows <= 0 || C <= 0 || (C % 8) || (ldx % 8) || (x_gs % 8) || (reinterpret_cast<uintptr_t>(x) & 15))
+static int colsum_launch(const void* x, const void* x_lo, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C, int32_t groups,
+                         float* out, int64_t out_gs, void* stream) {
+  if (!x || !out || rows <= 0 || C <= 0 || (C % 8) || (ldx % 8) || (x_gs % 8) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(x_lo) & 15))
     return fail(CAVIT_E_BADARG, "cavit_colsum_bf16: bad args (C, ld must be multiples of 8; 16-byte aligned base)");
   cudaStream_t st = as_stream(stream);
   if (out_gs == C) {
@@ -547,9 +734,21 @@ int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, in
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
   dim3 grid(cblocks, groups, slices);
-  colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, x_gs, rows, C, out, out_gs);
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(x_lo), ldx, x_gs, rows,
+                                           C, out, out_gs);
   count_launch();
   return check_launch("cavit_colsum_bf16");
+}
+
+int cavit_colsum_bf16(const void* x, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C, int32_t groups, float* out,
+                      int64_t out_gs, void* stream) {
+  return colsum_launch(x, nullptr, ldx, x_gs, rows, C, groups, out, out_gs, stream);
+}
+
+int cavit_colsum_split(const void* x_hi, const void* x_lo, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C, int32_t groups,
+                       float* out, int64_t out_gs, void* stream) {
+  if (!x_lo) return fail(CAVIT_E_BADARG, "cavit_colsum_split: null lo plane");
+  return colsum_launch(x_hi, x_lo, ldx, x_gs, rows, C, groups, out, out_gs, stream);
 }
 
 int cavit_gather_rows_f32(float* src, int64_t srs, int64_t sgs, float* dst, int64_t drs, int64_t dgs, int32_t rows,
@@ -609,18 +808,6 @@ int cavit_compact_patch_rows_bf16(const void* in, void* out, int32_t S, int32_t 
   return check_launch("cavit_compact_patch_rows_bf16");
 }
 
-static int make_drop(float p, const uint64_t* seed_dev, uint32_t site, DropCfg* d) {
-  d->seed = reinterpret_cast<const unsigned long long*>(seed_dev);
-  d->site = site;
-  d->thresh = 0;
-  d->inv_keep = 1.f;
-  if (p <= 0.f) return 0;
-  if (p >= 1.f || !seed_dev) return -1;
-  d->thresh = drop_threshold(p);
-  d->inv_keep = 1.0f / (1.0f - p);
-  return 1;
-}
-
 int cavit_dropout(int32_t mode, const void* a, const void* b, void* out, int64_t n, float p, const uint64_t* seed_dev,
                   uint32_t site, void* stream) {
   if (mode < 0 || mode > 4 || !out || n <= 0 || (mode != 4 && !a) || (mode == 2 && !b))
@@ -652,40 +839,28 @@ int cavit_adam_step(float* params, const float* grads, float* exp_avg, float* ex
 int cavit_head_loss_fwd(const void* h, const float* W2, const float* b2, const int64_t* labels, float* logits, float* loss,
                         int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing, float p_drop,
                         const uint64_t* seed_dev, uint32_t site, void* stream) {
-  if (!h || !W2 || !b2 || !labels || !logits || !loss) return fail(CAVIT_E_BADARG, "cavit_head_loss_fwd: null pointer");
-  if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d (max %d)", classes, HEAD_MAX_CLASSES);
-  cudaStream_t st = as_stream(stream);
-  DropCfg d;
-  const int use = make_drop(p_drop, seed_dev, site, &d);
-  if (use < 0) return fail(CAVIT_E_BADARG, "cavit_head_loss_fwd: bad dropout arguments");
-  head_logits_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const bf16*>(h), W2, b2, logits, M, B, F, classes, d, use);
-  ce_loss_kernel<<<1, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), loss, B, classes, smoothing);
-  count_launch(2);
-  return check_launch("cavit_head_loss_fwd");
+  return head_fwd_launch<bf16>(reinterpret_cast<const bf16*>(h), W2, b2, labels, logits, loss, M, B, F, classes, smoothing,
+                               p_drop, seed_dev, site, stream);
 }
 
 int cavit_head_loss_bwd(const void* h, const float* W2, const int64_t* labels, const float* logits, float loss_scale,
                         const float* loss_scale_dev, void* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing,
                         float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream) {
-  if (!h || !W2 || !labels || !logits || !dh || !dW2 || !db2) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: null pointer");
-  if (classes < 1 || classes > HEAD_MAX_CLASSES) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "num_classes=%d", classes);
-  cudaStream_t st = as_stream(stream);
-  const long long* lab = reinterpret_cast<const long long*>(labels);
-  DropCfg d;
-  const int use = make_drop(p_drop, seed_dev, site, &d);
-  if (use < 0) return fail(CAVIT_E_BADARG, "cavit_head_loss_bwd: bad dropout arguments");
-  head_dh_kernel<<<dim3(B, M), 256, 0, st>>>(W2, lab, logits, loss_scale, loss_scale_dev, reinterpret_cast<bf16*>(dh), M, B, F, classes,
-                                             smoothing, d, use);
-  if ((size_t)B * classes * sizeof(float) > 96 * 1024) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_head_loss_bwd: batch %d too large", B);
-  static PerDeviceFlag dw_attr;
-  if (dw_attr.unset()) {
-    cudaFuncSetAttribute(head_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    dw_attr.set();
-  }
-  head_dw_kernel<<<dim3((F + 255) / 256, M), 256, (size_t)B * classes * sizeof(float), st>>>(reinterpret_cast<const bf16*>(h), lab, logits, loss_scale,
-                                                           loss_scale_dev, dW2, db2, M, B, F, classes, smoothing, d, use);
-  count_launch(2);
-  return check_launch("cavit_head_loss_bwd");
+  return head_bwd_launch<bf16>(reinterpret_cast<const bf16*>(h), W2, labels, logits, loss_scale, loss_scale_dev,
+                               reinterpret_cast<bf16*>(dh), dW2, db2, M, B, F, classes, smoothing, p_drop, seed_dev, site, stream);
+}
+
+/* fp32-tolerance mode: the hidden activations of the heads and their gradient are fp32 */
+int cavit_head_loss_fwd_f32(const float* h, const float* W2, const float* b2, const int64_t* labels, float* logits,
+                            float* loss, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing, void* stream) {
+  return head_fwd_launch<float>(h, W2, b2, labels, logits, loss, M, B, F, classes, smoothing, 0.f, nullptr, 0, stream);
+}
+
+int cavit_head_loss_bwd_f32(const float* h, const float* W2, const int64_t* labels, const float* logits, float loss_scale,
+                            const float* loss_scale_dev, float* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F,
+                            int32_t classes, float smoothing, void* stream) {
+  return head_bwd_launch<float>(h, W2, labels, logits, loss_scale, loss_scale_dev, dh, dW2, db2, M, B, F, classes, smoothing,
+                                0.f, nullptr, 0, stream);
 }
 
 }  // extern "C"

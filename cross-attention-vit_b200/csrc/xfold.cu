@@ -37,6 +37,7 @@ struct XfoldParams {
   const float* beta;    // [K][C]
   float* zhat;          // [K][B][H][C] fp32
   bf16* z;              // [K][B][H][C] bf16 (forward only)
+  bf16* z_lo;           // fp32-tolerance mode: second bf16 plane, z ~ z + z_lo (NULL otherwise)
   float* probs;         // [K][B][H][N] softmax (pre-dropout)
   float* mean;          // [K][B][N]
   float* rstd;          // [K][B][N]
@@ -288,7 +289,13 @@ xfold_fwd_kernel(const XfoldParams p) {
     for (int h = 0; h < H; ++h) {
       const float zx = acc[h].x - s_m[h], zy = acc[h].y - s_m[h];
       *reinterpret_cast<float2*>(p.zhat + (kb * H + h) * C + c) = make_float2(zx, zy);
-      *reinterpret_cast<uint32_t*>(p.z + (kb * H + h) * C + c) = pack_bf16(fmaf(g.x, zx, be.x), fmaf(g.y, zy, be.y));
+      const float z0 = fmaf(g.x, zx, be.x), z1 = fmaf(g.y, zy, be.y);
+      const uint32_t zh = pack_bf16(z0, z1);
+      *reinterpret_cast<uint32_t*>(p.z + (kb * H + h) * C + c) = zh;
+      if (p.z_lo) {
+        const float2 r = unpack_bf16_fast(zh);
+        *reinterpret_cast<uint32_t*>(p.z_lo + (kb * H + h) * C + c) = pack_bf16(z0 - r.x, z1 - r.y);
+      }
     }
   }
 }
@@ -598,7 +605,7 @@ int64_t cavit_xfold_scratch_floats(int32_t K, int32_t B, int32_t N, int32_t H) {
 }
 
 int cavit_xfold_fwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* beta, float* zhat,
-                    void* z, float* probs, float* mean, float* rstd, float* scratch, int32_t K, int32_t B, int32_t N,
+                    void* z, void* z_lo, float* probs, float* mean, float* rstd, float* scratch, int32_t K, int32_t B, int32_t N,
                     int32_t C, int32_t H, const int32_t* cls_src, const int32_t* tok_src, float scale, float eps, float p_drop,
                     const uint64_t* seed_dev, uint32_t site, void* stream) {
   if (!x || !cls || !qp || !gamma || !beta || !zhat || !z || !probs || !mean || !rstd || !scratch || !cls_src || !tok_src)
@@ -606,7 +613,7 @@ int cavit_xfold_fwd(const float* x, const float* cls, const float* qp, const flo
   XfoldParams p = {};
   int rc = xfold_fill(p, x, cls, qp, gamma, beta, K, B, N, C, H, cls_src, tok_src, scale, eps, p_drop, seed_dev, site);
   if (rc) return rc;
-  p.zhat = zhat; p.z = reinterpret_cast<bf16*>(z); p.probs = probs; p.mean = mean; p.rstd = rstd; p.scratch = scratch;
+  p.zhat = zhat; p.z = reinterpret_cast<bf16*>(z); p.z_lo = reinterpret_cast<bf16*>(z_lo); p.probs = probs; p.mean = mean; p.rstd = rstd; p.scratch = scratch;
   return xfold_dispatch(false, p, as_stream(stream));
 }
 

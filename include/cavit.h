@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CAVIT_ABI_VERSION 1
+#define CAVIT_ABI_VERSION 2
 
 enum {
   CAVIT_OK = 0,
@@ -88,6 +88,12 @@ typedef struct cavit_gemm_args {
                           fp32 atomics into `out` (fp32, EPI_NONE only; zeroed by the call unless accumulate).
                           0/1: no split. Used by wgrad, whose reduction axis (tokens) is the long one. */
   int32_t embed_np;    /* EPI_EMBED: patches per sample (row m -> out row (m / Np) * (Np + 1) + 1 + m % Np) */
+  /* fp32-tolerance mode (ABI 2): when non-NULL (both or neither) the operands are bf16 hi + lo pairs, A ~ A + A_lo and
+   * B ~ B + B_lo (same layout / strides as the hi planes), and D = A B^T + A_lo B^T + A B_lo^T is accumulated in ONE pass
+   * over TMEM (three MMAs per product, ~2^-16 relative operand error instead of 2^-9). The reference computes every
+   * nn.Linear in fp32 (L.Trainer without precision=, /root/reference/main_mist.py:211-218). */
+  const void* A_lo;
+  const void* B_lo;
 } cavit_gemm_args;
 int cavit_gemm(const cavit_gemm_args* a, void* stream);
 
@@ -192,7 +198,8 @@ int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const fl
  * ------------------------------------------------------------------------------------------- */
 int64_t cavit_xfold_scratch_floats(int32_t K, int32_t B, int32_t N, int32_t H);
 int cavit_xfold_fwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* beta,
-                    float* zhat, void* z, float* probs, float* mean, float* rstd, float* scratch, int32_t K,
+                    float* zhat, void* z, void* z_lo /* nullable: second bf16 plane of z, fp32-tolerance mode (ABI 2) */,
+                    float* probs, float* mean, float* rstd, float* scratch, int32_t K,
                     int32_t B, int32_t N, int32_t C, int32_t H, const int32_t* cls_src, const int32_t* tok_src,
                     float scale, float eps, float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream);
 int cavit_xfold_bwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* zhat,
@@ -359,6 +366,50 @@ int cavit_stage_volumes(const void* raw, const cavit_volume_desc* desc, float* o
  * holds a single class (torchmetrics' convention). 1 <= B <= 8192. */
 int cavit_batch_metrics(const float* logits, const int64_t* labels, const float* loss, double* accum, int32_t B,
                         int32_t classes, void* stream);
+
+/* =============================================================================================
+ * fp32-tolerance mode (north_star: ~1e-3 on logits and attention outputs "in fp32"; the reference runs fp32 throughout,
+ * /root/reference/main_mist.py:211-218). GEMM operands travel as TWO bf16 planes, x ~ hi + lo with hi = bf16(x),
+ * lo = bf16(x - hi); cavit_gemm (A_lo / B_lo) multiplies them with three tensor-core MMAs per product; everything
+ * between the GEMMs (attention, GELU, LayerNorm, head, loss) is fp32. The entry points below produce / consume the
+ * planes. `n` counts elements.
+ * ============================================================================================= */
+/* hi / lo planes of an fp32 array (weights once per step, activations that no fused producer splits). */
+int cavit_cast_split(const float* src, void* hi, void* lo, int64_t n, void* stream);
+/* Exact-erf GELU (nn.GELU(), /root/reference/model_cross.py:24,179) of fp32 pre-activations u: h = gelu(u) as hi / lo
+ * planes (NULL pair allowed) and / or as fp32 (NULL allowed); n % 4 == 0. */
+int cavit_gelu_split(const float* u, void* h_hi, void* h_lo, float* h_f32, int64_t n, void* stream);
+/* du = dh * gelu'(u), fp32 in, hi / lo planes out (autograd of the above). */
+int cavit_gelu_bwd_split(const float* dh, const float* u, void* du_hi, void* du_lo, int64_t n, void* stream);
+/* cavit_ln_fwd with the normalised rows as hi / lo planes. */
+int cavit_ln_fwd_split(const float* x, int64_t x_row_stride, int64_t x_gs, int32_t rows_per_group, int32_t groups,
+                       int32_t C, const float* gamma, const float* beta, float eps, void* y_hi, void* y_lo, float* mean,
+                       float* rstd, void* stream);
+/* cavit_ln_bwd_f32 (fp32 incoming gradient) whose bf16 copy of dx is a hi / lo pair (NULL pair allowed). */
+int cavit_ln_bwd_split(const float* dy_f32, const float* x, int64_t x_row_stride, int64_t x_gs, const float* mean,
+                       const float* rstd, const float* gamma, int32_t rows_per_group, int32_t groups, int32_t C,
+                       const float* dresid, float* dx, int64_t dx_row_stride, int64_t dx_gs, void* dx_hi, void* dx_lo,
+                       float* dgamma, float* dbeta, float* dcol, float* partials, void* stream);
+/* cavit_colsum_bf16 over hi + lo rows (bias gradients). */
+int cavit_colsum_split(const void* x_hi, const void* x_lo, int64_t ldx, int64_t x_gs, int32_t rows, int32_t C,
+                       int32_t groups, float* out, int64_t out_gs, void* stream);
+/* cavit_patchify with the patch rows as hi / lo planes (raw MRI intensities reach 1.7e4: 8 mantissa bits are not enough). */
+int cavit_patchify_split(const float* img, void* patches_hi, void* patches_lo, int32_t B, int32_t M, int32_t D, int32_t H,
+                         int32_t W, int32_t dp, int32_t hp, int32_t wp, int32_t sample_major, void* stream);
+/* Self-attention softmax(q k^T * scale) v in fp32 on the CUDA cores (head_dim 64), online softmax, no N x N matrix in
+ * memory. Replaces Attention.forward's matmul / softmax / matmul and their autograd
+ * (/root/reference/model_cross.py:50-61) in the fp32 mode. qkv: fp32 [G][B*N][3C] (q | k | v thirds, each (h d));
+ * out / dout: fp32 [G][B*N][C]; lse, delta: fp32 [G][B][H][N] (delta is scratch); dqkv like qkv. */
+int cavit_attn_fwd_f32(const float* qkv, float* out, float* lse, int32_t G, int32_t B, int32_t N, int32_t H, float scale,
+                       void* stream);
+int cavit_attn_bwd_f32(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, float* delta,
+                       int32_t G, int32_t B, int32_t N, int32_t H, float scale, void* stream);
+/* cavit_head_loss_fwd / _bwd with fp32 hidden activations h [M][B][F] (and fp32 dh); no dropout in this mode. */
+int cavit_head_loss_fwd_f32(const float* h, const float* W2, const float* b2, const int64_t* labels, float* logits,
+                            float* loss, int32_t M, int32_t B, int32_t F, int32_t classes, float smoothing, void* stream);
+int cavit_head_loss_bwd_f32(const float* h, const float* W2, const int64_t* labels, const float* logits, float loss_scale,
+                            const float* loss_scale_dev, float* dh, float* dW2, float* db2, int32_t M, int32_t B, int32_t F,
+                            int32_t classes, float smoothing, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound():
         assert name in exported, f"{name} declared in include/cavit.h but not exported"
         assert hasattr(L, name)
     assert set(_abi.EXPORTS) == set(declared), "ctypes binding table and header disagree"
-    assert L.cavit_abi_version() == 1
+    assert L.cavit_abi_version() == _abi.ABI_VERSION
 
 
 def test_library_is_sm100a_only_and_uses_tcgen05_tma():
