@@ -542,7 +542,19 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
+        # NCCL keeps a communicator alive while a captured CUDA graph references it (the overlapped slab all-reduces are
+        # recorded into the backward graph): drop the graphs first, and never let teardown outlive the measurement
+        def _force_exit():
+            sys.stdout.flush()
+            os._exit(0)
+        t = threading.Timer(30.0, _force_exit)
+        t.daemon = True
+        t.start()
+        if hasattr(runner, "close"):
+            runner.close()
+        dist.barrier()
         dist.destroy_process_group()
+        t.cancel()
 
 
 if __name__ == "__main__":

@@ -174,6 +174,18 @@ class DataParallel:
             self.comm_stream.wait_event(ev)
             self._reducer.reduce_(flat, start, end)
 
+    def close(self):
+        """Drop every CUDA graph that recorded collectives of this process group. NCCL keeps a communicator alive while a
+        captured graph still references it: `dist.destroy_process_group()` blocks until those graphs are gone, so call
+        this (or delete the model) before tearing the process group down."""
+        eng = self.engine
+        eng.on_range_done = eng.post_backward = None
+        eng.hook_capturable = False
+        eng.drop_graphs()
+        if self.stem is not None:
+            self.stem.remove()
+        torch.cuda.synchronize(eng.device)
+
     def __call__(self, img, labels):
         eng = self.engine
         if self.mode == "overlap" and eng._hook_capture_failed and eng.layout.total * 4 < (512 << 20):

@@ -812,6 +812,15 @@ class Engine:
                                     dst_gs=T * C, dst_groups=self.cls_src)
 
     # ------------------------------------------------------------------ backward
+    def drop_graphs(self):
+        """Forget every captured CUDA graph (current and parked plans); the next steps run eagerly and re-capture."""
+        import gc
+        self._fwd_graphs.clear()
+        self._bwd_graphs.clear()
+        for key, (a, _f, _b, fold) in list(self._plans.items()):
+            self._plans[key] = (a, {}, {}, fold)
+        gc.collect()
+
     def _next_grad_buffer(self):
         """Gradient buffer for this backward. If a parameter's .grad still aliases the candidate
         (gradient accumulation without zero_grad), switch to another buffer so nothing is clobbered."""

@@ -63,8 +63,16 @@ def main():
     gathered = [torch.empty_like(g) for _ in range(world)]
     dist.all_gather(gathered, g)
     ok = ok and all(torch.equal(gathered[0], t) for t in gathered)
+    dp.close()          # the backward graph recorded NCCL collectives: it has to go before the communicator does
+    del model, ref_model, dp
     dist.barrier()
+    print(f"rank {rank} ok={ok}", flush=True)
+    import threading
+    t = threading.Timer(30.0, lambda: os._exit(0 if ok else 1))    # teardown must never outlive the check
+    t.daemon = True
+    t.start()
     dist.destroy_process_group()
+    t.cancel()
     sys.exit(0 if ok else 1)
 
 

@@ -22,6 +22,6 @@ def test_two_rank_nccl_gradients_match_global_batch(mode):
     env.pop("NCCL_DEBUG", None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29611" if mode == "overlap" else "29612", os.path.join(HERE, "ddp_nccl_worker.py"), mode]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     print(r.stdout[-4000:], r.stderr[-4000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
