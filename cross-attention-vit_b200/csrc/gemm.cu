@@ -122,78 +122,146 @@ template <int EPI>
 __device__ __forceinline__ void epi_prefetch(const EpiLane& L, int col, EpiPre<EPI>& pre) {
   if (EPI != CAVIT_EPI_BIAS_RESID && EPI != CAVIT_EPI_GELU_BWD && EPI != CAVIT_EPI_RELU_BWD) return;
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    if (it * 4 < L.rows_left) {
-      if (EPI == CAVIT_EPI_BIAS_RESID) pre.r[it] = ldg_v4f(L.resid + it * L.resid_step + col * 4);
-      else pre.a[it] = ldg_v2(L.aux + it * L.aux_step + col * 2);
-    }
+  for (int it = 0; it < 8; ++it) {   // full 32-row slabs only (partial slabs take the generic path): no guards, no branches
+    if (EPI == CAVIT_EPI_BIAS_RESID) pre.r[it] = ldg_v4f(L.resid + it * L.resid_step + col * 4);
+    else pre.a[it] = ldg_v2(L.aux + it * L.aux_step + col * 2);
   }
 }
 
-// Fast path: all pointers / leading dimensions vector-aligned and the chunk's 32 columns inside N.
+// GELU / GELU' of NP pairs evaluated as ONE interleaved stream: every polynomial step runs over all pairs before the next
+// step, so each warp carries NP independent dependency chains. The epilogue warps (two per scheduler) were stalled on
+// fixed-latency dependencies ('wait' 0.92 and 'short scoreboard' 0.77 cycles per issued instruction, ncu round 1) because
+// every row group was a separate predicated block: one chain of 7 dependent FFMA2 + MUFU at a time.
+template <int NP>
+__device__ __forceinline__ void gelu_terms_batch(const float2 (&u)[NP], float2 (&e)[NP], float2 (&r)[NP], float2 (&ac)[NP]) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    ac[j] = make_float2(fminf(fabsf(u[j].x), 5.0f), fminf(fabsf(u[j].y), 5.0f));
+    const float2 earg = mul2(mul2(u[j], u[j]), splat2(-0.72134752044448170f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j].x) : "f"(earg.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j].y) : "f"(earg.y));
+  }
+#pragma unroll
+  for (int j = 0; j < NP; ++j) r[j] = fma2(ac[j], splat2(-2.501152098e-05f), splat2(5.606001891e-04f));
+#pragma unroll
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(-5.354749036e-03f));
+#pragma unroll
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(2.881915092e-02f));
+#pragma unroll
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(-9.833444611e-02f));
+#pragma unroll
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(2.302476772e-01f));
+#pragma unroll
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(-3.942042539e-01f));
+#pragma unroll
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(4.997907545e-01f));
+}
+template <int NP>
+__device__ __forceinline__ void gelu_batch(float2 (&u)[NP]) {   // u -> gelu(u), same formula as gelu_pair (common.cuh)
+  float2 e[NP], r[NP], ac[NP];
+  gelu_terms_batch<NP>(u, e, r, ac);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float2 w = mul2(u[j], mul2(e[j], r[j]));
+    u[j] = make_float2(fmaxf(u[j].x, 0.f) - fabsf(w.x), fmaxf(u[j].y, 0.f) - fabsf(w.y));
+  }
+}
+template <int NP>
+__device__ __forceinline__ void gelu_grad_batch(float2 (&u)[NP]) {   // u -> gelu'(u), same formula as gelu_grad_pair
+  float2 e[NP], r[NP], ac[NP];
+  gelu_terms_batch<NP>(u, e, r, ac);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float2 t = mul2(e[j], fma2(ac[j], splat2(-0.3989422804014327f), r[j]));
+    u[j] = make_float2(u[j].x < 0.f ? t.x : 1.0f - t.x, u[j].y < 0.f ? t.y : 1.0f - t.y);
+  }
+}
+
+// Fast path: all pointers / leading dimensions vector-aligned, the chunk's 32 columns inside N and all 32 rows of the
+// warp's slab inside M. Straight-line code in phases (loads, bias, activation over all 16 pairs, stores).
 template <int EPI, int OUT>
 __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const float* stage, int lane, const EpiPre<EPI>& pre,
                                                const float4 bias4) {
   const int c4 = lane & 7, rsub = lane >> 3;
-  float4 t[8];
+  // v[2 * it], v[2 * it + 1]: columns (col, col+1) and (col+2, col+3) of row 4 * it + rsub
+  float2 v[16];
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rsub;
-    t[it] = reinterpret_cast<const float4*>(stage + r * 32)[c4 ^ (r & 7)];
+    const float4 t = reinterpret_cast<const float4*>(stage + r * 32)[c4 ^ (r & 7)];
+    v[2 * it] = make_float2(t.x, t.y);
+    v[2 * it + 1] = make_float2(t.z, t.w);
   }
-  float2 b01 = make_float2(0.f, 0.f), b23 = make_float2(0.f, 0.f);
   constexpr bool kBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID ||
                           EPI == CAVIT_EPI_EMBED || EPI == CAVIT_EPI_BIAS_RELU);
   if (kBias) {   // loaded by the caller before the accumulator wait (an L2 round trip per chunk otherwise)
-    b01 = make_float2(bias4.x, bias4.y);
-    b23 = make_float2(bias4.z, bias4.w);
-  }
-  // running row pointers (4 rows per step) instead of 64-bit it * stride products in every iteration
-  char* o = L.out + col * ((OUT == OUT_BF16) ? 2 : 4);
-  char* ax = L.aux + col * 2;
+    const float2 b01 = make_float2(bias4.x, bias4.y), b23 = make_float2(bias4.z, bias4.w);
 #pragma unroll
-  for (int it = 0; it < 8; ++it, o += L.out_step, ax += L.aux_step) {
-    if (it * 4 < L.rows_left) {
-      // two packed fp32 pairs per lane: columns (col, col+1) and (col+2, col+3)
-      float2 v01 = make_float2(t[it].x, t[it].y), v23 = make_float2(t[it].z, t[it].w);
-      if (kBias) { v01 = add2(v01, b01); v23 = add2(v23, b23); }
-      if (EPI == CAVIT_EPI_BIAS_GELU) {
-        const uint32_t q0 = pack_bf16(v01.x, v01.y), q1 = pack_bf16(v23.x, v23.y);
-        stg_v2(ax, q0, q1);
-        // GELU of the bf16-rounded pre-activation: backward differentiates exactly what forward evaluated
-        v01 = gelu_pair(unpack_bf16_fast(q0));
-        v23 = gelu_pair(unpack_bf16_fast(q1));
-      } else if (EPI == CAVIT_EPI_GELU_BWD) {
-        v01 = mul2(v01, gelu_grad_pair(unpack_bf16_fast(pre.a[it].x)));
-        v23 = mul2(v23, gelu_grad_pair(unpack_bf16_fast(pre.a[it].y)));
-      } else if (EPI == CAVIT_EPI_BIAS_RELU) {   // nn.TransformerEncoderLayer's default activation (modelv2.py:72-78)
-        v01 = make_float2(fmaxf(v01.x, 0.f), fmaxf(v01.y, 0.f));
-        v23 = make_float2(fmaxf(v23.x, 0.f), fmaxf(v23.y, 0.f));
-      } else if (EPI == CAVIT_EPI_RELU_BWD) {    // dY * [h > 0] with h = relu(u) as stored by the forward
-        const float2 h01 = unpack_bf16_fast(pre.a[it].x), h23 = unpack_bf16_fast(pre.a[it].y);
-        v01 = make_float2(h01.x > 0.f ? v01.x : 0.f, h01.y > 0.f ? v01.y : 0.f);
-        v23 = make_float2(h23.x > 0.f ? v23.x : 0.f, h23.y > 0.f ? v23.y : 0.f);
-      } else if (EPI == CAVIT_EPI_BIAS_RESID) {
-        v01 = add2(v01, make_float2(pre.r[it].x, pre.r[it].y));
-        v23 = add2(v23, make_float2(pre.r[it].z, pre.r[it].w));
-      } else if (EPI == CAVIT_EPI_EMBED) {
-        const long long r = L.embed_row + 4 * it;
-        const long long sq = r / L.embed_np;
-        const int t = (int)(r - sq * L.embed_np);
-        const float4 pe = ldg_v4f(L.pos_base + (long long)(1 + t) * L.ldr_bytes + col * 4);
-        v01 = add2(v01, make_float2(pe.x, pe.y));
-        v23 = add2(v23, make_float2(pe.z, pe.w));
-        stg_v4f(L.out_base + (sq * (L.embed_np + 1) + 1 + t) * L.ldo_bytes + col * 4, v01.x, v01.y, v23.x, v23.y);
-        continue;
-      }
-      if (OUT == OUT_RED) {
-        float* of = reinterpret_cast<float*>(o);
-        red_add_f32(of, v01.x); red_add_f32(of + 1, v01.y); red_add_f32(of + 2, v23.x); red_add_f32(of + 3, v23.y);
-      } else if (OUT == OUT_F32) {
-        stg_v4f(o, v01.x, v01.y, v23.x, v23.y);
-      } else {
-        stg_v2(o, pack_bf16(v01.x, v01.y), pack_bf16(v23.x, v23.y));
-      }
+    for (int it = 0; it < 8; ++it) { v[2 * it] = add2(v[2 * it], b01); v[2 * it + 1] = add2(v[2 * it + 1], b23); }
+  }
+  char* o = L.out + col * ((OUT == OUT_BF16) ? 2 : 4);
+  if (EPI == CAVIT_EPI_BIAS_GELU) {
+    // pre-activation u (bf16) out; GELU of the bf16-ROUNDED u: backward differentiates exactly what forward evaluated
+    char* ax = L.aux + col * 2;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const uint32_t q0 = pack_bf16(v[2 * it].x, v[2 * it].y), q1 = pack_bf16(v[2 * it + 1].x, v[2 * it + 1].y);
+      stg_v2(ax + it * L.aux_step, q0, q1);
+      v[2 * it] = unpack_bf16_fast(q0);
+      v[2 * it + 1] = unpack_bf16_fast(q1);
+    }
+    gelu_batch<16>(v);
+  } else if (EPI == CAVIT_EPI_GELU_BWD) {
+    float2 g[16];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) { g[2 * it] = unpack_bf16_fast(pre.a[it].x); g[2 * it + 1] = unpack_bf16_fast(pre.a[it].y); }
+    gelu_grad_batch<16>(g);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = mul2(v[j], g[j]);
+  } else if (EPI == CAVIT_EPI_BIAS_RELU) {   // nn.TransformerEncoderLayer's default activation (modelv2.py:72-78)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = make_float2(fmaxf(v[j].x, 0.f), fmaxf(v[j].y, 0.f));
+  } else if (EPI == CAVIT_EPI_RELU_BWD) {    // dY * [h > 0] with h = relu(u) as stored by the forward
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const float2 h01 = unpack_bf16_fast(pre.a[it].x), h23 = unpack_bf16_fast(pre.a[it].y);
+      v[2 * it] = make_float2(h01.x > 0.f ? v[2 * it].x : 0.f, h01.y > 0.f ? v[2 * it].y : 0.f);
+      v[2 * it + 1] = make_float2(h23.x > 0.f ? v[2 * it + 1].x : 0.f, h23.y > 0.f ? v[2 * it + 1].y : 0.f);
+    }
+  } else if (EPI == CAVIT_EPI_BIAS_RESID) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      v[2 * it] = add2(v[2 * it], make_float2(pre.r[it].x, pre.r[it].y));
+      v[2 * it + 1] = add2(v[2 * it + 1], make_float2(pre.r[it].z, pre.r[it].w));
+    }
+  } else if (EPI == CAVIT_EPI_EMBED) {
+    float4 pe[8];
+    long long orow[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const long long r = L.embed_row + 4 * it;
+      const long long sq = r / L.embed_np;
+      const int t = (int)(r - sq * L.embed_np);
+      pe[it] = ldg_v4f(L.pos_base + (long long)(1 + t) * L.ldr_bytes + col * 4);
+      orow[it] = sq * (L.embed_np + 1) + 1 + t;
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const float2 a01 = add2(v[2 * it], make_float2(pe[it].x, pe[it].y)), a23 = add2(v[2 * it + 1], make_float2(pe[it].z, pe[it].w));
+      stg_v4f(L.out_base + orow[it] * L.ldo_bytes + col * 4, a01.x, a01.y, a23.x, a23.y);
+    }
+    return;
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    char* oi = o + it * L.out_step;
+    if (OUT == OUT_RED) {
+      float* of = reinterpret_cast<float*>(oi);
+      red_add_f32(of, v[2 * it].x); red_add_f32(of + 1, v[2 * it].y); red_add_f32(of + 2, v[2 * it + 1].x); red_add_f32(of + 3, v[2 * it + 1].y);
+    } else if (OUT == OUT_F32) {
+      stg_v4f(oi, v[2 * it].x, v[2 * it].y, v[2 * it + 1].x, v[2 * it + 1].y);
+    } else {
+      stg_v2(oi, pack_bf16(v[2 * it].x, v[2 * it].y), pack_bf16(v[2 * it + 1].x, v[2 * it + 1].y));
     }
   }
 }
@@ -289,15 +357,17 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
       L.ldo_bytes = p.ldo * osz;
       L.ldr_bytes = p.ldr * 4;
     }
+    // the fast path needs the warp's whole 32-row slab inside M; the (last) partial slab of a group takes the generic path
+    const bool fast_tile = fast_kind && ((long long)p.M - row0 >= 32);   // warp-uniform
     EpiPre<EPI> pre;
-    if (kPrefetch && fast_kind && n0 + 32 <= p.N) epi_prefetch<EPI>(L, n0 + c4 * 4, pre);  // overlaps the tile's mainloop
+    if (kPrefetch && fast_tile && n0 + 32 <= p.N) epi_prefetch<EPI>(L, n0 + c4 * 4, pre);  // overlaps the tile's mainloop
     constexpr bool kHasBias = (EPI == CAVIT_EPI_BIAS || EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_BIAS_RESID ||
                                EPI == CAVIT_EPI_EMBED || EPI == CAVIT_EPI_BIAS_RELU);
     float4 bias4[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       bias4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kHasBias && fast_kind && n0 + c * 32 + 32 <= p.N) bias4[c] = __ldg(reinterpret_cast<const float4*>(L.bias + n0 + c * 32 + c4 * 4));
+      if (kHasBias && fast_tile && n0 + c * 32 + 32 <= p.N) bias4[c] = __ldg(reinterpret_cast<const float4*>(L.bias + n0 + c * 32 + c4 * 4));
     }
     mbar_wait(tfull0 + 8u * as, aphase, abort_flag, p.status, ERR_TIMEOUT_TMEM_FULL);
     tc_fence_after();
@@ -315,7 +385,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
         srow[j ^ (lane & 7)] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
                                            __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
       __syncwarp();
-      if (fast_kind && (col0 + 32 <= p.N)) {  // warp-uniform
+      if (fast_tile && (col0 + 32 <= p.N)) {  // warp-uniform
         if (!kPrefetch) epi_prefetch<EPI>(L, col0 + c4 * 4, pre);  // many warps: latency is hidden by the other warps
         const EpiPre<EPI> cur = pre;
         if (kPrefetch && c + 1 < CH && col0 + 64 <= p.N) epi_prefetch<EPI>(L, col0 + 32 + c4 * 4, pre);

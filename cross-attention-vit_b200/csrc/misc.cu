@@ -209,6 +209,7 @@ __global__ void embed_param_grads_kernel(const float* __restrict__ dtok, float* 
 // owns 8 consecutive columns (one 16-byte load per row), each warp strides over the rows of its slice;
 // the 8 warps are combined through shared memory and the row slices with fp32 atomics into a
 // zero-initialised out.
+template <bool LO>   // LO: rows are hi + lo pairs (fp32-tolerance mode); compile-time so that the plain loop keeps its unrolling
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x_lo, long long ldx, long long gs, int rows, int C,
                    float* __restrict__ out, long long out_gs) {
@@ -232,7 +233,7 @@ colsum_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x_lo, lo
       f = unpack_bf16(v.y); acc[2] += f.x; acc[3] += f.y;
       f = unpack_bf16(v.z); acc[4] += f.x; acc[5] += f.y;
       f = unpack_bf16(v.w); acc[6] += f.x; acc[7] += f.y;
-      if (x_lo) {   // fp32-tolerance mode: the rows are hi + lo pairs
+      if (LO) {
         const uint4 w = __ldg(reinterpret_cast<const uint4*>(x_lo + (long long)g * gs + c + (long long)r * ldx));
         f = unpack_bf16(w.x); acc[0] += f.x; acc[1] += f.y;
         f = unpack_bf16(w.y); acc[2] += f.x; acc[3] += f.y;
@@ -734,8 +735,11 @@ static int colsum_launch(const void* x, const void* x_lo, int64_t ldx, int64_t x
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
   dim3 grid(cblocks, groups, slices);
-  colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(x_lo), ldx, x_gs, rows,
-                                           C, out, out_gs);
+  if (x_lo)
+    colsum_bf16_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(x_lo), ldx, x_gs,
+                                                   rows, C, out, out_gs);
+  else
+    colsum_bf16_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), nullptr, ldx, x_gs, rows, C, out, out_gs);
   count_launch();
   return check_launch("cavit_colsum_bf16");
 }
