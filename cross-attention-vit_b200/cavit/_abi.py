@@ -91,6 +91,12 @@ _SIGS = {
                                     C.c_uint32, c_vp]),
     "cavit_head_loss_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
                                     c_f32, c_f32, c_vp, C.c_uint32, c_vp]),
+    # ---- K-EMBED: TMA-staged patch unfold fused with the embedding GEMM (forward) and its weight gradient
+    "cavit_embed_fused_supported": (c_i32, [c_i32] * 9),
+    "cavit_embed_fused_wgrad_supported": (c_i32, [c_i32] * 9),
+    "cavit_embed_fused_fwd": (c_i32, [c_vp] * 5 + [c_i32] * 10 + [c_vp]),
+    "cavit_embed_fused_wgrad": (c_i32, [c_vp] * 3 + [c_i32] * 10 + [c_vp]),
+    "cavit_embed_bias_grad": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp]),
     # ---- fp32-tolerance mode (split bf16 hi + lo operands, fp32 attention / GELU / head)
     "cavit_cast_split": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "cavit_gelu_split": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),

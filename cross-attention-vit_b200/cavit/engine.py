@@ -296,6 +296,8 @@ class Engine:
         self.fold_ok = (self.H in (1, 2, 3, 4, 6, 8, 12, 16) and self.C <= 1024 and self.K <= 16
                         and os.environ.get("CAVIT_XFOLD", "1") != "0")
         self.fold = False
+        self.embed_fused = False
+        self._img = None                       # the forward's input volumes (the fused embedding wgrad re-reads them)
         self.scale = 64 ** -0.5
         self.p_drop = float(cfg.dropout)
         self.drop = False                      # dropout active for the current forward/backward pair
@@ -430,17 +432,18 @@ class Engine:
         if self._plan_key == key:
             return
         if self._plan_key is not None:      # park the current plan (LRU order: most recent last)
-            self._plans[self._plan_key] = (self.a, self._fwd_graphs, self._bwd_graphs, self.fold)
+            self._plans[self._plan_key] = (self.a, self._fwd_graphs, self._bwd_graphs, (self.fold, self.embed_fused))
             self._plans.move_to_end(self._plan_key)
             while len(self._plans) > self.max_plans:
                 self._plans.popitem(last=False)
         self.saved_valid = False
         if key in self._plans:
-            self.a, self._fwd_graphs, self._bwd_graphs, self.fold = self._plans.pop(key)
+            self.a, self._fwd_graphs, self._bwd_graphs, (self.fold, self.embed_fused) = self._plans.pop(key)
             self._plan_key = key
             self.B, self.T = B, B * self.N
             return
         self._fwd_graphs, self._bwd_graphs = {}, {}
+        self.embed_fused = False
         if self.split:
             from . import engine_fp32
             self.a = engine_fp32.plan(self, B, train)
@@ -468,7 +471,12 @@ class Engine:
         min_ctas = int(os.environ.get("CAVIT_XFOLD_MIN_CTAS", "296"))
         self.fold = bool(K) and not drop and self.fold_ok and K * B >= min_ctas
         fold = self.fold
-        a["patches"] = e((self.Mimg * B * self.Np, self.P), BF16)
+        # K-EMBED: TMA-staged unfold fused with the embedding GEMM (csrc/embed.cu) wherever its brick geometry fits;
+        # then neither the unfolded patch tensor nor the compacted token gradient exists
+        self.embed_fused = (self.kind in ("cross", "vit") and os.environ.get("CAVIT_EMBED_FUSED", "1") != "0" and
+                            ops.embed_fused_supported((B, self.Mimg, 1) + tuple(self.cfg.img_size), self.cfg.patch_size, C))
+        if not self.embed_fused:
+            a["patches"] = e((self.Mimg * B * self.Np, self.P), BF16)
         nL = self.L if train else 1
         nX = 2 * self.L + 1 if train else 3
         a["X"] = [e((G, T, C)) for _ in range(nX)]
@@ -516,7 +524,8 @@ class Engine:
             a["dq_acc"] = e((G, T, C))
             a["ln_ws"] = ops.ln_bwd_workspace(max(G, K, 1), C, dev)
             a["dhh"], a["duh"], a["dclsn"] = e((G, B, F), BF16), e((G, B, F), BF16), e((G, B, C), BF16)
-            a["dcomp"] = e((self.Mimg * B * self.Np, C), BF16)
+            if not self.embed_fused:
+                a["dcomp"] = e((self.Mimg * B * self.Np, C), BF16)
             if K:
                 a["d_z"], a["d_zb"] = e((K, B, C)), e((K, B, C), BF16)
                 a["d_u"], a["d_yn"] = e((K, B, F), BF16), e((K, B, C), BF16)
@@ -652,6 +661,7 @@ class Engine:
         st["graph"].replay()
         self.graph_launches += st["launches"]
         self._labels = st["labels"]
+        self._img = st["img"]
         self.saved_valid = train
         return self.a["logits"], self.a["loss"]
 
@@ -680,11 +690,16 @@ class Engine:
             for m in range(self.Mimg):
                 ops.gather_rows_f32(self.w("pos")[1:], pos[1 + m * self.Np:], rows=self.Np, C_=C, groups=1,
                                     src_row_stride=C, src_gs=0, dst_row_stride=C, dst_gs=0)
+        elif self.embed_fused:
+            self._img = img
+            ops.embed_fused_fwd(img, self.wb("embed.w"), self.w("embed.b"), self.w("pos"), X0, patch_size=cfg.patch_size,
+                                C_=C, sample_major=(self.kind == "vit"))
         else:
             ops.patchify(img, a["patches"], patch_size=cfg.patch_size, sample_major=(self.kind == "vit"))
             pos = self.w("pos")
-        ops.gemm(a["patches"], self.wb("embed.w"), X0, M=self.Mimg * B * self.Np, N=C, K=self.P, lda=self.P,
-                 ldb=self.P, ldo=C, epi=EPI_EMBED, bias=self.w("embed.b"), resid=pos, ldr=C, embed_np=np_seq)
+        if not self.embed_fused:
+            ops.gemm(a["patches"], self.wb("embed.w"), X0, M=self.Mimg * B * self.Np, N=C, K=self.P, lda=self.P,
+                     ldb=self.P, ldo=C, epi=EPI_EMBED, bias=self.w("embed.b"), resid=pos, ldr=C, embed_np=np_seq)
         ops.cls_rows(self.w("cls"), self.w("pos"), X0, M=G, B=B, N=N, C_=C)
         drop = self.drop
         if drop:   # x = dropout(x) after the positional add (model_cross.py:198)
@@ -859,7 +874,10 @@ class Engine:
         hook_ok = on_range_done is None or (self.hook_capturable and not self._hook_capture_failed)
         if not (self.use_graphs and ops.PROFILE is None and hook_ok):
             return self._backward_impl(loss_scale, on_range_done, loss_scale_dev)
-        st = self._bwd_graphs.setdefault((self.B, self._grad_idx, self.drop, on_range_done is not None), {"runs": 0, "graph": None})
+        # (the fused embedding wgrad re-reads the forward's input volumes: a graph is tied to the buffer it recorded)
+        bkey = (self.B, self._grad_idx, self.drop, on_range_done is not None,
+                self._img.data_ptr() if (self.embed_fused and self._img is not None) else 0)
+        st = self._bwd_graphs.setdefault(bkey, {"runs": 0, "graph": None})
         if st["graph"] is None:
             st["runs"] += 1
             if st["runs"] <= 2:
@@ -879,7 +897,7 @@ class Engine:
                 except Exception as exc:   # this stack cannot capture the hook's work: stay eager from now on (and say so)
                     self._hook_capture_failed = True
                     self.hook_capture_error = repr(exc)
-                    del self._bwd_graphs[(self.B, self._grad_idx, self.drop, True)]
+                    del self._bwd_graphs[bkey]
                     torch.cuda.synchronize(self.device)
                     return self._backward_impl(loss_scale, on_range_done, loss_scale_dev)
             st["launches"] = _abi.launch_count() - n0
@@ -939,10 +957,15 @@ class Engine:
             ops.cast_bf16(dX, dXb)
         ops.embed_param_grads(dX, self.g("pos"), self.g("cls"), M=G, B=B, N=N, C_=C)
         np_seq = self.N - 1
-        ops.compact_patch_rows_bf16(dXb, a["dcomp"], S=G * B, Np=np_seq, C_=C)
-        R = self.Mimg * B * self.Np
-        self._wgrad(a["dcomp"], a["patches"], self.g("embed.w"), G=1, T=R, N=C, K=self.P)
-        self._colsum(a["dcomp"], self.g("embed.b"), G=1, T=R, N=C)
+        if self.embed_fused:    # dW = dY^T unfold(x) with the unfold redone by TMA; db = sum of the patch rows of d(pos)
+            ops.embed_fused_wgrad(self._img, dXb, self.g("embed.w"), patch_size=cfg.patch_size, C_=C,
+                                  sample_major=(self.kind == "vit"))
+            ops.embed_bias_grad(self.g("pos"), self.g("embed.b"), N=N, C_=C)
+        else:
+            ops.compact_patch_rows_bf16(dXb, a["dcomp"], S=G * B, Np=np_seq, C_=C)
+            R = self.Mimg * B * self.Np
+            self._wgrad(a["dcomp"], a["patches"], self.g("embed.w"), G=1, T=R, N=C, K=self.P)
+            self._colsum(a["dcomp"], self.g("embed.b"), G=1, T=R, N=C)
         done("embed")
         return self.grad
 

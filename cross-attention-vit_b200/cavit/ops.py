@@ -286,6 +286,35 @@ def patchify(img, patches, *, patch_size, sample_major=False):
           "cavit_patchify")
 
 
+def embed_fused_supported(img_shape, patch_size, C_) -> bool:
+    """True when the TMA-staged fused patch embedding (forward AND weight gradient) covers this geometry."""
+    B, M, _, D, H, W = img_shape
+    dp, hp, wp = patch_size
+    return bool(lib().cavit_embed_fused_supported(B, M, D, H, W, dp, hp, wp, C_)) and \
+        bool(lib().cavit_embed_fused_wgrad_supported(B, M, D, H, W, dp, hp, wp, C_))
+
+
+def embed_fused_fwd(img, w_bf16, bias, pos, tokens, *, patch_size, C_, sample_major=False):
+    """tokens[.., 1 + t, :] = unfold(img) W^T + bias + pos[1 + t] without materialising the unfolded patches
+    (include/cavit.h: cavit_embed_fused_fwd). The CLS rows are written by cls_rows."""
+    B, M, _, D, H, W = img.shape
+    dp, hp, wp = patch_size
+    check(lib().cavit_embed_fused_fwd(img.data_ptr(), w_bf16.data_ptr(), bias.data_ptr(), pos.data_ptr(), tokens.data_ptr(),
+                                      B, M, D, H, W, dp, hp, wp, C_, int(sample_major), _stream()), "cavit_embed_fused_fwd")
+
+
+def embed_fused_wgrad(img, dtokens_bf16, dW, *, patch_size, C_, sample_major=False):
+    """dW[C, P] = sum over patch tokens of dtokens^T unfold(img) (include/cavit.h: cavit_embed_fused_wgrad)."""
+    B, M, _, D, H, W = img.shape
+    dp, hp, wp = patch_size
+    check(lib().cavit_embed_fused_wgrad(img.data_ptr(), dtokens_bf16.data_ptr(), dW.data_ptr(), B, M, D, H, W, dp, hp, wp, C_,
+                                        int(sample_major), _stream()), "cavit_embed_fused_wgrad")
+
+
+def embed_bias_grad(dpos, db, *, N, C_):
+    check(lib().cavit_embed_bias_grad(dpos.data_ptr(), db.data_ptr(), N, C_, _stream()), "cavit_embed_bias_grad")
+
+
 def cls_rows(cls, pos, tokens, *, M, B, N, C_):
     check(lib().cavit_cls_rows(cls.data_ptr(), pos.data_ptr(), tokens.data_ptr(), M, B, N, C_, _stream()),
           "cavit_cls_rows")
@@ -464,6 +493,8 @@ def _instrument(name, fn):
     return wrapped
 
 
+for _n in ("embed_fused_fwd", "embed_fused_wgrad", "embed_bias_grad"):
+    globals()[_n] = _instrument(_n, globals()[_n])
 for _n in ("ln_fwd_split", "ln_bwd_split", "cast_split", "gelu_split", "gelu_bwd_split", "attn_fwd_f32", "attn_bwd_f32",
            "head_loss_fwd_f32", "head_loss_bwd_f32"):
     globals()[_n] = _instrument(_n, globals()[_n])

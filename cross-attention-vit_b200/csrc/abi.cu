@@ -83,7 +83,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 struct MapKey {
-  uint64_t v[14];
+  uint64_t v[20];
   bool operator<(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
 };
 static std::mutex g_map_mu;
@@ -120,6 +120,55 @@ static const CUtensorMap* lookup_or_encode(const MapKey& key, uint32_t rank, con
     return nullptr;
   }
   if (g_maps.size() > 65536) g_maps.clear();  // descriptors stay alive (leaked) — bounded by churn
+  g_maps[key] = m;
+  return m;
+}
+
+// Generic tiled map (any rank <= 5, fp32 or bf16, any swizzle; zero fill outside the tensor). strides_bytes: dims 1..rank-1.
+const CUtensorMap* tensor_map_nd(int dtype_f32, uint32_t rank, const void* base, const uint64_t* dims,
+                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+  if (rank < 1 || rank > 5) {
+    fail(CAVIT_E_BADARG, "tensor_map_nd: rank %u", rank);
+    return nullptr;
+  }
+  MapKey key{};
+  key.v[0] = 100 + rank;
+  key.v[1] = reinterpret_cast<uint64_t>(base);
+  key.v[2] = (uint64_t)dtype_f32 | ((uint64_t)swizzle128 << 8);
+  for (uint32_t i = 0; i < rank; ++i) key.v[3 + i] = dims[i];
+  for (uint32_t i = 0; i + 1 < rank; ++i) key.v[8 + i] = strides_bytes[i];
+  for (uint32_t i = 0; i < rank; ++i) key.v[12 + i] = box[i];
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    fail(CAVIT_E_DEVICE, "cuTensorMapEncodeTiled not available from the driver");
+    return nullptr;
+  }
+  CUtensorMap* m = nullptr;
+  if (posix_memalign(reinterpret_cast<void**>(&m), 64, sizeof(CUtensorMap)) != 0) {
+    fail(CAVIT_E_DEVICE, "posix_memalign failed");
+    return nullptr;
+  }
+  cuuint64_t d[5] = {1, 1, 1, 1, 1}, st[4] = {0, 0, 0, 0};
+  cuuint32_t bx[5] = {1, 1, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+  for (uint32_t i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (uint32_t i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = fn(m, dtype_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                  const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fail(CAVIT_E_BADARG,
+         "cuTensorMapEncodeTiled failed (%d): rank %u base %p dims [%llu,%llu,%llu,%llu,%llu] strideB [%llu,%llu,%llu,%llu] "
+         "box [%u,%u,%u,%u,%u]", (int)r, rank, base, (unsigned long long)d[0], (unsigned long long)d[1],
+         (unsigned long long)d[2], (unsigned long long)d[3], (unsigned long long)d[4], (unsigned long long)st[0],
+         (unsigned long long)st[1], (unsigned long long)st[2], (unsigned long long)st[3], bx[0], bx[1], bx[2], bx[3], bx[4]);
+    free(m);
+    return nullptr;
+  }
+  if (g_maps.size() > 65536) g_maps.clear();
   g_maps[key] = m;
   return m;
 }
