@@ -4,9 +4,10 @@ reference's ``ModelCross`` (/root/reference/model_cross.py:152-212) and ``ModelV
 (/root/reference/modelv3.py:90-147) — but ``forward`` runs the sm_100a kernel path of
 ``cavit.engine`` instead of ATen ops.
 
-The sub-modules below exist to own the parameters under the reference's names (so reference
-checkpoints load and `torch.manual_seed(s)` reproduces the reference's random init); the compute
-is done by the whole-model engine, which fuses across them.
+The sub-modules below own the parameters under the reference's names (so reference checkpoints load and
+`torch.manual_seed(s)` reproduces the reference's random init). The top-level models run the whole-model engine, which
+fuses across them; each sub-module's own `forward` stays usable on its own and runs the same C-ABI kernels unfused
+(cavit/functional.py) with the reference's semantics — fp32 tensors in and out.
 """
 from __future__ import annotations
 
@@ -16,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _abi
+from . import functional as CF
 from .engine import Engine
 
 try:  # the reference derives from lightning.LightningModule; keep that when lightning exists
@@ -28,30 +30,41 @@ except Exception:  # pragma: no cover - lightning is not installed in the build 
 
 
 def _engine_only(name):
+    """forward of a container whose compute only exists inside the fused whole-model path."""
     def forward(self, *a, **k):
         raise _abi.CavitError(
-            f"{name} is a parameter container in cavit; call the top-level model's forward(img, labels), "
-            "which runs the fused sm_100a path")
+            f"{name} is a parameter container in cavit; call the top-level model's forward, which runs the fused sm_100a path")
     return forward
 
 
 class PreNorm(nn.Module):
+    """/root/reference/model_cross.py:11-17: fn(LayerNorm(x))."""
+
     def __init__(self, config, fn):
         super().__init__()
         self.norm = nn.LayerNorm(config.hidden_dim)
         self.fn = fn
-    forward = _engine_only("PreNorm")
+
+    def forward(self, x, **kwargs):
+        return self.fn(CF.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps), **kwargs)
 
 
 class FeedForward(nn.Module):
+    """/root/reference/model_cross.py:19-31: Linear, GELU, Dropout, Linear, Dropout."""
+
     def __init__(self, config):
         super().__init__()
         self.net = nn.Sequential(nn.Linear(config.hidden_dim, config.mlp_dim), nn.GELU(), nn.Dropout(config.dropout),
                                  nn.Linear(config.mlp_dim, config.hidden_dim), nn.Dropout(config.dropout))
-    forward = _engine_only("FeedForward")
+
+    def forward(self, x):
+        CF._no_dropout(self.training, self.net[2].p, "FeedForward")
+        return CF.feed_forward(x, self.net[0].weight, self.net[0].bias, self.net[3].weight, self.net[3].bias)
 
 
 class Attention(nn.Module):
+    """/root/reference/model_cross.py:33-61."""
+
     def __init__(self, config, dim_head):
         super().__init__()
         inner = dim_head * config.num_heads
@@ -64,18 +77,31 @@ class Attention(nn.Module):
         single = config.num_heads == 1 and dim_head == config.hidden_dim
         self.to_out = nn.Identity() if single else nn.Sequential(nn.Linear(inner, config.hidden_dim),
                                                                  nn.Dropout(config.dropout))
-    forward = _engine_only("Attention")
+
+    def forward(self, x):
+        if isinstance(self.to_out, nn.Identity):
+            return CF.self_attention(x, self.to_qkv.weight, None, None, self.heads)
+        CF._no_dropout(self.training, self.to_out[1].p, "Attention")
+        return CF.self_attention(x, self.to_qkv.weight, self.to_out[0].weight, self.to_out[0].bias, self.heads)
 
 
 class SelfAttentionBlock(nn.Module):
+    """/root/reference/model_cross.py:64-72."""
+
     def __init__(self, config):
         super().__init__()
         self.attn = PreNorm(config, Attention(config, dim_head=config.hidden_dim // config.num_heads))
         self.ffn = PreNorm(config, FeedForward(config))
-    forward = _engine_only("SelfAttentionBlock")
+
+    def forward(self, x):
+        x = self.attn(x) + x
+        x = self.ffn(x) + x
+        return x
 
 
 class CrossAttention(nn.Module):
+    """/root/reference/model_cross.py:74-102: the query is token 0 only."""
+
     def __init__(self, config):
         super().__init__()
         self.num_heads = config.num_heads
@@ -86,18 +112,30 @@ class CrossAttention(nn.Module):
         self.attn_drop = nn.Dropout(config.dropout)
         self.proj = nn.Linear(config.hidden_dim, config.hidden_dim)
         self.proj_drop = nn.Dropout(config.dropout)
-    forward = _engine_only("CrossAttention")
+
+    def forward(self, x):
+        CF._no_dropout(self.training, self.attn_drop.p, "CrossAttention")
+        return CF.cross_attention(x, self.wq.weight, self.wq.bias, self.wk.weight, self.wk.bias, self.wv.weight, self.wv.bias,
+                                  self.proj.weight, self.proj.bias, self.num_heads)
 
 
 class CrossAttentionBlock(nn.Module):
+    """/root/reference/model_cross.py:104-114: the residual uses the UN-normalised CLS row."""
+
     def __init__(self, config, act_layer=nn.GELU):
         super().__init__()
         self.attn = PreNorm(config, CrossAttention(config))
         self.ffn = PreNorm(config, FeedForward(config))
-    forward = _engine_only("CrossAttentionBlock")
+
+    def forward(self, x):
+        y = self.attn(x) + x[:, 0:1]
+        y = self.ffn(y) + y
+        return y
 
 
 class MultiScaleBlock(nn.Module):
+    """/root/reference/model_cross.py:116-148."""
+
     def __init__(self, config, act_layer=nn.GELU):
         super().__init__()
         self.attn_order = config.attn_order
@@ -105,7 +143,21 @@ class MultiScaleBlock(nn.Module):
             nn.Sequential(*[SelfAttentionBlock(config) for _ in range(config.num_self_blocks)])
             for _ in range(config.num_modalities)])
         self.fusion = nn.ModuleList([CrossAttentionBlock(config) for _ in range(len(self.attn_order))])
-    forward = _engine_only("MultiScaleBlock")
+
+    def forward(self, x):
+        attn = [block(x_) for x_, block in zip(x, self.blocks)]
+        outs, cross_count = [], 0
+        order = dict(self.attn_order)
+        for i in range(len(attn)):
+            if str(i) in order:     # all fusions read `attn` (this block's self-attention outputs), never `outs`
+                j = int(order[str(i)])
+                tmp = torch.cat((attn[i][:, 0:1], attn[j][:, 1:]), dim=1)
+                tmp = self.fusion[cross_count](tmp)
+                outs.append(torch.cat((tmp, attn[i][:, 1:]), dim=1))
+                cross_count += 1
+            else:
+                outs.append(attn[i])
+        return outs
 
 
 class Transformer(nn.Module):
@@ -122,7 +174,12 @@ class Transformer(nn.Module):
                 PreNorm(config, FeedForward(config)),
                 nn.Identity(),
             ]))
-    forward = _engine_only("Transformer")
+
+    def forward(self, x):
+        for attn, drop1, ff, drop2 in self.layers:
+            x = drop1(attn(x)) + x
+            x = drop2(ff(x)) + x
+        return x
 
 
 class _CavitFn(torch.autograd.Function):
