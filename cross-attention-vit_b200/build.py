@@ -14,8 +14,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "cavit", "libcavit_sm100a.so")
+# CAVIT_BUILD_TAG=x builds a second library cavit/libcavit_sm100a_x.so (objects in build_x/) for same-box A/B experiments:
+# select it at run time with CAVIT_LIB=<path> (cavit/_abi.py).
+_TAG = os.environ.get("CAVIT_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "cavit", "libcavit_sm100a" + ("_" + _TAG if _TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-cudart", "static", "--expt-relaxed-constexpr"] + os.environ.get("NVCC_EXTRA", "").split()

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcavit_sm100a.so")
+LIB_PATH = os.environ.get("CAVIT_LIB") or os.path.join(_HERE, "libcavit_sm100a.so")   # CAVIT_LIB: an A/B build (build.py)
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 

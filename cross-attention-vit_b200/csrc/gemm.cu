@@ -46,13 +46,30 @@ struct GemmDev {
 // an operand stage (shared memory) and registers (96 / thread at 576 threads): all epilogues use two.
 template <int BN, int CTAS, int EPI>
 struct GemmCfg {
-  static constexpr int EW = 2;
+// The GELU / GELU' epilogues run ~660 warp instructions per 32-column chunk (one MUFU + a degree-7 polynomial per element) and
+// are bounded by issue + dependent-instruction latency: FOUR warps per quadrant (16 epilogue warps, four per scheduler, 64
+// columns each) hide that latency better than two — same-box A/B round 2: fc1+GELU 0.388 -> 0.359 ms, fc2-dgrad.GELU' 0.418 ->
+// 0.389 ms, cfg2 step 29.78 -> 29.17 ms. (Round 1 measured no gain from this; the difference is the branch-free batched fast
+// path, which fits 90 registers per thread.) The plain epilogues keep two (CAVIT_EPI_EW_OTHER for experiments).
+#ifndef CAVIT_GELU_EW
+#define CAVIT_GELU_EW 4
+#endif
+#ifndef CAVIT_EPI_EW_OTHER
+#define CAVIT_EPI_EW_OTHER 2
+#endif
+  // (every warp takes whole 32-column chunks: 192-wide tiles split three ways, 128 / 256-wide tiles four ways)
+  static constexpr int EW_WANT = (EPI == CAVIT_EPI_BIAS_GELU || EPI == CAVIT_EPI_GELU_BWD) ? CAVIT_GELU_EW : CAVIT_EPI_EW_OTHER;
+  static constexpr int EW = (EW_WANT == 4 && BN == 192) ? 3 : EW_WANT;
+  static_assert(BN % (EW * 32) == 0, "epilogue warps must own whole 32-column chunks");
   static constexpr int EPI_WARPS = 4 * EW;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, epilogue warps
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (CTAS == 2) ? ((BN == 128) ? 8 : (EW == 4 ? 5 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 4));
+  // as many operand stages as fit beside the epilogue's transposition stages in 227 KB (EW = 2: 8 / 6 / 6 stages for pair tiles
+  // of 128 / 192 / 256 columns, 6 / 4 / 4 for single-CTA tiles; EW = 4: 6 / 5 / 5 and 5 / 4 / 3)
+  static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256 - EPI_WARPS * 4096;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 4096 /*epilogue transpose stages*/;
 };
@@ -210,12 +227,30 @@ __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const 
       v[2 * it] = unpack_bf16_fast(q0);
       v[2 * it + 1] = unpack_bf16_fast(q1);
     }
+#if CAVIT_GELU_EW == 4
+    {   // 16 epilogue warps: 113 registers per thread, two half batches
+      float2 (&va)[8] = *reinterpret_cast<float2(*)[8]>(&v[0]);
+      float2 (&vb)[8] = *reinterpret_cast<float2(*)[8]>(&v[8]);
+      gelu_batch<8>(va);
+      gelu_batch<8>(vb);
+    }
+#else
     gelu_batch<16>(v);
+#endif
   } else if (EPI == CAVIT_EPI_GELU_BWD) {
     float2 g[16];
 #pragma unroll
     for (int it = 0; it < 8; ++it) { g[2 * it] = unpack_bf16_fast(pre.a[it].x); g[2 * it + 1] = unpack_bf16_fast(pre.a[it].y); }
+#if CAVIT_GELU_EW == 4
+    {
+      float2 (&ga)[8] = *reinterpret_cast<float2(*)[8]>(&g[0]);
+      float2 (&gb)[8] = *reinterpret_cast<float2(*)[8]>(&g[8]);
+      gelu_grad_batch<8>(ga);
+      gelu_grad_batch<8>(gb);
+    }
+#else
     gelu_grad_batch<16>(g);
+#endif
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = mul2(v[j], g[j]);
   } else if (EPI == CAVIT_EPI_BIAS_RELU) {   // nn.TransformerEncoderLayer's default activation (modelv2.py:72-78)
