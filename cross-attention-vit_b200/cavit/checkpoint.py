@@ -13,10 +13,20 @@ import torch
 from . import _abi
 
 
-def load_reference_checkpoint(model: torch.nn.Module, path: str, strict: bool = True) -> Dict[str, Any]:
+def load_reference_checkpoint(model: torch.nn.Module, path: str, strict: bool = True, trusted: bool = False) -> Dict[str, Any]:
     """Load a Lightning ``.ckpt`` (or a bare ``state_dict`` file) of the reference model into the drop-in ``model``.
-    Returns the rest of the checkpoint dictionary (epoch, optimizer states, ...)."""
-    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    Returns the rest of the checkpoint dictionary (epoch, optimizer states, ...).
+
+    The file is read with ``weights_only=True`` (tensors and plain containers only). Lightning checkpoints that pickle
+    arbitrary objects (hyper-parameter namespaces, callbacks) need ``trusted=True``, which unpickles — i.e. can execute —
+    whatever the file contains: only for files you wrote yourself."""
+    try:
+        ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as exc:
+        if not trusted:
+            raise _abi.CavitError(f"{path}: cannot be read with weights_only=True ({type(exc).__name__}); pass trusted=True "
+                                  "to unpickle it if you trust its origin") from exc
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
     if not isinstance(ckpt, dict):
         raise _abi.CavitError(f"{path}: not a checkpoint dictionary")
     sd = ckpt.get("state_dict", ckpt)
@@ -25,7 +35,12 @@ def load_reference_checkpoint(model: torch.nn.Module, path: str, strict: bool = 
 
 
 def save_reference_checkpoint(model: torch.nn.Module, path: str, **extra) -> None:
-    """Write ``{"state_dict": ..., **extra}`` with CPU tensors — the layout ``LightningModule.load_from_checkpoint`` and
-    ``load_reference_checkpoint`` read."""
+    """Write ``{"state_dict": ..., "epoch", "global_step", "pytorch-lightning_version", **extra}`` with CPU tensors: the
+    layout of a ``ModelCheckpoint`` file as far as the weights go — ``model.load_state_dict(torch.load(p)["state_dict"])`` on
+    the reference model and ``load_reference_checkpoint`` read it. (Whether ``LightningModule.load_from_checkpoint`` accepts it
+    unchanged could not be checked here: Lightning is not installed; the version / epoch / step keys its loader looks for are
+    written.)"""
     sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
-    torch.save({"state_dict": sd, **extra}, path)
+    meta = {"epoch": 0, "global_step": 0, "pytorch-lightning_version": "2.0.0"}
+    meta.update(extra)
+    torch.save({"state_dict": sd, **meta}, path)

@@ -39,9 +39,12 @@ class SlabReducer:
                 self.pending = (start, pe)
             elif start == pe:
                 self.pending = (ps, end)
-            else:  # non-adjacent: flush what we have
+            else:  # non-adjacent: flush what we have; the new range may itself already be a full slab
                 out = [self.pending]
                 self.pending = (start, end)
+                if end - start >= self.min_elems:
+                    out.append(self.pending)
+                    self.pending = None
                 self.issued += out
                 return out
         if self.pending[1] - self.pending[0] >= self.min_elems:

@@ -136,7 +136,7 @@ __device__ __forceinline__ void xf_dots(const float* s_vec, int C, int nv, int l
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// smem: a[H][C] | A[H] | m[H] | chunk[XF_CHUNK][HP]
+// smem: a[H][C] | A[H] | m[H] | chunk[XF_CHUNK][HP] | mu[XF_CHUNK] | rstd[XF_CHUNK] | f[H]
 template <int H>
 __global__ void __launch_bounds__(XfCfg<H>::THREADS, XfCfg<H>::MINB)
 xfold_fwd_kernel(const XfoldParams p) {
@@ -145,14 +145,16 @@ xfold_fwd_kernel(const XfoldParams p) {
   float* s_a = sm;                 // [H][C]
   float* s_A = s_a + H * p.C;      // [H]
   float* s_m = s_A + H;            // [H]
-  float* s_ch = s_m + H + ((4 - ((2 * H) & 3)) & 3);   // [XF_CHUNK][HP], 16-byte aligned
+  float* s_ch = s_m + H + ((4 - ((2 * H) & 3)) & 3);   // [XF_CHUNK][HP], 16-byte aligned: scores, then weights of the chunk
+  float* s_mu = s_ch + XF_CHUNK * HP;                  // [XF_CHUNK] mean of the chunk's rows
+  float* s_rs = s_mu + XF_CHUNK;                       // [XF_CHUNK] rstd
+  float* s_f = s_rs + XF_CHUNK;                        // [H] rescale factor of the running accumulators (then 1 / L_h)
   const int b = blockIdx.x, k = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int C = p.C, N = p.N;
   const long long kb = (long long)k * p.B + b;
   const float* qp = p.qp + kb * H * C;
   const float* gamma = p.gamma + (long long)k * C;
-  float* wgt = p.scratch + kb * N * HP;   // [N][HP]: score, then p_eff * rstd
   // a_h = q'_h o gamma; A_h = sum_c a_h[c]
   for (int h = 0; h < H; ++h)
     for (int c = tid; c < C; c += blockDim.x) s_a[h * C + c] = qp[h * C + c] * gamma[c];
@@ -164,99 +166,115 @@ xfold_fwd_kernel(const XfoldParams p) {
     if (lane == 0) s_A[h] = s;
   }
   __syncthreads();
-  // ---- pass 1: one warp per PAIR of token rows: LayerNorm statistics and the H scores of each
+  // The token rows are walked ONCE from HBM, in chunks of XF_CHUNK rows (round 2; before, pass 2 re-read all N rows after
+  // pass 1 had streamed them and 2x the algorithmic bytes came from DRAM: 629 MB for 310 MB, L2 hit rate 4 %, ncu):
+  //   (A) one warp per PAIR of rows of the chunk: LayerNorm statistics and the H scores of each row (into shared memory);
+  //   (B) one warp per head: ONLINE softmax update — running max M_h, running sum L_h, rescale factor f_h for what has
+  //       been accumulated so far, weights w_hn = exp(s_hn - M_h) rstd_n of the chunk's rows;
+  //   (C) one thread per channel pair: acc_h = acc_h f_h + sum_n w_hn x_n — the second read of the chunk's rows comes out of
+  //       L1 / L2, they were fetched a few microseconds earlier by this same CTA.
+  // Afterwards zhat_h = acc_h / L_h - m_h and the probabilities are normalised from the raw scores kept in `probs`.
   const int nv = C >> 2;  // float4 per row
-  for (int n = 2 * warp; n < N; n += 2 * nwarps) {
-    const bool two = n + 1 < N;
-    const float4* row0 = reinterpret_cast<const float4*>(xf_row(p, k, b, n));
-    const float4* row1 = reinterpret_cast<const float4*>(xf_row(p, k, b, two ? n + 1 : n));
-    float4 v0[NVL], v1[NVL];
-    float s0 = 0.f, s1 = 0.f;
+  const int c = 2 * tid;
+  float2 acc[H];
 #pragma unroll
-    for (int i = 0; i < NVL; ++i) {
-      const int c4 = lane + 32 * i;
-      if (c4 < nv) {
-        v0[i] = __ldg(row0 + c4);
-        v1[i] = __ldg(row1 + c4);
-        s0 += (v0[i].x + v0[i].y) + (v0[i].z + v0[i].w);
-        s1 += (v1[i].x + v1[i].y) + (v1[i].z + v1[i].w);
+  for (int h = 0; h < H; ++h) acc[h] = make_float2(0.f, 0.f);
+  const float* xs = p.x + ((long long)p.tok_src[k] * p.B * N + (long long)b * N) * C + c;
+  const float* x0 = p.cls + kb * C + c;
+  float run_M = -INFINITY, run_L = 0.f, run_m = 0.f;      // per head, kept by lane 0.. of warp (h % nwarps); see (B)
+  for (int n0 = 0; n0 < N; n0 += XF_CHUNK) {
+    const int rows = min(XF_CHUNK, N - n0);
+    // ---- (A)
+    for (int rr = 2 * warp; rr < rows; rr += 2 * nwarps) {
+      const int n = n0 + rr;
+      const bool two = rr + 1 < rows;
+      const float4* row0 = reinterpret_cast<const float4*>(xf_row(p, k, b, n));
+      const float4* row1 = reinterpret_cast<const float4*>(xf_row(p, k, b, two ? n + 1 : n));
+      float4 v0[NVL], v1[NVL];
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVL; ++i) {
+        const int c4 = lane + 32 * i;
+        if (c4 < nv) {
+          v0[i] = __ldg(row0 + c4);
+          v1[i] = __ldg(row1 + c4);
+          s0 += (v0[i].x + v0[i].y) + (v0[i].z + v0[i].w);
+          s1 += (v1[i].x + v1[i].y) + (v1[i].z + v1[i].w);
+        }
+      }
+      const float mu0 = warp_sum(s0) / (float)C, mu1 = warp_sum(s1) / (float)C;
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVL; ++i) {
+        const int c4 = lane + 32 * i;
+        if (c4 < nv) {
+          float d0 = v0[i].x - mu0, d1 = v0[i].y - mu0, d2 = v0[i].z - mu0, d3 = v0[i].w - mu0;
+          q0 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          d0 = v1[i].x - mu1; d1 = v1[i].y - mu1; d2 = v1[i].z - mu1; d3 = v1[i].w - mu1;
+          q1 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+      }
+      const float rs0 = rsqrtf(warp_sum(q0) / (float)C + p.eps), rs1 = rsqrtf(warp_sum(q1) / (float)C + p.eps);
+      float d0[H], d1[H];
+      xf_dots<H, NVL, 1>(s_a, C, nv, lane, v0, v1, d0, d1);
+      constexpr int HQ = xf_pow2(H);
+      float red[2 * HQ];
+#pragma unroll
+      for (int h = 0; h < HQ; ++h) {
+        red[h] = h < H ? d0[h] : 0.f;
+        red[HQ + h] = h < H ? d1[h] : 0.f;
+      }
+      const float tot = warp_multi_reduce<2 * HQ>(red, lane);
+      const int idx = warp_multi_index<2 * HQ>(lane), r = idx / HQ, h = idx % HQ;
+      if (h < H && (r == 0 || two) && (lane & (32 / (2 * HQ) - 1)) == 0) {  // one lane per (row, head)
+        const float mu = r ? mu1 : mu0, rs = r ? rs1 : rs0;
+        s_ch[(rr + r) * HP + h] = p.scale * rs * (tot - mu * s_A[h]);        // score s_hn
+      }
+      if (lane == 0) {
+        s_mu[rr] = mu0; s_rs[rr] = rs0;
+        p.mean[kb * N + n] = mu0;
+        p.rstd[kb * N + n] = rs0;
+        if (two) {
+          s_mu[rr + 1] = mu1; s_rs[rr + 1] = rs1;
+          p.mean[kb * N + n + 1] = mu1;
+          p.rstd[kb * N + n + 1] = rs1;
+        }
       }
     }
-    const float mu0 = warp_sum(s0) / (float)C, mu1 = warp_sum(s1) / (float)C;
-    float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NVL; ++i) {
-      const int c4 = lane + 32 * i;
-      if (c4 < nv) {
-        float d0 = v0[i].x - mu0, d1 = v0[i].y - mu0, d2 = v0[i].z - mu0, d3 = v0[i].w - mu0;
-        q0 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-        d0 = v1[i].x - mu1; d1 = v1[i].y - mu1; d2 = v1[i].z - mu1; d3 = v1[i].w - mu1;
-        q1 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    __syncthreads();
+    // ---- (B) heads h = warp, warp + nwarps, ...: each warp owns the running statistics of its heads in registers; a warp
+    // owns at most ONE head when nwarps >= H, which holds for every instantiation (threads = 32 H)
+    if (warp < H) {
+      const int h = warp;
+      float mx = run_M;
+      for (int r = lane; r < rows; r += 32) mx = fmaxf(mx, s_ch[r * HP + h]);
+      mx = warp_max(mx);
+      const float f = __expf(run_M - mx);       // first chunk: exp(-inf) = 0
+      float sum = 0.f, m = 0.f;
+      float* pr = p.probs + (kb * H + h) * N + n0;
+      for (int r = lane; r < rows; r += 32) {
+        const float sc = s_ch[r * HP + h];
+        pr[r] = sc;                              // raw score; normalised after the last chunk
+        const float e = __expf(sc - mx);
+        sum += e;
+        const float w = e * s_rs[r];
+        s_ch[r * HP + h] = w;
+        m += w * s_mu[r];
       }
+      run_L = run_L * f + warp_sum(sum);
+      run_m = run_m * f + warp_sum(m);
+      run_M = mx;
+      if (lane == 0) s_f[h] = f;
     }
-    const float rs0 = rsqrtf(warp_sum(q0) / (float)C + p.eps), rs1 = rsqrtf(warp_sum(q1) / (float)C + p.eps);
-    float d0[H], d1[H];
-    xf_dots<H, NVL, 1>(s_a, C, nv, lane, v0, v1, d0, d1);
-    constexpr int HQ = xf_pow2(H);
-    float red[2 * HQ];
+    __syncthreads();
+    // ---- (C)
+    {
 #pragma unroll
-    for (int h = 0; h < HQ; ++h) {
-      red[h] = h < H ? d0[h] : 0.f;
-      red[HQ + h] = h < H ? d1[h] : 0.f;
-    }
-    const float tot = warp_multi_reduce<2 * HQ>(red, lane);
-    const int idx = warp_multi_index<2 * HQ>(lane), r = idx / HQ, h = idx % HQ;
-    if (h < H && (r == 0 || two) && (lane & (32 / (2 * HQ) - 1)) == 0) {  // one lane per (row, head)
-      const float mu = r ? mu1 : mu0, rs = r ? rs1 : rs0;
-      wgt[(long long)(n + r) * HP + h] = p.scale * rs * (tot - mu * s_A[h]);  // score s_hn
-    }
-    if (lane == 0) {
-      p.mean[kb * N + n] = mu0;
-      p.rstd[kb * N + n] = rs0;
-      if (two) {
-        p.mean[kb * N + n + 1] = mu1;
-        p.rstd[kb * N + n + 1] = rs1;
+      for (int h = 0; h < H; ++h) {
+        const float f = s_f[h];
+        acc[h].x *= f;
+        acc[h].y *= f;
       }
-    }
-  }
-  __threadfence_block();
-  __syncthreads();
-  // ---- softmax over n per head (one warp per head), weights p_eff * rstd back into the scratch
-  for (int h = warp; h < H; h += nwarps) {
-    float mx = -INFINITY;
-    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, wgt[(long long)n * HP + h]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int n = lane; n < N; n += 32) sum += __expf(wgt[(long long)n * HP + h] - mx);
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    float* pr = p.probs + (kb * H + h) * N;
-    float m = 0.f;
-    for (int n = lane; n < N; n += 32) {
-      const float pn = __expf(wgt[(long long)n * HP + h] - mx) * inv;
-      pr[n] = pn;
-      const float w = pn * p.rstd[kb * N + n];
-      wgt[(long long)n * HP + h] = w;
-      m += w * p.mean[kb * N + n];
-    }
-    m = warp_sum(m);
-    if (lane == 0) s_m[h] = m;
-  }
-  __threadfence_block();
-  __syncthreads();
-  // ---- pass 2: one thread per channel pair: zhat_h[c] = sum_n w_hn x_n[c] - m_h; weights staged per chunk of rows
-  {
-    const int c = 2 * tid;
-    float2 acc[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) acc[h] = make_float2(0.f, 0.f);
-    const float* xs = p.x + ((long long)p.tok_src[k] * p.B * N + (long long)b * N) * C + c;
-    const float* x0 = p.cls + kb * C + c;
-    for (int n0 = 0; n0 < N; n0 += XF_CHUNK) {
-      const int rows = min(XF_CHUNK, N - n0);
-      __syncthreads();
-      for (int i = tid; i < rows * HP; i += blockDim.x) s_ch[i] = wgt[(long long)n0 * HP + i];
-      __syncthreads();
       for (int r0 = 0; r0 < rows; r0 += 8) {
         float2 xv[8];
 #pragma unroll
@@ -282,6 +300,26 @@ xfold_fwd_kernel(const XfoldParams p) {
           }
         }
       }
+    }
+    __syncthreads();     // s_ch / s_mu / s_rs / s_f are rewritten by the next chunk
+  }
+  // ---- final normalisation: 1 / L_h, m_h / L_h, probabilities
+  if (warp < H) {
+    const int h = warp;
+    const float inv = 1.0f / run_L;
+    if (lane == 0) {
+      s_f[h] = inv;
+      s_m[h] = run_m * inv;
+    }
+    float* pr = p.probs + (kb * H + h) * N;
+    for (int n = lane; n < N; n += 32) pr[n] = __expf(pr[n] - run_M) * inv;
+  }
+  __syncthreads();
+  {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      acc[h].x *= s_f[h];
+      acc[h].y *= s_f[h];
     }
     const float2 g = *reinterpret_cast<const float2*>(gamma + c);
     const float2 be = *reinterpret_cast<const float2*>(p.beta + (long long)k * C + c);
@@ -510,7 +548,7 @@ static int xfold_launch(bool bwd, const XfoldParams& p, cudaStream_t st) {
   constexpr int HP = XfCfg<H>::HP;
   const int threads = XfCfg<H>::THREADS;
   size_t smem = sizeof(float) * (bwd ? (2 * (size_t)H * p.C + 2 * H + 4 + XF_CHUNK * (2 * HP + 4))
-                                     : ((size_t)H * p.C + 2 * H + 4 + XF_CHUNK * HP));
+                                     : ((size_t)H * p.C + 2 * H + 4 + XF_CHUNK * HP + 2 * XF_CHUNK + H + 4));
   // Residency cap (experiment knob): the token rows of a (fusion, sample) pair are read twice; with every SM holding MINB
   // CTAs the rows in flight between the two passes exceed L2. Padding the dynamic shared memory request lowers residency.
   static const int pad_kb = [] { const char* e = getenv("CAVIT_XFOLD_PAD_KB"); return e ? atoi(e) : 0; }();

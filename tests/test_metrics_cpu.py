@@ -69,7 +69,15 @@ def test_checkpoint_round_trip_and_reference_ckpt(tmp_path):
     p = str(tmp_path / "epoch=3.ckpt")
     save_reference_checkpoint(a, p, epoch=3, global_step=120)
     rest = load_reference_checkpoint(b, p)
-    assert rest == {"epoch": 3, "global_step": 120}
+    assert rest["epoch"] == 3 and rest["global_step"] == 120 and "pytorch-lightning_version" in rest
+    # weights_only loading: a checkpoint that pickles arbitrary objects is refused unless the caller vouches for it
+    import types
+    from cavit import CavitError
+    bad = str(tmp_path / "pickled.ckpt")
+    torch.save({"state_dict": a.state_dict(), "hyper_parameters": types.SimpleNamespace(lr=1e-4)}, bad)
+    with pytest.raises(CavitError):
+        load_reference_checkpoint(b, bad)
+    load_reference_checkpoint(b, bad, trusted=True)
     for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.equal(x, y), k
     # a checkpoint of the REAL reference model (container only): Lightning's layout is {"state_dict": module.state_dict(), ...}
