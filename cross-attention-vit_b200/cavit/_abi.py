@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CAVIT_LIB") or os.path.join(_HERE, "libcavit_sm100a.s
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_GELU_BWD, EPI_EMBED, EPI_BIAS_RELU, EPI_RELU_BWD = range(8)
 

@@ -692,7 +692,7 @@ class Engine:
                                     src_row_stride=C, src_gs=0, dst_row_stride=C, dst_gs=0)
         elif self.embed_fused:
             self._img = img
-            ops.embed_fused_fwd(img, self.wb("embed.w"), self.w("embed.b"), self.w("pos"), X0, patch_size=cfg.patch_size,
+            ops.embed_fused_fwd(img, self.w("embed.w"), self.w("embed.b"), self.w("pos"), X0, patch_size=cfg.patch_size,
                                 C_=C, sample_major=(self.kind == "vit"))
         else:
             ops.patchify(img, a["patches"], patch_size=cfg.patch_size, sample_major=(self.kind == "vit"))

@@ -294,12 +294,12 @@ def embed_fused_supported(img_shape, patch_size, C_) -> bool:
         bool(lib().cavit_embed_fused_wgrad_supported(B, M, D, H, W, dp, hp, wp, C_))
 
 
-def embed_fused_fwd(img, w_bf16, bias, pos, tokens, *, patch_size, C_, sample_major=False):
+def embed_fused_fwd(img, w_f32, bias, pos, tokens, *, patch_size, C_, sample_major=False):
     """tokens[.., 1 + t, :] = unfold(img) W^T + bias + pos[1 + t] without materialising the unfolded patches
     (include/cavit.h: cavit_embed_fused_fwd). The CLS rows are written by cls_rows."""
     B, M, _, D, H, W = img.shape
     dp, hp, wp = patch_size
-    check(lib().cavit_embed_fused_fwd(img.data_ptr(), w_bf16.data_ptr(), bias.data_ptr(), pos.data_ptr(), tokens.data_ptr(),
+    check(lib().cavit_embed_fused_fwd(img.data_ptr(), w_f32.data_ptr(), bias.data_ptr(), pos.data_ptr(), tokens.data_ptr(),
                                       B, M, D, H, W, dp, hp, wp, C_, int(sample_major), _stream()), "cavit_embed_fused_fwd")
 
 

@@ -126,7 +126,7 @@ static const CUtensorMap* lookup_or_encode(const MapKey& key, uint32_t rank, con
 
 // Generic tiled map (any rank <= 5, fp32 or bf16, any swizzle; zero fill outside the tensor). strides_bytes: dims 1..rank-1.
 const CUtensorMap* tensor_map_nd(int dtype_f32, uint32_t rank, const void* base, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   if (rank < 1 || rank > 5) {
     fail(CAVIT_E_BADARG, "tensor_map_nd: rank %u", rank);
     return nullptr;
@@ -134,7 +134,7 @@ const CUtensorMap* tensor_map_nd(int dtype_f32, uint32_t rank, const void* base,
   MapKey key{};
   key.v[0] = 100 + rank;
   key.v[1] = reinterpret_cast<uint64_t>(base);
-  key.v[2] = (uint64_t)dtype_f32 | ((uint64_t)swizzle128 << 8);
+  key.v[2] = (uint64_t)dtype_f32 | ((uint64_t)swizzle_bytes << 8);
   for (uint32_t i = 0; i < rank; ++i) key.v[3 + i] = dims[i];
   for (uint32_t i = 0; i + 1 < rank; ++i) key.v[8 + i] = strides_bytes[i];
   for (uint32_t i = 0; i < rank; ++i) key.v[12 + i] = box[i];
@@ -155,9 +155,13 @@ const CUtensorMap* tensor_map_nd(int dtype_f32, uint32_t rank, const void* base,
   cuuint32_t bx[5] = {1, 1, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
   for (uint32_t i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
   for (uint32_t i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  // swizzle_bytes: 0 = none, 1 or 128 = SWIZZLE_128B, 64 = SWIZZLE_64B, 32 = SWIZZLE_32B
+  const CUtensorMapSwizzle swz = (swizzle_bytes == 1 || swizzle_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(m, dtype_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
                   const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fail(CAVIT_E_BADARG,

@@ -25,10 +25,11 @@ const CUtensorMap* tensor_map_bf16_3d(const void* base, uint64_t inner, uint64_t
 const CUtensorMap* tensor_map_bf16_4d(const void* base, const uint64_t dims[4], const uint64_t strides_elems[3],
                                       const uint32_t box[4]);
 
-// Generic tiled map: rank <= 5, fp32 (dtype_f32 = 1) or bf16 elements, 128-byte or no swizzle, zero fill out of bounds.
+// Generic tiled map: rank <= 5, fp32 (dtype_f32 = 1) or bf16 elements, swizzle_bytes 0 (none) / 32 / 64 / 128 (1 = 128),
+// zero fill out of bounds.
 // strides_bytes holds the strides of dims 1 .. rank-1. Cached by value; nullptr on failure.
 const CUtensorMap* tensor_map_nd(int dtype_f32, uint32_t rank, const void* base, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
+                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 // p * 2^32 threshold for the counter-based dropout masks (common.cuh); p in [0, 1)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CAVIT_ABI_VERSION 2
+#define CAVIT_ABI_VERSION 3
 
 enum {
   CAVIT_OK = 0,
@@ -372,22 +372,26 @@ int cavit_batch_metrics(const float* logits, const int64_t* labels, const float*
  * add — the unfolded [B, Np, P] patch tensor never exists. Replaces einops.rearrange + patch_to_embedding + cat(cls) +
  * `x += pos_embedding` of /root/reference/model_cross.py:189-198 and modelv3.py:125-140 (forward) and the
  * patch_to_embedding weight gradient of their autograd (the input volumes need no gradient).
- *   img: fp32 [B][M][1][D][H][W];  W: bf16 [C][P], P = dp*hp*wp, feature order (a, b, c);  bias fp32 [C];
- *   pos: fp32 [Ntok][C];  tokens: fp32, sample_major = 0: [M][B*(Np+1)][C] (ModelCross), 1: [B*(M*Np+1)][C] (ModelVIT);
- *   token t = (hi*Wn + wi)*Dn + di of a volume goes to row 1 + t (+ m*Np) of its sequence — bit-exact index map.
- * TMA fetches fp32 bricks {c: wp, wi: W/wp, b: 64/wp rows, z: 1, v: volumes} of the volume per k-block; converter warps
- * round them to bf16 into the 128-byte-swizzled operand stage of the tcgen05 MMA. The CLS rows are cavit_cls_rows'.
- * *_supported() != 0 iff the geometry is inside the kernels' reach (wp in {8,16,32,64}, hp % (64/wp) == 0, W % 4 == 0,
- * W/wp <= 128, C % 32 == 0; wgrad: M * W/wp <= 64 and 128-feature tiles made of whole (a, b) rows); otherwise the
- * calls fail with CAVIT_E_UNSUPPORTED_SHAPE and the caller uses cavit_patchify + cavit_gemm.
- * wgrad: dtokens bf16 in the tokens layout; dW fp32 [C][P] is overwritten (zeroed, then fp32 red.add of the partial tiles).
+ *   img: fp32 [B][M][1][D][H][W];  W: fp32 [C][P] (the master weights), P = dp*hp*wp, feature order (a, b, c);
+ *   bias fp32 [C];  pos: fp32 [Ntok][C];  tokens: fp32, sample_major = 0: [M][B*(Np+1)][C] (ModelCross),
+ *   1: [B*(M*Np+1)][C] (ModelVIT); token t = (hi*Wn + wi)*Dn + di of a volume goes to row 1 + t (+ m*Np) of its sequence —
+ *   bit-exact index map.
+ * TMA fetches fp32 bricks {c: wp, h: 32/wp rows, wi: W/wp, z: 1, v: volumes} of the volume per 32-feature k-block straight
+ * into the 128-byte-swizzled operand stage; tcgen05.mma.kind::tf32 reads the fp32 words as TF32 (10 mantissa bits), fp32
+ * accumulation — no conversion pass, no bf16 copy of the weights. The CLS rows are cavit_cls_rows'.
+ * *_supported() != 0 iff the geometry is inside the kernels' reach (wp in {8,16,32} with hp % (32/wp) == 0, or wp % 32 == 0;
+ * W % 4 == 0, W/wp <= 128, C % 32 == 0; wgrad: wp in {8,16,32,64}, M * W/wp <= 64 and 128-feature tiles made of whole
+ * (a, b) rows); otherwise the calls fail with CAVIT_E_UNSUPPORTED_SHAPE and the caller uses cavit_patchify + cavit_gemm.
+ * wgrad: dtokens bf16 in the tokens layout, volume bricks staged in fp32 and rounded to bf16 by converter warps (tcgen05
+ * reads MN-major TF32 only from 128-byte rows, which 8- / 16-wide patch rows cannot form); dW fp32 [C][P] is overwritten
+ * (zeroed, then fp32 red.add of the partial tiles).
  * cavit_embed_bias_grad: db[c] = sum_{n >= 1} dpos[n][c] (dpos from cavit_embed_param_grads).
  * ------------------------------------------------------------------------------------------- */
 int cavit_embed_fused_supported(int32_t B, int32_t M, int32_t D, int32_t H, int32_t W, int32_t dp, int32_t hp, int32_t wp,
                                 int32_t C);
 int cavit_embed_fused_wgrad_supported(int32_t B, int32_t M, int32_t D, int32_t H, int32_t W, int32_t dp, int32_t hp,
                                       int32_t wp, int32_t C);
-int cavit_embed_fused_fwd(const float* img, const void* W_bf16, const float* bias, const float* pos, float* tokens, int32_t B,
+int cavit_embed_fused_fwd(const float* img, const float* W_f32, const float* bias, const float* pos, float* tokens, int32_t B,
                           int32_t M, int32_t D, int32_t H, int32_t W, int32_t dp, int32_t hp, int32_t wp, int32_t C,
                           int32_t sample_major, void* stream);
 int cavit_embed_fused_wgrad(const float* img, const void* dtokens_bf16, float* dW, int32_t B, int32_t M, int32_t D, int32_t H,

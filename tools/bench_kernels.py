@@ -141,6 +141,23 @@ def main():
         dg, db = torch.zeros(Kf, C, **f32), torch.zeros(Kf, C, **f32)
         mem_line("xfold bwd", lambda: ops.xfold_bwd(X, cls, qp, lnw, zhat, probs, mean, rstd, gz, scratch, dX, dqp, dg, db, **kw),
                  Kf * B * N * C * 12)
+    if not a.only or "embed" in a.only:
+        # K-EMBED at the BASELINE geometries (cfg2 batch = --B; the volumetric ones at a batch that fits one tile wave)
+        for name, Bv, dims, patch, Ce in (("cfg2", B, (224, 224, 1), (16, 16, 1), 384), ("cfg1 B=2", 2, (128, 128, 64), (16, 16, 8), 1024),
+                                          ("cfg5 B=8", 8, (128, 128, 128), (8, 8, 8), 512)):
+            Mv = 4
+            img = rnd(Bv, Mv, 1, *dims)
+            P = patch[0] * patch[1] * patch[2]
+            Np = (dims[0] // patch[0]) * (dims[1] // patch[1]) * (dims[2] // patch[2])
+            Ne = Np + 1
+            We = rnd(Ce, P) / P ** 0.5
+            be, pe = rnd(Ce), rnd(Ne, Ce)
+            tok = torch.zeros(Mv, Bv * Ne, Ce, device=DEV)
+            dYb = rnd(Mv, Bv * Ne, Ce).to(BF)
+            dWe = torch.empty(Ce, P, device=DEV)
+            vol, tokb = img.numel() * 4, Mv * Bv * Np * Ce
+            mem_line(f"embed fused fwd {name}", lambda: ops.embed_fused_fwd(img, We, be, pe, tok, patch_size=patch, C_=Ce), vol + tokb * 4)
+            mem_line(f"embed fused wgrad {name}", lambda: ops.embed_fused_wgrad(img, dYb, dWe, patch_size=patch, C_=Ce), vol + tokb * 2)
     print("status", _abi.device_status())
 
 
