@@ -336,14 +336,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     (void)ntr;
     const bool tracer = (quad == 0 && part == 0 && lane == 0);
     (void)tracer;
+    // Item coordinates (qp, h, b, g) are advanced incrementally — item += gridDim.x is a mixed-radix add with carries — because
+    // div / mod by run-time values cost ~150 dependent instructions per item on the softmax warps' critical path (the launcher
+    // rejects problems with >= 2^31 items, so everything is 32-bit).
+    int qp, h, b, g;
+    int d_qp, d_h, d_b, d_g;   // gridDim.x in the same radix
+    {
+      unsigned v = blockIdx.x;
+      qp = (int)(v % (unsigned)nqp); v /= (unsigned)nqp;
+      h = (int)(v % (unsigned)p.H); v /= (unsigned)p.H;
+      b = (int)(v % (unsigned)p.B); g = (int)(v / (unsigned)p.B);
+      v = gridDim.x;
+      d_qp = (int)(v % (unsigned)nqp); v /= (unsigned)nqp;
+      d_h = (int)(v % (unsigned)p.H); v /= (unsigned)p.H;
+      d_b = (int)(v % (unsigned)p.B); d_g = (int)(v / (unsigned)p.B);
+    }
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-      // 32-bit index math (the launcher rejects problems with >= 2^31 items): 64-bit div / mod cost hundreds of instructions
-      // per item on the softmax warps' critical path
-      const unsigned item_u = (unsigned)item;
-      const int qp = (int)(item_u % (unsigned)nqp);
-      const unsigned gbh = item_u / (unsigned)nqp;
-      const int bh = (int)(gbh % (unsigned)BH), g = (int)(gbh / (unsigned)BH);
-      const int b = bh / p.H, h = bh % p.H;
       const int row_base = b * p.N;
       float o[32];
 #pragma unroll
@@ -448,12 +456,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(r[i]);
       }
+      if (tracer) FWD_TRACE(2 + sl, ntr, 28);
       tc_fence_before();
       // Output rows go through the slot's P buffer (free: the last P.V has retired) so that the global stores are whole
       // 128-byte rows (8 lanes x 16 B) instead of 32 scattered 16-byte pieces per warp instruction, which kept the LSU busy
       // for ~2000 cycles per item. Staging layout: [128 rows][8 x 16 B], 16-byte chunk index XOR (row & 7).
       {
-        const float inv_l = 1.0f / l_run;
+        const float inv_l = __fdividef(1.0f, l_run);
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 w;
@@ -465,21 +474,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         }
         const int q = qp * 2 * ATT_TILE + sl * ATT_TILE + row;
         if (part == 0 && q < p.N)
-          p.lse[(((long long)g * p.B + b) * p.H + h) * p.N + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+          p.lse[(((long long)g * p.B + b) * p.H + h) * p.N + q] = (m_run + __log2f(l_run)) * 0.6931471805599453f;
+        if (tracer) FWD_TRACE(2 + sl, ntr, 29);
         named_bar_sync(bar_id, 64);   // both column halves of this quadrant's 32 rows are staged
+        if (tracer) FWD_TRACE(2 + sl, ntr, 30);
         // the two warps of the quadrant store 16 rows each; the next use of this P region (pass 2 of the next item) comes
         // after the max-exchange barrier of the same two warps, so the staged rows are not overwritten while being read
         const int c16 = lane & 7;
+        const int r0 = quad * 32 + part * 16 + (lane >> 3), qr0 = qp * 2 * ATT_TILE + sl * ATT_TILE + r0;
+        bf16* orow = p.out + (long long)g * p.out_gs + (long long)(row_base + qr0) * p.C + h * ATT_D + c16 * 8;
+        const long long ostep = 4ll * p.C;
 #pragma unroll
         for (int it2 = 0; it2 < 4; ++it2) {
-          const int r = quad * 32 + part * 16 + it2 * 4 + (lane >> 3);
-          const int qr = qp * 2 * ATT_TILE + sl * ATT_TILE + r;
-          if (qr < p.N) {
+          const int r = r0 + it2 * 4;
+          if (qr0 + it2 * 4 < p.N) {
             const uint4 v = *reinterpret_cast<const uint4*>(myP + r * 128 + ((c16 ^ (r & 7)) << 4));
-            *reinterpret_cast<uint4*>(p.out + (long long)g * p.out_gs + (long long)(row_base + qr) * p.C + h * ATT_D + c16 * 8) = v;
+            *reinterpret_cast<uint4*>(orow + it2 * ostep) = v;
           }
         }
+        if (tracer) FWD_TRACE(2 + sl, ntr, 31);
       }
+      qp += d_qp; h += d_h; b += d_b; g += d_g;
+      if (qp >= nqp) { qp -= nqp; ++h; }
+      if (h >= p.H) { h -= p.H; ++b; }
+      if (b >= p.B) { b -= p.B; ++g; }
     }
   }
   tc_fence_before();

@@ -8,7 +8,7 @@ NAMES = {0: 'TMA: item top (wait qempty)', 1: 'TMA: qempty ok -> load Q', 2: 'TM
          10: 'MMA: sfree0 ok -> S0', 11: 'MMA: sfree1 ok -> S1', 12: 'MMA: pfull0 ok -> PV0', 13: 'MMA: pfull1 ok -> PV1',
          14: 'MMA: item top', 15: 'MMA: next qfull ok', 16: 'MMA: next kvfull ok',
          20: 'wait sfull', 21: 'sfull ok', 22: 'pass1 done', 23: 'max exchanged', 24: 'ofull(prev) ok', 25: 'pass2 done',
-         26: 'wait last O', 27: 'last O ok'}
+         26: 'wait last O', 27: 'last O ok', 28: 'last O folded', 29: 'O staged', 30: 'staging barrier', 31: 'O rows stored'}
 WHO = {0: 'TMA ', 1: 'MMA ', 2: 'SM0 ', 3: 'SM1 '}
 
 
