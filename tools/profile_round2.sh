@@ -7,7 +7,7 @@ O=gpurun_out
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active
 timeout 120 python tools/one_step.py > $O/plain_step.log 2>&1 && \
   timeout 400 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file $O/launches_$TAG.csv python tools/one_step.py > $O/ncu_step.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:embed_fused -c 2 -o $O/prof_embed_$TAG -f python tools/one_step.py > $O/ncu_embed.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:embed_ -c 3 -o $O/prof_embed_$TAG -f python tools/one_step.py > $O/ncu_embed.log 2>&1
 timeout 100 python tools/one_gemm.py fc1 > $O/plain_fc1.log 2>&1 && \
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 1 -o $O/prof_gemm_fc1_$TAG -f python tools/one_gemm.py fc1 > $O/ncu_fc1.log 2>&1
 timeout 100 python tools/one_attn.py > $O/plain_attn.log 2>&1 && \
