@@ -237,6 +237,12 @@ def xfold_scratch(K, B, N, H, device) -> torch.Tensor:
     return torch.empty(lib().cavit_xfold_scratch_floats(K, B, N, H), dtype=F32, device=device)
 
 
+def xfold_tensor_cores(on: int = -1) -> int:
+    """Select (1) / deselect (0) / query (-1) the tcgen05 variant of the folded forward; returns the previous setting
+    (include/cavit.h: cavit_xfold_tensor_cores)."""
+    return int(lib().cavit_xfold_tensor_cores(int(on)))
+
+
 def xfold_fwd(x, cls, qp, gamma, beta, zhat, z, probs, mean, rstd, scratch, *, K, B, N, C_, H, cls_src, tok_src, scale,
               eps=1e-5, p_drop=0.0, seed=None, site=0):
     """Folded single-query cross attention, forward (include/cavit.h: cavit_xfold_fwd)."""

@@ -22,6 +22,8 @@
 // 12*C bytes per token backward (read x, read-modify-write the stream gradient).
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -55,6 +57,7 @@ struct XfoldParams {
   DropCfg drop;
   int use_drop;
   int disjoint;   // every token stream is read by at most one fusion: plain read-modify-write instead of atomics
+  int* status_word;   // device status word (bounded mbarrier waits of the tcgen05 variant)
 };
 
 __device__ __forceinline__ const float* xf_row(const XfoldParams& p, int k, int b, int n) {
@@ -574,7 +577,316 @@ static int xfold_launch(bool bwd, const XfoldParams& p, cudaStream_t st) {
   return check_launch(bwd ? "cavit_xfold_bwd" : "cavit_xfold_fwd");
 }
 
+// ------------------------------------------------------------------------------------------------ forward on tcgen05
+// The same fold with both contractions on the tensor cores (bf16 mode; N <= 256, C % 128 == 0, the tile below fits shared
+// memory). The SIMT kernel above spends ~55 thread instructions per token element (ncu: 58 % issue slots busy at 20 % of the
+// HBM peak): its two skinny contractions — H scores per token, H weighted sums per channel — are 12 FMA per element plus
+// the shared-memory traffic and index arithmetic to feed them. Here, per (fusion, sample):
+//   1. sixteen warps stream the fp32 token rows ONCE, compute the LayerNorm statistics and write xhat = (x - mu) rstd as bf16
+//      into ONE 128-byte-swizzled tile [n][c] (C/64 column chunks of [RA rows][128 B]);
+//   2. S[n][h]  = sum_c xhat[n][c] a_h[c]    tcgen05, A = the tile read K-major,  B = a (bf16, [16][C]);   D in TMEM [n][16]
+//   3. softmax over n per head (one thread per token row, block reductions), probabilities to HBM (backward needs them) and
+//      as bf16 into a K-major tile P[h][n];
+//   4. zhat[c][h] = sum_n xhat[n][c] P[h][n]  tcgen05, A = THE SAME tile read MN-major (M = channels), B = P;  D in TMEM [c][16]
+//   5. epilogue: zhat (fp32) and z = gamma o zhat + beta (bf16), one thread per channel.
+// xhat in bf16 is what the unfolded route feeds its K / V GEMMs too; accumulation is fp32. About 7 thread instructions per
+// token element remain (step 1), the rest is HBM time.
+constexpr int XT_THREADS = 512;                 // 16 warps: 64 token rows (4 per warp) in flight while streaming; rows / channels use the first 8
+constexpr int XT_WARPS = XT_THREADS / 32;
+constexpr int XT_HP = 16;                      // heads padded to the smallest UMMA N for M = 128
+
+struct XtLayout {
+  int RA, pitch, chunks, kchunks, off_b1, off_p, off_red, off_bar, bytes;
+};
+static XtLayout xt_layout(int N, int C) {
+  XtLayout L;
+  L.RA = (N + 15) & ~15;
+  L.pitch = L.RA * 128;
+  L.chunks = C / 64;
+  L.kchunks = (L.RA + 63) / 64;
+  L.off_b1 = L.chunks * L.pitch;                 // a tile: [chunks][16 rows][128 B]
+  L.off_p = L.off_b1 + L.chunks * 2048;          // P tile: [kchunks][16 rows][128 B]
+  L.off_red = L.off_p + 4 * 2048;                // always 4 k-chunks: the M = 128 reads of step 2 may run over the tile end
+  L.off_bar = L.off_red + 2 * XT_WARPS * XT_HP * 4;     // [max | sum][warp][head]
+  L.bytes = L.off_bar + 64 + 1024;               // + alignment slack
+  return L;
+}
+
+template <int H, int NV>     // NV = C / 128 float4 per lane and token row
+__global__ void __launch_bounds__(XT_THREADS, 1)
+xfold_tc_fwd_kernel(const XfoldParams p, const XtLayout L) {
+  extern __shared__ uint8_t xt_raw[];
+  const uint32_t base = (smem_u32(xt_raw) + 1023u) & ~1023u;
+  uint8_t* gen = xt_raw + (base - smem_u32(xt_raw));
+  uint8_t* g_b1 = gen + L.off_b1;
+  uint8_t* g_p = gen + L.off_p;
+  float* s_red = reinterpret_cast<float*>(gen + L.off_red);
+  const uint32_t bar1 = base + L.off_bar, bar2 = bar1 + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + L.off_bar + 16);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int C = 128 * NV, ctiles = NV;
+  const int N = p.N, mtiles = (N + 127) >> 7;
+
+  if (tid == 0) {
+    *abort_flag = 0;
+    mbar_init(bar1, 1);
+    mbar_init(bar2, 1);
+    fence_barrier_init();
+  }
+  // rows h >= H of the a tile and of P are never written: zero both tiles once
+  for (int i = tid; i < (L.off_red - L.off_b1) / 16; i += XT_THREADS) reinterpret_cast<uint4*>(g_b1)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;              // S tiles: columns [0, 32); zhat tiles: [32 + 16 j, ...)
+  const uint32_t idesc1 = umma_idesc_bf16(XT_HP, 0, 0, 128), idesc2 = umma_idesc_bf16(XT_HP, 1, 0, 128);
+  const float inv_c = 1.0f / (float)C;
+  const int items = p.K * p.B;
+  uint32_t phase = 0;
+
+  for (int item = blockIdx.x; item < items; item += gridDim.x, phase ^= 1u) {
+    const int k = item / p.B, b = item - k * p.B;
+    const long long kb = item;
+    const float* xs = p.x + ((long long)p.tok_src[k] * p.B * N + (long long)b * N) * C;   // token rows n >= 1 of the fused sequence
+    const float* x0 = p.cls + kb * C;                                                    // row 0: the CLS row
+    // ---- a_h = q'_h o gamma as bf16 into the K-major B tile of step 2
+    {
+      const float* qp = p.qp + kb * H * C;
+      const float* gamma = p.gamma + (long long)k * C;
+      for (int i = tid; i < H * (C >> 3); i += XT_THREADS) {
+        const int h = i / (C >> 3), c8 = i - h * (C >> 3);          // 8 channels = one 16-byte unit
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(qp + h * C + c8 * 8)), q1 = __ldg(reinterpret_cast<const float4*>(qp + h * C + c8 * 8) + 1);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8) + 1);
+        uint4 w;
+        w.x = pack_bf16(q0.x * g0.x, q0.y * g0.y); w.y = pack_bf16(q0.z * g0.z, q0.w * g0.w);
+        w.z = pack_bf16(q1.x * g1.x, q1.y * g1.y); w.w = pack_bf16(q1.z * g1.z, q1.w * g1.w);
+        *reinterpret_cast<uint4*>(g_b1 + (c8 >> 3) * 2048 + h * 128 + (((c8 & 7) ^ (h & 7)) << 4)) = w;
+      }
+    }
+    // ---- step 1: token rows -> LayerNorm statistics -> xhat (bf16) tile; four rows per warp in flight. Rows are written
+    // in order, so the S MMAs of the first 128 rows (step 2, tile 0) are issued as soon as those rows are in shared memory
+    // and run under the streaming of the remaining rows.
+    auto issue_s_tile = [&](int m) {
+      for (int cc = 0; cc < L.chunks; ++cc) {
+        const uint64_t ad = umma_desc_sw128(base + cc * L.pitch + m * 16384, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(base + L.off_b1 + cc * 2048, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem + m * XT_HP, ad + 2 * kk, bd + 2 * kk, idesc1, (cc | kk) != 0 ? 1u : 0u);
+      }
+    };
+    bool tile0_issued = false;
+    for (int r0 = warp; r0 < L.RA; r0 += 4 * XT_WARPS) {
+      if (mtiles == 2 && !tile0_issued && r0 - warp >= 128) {   // block-uniform: rows 0 .. 127 are complete
+        tile0_issued = true;
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) issue_s_tile(0);
+          __syncwarp();
+        }
+      }
+      float4 v[4][NV];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = r0 + XT_WARPS * j;
+        if (n < N) {
+          const float4* row = reinterpret_cast<const float4*>(n == 0 ? x0 : xs + (long long)n * C) + lane;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[j][i] = __ldg(row + 32 * i);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = r0 + XT_WARPS * j;
+        if (n >= L.RA) continue;                 // warp-uniform
+        uint8_t* dst = gen + n * 128;
+        const uint32_t sw = static_cast<uint32_t>(n & 7);
+        // this lane's float4 i sits in column chunk (lane >> 4) + 2 i, 16-byte unit ((lane & 15) >> 1) ^ (n & 7), half lane & 1
+        uint8_t* d0 = dst + (lane >> 4) * L.pitch + (((static_cast<uint32_t>(lane & 15) >> 1) ^ sw) << 4) + (lane & 1) * 8;
+        if (n >= N) {                            // rows of the last 16-row group beyond N: zero (step 4 reads them)
+#pragma unroll
+          for (int i = 0; i < NV; ++i) *reinterpret_cast<uint2*>(d0 + 2 * i * L.pitch) = make_uint2(0u, 0u);
+          continue;
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sum += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+        const float mu = warp_sum(sum) * inv_c;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          v[j][i].x -= mu; v[j][i].y -= mu; v[j][i].z -= mu; v[j][i].w -= mu;
+          q += (v[j][i].x * v[j][i].x + v[j][i].y * v[j][i].y) + (v[j][i].z * v[j][i].z + v[j][i].w * v[j][i].w);
+        }
+        const float rs = rsqrtf(warp_sum(q) * inv_c + p.eps);
+        if (lane == 0) {
+          p.mean[kb * N + n] = mu;
+          p.rstd[kb * N + n] = rs;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          uint2 w;
+          w.x = pack_bf16(v[j][i].x * rs, v[j][i].y * rs);
+          w.y = pack_bf16(v[j][i].z * rs, v[j][i].w * rs);
+          *reinterpret_cast<uint2*>(d0 + 2 * i * L.pitch) = w;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    // ---- step 2: S = xhat a^T
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int m = tile0_issued ? 1 : 0; m < mtiles; ++m) issue_s_tile(m);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar1, phase, abort_flag, p.status_word, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+    // ---- step 3: softmax over the token axis, one thread per token row (TMEM lane)
+    {
+      const int n = tid, m = tid >> 7;
+      float sc[XT_HP];
+      if (m < mtiles) {
+        uint32_t r[16];
+        tmem_ld16(tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + m * XT_HP, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < XT_HP; ++h) sc[h] = (n < N) ? __uint_as_float(r[h]) * p.scale : -INFINITY;
+      } else {
+#pragma unroll
+        for (int h = 0; h < XT_HP; ++h) sc[h] = -INFINITY;
+      }
+      float* s_max = s_red;                       // [warp][head]
+      float* s_sum = s_red + XT_WARPS * XT_HP;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float mx = warp_max(sc[h]);
+        if (lane == 0) s_max[warp * XT_HP + h] = mx;
+      }
+      __syncthreads();
+      float e[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float mx = s_max[h];
+#pragma unroll
+        for (int w = 1; w < XT_WARPS; ++w) mx = fmaxf(mx, s_max[w * XT_HP + h]);
+        e[h] = __expf(sc[h] - mx);               // rows beyond N: exp(-inf) = 0
+        const float sm = warp_sum(e[h]);
+        if (lane == 0) s_sum[warp * XT_HP + h] = sm;
+      }
+      __syncthreads();
+      float* pr = p.probs + kb * H * N;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float tot = s_sum[h];
+#pragma unroll
+        for (int w = 1; w < XT_WARPS; ++w) tot += s_sum[w * XT_HP + h];
+        const float pv = __fdividef(e[h], tot);
+        if (n < N) pr[h * N + n] = pv;
+        if (n < 4 * 64)                           // P[h][n], K-major: k-chunk n / 64, 16-byte unit (n % 64) / 8
+          *reinterpret_cast<bf16*>(g_p + (n >> 6) * 2048 + h * 128 + ((((n & 63) >> 3) ^ (h & 7)) << 4) + (n & 7) * 2) = __float2bfloat16(pv);
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    // ---- step 4: zhat^T = xhat^T P^T   (A = the xhat tile read MN-major: M = 128 channels = two 64-column chunks)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const int ksteps = L.RA >> 4;
+        for (int j = 0; j < ctiles; ++j) {
+          const uint64_t ad = umma_desc_sw128(base + (2 * j) * L.pitch, L.pitch, 1024);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t bd = umma_desc_sw128(base + L.off_p + (ks >> 2) * 2048, 16, 1024) + 2 * (ks & 3);
+            umma_bf16_ss(tmem + 32 + j * XT_HP, ad + ks * 128, bd, idesc2, ks != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(bar2);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar2, phase, abort_flag, p.status_word, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+    // ---- step 5: one thread per channel; channel tile j is read by the warps whose TMEM lane quadrants cover it
+    for (int j = warp >> 2; j < ctiles; j += XT_WARPS / 4) {
+      const int c = j * 128 + (warp & 3) * 32 + lane;
+      uint32_t r[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 32 + j * XT_HP, r);
+      tmem_ld_wait();
+      const float g = __ldg(p.gamma + (long long)k * C + c), be = __ldg(p.beta + (long long)k * C + c);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float zh = __uint_as_float(r[h]);
+        p.zhat[(kb * H + h) * C + c] = zh;
+        p.z[(kb * H + h) * C + c] = __float2bfloat16(fmaf(g, zh, be));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();          // TMEM and the tiles are rewritten by the next item
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// -1 = not decided yet (environment CAVIT_XFOLD_TC, default on); 0 / 1 set by cavit_xfold_tensor_cores()
+static std::atomic<int> g_xfold_tc{-1};
+static bool xfold_tc_enabled() {
+  int v = g_xfold_tc.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("CAVIT_XFOLD_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+    g_xfold_tc.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+static bool xfold_tc_fwd_ok(const XfoldParams& p) {
+  if (!xfold_tc_enabled() || p.z_lo || p.N > 256 || (p.C % 128) || p.C > 512 || p.H > XT_HP) return false;
+  return xt_layout(p.N, p.C).bytes <= 227 * 1024;
+}
+template <int H, int NV>
+static int xfold_tc_fwd_launch_nv(const XfoldParams& p, cudaStream_t st) {
+  const XtLayout L = xt_layout(p.N, p.C);
+  static PerDeviceMax cur;
+  if (L.bytes > cur.get()) {
+    if (cudaFuncSetAttribute(xfold_tc_fwd_kernel<H, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes) != cudaSuccess)
+      return fail(CAVIT_E_LAUNCH, "xfold tc fwd smem attribute");
+    cur.set(L.bytes);
+  }
+  const int items = p.K * p.B;
+  xfold_tc_fwd_kernel<H, NV><<<items < sm_count() ? items : sm_count(), XT_THREADS, L.bytes, st>>>(p, L);
+  count_launch();
+  return check_launch("cavit_xfold_fwd");
+}
+template <int H>
+static int xfold_tc_fwd_launch(const XfoldParams& p, cudaStream_t st) {
+  static_assert(H % 2 == 0 && H <= 8, "C = 64 H must be a multiple of 128 and at most 512");
+  return xfold_tc_fwd_launch_nv<H, H / 2>(p, st);
+}
+
 static int xfold_dispatch(bool bwd, const XfoldParams& p, cudaStream_t st) {
+  if (!bwd && xfold_tc_fwd_ok(p)) {
+    switch (p.H) {     // C = 64 H and C % 128 == 0: even head counts
+      case 2: return xfold_tc_fwd_launch<2>(p, st);
+      case 4: return xfold_tc_fwd_launch<4>(p, st);
+      case 6: return xfold_tc_fwd_launch<6>(p, st);
+      case 8: return xfold_tc_fwd_launch<8>(p, st);
+      default: break;
+    }
+  }
   switch (p.H) {
     case 1: return xfold_launch<1>(bwd, p, st);
     case 2: return xfold_launch<2>(bwd, p, st);
@@ -627,6 +939,8 @@ static int xfold_fill(XfoldParams& p, const float* x, const float* cls, const fl
   p.drop.seed = reinterpret_cast<const unsigned long long*>(seed_dev);
   p.drop.site = site; p.drop.thresh = 0; p.drop.inv_keep = 1.f;
   p.use_drop = 0;
+  p.status_word = status_word();
+  if (!p.status_word) return fail(CAVIT_E_DEVICE, "cavit_xfold: no device status word");
   p.disjoint = 1;
   for (int i = 0; i < K; ++i)
     for (int j = 0; j < i; ++j)
@@ -635,6 +949,12 @@ static int xfold_fill(XfoldParams& p, const float* x, const float* cls, const fl
   // callers use the unfolded path (cavit_xattn_*) when dropout is active.
   if (p_drop > 0.f) return fail(CAVIT_E_UNSUPPORTED_SHAPE, "cavit_xfold: attention dropout needs the unfolded path");
   return CAVIT_OK;
+}
+
+int cavit_xfold_tensor_cores(int on) {
+  const int prev = xfold_tc_enabled() ? 1 : 0;
+  if (on >= 0) g_xfold_tc.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev;
 }
 
 int64_t cavit_xfold_scratch_floats(int32_t K, int32_t B, int32_t N, int32_t H) {

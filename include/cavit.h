@@ -197,6 +197,12 @@ int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const fl
  * to one and the fold is not exact (CAVIT_E_UNSUPPORTED_SHAPE; use cavit_xattn_* then).
  * ------------------------------------------------------------------------------------------- */
 int64_t cavit_xfold_scratch_floats(int32_t K, int32_t B, int32_t N, int32_t H);
+/* Variant of the folded forward in bf16 mode (z_lo == NULL): 1 (default, or environment CAVIT_XFOLD_TC=0 to start with 0) =
+ * both contractions on tcgen05 from one bf16 xhat tile in shared memory when N <= 256, C % 128 == 0, C <= 512 and the tile
+ * fits (xhat in bf16 is what the reference-equivalent unfolded route feeds its K / V GEMMs; fp32 accumulation); 0 = the
+ * all-fp32 CUDA-core kernel (always used in the fp32 mode and for other shapes). on < 0 only queries. Returns the previous
+ * setting; process-wide. */
+int cavit_xfold_tensor_cores(int on);
 int cavit_xfold_fwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* beta,
                     float* zhat, void* z, void* z_lo /* nullable: second bf16 plane of z, fp32-tolerance mode (ABI 2) */,
                     float* probs, float* mean, float* rstd, float* scratch, int32_t K,

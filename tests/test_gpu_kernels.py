@@ -486,7 +486,21 @@ def _xfold_reference(X, cls_src, tok_src, lnw, lnb, Wq, bq, Wk, bk, Wv, bv, H, d
     (2, 3, 9, 1, [0], [1], 0.0), (3, 2, 37, 2, [0, 1], [1, 2], 0.0), (4, 5, 197, 6, [0, 1, 2, 3], [1, 2, 3, 0], 0.0),
     (2, 2, 65, 3, [0, 1], [1, 1], 0.0),      # two fusions reading the SAME token stream (atomic scatter)
     (2, 2, 130, 12, [1], [0], 0.0), (2, 1, 40, 16, [0], [1], 0.0)])
-def test_folded_cross_attention_fwd_bwd(M, B, N, H, cls_src, tok_src, p_drop):
+@pytest.mark.parametrize("tensor_cores", [0, 1])
+def test_folded_cross_attention_fwd_bwd(M, B, N, H, cls_src, tok_src, p_drop, tensor_cores):
+    """tensor_cores = 0: the all-fp32 CUDA-core forward (fp32-level agreement with the fp64 unfolded restatement);
+    1: the tcgen05 forward where the shape qualifies (H in {2, 6} here: C % 128 == 0) — xhat and the probabilities enter the
+    two contractions as bf16, so the agreement is bf16-level; the backward (fp32 kernel either way) then runs on that forward's
+    saved probabilities / statistics."""
+    from cavit import ops
+    prev = ops.xfold_tensor_cores(tensor_cores)
+    try:
+        _folded_cross_attention_case(M, B, N, H, cls_src, tok_src, p_drop, tensor_cores and (H * 64) % 128 == 0 and H <= 8)
+    finally:
+        ops.xfold_tensor_cores(prev)
+
+
+def _folded_cross_attention_case(M, B, N, H, cls_src, tok_src, p_drop, tc):
     from cavit import ops
     torch.manual_seed(21)
     C, Kf = H * 64, len(cls_src)
@@ -517,7 +531,7 @@ def test_folded_cross_attention_fwd_bwd(M, B, N, H, cls_src, tok_src, p_drop):
         dm = (mk.view(Kf, B, H, 1, N).double() / (1.0 - p_drop))
     leaves = [t.double().requires_grad_(True) for t in (X, lnw, lnb, Wq, bq, Wk, bk, Wv, bv)]
     ref = _xfold_reference(leaves[0], cls_src, tok_src, *leaves[1:], H, dm=dm)
-    assert rel(o, ref) < 2e-5
+    assert rel(o, ref) < (6e-3 if tc else 2e-5)
     assert rel(z.float(), lnw[:, None, None] * zhat + lnb[:, None, None]) < 5e-3
     # ---- backward: upstream gradient do [K][B][C]
     do = torch.randn(Kf, B, C, **f32)
@@ -539,14 +553,15 @@ def test_folded_cross_attention_fwd_bwd(M, B, N, H, cls_src, tok_src, p_drop):
     got = dX.double().clone()
     for k in range(Kf):
         got[cls_src[k]][:, 0] += cls_leaf.grad[k]
-    assert rel(got, want_dX) < 1e-4
-    assert rel(dgam.double() + lw.grad, leaves[1].grad) < 1e-4
-    assert rel(dbet.double() + lb.grad, leaves[2].grad) < 1e-4
-    assert rel(torch.einsum("kbd,kbc->kdc", dq, xn0_leaf), leaves[3].grad) < 1e-4            # dWq
-    assert rel(torch.einsum("kbhd,kbhc->khdc", q.view(Kf, B, H, 64), dqp).reshape(Kf, C, C), leaves[5].grad) < 1e-4  # dWk
+    gtol = 1.5e-2 if tc else 1e-4     # tensor-core forward: backward inherits the bf16-level probabilities / zhat
+    assert rel(got, want_dX) < gtol
+    assert rel(dgam.double() + lw.grad, leaves[1].grad) < gtol
+    assert rel(dbet.double() + lb.grad, leaves[2].grad) < gtol
+    assert rel(torch.einsum("kbd,kbc->kdc", dq, xn0_leaf), leaves[3].grad) < gtol            # dWq
+    assert rel(torch.einsum("kbhd,kbhc->khdc", q.view(Kf, B, H, 64), dqp).reshape(Kf, C, C), leaves[5].grad) < gtol  # dWk
     assert float(leaves[6].grad.abs().max()) < 1e-9                                           # dbk == 0 analytically
     zz = lnw[:, None, None] * zhat + lnb[:, None, None]
-    assert rel(torch.einsum("kbhd,kbhc->khdc", do.view(Kf, B, H, 64), zz).reshape(Kf, C, C), leaves[7].grad) < 1e-4  # dWv
+    assert rel(torch.einsum("kbhd,kbhc->khdc", do.view(Kf, B, H, 64), zz).reshape(Kf, C, C), leaves[7].grad) < gtol  # dWv
     assert rel(do.sum(1), leaves[8].grad) < 1e-5                                              # dbv
 
 
