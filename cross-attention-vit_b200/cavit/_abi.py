@@ -73,7 +73,7 @@ _SIGS = {
     "cavit_xfold_fwd": (c_i32, [c_vp] * 12 + [c_i32] * 5 + [C.POINTER(c_i32), C.POINTER(c_i32), c_f32, c_f32, c_f32, c_vp,
                                 C.c_uint32, c_vp]),
     "cavit_xfold_bwd": (c_i32, [c_vp] * 14 + [c_i32] * 5 + [C.POINTER(c_i32), C.POINTER(c_i32), c_f32, c_f32, c_vp,
-                                C.c_uint32, c_vp]),
+                                C.c_uint32, c_i32, c_vp]),
     "cavit_expand_heads": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cavit_fold_heads": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cavit_dropout": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, C.c_uint32, c_vp]),

@@ -306,7 +306,7 @@ def _fusion_bwd(eng, mb: int, dX):
                         dst_gs=0)     # dbk = 0
     ops.xfold_bwd(eng._x_for_fusion(mb), a["f_cls"][s], a["f_qp"][s], w(f"{tag}.lnA.w"), a["f_zhat"][s], a["f_probs"][s],
                   a["f_mean"][s], a["f_rstd"][s], a["d_gz"], a["xf_scratch"], dX, a["d_qp"], a["d_lnA"][0], a["d_lnA"][1], K=K,
-                  B=B, N=N, C_=C, H=H, cls_src=eng.cls_src, tok_src=eng.tok_src, scale=eng.scale)
+                  B=B, N=N, C_=C, H=H, cls_src=eng.cls_src, tok_src=eng.tok_src, scale=eng.scale, exact_fp32=True)
     # key side: dq_h = Wk_h dq'_h, dWk (expanded) = q^T dq'
     ops.cast_split(a["d_qp"], a["d_qpb"])
     ops.gemm(a["d_qpb"], Ekv, a["d_q32"], M=B, N=C, K=HC, groups=K, lda=HC, ldb=HC, ldo=C, a_gs=B * HC, b_gs=2 * C * HC,

@@ -253,12 +253,14 @@ def xfold_fwd(x, cls, qp, gamma, beta, zhat, z, probs, mean, rstd, scratch, *, K
 
 
 def xfold_bwd(x, cls, qp, gamma, zhat, probs, mean, rstd, gz, scratch, dx, dqp, dgamma, dbeta, *, K, B, N, C_, H,
-              cls_src, tok_src, scale, p_drop=0.0, seed=None, site=0):
+              cls_src, tok_src, scale, p_drop=0.0, seed=None, site=0, exact_fp32=False):
+    """Folded single-query cross attention, backward (include/cavit.h: cavit_xfold_bwd). exact_fp32: keep the all-fp32
+    CUDA-core kernel (the fp32-tolerance mode) instead of the tcgen05 variant."""
     check(lib().cavit_xfold_bwd(x.data_ptr(), cls.data_ptr(), qp.data_ptr(), gamma.data_ptr(), zhat.data_ptr(),
                                 probs.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gz.data_ptr(), scratch.data_ptr(),
                                 dx.data_ptr(), dqp.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), K, B, N,
-                                C_, H, _i32arr(cls_src), _i32arr(tok_src), scale, p_drop, _p(seed), site, _stream()),
-          "cavit_xfold_bwd")
+                                C_, H, _i32arr(cls_src), _i32arr(tok_src), scale, p_drop, _p(seed), site, int(bool(exact_fp32)),
+                                _stream()), "cavit_xfold_bwd")
 
 
 def expand_heads(W, E, *, groups, C_, H):

@@ -281,6 +281,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same with an explicit layout type: 2 / 4 / 6 = SWIZZLE_128B / 64B / 32B (rows of 128 / 64 / 32 bytes; SBO = 8 rows).
+__device__ __forceinline__ uint64_t umma_desc_layout(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D, M = 128.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int a_mn, int b_mn, int m = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |

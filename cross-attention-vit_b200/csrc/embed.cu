@@ -80,17 +80,6 @@ __device__ __forceinline__ void piece_coords(const EmbedParams& p, int q, int hi
   z = di * p.dp + a;
 }
 
-// Shared-memory matrix descriptor with an explicit layout type (common.cuh: umma_desc_sw128 is layout 2).
-__device__ __forceinline__ uint64_t umma_desc_layout(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(layout) << 61;
-  return d;
-}
-
 template <int BN>
 struct EmbedCfg {
   static constexpr int B_BYTES = BN * 128;

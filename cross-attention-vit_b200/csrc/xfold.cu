@@ -58,6 +58,7 @@ struct XfoldParams {
   int use_drop;
   int disjoint;   // every token stream is read by at most one fusion: plain read-modify-write instead of atomics
   int* status_word;   // device status word (bounded mbarrier waits of the tcgen05 variant)
+  int precise;        // backward: keep the all-fp32 CUDA-core kernel (fp32-tolerance mode)
 };
 
 __device__ __forceinline__ const float* xf_row(const XfoldParams& p, int k, int b, int n) {
@@ -842,6 +843,340 @@ xfold_tc_fwd_kernel(const XfoldParams p, const XtLayout L) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward on tcgen05
+// The exact adjoint with its three contractions on the tensor cores, same xhat tile (bf16 mode, same shape conditions, C <= 384
+// for the TMEM budget). Per (fusion, sample), with B1 = [a_h ; w_h] (bf16, [32][C]; a_h = q'_h o gamma, w_h = gz_h o gamma):
+//   1. stream the token rows once, xhat = (x - mu) rstd with the SAVED statistics -> bf16 tile [n][c];
+//   2. [sa | dp][n][32] = xhat B1^T                      (A = tile K-major)            sa_hn = a_h . xhat_n, dp_hn = w_h . xhat_n
+//   3. one thread per token row: D_h = sum_n p_hn dp_hn (block reduction), ds_hn = p_hn (dp_hn - D_h),
+//      c1_n = mean_c(dxhat_n), c2_n = mean_c(dxhat_n o xhat_n) in closed form; Q[n][32] = [scale ds | p] as bf16, 64-byte rows;
+//   4. da^T[c][16] = sum_n xhat[n][c] Q[n][0..15]        (A = tile MN-major, B = Q MN-major)     da_h = scale sum_n ds_hn xhat_n
+//      dxhat^T[c][n] = sum_j B1[j][c] Q[n][j]            (A = B1 MN-major, B = Q K-major), 128 channels at a time, two TMEM buffers
+//   5. one thread per channel (so a warp covers 128 contiguous bytes of a token row): dx_n = rstd_n (dxhat_n - c1_n - xhat_n c2_n)
+//      added to the stream gradient (read-modify-write); dq'_h = da_h o gamma; dgamma, dbeta by atomics.
+constexpr int XB_COLS = 32;
+constexpr int XB_D3_STRIDE = 224;     // TMEM columns per dxhat^T buffer: token rows (RA <= 224)
+
+struct XbLayout {
+  int RA, pitch, chunks, off_b1, off_q, off_row, off_sums, off_red, off_bar, bytes;
+};
+static XbLayout xb_layout(int N, int C) {
+  XbLayout L;
+  L.RA = (N + 15) & ~15;
+  L.pitch = L.RA * 128;
+  L.chunks = C / 64;
+  L.off_b1 = L.chunks * L.pitch;                  // [chunks][32 rows][128 B]
+  L.off_q = L.off_b1 + L.chunks * 4096;           // [256 rows][64 B]
+  L.off_row = L.off_q + 256 * 64;                 // per token row: c1 | c2 | rstd | -  (float4)
+  L.off_sums = L.off_row + 256 * 16;              // A_h[16] | W_h[16]
+  L.off_red = L.off_sums + 256;                   // [warp][16]
+  L.off_bar = L.off_red + XT_WARPS * 16 * 4;
+  L.bytes = L.off_bar + 64 + 1024;
+  return L;
+}
+
+template <int H, int NV>
+__global__ void __launch_bounds__(XT_THREADS, 1)
+xfold_tc_bwd_kernel(const XfoldParams p, const XbLayout L) {
+  extern __shared__ uint8_t xt_raw[];
+  const uint32_t base = (smem_u32(xt_raw) + 1023u) & ~1023u;
+  uint8_t* gen = xt_raw + (base - smem_u32(xt_raw));
+  uint8_t* g_b1 = gen + L.off_b1;
+  uint8_t* g_q = gen + L.off_q;
+  float* s_c1 = reinterpret_cast<float*>(gen + L.off_row);     // float4 per token row
+  float* s_sums = reinterpret_cast<float*>(gen + L.off_sums);
+  float* s_red = reinterpret_cast<float*>(gen + L.off_red);
+  const uint32_t bar1 = base + L.off_bar, bar2 = bar1 + 8, bar3 = bar1 + 16;   // bar3, bar3 + 8: the two dxhat buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + L.off_bar + 32);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int C = 128 * NV;
+  const int N = p.N, mtiles = (N + 127) >> 7;
+
+  if (tid == 0) {
+    *abort_flag = 0;
+    mbar_init(bar1, 1);
+    mbar_init(bar2, 1);
+    mbar_init(bar3, 1);
+    mbar_init(bar3 + 8, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < (L.off_row - L.off_b1) / 16; i += XT_THREADS) reinterpret_cast<uint4*>(g_b1)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // TMEM: [sa | dp] tiles in [0, 64), reused by the da tiles once step 3 has read them; dxhat^T buffers at 64 and 64 + 224
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tD2 = tmem, tD3 = tmem + 64;
+  const uint32_t idesc1 = umma_idesc_bf16(XB_COLS, 0, 0, 128), idesc2 = umma_idesc_bf16(16, 1, 1, 128);
+  const uint32_t idesc3 = umma_idesc_bf16(L.RA, 1, 0, 128);
+  const float inv_c = 1.0f / (float)C;
+  const int items = p.K * p.B;
+  uint32_t phase = 0, ph3 = 0;
+
+  for (int item = blockIdx.x; item < items; item += gridDim.x, phase ^= 1u) {
+    const int k = item / p.B, b = item - k * p.B;
+    const long long kb = item;
+    const float* xs = p.x + ((long long)p.tok_src[k] * p.B * N + (long long)b * N) * C;
+    const float* x0 = p.cls + kb * C;
+    float* dxs = p.dx + ((long long)p.tok_src[k] * p.B * N + (long long)b * N) * C;
+    float* dx0 = p.dx + ((long long)p.cls_src[k] * p.B * N + (long long)b * N) * C;
+    const float* qp = p.qp + kb * H * C;
+    const float* gz = p.gz + kb * H * C;
+    const float* gamma = p.gamma + (long long)k * C;
+    if (tid < 32) s_sums[tid] = 0.f;
+    __syncthreads();
+    // ---- B1 = [a ; w] as bf16 (rows h and 16 + h), and A_h = sum_c a_h[c], W_h = sum_c w_h[c] of the rounded values
+    for (int i = tid; i < 2 * H * (C >> 3); i += XT_THREADS) {
+      const int which = i / (H * (C >> 3)), r = i - which * (H * (C >> 3));
+      const int h = r / (C >> 3), c8 = r - h * (C >> 3);
+      const float* src = (which ? gz : qp) + h * C + c8 * 8;
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8) + 1);
+      uint4 w;
+      w.x = pack_bf16(q0.x * g0.x, q0.y * g0.y); w.y = pack_bf16(q0.z * g0.z, q0.w * g0.w);
+      w.z = pack_bf16(q1.x * g1.x, q1.y * g1.y); w.w = pack_bf16(q1.z * g1.z, q1.w * g1.w);
+      const int j = which * 16 + h;
+      *reinterpret_cast<uint4*>(g_b1 + (c8 >> 3) * 4096 + j * 128 + (((c8 & 7) ^ (j & 7)) << 4)) = w;
+      const float2 a0 = unpack_bf16_fast(w.x), a1 = unpack_bf16_fast(w.y), a2 = unpack_bf16_fast(w.z), a3 = unpack_bf16_fast(w.w);
+      atomicAdd(s_sums + j, ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y)));
+    }
+    // ---- step 1: token rows -> xhat (bf16) tile with the saved statistics
+    for (int r0 = warp; r0 < L.RA; r0 += 4 * XT_WARPS) {
+      float4 v[4][NV];
+      float mu[4], rs[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = r0 + XT_WARPS * j;
+        if (n < N) {
+          const float4* row = reinterpret_cast<const float4*>(n == 0 ? x0 : xs + (long long)n * C) + lane;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[j][i] = __ldg(row + 32 * i);
+          mu[j] = __ldg(p.mean + kb * N + n);
+          rs[j] = __ldg(p.rstd + kb * N + n);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = r0 + XT_WARPS * j;
+        if (n >= L.RA) continue;                 // warp-uniform
+        const uint32_t sw = static_cast<uint32_t>(n & 7);
+        uint8_t* d0 = gen + n * 128 + (lane >> 4) * L.pitch + (((static_cast<uint32_t>(lane & 15) >> 1) ^ sw) << 4) + (lane & 1) * 8;
+        if (n >= N) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) *reinterpret_cast<uint2*>(d0 + 2 * i * L.pitch) = make_uint2(0u, 0u);
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          uint2 w;
+          w.x = pack_bf16((v[j][i].x - mu[j]) * rs[j], (v[j][i].y - mu[j]) * rs[j]);
+          w.y = pack_bf16((v[j][i].z - mu[j]) * rs[j], (v[j][i].w - mu[j]) * rs[j]);
+          *reinterpret_cast<uint2*>(d0 + 2 * i * L.pitch) = w;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    // ---- step 2: [sa | dp] = xhat B1^T
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int m = 0; m < mtiles; ++m)
+          for (int cc = 0; cc < L.chunks; ++cc) {
+            const uint64_t ad = umma_desc_sw128(base + cc * L.pitch + m * 16384, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(base + L.off_b1 + cc * 4096, 16, 1024);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem + m * XB_COLS, ad + 2 * kk, bd + 2 * kk, idesc1, (cc | kk) != 0 ? 1u : 0u);
+          }
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar1, phase, abort_flag, p.status_word, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+    // ---- step 3: softmax backward and the per-row coefficients, one thread per token row
+    {
+      const int n = tid, m = tid >> 7;
+      float sa[H], dp[H], pe[H];
+      if (m < mtiles) {
+        uint32_t r[32];
+        tmem_ld32(tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + m * XB_COLS, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          sa[h] = __uint_as_float(r[h]);
+          dp[h] = __uint_as_float(r[16 + h]);
+          pe[h] = (n < N) ? __ldg(p.probs + (kb * H + h) * N + n) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) sa[h] = dp[h] = pe[h] = 0.f;
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float part = warp_sum(pe[h] * dp[h]);
+        if (lane == 0) s_red[warp * 16 + h] = part;
+      }
+      __syncthreads();
+      if (tid < 256) {
+        float c1 = 0.f, c2 = 0.f;
+        float sds[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float D = s_red[h];
+#pragma unroll
+          for (int w = 1; w < XT_WARPS; ++w) D += s_red[w * 16 + h];
+          sds[h] = p.scale * pe[h] * (dp[h] - D);
+          c1 += sds[h] * s_sums[h] + pe[h] * s_sums[16 + h];
+          c2 += sds[h] * sa[h] + pe[h] * dp[h];
+        }
+        *reinterpret_cast<float4*>(s_c1 + 4 * n) = make_float4(c1 * inv_c, c2 * inv_c, (n < N) ? __ldg(p.rstd + kb * N + n) : 0.f, 0.f);
+        // Q[n][0..15] = scale ds, Q[n][16..31] = p: 64-byte rows, SWIZZLE_64B (16-byte unit u of row n at u ^ ((n >> 1) & 3))
+        float qv[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          qv[j] = j < H ? sds[j < H ? j : 0] : 0.f;
+          qv[16 + j] = j < H ? pe[j < H ? j : 0] : 0.f;
+        }
+        const uint32_t sw = static_cast<uint32_t>((n >> 1) & 3);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16(qv[8 * u], qv[8 * u + 1]); w.y = pack_bf16(qv[8 * u + 2], qv[8 * u + 3]);
+          w.z = pack_bf16(qv[8 * u + 4], qv[8 * u + 5]); w.w = pack_bf16(qv[8 * u + 6], qv[8 * u + 7]);
+          *reinterpret_cast<uint4*>(g_q + n * 64 + ((static_cast<uint32_t>(u) ^ sw) << 4)) = w;
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    // ---- step 4: da^T[c][16] = xhat^T Q[:, 0..15]  and  dxhat^T[c][n] = B1^T Q^T, 128 channels at a time, two TMEM buffers
+    auto issue_dxhat = [&](int j) {     // channel tile j -> buffer j & 1
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint64_t ad = umma_desc_sw128(base + L.off_b1 + (2 * j) * 4096, 4096, 1024) + kk * 128;   // B1 read MN-major, K = 32 rows
+        const uint64_t bd = umma_desc_layout(base + L.off_q, 16, 512, 4) + 2 * kk;                       // Q read K-major, N = RA rows
+        umma_bf16_ss(tD3 + (j & 1) * XB_D3_STRIDE, ad, bd, idesc3, kk != 0 ? 1u : 0u);
+      }
+      umma_commit(bar3 + 8u * (j & 1));
+    };
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const int ksteps = L.RA >> 4;
+        for (int j = 0; j < NV; ++j) {
+          const uint64_t ad = umma_desc_sw128(base + (2 * j) * L.pitch, L.pitch, 1024);
+          const uint64_t bd = umma_desc_layout(base + L.off_q, 16, 512, 4);
+          for (int ks = 0; ks < ksteps; ++ks) umma_bf16_ss(tD2 + j * 16, ad + ks * 128, bd + ks * 64, idesc2, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(bar2);
+        issue_dxhat(0);
+        if (NV > 1) issue_dxhat(1);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar2, phase, abort_flag, p.status_word, ERR_TIMEOUT_ATTN);
+    tc_fence_after();
+    // ---- step 5a: dq' = da o gamma, dgamma, dbeta; one thread per channel
+    {
+      const int j = warp >> 2;
+      if (j < NV) {
+        const int c = j * 128 + (warp & 3) * 32 + lane;
+        uint32_t r[16];
+        tmem_ld16(tD2 + (static_cast<uint32_t>((warp & 3) * 32) << 16) + j * 16, r);
+        tmem_ld_wait();
+        const float g = __ldg(gamma + c);
+        float dg = 0.f, db = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float da = __uint_as_float(r[h]);
+          p.dqp[(kb * H + h) * C + c] = da * g;
+          const float gzh = __ldg(gz + h * C + c);
+          dg += da * __ldg(qp + h * C + c) + gzh * __ldg(p.zhat + (kb * H + h) * C + c);
+          db += gzh;
+        }
+        atomicAdd(p.dgamma + (long long)k * C + c, dg);
+        atomicAdd(p.dbeta + (long long)k * C + c, db);
+      }
+    }
+    // ---- step 5b: dx, one thread per channel (a warp instruction covers 128 contiguous bytes of a token row); the four
+    // warps of a TMEM lane quadrant take every fourth group of 16 token rows
+    for (int j = 0; j < NV; ++j) {
+      mbar_wait(bar3 + 8u * (j & 1), (ph3 >> (j & 1)) & 1u, abort_flag, p.status_word, ERR_TIMEOUT_ATTN);
+      ph3 ^= 1u << (j & 1);
+      tc_fence_after();
+      const int c = j * 128 + (warp & 3) * 32 + lane;
+      const uint8_t* xcol = gen + (c >> 6) * L.pitch + (c & 7) * 2;
+      const uint32_t cu = static_cast<uint32_t>(c & 63) >> 3;
+      uint32_t xo[8];                              // byte offset of this channel's 16-byte unit in a row with n % 8 == k
+#pragma unroll
+      for (int kx = 0; kx < 8; ++kx) xo[kx] = (cu ^ static_cast<uint32_t>(kx)) << 4;
+      for (int u = warp >> 2; u < (L.RA >> 4); u += XT_WARPS / 4) {
+        uint32_t r[16];
+        tmem_ld16(tD3 + (j & 1) * XB_D3_STRIDE + (static_cast<uint32_t>((warp & 3) * 32) << 16) + u * 16, r);
+        const int n0 = u * 16;
+        const uint8_t* xb = xcol + n0 * 128;
+        const float4* rcb = reinterpret_cast<const float4*>(s_c1) + n0;
+        if (p.disjoint && n0 > 0 && n0 + 16 <= N) {
+          // sixteen whole token rows of the donor stream: constant row offsets, no predicates (warp-uniform branch)
+          float* d = dxs + (long long)n0 * C + c;
+          float old[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) old[e] = d[e * C];
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float4 rc = rcb[e];               // c1 | c2 | rstd | -
+            const float xh = __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(xb + e * 128 + xo[e & 7])) << 16);
+            d[e * C] = old[e] + rc.z * (__uint_as_float(r[e]) - rc.x - xh * rc.y);
+          }
+        } else {
+          float old[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int n = n0 + e;
+            if (p.disjoint && n < N) old[e] = (n == 0 ? dx0 : dxs + (long long)n * C)[c];
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int n = n0 + e;
+            if (n < N) {
+              const float4 rc = rcb[e];
+              const float xh = __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(xb + e * 128 + xo[e & 7])) << 16);
+              const float o = rc.z * (__uint_as_float(r[e]) - rc.x - xh * rc.y);
+              float* d = (n == 0 ? dx0 : dxs + (long long)n * C) + c;
+              if (p.disjoint) *d = old[e] + o;
+              else atomicAdd(d, o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();                           // this dxhat buffer is free again
+      if (j + 2 < NV && warp == 0) {
+        tc_fence_after();
+        if (elect_one()) issue_dxhat(j + 2);
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+    __syncthreads();          // TMEM and the tiles are rewritten by the next item
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // -1 = not decided yet (environment CAVIT_XFOLD_TC, default on); 0 / 1 set by cavit_xfold_tensor_cores()
 static std::atomic<int> g_xfold_tc{-1};
 static bool xfold_tc_enabled() {
@@ -857,6 +1192,28 @@ static bool xfold_tc_fwd_ok(const XfoldParams& p) {
   if (!xfold_tc_enabled() || p.z_lo || p.N > 256 || (p.C % 128) || p.C > 512 || p.H > XT_HP) return false;
   return xt_layout(p.N, p.C).bytes <= 227 * 1024;
 }
+static bool xfold_tc_bwd_ok(const XfoldParams& p) {
+  // the forward must have been the tensor-core one too? No: both variants save the same probabilities / statistics.
+  if (!xfold_tc_enabled() || p.use_drop || p.N > XB_D3_STRIDE || (p.C % 128) || p.C > 384 || p.H > 16) return false;
+  return xb_layout(p.N, p.C).bytes <= 227 * 1024;
+}
+template <int H>
+static int xfold_tc_bwd_launch(const XfoldParams& p, cudaStream_t st) {
+  static_assert(H % 2 == 0 && H <= 6, "C = 64 H must be a multiple of 128 and at most 384");
+  constexpr int NV = H / 2;
+  const XbLayout L = xb_layout(p.N, p.C);
+  static PerDeviceMax cur;
+  if (L.bytes > cur.get()) {
+    if (cudaFuncSetAttribute(xfold_tc_bwd_kernel<H, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes) != cudaSuccess)
+      return fail(CAVIT_E_LAUNCH, "xfold tc bwd smem attribute");
+    cur.set(L.bytes);
+  }
+  const int items = p.K * p.B;
+  xfold_tc_bwd_kernel<H, NV><<<items < sm_count() ? items : sm_count(), XT_THREADS, L.bytes, st>>>(p, L);
+  count_launch();
+  return check_launch("cavit_xfold_bwd");
+}
+
 template <int H, int NV>
 static int xfold_tc_fwd_launch_nv(const XfoldParams& p, cudaStream_t st) {
   const XtLayout L = xt_layout(p.N, p.C);
@@ -884,6 +1241,14 @@ static int xfold_dispatch(bool bwd, const XfoldParams& p, cudaStream_t st) {
       case 4: return xfold_tc_fwd_launch<4>(p, st);
       case 6: return xfold_tc_fwd_launch<6>(p, st);
       case 8: return xfold_tc_fwd_launch<8>(p, st);
+      default: break;
+    }
+  }
+  if (bwd && p.precise == 0 && xfold_tc_bwd_ok(p)) {
+    switch (p.H) {
+      case 2: return xfold_tc_bwd_launch<2>(p, st);
+      case 4: return xfold_tc_bwd_launch<4>(p, st);
+      case 6: return xfold_tc_bwd_launch<6>(p, st);
       default: break;
     }
   }
@@ -979,7 +1344,7 @@ int cavit_xfold_bwd(const float* x, const float* cls, const float* qp, const flo
                     const float* probs, const float* mean, const float* rstd, const float* gz, float* scratch, float* dx,
                     float* dqp, float* dgamma, float* dbeta, int32_t K, int32_t B, int32_t N, int32_t C, int32_t H,
                     const int32_t* cls_src, const int32_t* tok_src, float scale, float p_drop, const uint64_t* seed_dev,
-                    uint32_t site, void* stream) {
+                    uint32_t site, int32_t exact_fp32, void* stream) {
   if (!x || !cls || !qp || !gamma || !zhat || !probs || !mean || !rstd || !gz || !scratch || !dx || !dqp || !dgamma ||
       !dbeta || !cls_src || !tok_src)
     return fail(CAVIT_E_BADARG, "cavit_xfold_bwd: null pointer");
@@ -989,6 +1354,7 @@ int cavit_xfold_bwd(const float* x, const float* cls, const float* qp, const flo
   p.zhat = const_cast<float*>(zhat); p.probs = const_cast<float*>(probs);
   p.mean = const_cast<float*>(mean); p.rstd = const_cast<float*>(rstd);
   p.gz = gz; p.scratch = scratch; p.dx = dx; p.dqp = dqp; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.precise = exact_fp32;
   return xfold_dispatch(true, p, as_stream(stream));
 }
 

@@ -197,11 +197,11 @@ int cavit_xattn_bwd(const float* q, const void* kv, const float* probs, const fl
  * to one and the fold is not exact (CAVIT_E_UNSUPPORTED_SHAPE; use cavit_xattn_* then).
  * ------------------------------------------------------------------------------------------- */
 int64_t cavit_xfold_scratch_floats(int32_t K, int32_t B, int32_t N, int32_t H);
-/* Variant of the folded forward in bf16 mode (z_lo == NULL): 1 (default, or environment CAVIT_XFOLD_TC=0 to start with 0) =
- * both contractions on tcgen05 from one bf16 xhat tile in shared memory when N <= 256, C % 128 == 0, C <= 512 and the tile
- * fits (xhat in bf16 is what the reference-equivalent unfolded route feeds its K / V GEMMs; fp32 accumulation); 0 = the
- * all-fp32 CUDA-core kernel (always used in the fp32 mode and for other shapes). on < 0 only queries. Returns the previous
- * setting; process-wide. */
+/* Variant of the folded kernels in bf16 mode (forward: z_lo == NULL; backward: exact_fp32 == 0): 1 (default, or environment
+ * CAVIT_XFOLD_TC=0 to start with 0) = the contractions run on tcgen05 from one bf16 xhat tile in shared memory when N <= 256,
+ * C % 128 == 0, C <= 512 (backward: 384) and the tile fits (xhat in bf16 is what the reference-equivalent unfolded route feeds
+ * its K / V GEMMs; fp32 accumulation); 0 = the all-fp32 CUDA-core kernels (always used in the fp32 mode and for other shapes).
+ * on < 0 only queries. Returns the previous setting; process-wide. */
 int cavit_xfold_tensor_cores(int on);
 int cavit_xfold_fwd(const float* x, const float* cls, const float* qp, const float* gamma, const float* beta,
                     float* zhat, void* z, void* z_lo /* nullable: second bf16 plane of z, fp32-tolerance mode (ABI 2) */,
@@ -212,7 +212,7 @@ int cavit_xfold_bwd(const float* x, const float* cls, const float* qp, const flo
                     const float* probs, const float* mean, const float* rstd, const float* gz, float* scratch,
                     float* dx, float* dqp, float* dgamma, float* dbeta, int32_t K, int32_t B,
                     int32_t N, int32_t C, int32_t H, const int32_t* cls_src, const int32_t* tok_src, float scale,
-                    float p_drop, const uint64_t* seed_dev, uint32_t site, void* stream);
+                    float p_drop, const uint64_t* seed_dev, uint32_t site, int32_t exact_fp32, void* stream);
 /* E[g][c_out][h*C + c_in] = W[g][c_out][c_in] if c_out is a row of head h (c_out / 64 == h) else 0   (bf16)
  * dW[g][c_out][c_in] = dE[g][c_out][(c_out / 64)*C + c_in]                                          (fp32) */
 int cavit_expand_heads(const void* W, void* E, int32_t groups, int32_t C, int32_t H, void* stream);
