@@ -40,8 +40,7 @@ constexpr int SB_OFF_PT = 8 * SB_TILE;                             // P^T  [128 
 constexpr int SB_OFF_DST = 10 * SB_TILE;                           // dS^T
 constexpr int SB_OFF_AUX = 12 * SB_TILE;                           // [2 buffers][lse2 | delta][256] fp32
 constexpr int SB_OFF_BAR = SB_OFF_AUX + 4096;
-constexpr int SB_OFF_STG = SB_OFF_BAR + 256;                        // drain staging: [128 rows][128 B] bf16
-constexpr int SB_SMEM = SB_OFF_STG + SB_TILE + 1024;
+constexpr int SB_SMEM = SB_OFF_BAR + 256 + 1024;
 
 struct AttnBwdShortParams {
   const float* lse;
@@ -339,10 +338,11 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
     // block goes through a shared-memory staging tile so that the global stores are whole 128-byte rows (8 lanes x 16 B):
     // storing each thread's 32-byte slice directly made every warp instruction touch 32 different rows of the packed
     // [T][3C] gradient (2304-byte stride) — 50 % excess sectors under ncu and 2 - 3.7 k cycles per drain in the clock64
-    // timeline, a third of a head's 23 k. The four warps of a TMEM lane quadrant (parts 0 .. 3) own the staging rows of
-    // that quadrant and meet at a named barrier before and after the copy-out.
-    uint8_t* const stg = gen + SB_OFF_STG;
-    auto drain_block = [&](uint32_t taddr, float sc, bf16* out0, int rows_valid) {
+    // timeline, a third of a head's 23 k. Staging tiles: the P^T / dS^T buffers, which are free exactly here (the MMAs
+    // of the previous step have retired — bar_d — and this step's P^T / dS^T are stored after the drain). The four warps of a
+    // TMEM lane quadrant (parts 0 .. 3) own the rows of that quadrant in every tile — staging rows and P^T rows alike — and
+    // meet at a named barrier before and after the copy-out, so no warp overwrites rows another one is still copying.
+    auto stage_block = [&](uint32_t taddr, float sc, uint8_t* stg) {
       uint32_t r[16];
       tmem_ld16(taddr + t_col, r);
       tmem_ld_wait();
@@ -358,7 +358,8 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
       uint8_t* srow = stg + trow * 128;
       *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(2 * part) ^ sw) << 4)) = w0;
       *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(2 * part + 1) ^ sw) << 4)) = w1;
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+    };
+    auto copy_block = [&](const uint8_t* stg, bf16* out0, int rows_valid) {   // this warp: rows quad*32 + part*8 .. + 7
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int rr = quad * 32 + part * 8 + i * 4 + (lane >> 3);
@@ -367,19 +368,31 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_con
           *reinterpret_cast<uint4*>(out0 + (long long)rr * (3 * p.C) + (lane & 7) * 8) = v;
         }
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");   // the staging rows are rewritten by the next block
     };
     auto drain = [&](bf16* hb, int pj, int phf) {
-      if (phf == NH - 1) {  // dK_j (scaled) and dV_j of the key tile
+      const bool kv_done = (phf == NH - 1);   // dK_j (scaled) and dV_j of the key tile
+      const bool q_done = (pj == NKV - 1);    // dQ of this half (accumulated over the key tiles in TMEM)
+      if (!kv_done && !q_done) return;
+      uint8_t* const stg_k = gen + SB_OFF_PT;
+      uint8_t* const stg_v = gen + SB_OFF_PT + SB_TILE;
+      uint8_t* const stg_q = gen + SB_OFF_DST;
+      if (kv_done) {
+        stage_block(tDK, scale, stg_k);
+        stage_block(tDV, 1.0f, stg_v);
+      }
+      if (q_done) stage_block(tDQ + phf * 64, scale, stg_q);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+      if (kv_done) {
         bf16* blk = hb + (long long)(pj * 128) * (3 * p.C);
         const int rows_valid = min(128, N - pj * 128);
-        drain_block(tDK, scale, blk + p.C, rows_valid);
-        drain_block(tDV, 1.0f, blk + 2 * p.C, rows_valid);
+        copy_block(stg_k, blk + p.C, rows_valid);
+        copy_block(stg_v, blk + 2 * p.C, rows_valid);
       }
-      if (pj == NKV - 1) {  // dQ of this half is complete (accumulated over the key tiles in TMEM)
+      if (q_done) {
         const int hn = phf ? p.hN1 : p.hN0, q0 = phf ? p.hN0 : 0;
-        drain_block(tDQ + phf * 64, scale, hb + (long long)q0 * (3 * p.C), min(hn, N - q0));
+        copy_block(stg_q, hb + (long long)q0 * (3 * p.C), min(hn, N - q0));
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");   // the staging rows become P^T / dS^T rows again
     };
 
     uint32_t t = 0;
