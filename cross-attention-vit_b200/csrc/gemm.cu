@@ -149,8 +149,10 @@ __device__ __forceinline__ void epi_prefetch(const EpiLane& L, int col, EpiPre<E
 // step, so each warp carries NP independent dependency chains. The epilogue warps (two per scheduler) were stalled on
 // fixed-latency dependencies ('wait' 0.92 and 'short scoreboard' 0.77 cycles per issued instruction, ncu round 1) because
 // every row group was a separate predicated block: one chain of 7 dependent FFMA2 + MUFU at a time.
-template <int NP>
+// NEG: r = -R (all coefficients negated at compile time), which lets gelu() finish with one FFMA2 (see gelu_batch).
+template <int NP, bool NEG>
 __device__ __forceinline__ void gelu_terms_batch(const float2 (&u)[NP], float2 (&e)[NP], float2 (&r)[NP], float2 (&ac)[NP]) {
+  constexpr float sg = NEG ? -1.0f : 1.0f;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     ac[j] = make_float2(fminf(fabsf(u[j].x), 5.0f), fminf(fabsf(u[j].y), 5.0f));
@@ -159,34 +161,32 @@ __device__ __forceinline__ void gelu_terms_batch(const float2 (&u)[NP], float2 (
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j].y) : "f"(earg.y));
   }
 #pragma unroll
-  for (int j = 0; j < NP; ++j) r[j] = fma2(ac[j], splat2(-2.501152098e-05f), splat2(5.606001891e-04f));
+  for (int j = 0; j < NP; ++j) r[j] = fma2(ac[j], splat2(sg * -2.501152098e-05f), splat2(sg * 5.606001891e-04f));
 #pragma unroll
-  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(-5.354749036e-03f));
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(sg * -5.354749036e-03f));
 #pragma unroll
-  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(2.881915092e-02f));
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(sg * 2.881915092e-02f));
 #pragma unroll
-  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(-9.833444611e-02f));
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(sg * -9.833444611e-02f));
 #pragma unroll
-  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(2.302476772e-01f));
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(sg * 2.302476772e-01f));
 #pragma unroll
-  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(-3.942042539e-01f));
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(sg * -3.942042539e-01f));
 #pragma unroll
-  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(4.997907545e-01f));
+  for (int j = 0; j < NP; ++j) r[j] = fma2(r[j], ac[j], splat2(sg * 4.997907545e-01f));
 }
 template <int NP>
 __device__ __forceinline__ void gelu_batch(float2 (&u)[NP]) {   // u -> gelu(u), same formula as gelu_pair (common.cuh)
   float2 e[NP], r[NP], ac[NP];
-  gelu_terms_batch<NP>(u, e, r, ac);
+  gelu_terms_batch<NP, true>(u, e, r, ac);
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    const float2 w = mul2(u[j], mul2(e[j], r[j]));
-    u[j] = make_float2(fmaxf(u[j].x, 0.f) - fabsf(w.x), fmaxf(u[j].y, 0.f) - fabsf(w.y));
-  }
+  for (int j = 0; j < NP; ++j)   // max(u, 0) - a e R with r = -R; a = min(|u|, 5) instead of |u|: beyond 5 the term is < 2e-6 either way
+    u[j] = fma2(ac[j], mul2(e[j], r[j]), make_float2(fmaxf(u[j].x, 0.f), fmaxf(u[j].y, 0.f)));
 }
 template <int NP>
 __device__ __forceinline__ void gelu_grad_batch(float2 (&u)[NP]) {   // u -> gelu'(u), same formula as gelu_grad_pair
   float2 e[NP], r[NP], ac[NP];
-  gelu_terms_batch<NP>(u, e, r, ac);
+  gelu_terms_batch<NP, false>(u, e, r, ac);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const float2 t = mul2(e[j], fma2(ac[j], splat2(-0.3989422804014327f), r[j]));
@@ -218,15 +218,12 @@ __device__ __forceinline__ void epi_chunk_fast(const EpiLane& L, int col, const 
   }
   char* o = L.out + col * ((OUT == OUT_BF16) ? 2 : 4);
   if (EPI == CAVIT_EPI_BIAS_GELU) {
-    // pre-activation u (bf16) out; GELU of the bf16-ROUNDED u: backward differentiates exactly what forward evaluated
+    // pre-activation u (bf16) out for the backward pass; GELU of the fp32 u, as the reference evaluates it (the backward's
+    // GELU'(bf16 u) differs from GELU'(u) by less than the bf16 rounding of the gradient it multiplies)
     char* ax = L.aux + col * 2;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const uint32_t q0 = pack_bf16(v[2 * it].x, v[2 * it].y), q1 = pack_bf16(v[2 * it + 1].x, v[2 * it + 1].y);
-      stg_v2(ax + it * L.aux_step, q0, q1);
-      v[2 * it] = unpack_bf16_fast(q0);
-      v[2 * it + 1] = unpack_bf16_fast(q1);
-    }
+    for (int it = 0; it < 8; ++it)
+      stg_v2(ax + it * L.aux_step, pack_bf16(v[2 * it].x, v[2 * it].y), pack_bf16(v[2 * it + 1].x, v[2 * it + 1].y));
 #if CAVIT_GELU_EW == 4
     {   // 16 epilogue warps: 113 registers per thread, two half batches
       float2 (&va)[8] = *reinterpret_cast<float2(*)[8]>(&v[0]);
@@ -323,9 +320,8 @@ __device__ __noinline__ void epi_chunk_slow(const GemmDev* pp, int g, long long 
     if (EPI == CAVIT_EPI_BIAS_GELU) {
       bf16* aux = reinterpret_cast<bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col;
       for (int i = 0; i < ncols; ++i) {
-        const bf16 u = __float2bfloat16(v[i]);
-        aux[i] = u;
-        v[i] = gelu_erf(__bfloat162float(u));
+        aux[i] = __float2bfloat16(v[i]);
+        v[i] = gelu_erf(v[i]);
       }
     } else if (EPI == CAVIT_EPI_GELU_BWD) {
       const bf16* aux = reinterpret_cast<const bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col;
