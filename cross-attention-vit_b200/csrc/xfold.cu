@@ -613,6 +613,17 @@ static XtLayout xt_layout(int N, int C) {
   return L;
 }
 
+// L2 prefetch of the token rows of a warp's NEXT streaming iteration (4 rows, XT_WARPS apart, 4 NV lines of 128 bytes each)
+template <int NV>
+__device__ __forceinline__ void xt_prefetch_rows(const float* xs, int r_next, int N, int lane) {
+  constexpr int LINES = 4 * NV;                    // per row
+#pragma unroll
+  for (int q = lane; q < 4 * LINES; q += 32) {
+    const int nn = r_next + XT_WARPS * (q / LINES);
+    if (nn >= 1 && nn < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + (long long)nn * (128 * NV) + (q % LINES) * 32));
+  }
+}
+
 template <int H, int NV>     // NV = C / 128 float4 per lane and token row
 __global__ void __launch_bounds__(XT_THREADS, 1)
 xfold_tc_fwd_kernel(const XfoldParams p, const XtLayout L) {
@@ -692,6 +703,7 @@ xfold_tc_fwd_kernel(const XfoldParams p, const XtLayout L) {
           __syncwarp();
         }
       }
+      xt_prefetch_rows<NV>(xs, r0 + 4 * XT_WARPS, N, lane);
       float4 v[4][NV];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -947,6 +959,7 @@ xfold_tc_bwd_kernel(const XfoldParams p, const XbLayout L) {
     }
     // ---- step 1: token rows -> xhat (bf16) tile with the saved statistics
     for (int r0 = warp; r0 < L.RA; r0 += 4 * XT_WARPS) {
+      xt_prefetch_rows<NV>(xs, r0 + 4 * XT_WARPS, N, lane);
       float4 v[4][NV];
       float mu[4], rs[4];
 #pragma unroll
@@ -1123,6 +1136,11 @@ xfold_tc_bwd_kernel(const XfoldParams p, const XbLayout L) {
         const int n0 = u * 16;
         const uint8_t* xb = xcol + n0 * 128;
         const float4* rcb = reinterpret_cast<const float4*>(s_c1) + n0;
+        {   // L2 prefetch of the gradient rows this warp reads in its NEXT round: one 128-byte line per row, one lane each
+          const int nn = n0 + 16 * (XT_WARPS / 4) * ((lane >> 4) + 1) + (lane & 15);   // lanes 0-15: next round, 16-31: the one after
+          if (nn < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(dxs + (long long)nn * C + (c - lane)));
+          // (the first two rounds of a channel tile are not prefetched: they overlap the previous tile's stores)
+        }
         if (p.disjoint && n0 > 0 && n0 + 16 <= N) {
           // sixteen whole token rows of the donor stream: constant row offsets, no predicates (warp-uniform branch)
           float* d = dxs + (long long)n0 * C + c;
