@@ -388,6 +388,34 @@ __device__ __forceinline__ float2 gelu_grad_pair(float2 u) {
   return make_float2(u.x < 0.f ? t.x : 1.0f - t.x, u.y < 0.f ? t.y : 1.0f - t.y);
 }
 
+// Scalar twins of gelu_pair / gelu_grad_pair as the GEMM epilogue's fast path evaluates them (gemm.cu: gelu_batch,
+// gelu_grad_batch): the SAME operations in the same order, so that a row gets bit-identical results whether its 32-row slab
+// takes the vectorised fast path or the generic one — which slab is partial depends on the batch size, and a sample's logits
+// must not (tests/test_gpu_ddp_nccl.py: a shard of the batch reproduces the global-batch run).
+__device__ __forceinline__ void gelu_poly_terms(float u, float sg, float& e, float& r, float& ac) {
+  ac = fminf(fabsf(u), 5.0f);
+  const float earg = (u * u) * -0.72134752044448170f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(earg));
+  r = fmaf(ac, sg * -2.501152098e-05f, sg * 5.606001891e-04f);
+  r = fmaf(r, ac, sg * -5.354749036e-03f);
+  r = fmaf(r, ac, sg * 2.881915092e-02f);
+  r = fmaf(r, ac, sg * -9.833444611e-02f);
+  r = fmaf(r, ac, sg * 2.302476772e-01f);
+  r = fmaf(r, ac, sg * -3.942042539e-01f);
+  r = fmaf(r, ac, sg * 4.997907545e-01f);
+}
+__device__ __forceinline__ float gelu_poly(float u) {
+  float e, r, ac;
+  gelu_poly_terms(u, -1.0f, e, r, ac);
+  return fmaf(ac, __fmul_rn(e, r), fmaxf(u, 0.f));
+}
+__device__ __forceinline__ float gelu_poly_grad(float u) {
+  float e, r, ac;
+  gelu_poly_terms(u, 1.0f, e, r, ac);
+  const float t = __fmul_rn(e, fmaf(ac, -0.3989422804014327f, r));
+  return u < 0.f ? t : 1.0f - t;
+}
+
 // ---------------------------------------------------------------- dropout
 // Counter-based Bernoulli masks: keep(i) is a pure function of (seed, site, element index), so the
 // backward pass regenerates exactly the mask the forward pass used without storing it. One

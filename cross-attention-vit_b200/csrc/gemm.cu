@@ -321,11 +321,11 @@ __device__ __noinline__ void epi_chunk_slow(const GemmDev* pp, int g, long long 
       bf16* aux = reinterpret_cast<bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col;
       for (int i = 0; i < ncols; ++i) {
         aux[i] = __float2bfloat16(v[i]);
-        v[i] = gelu_erf(v[i]);
+        v[i] = gelu_poly(v[i]);   // bit-identical to the fast path (common.cuh)
       }
     } else if (EPI == CAVIT_EPI_GELU_BWD) {
       const bf16* aux = reinterpret_cast<const bf16*>(p.aux) + (long long)g * p.aux_gs + row * p.ldaux + col;
-      for (int i = 0; i < ncols; ++i) v[i] *= gelu_erf_grad(__bfloat162float(aux[i]));
+      for (int i = 0; i < ncols; ++i) v[i] *= gelu_poly_grad(__bfloat162float(aux[i]));
     } else if (EPI == CAVIT_EPI_BIAS_RELU) {
       for (int i = 0; i < ncols; ++i) v[i] = fmaxf(v[i], 0.f);
     } else if (EPI == CAVIT_EPI_RELU_BWD) {

@@ -299,3 +299,34 @@ def test_model_on_second_device_while_first_is_current():
     with torch.cuda.device(1):
         assert _abi.device_status() == 0
     assert rel(outs[1][0], outs[0][0]) < 1e-5 and rel(outs[1][1], outs[0][1]) < 1e-3
+
+
+@pytest.mark.parametrize("fold", [False, True])
+def test_batch_shard_reproduces_global_batch(fold, monkeypatch):
+    """A sample's logits must not depend on what else is in the batch: data parallelism shards the batch
+    (/root/reference/main_mist.py:211-219) and tests/test_gpu_ddp_nccl.py compares ranks against the global-batch run, which
+    needs 2 GPUs — this is its 1-GPU core. Bit-exact: which 32-row slab of a GEMM tile is partial (generic epilogue path)
+    depends on B*N, so both epilogue paths have to evaluate identical operations (the GELU of the two paths once differed)."""
+    from cavit.modules import ModelCross
+    from oracle.weights import make_inputs
+    monkeypatch.setenv("CAVIT_XFOLD_MIN_CTAS", "0" if fold else "1000000")
+    kind, cfg, state, _, _ = build_case("cross_ring4")
+    img, labels = make_inputs(cfg, 8, seed=99)
+
+    def run(x, y):
+        m = ModelCross(cfg)
+        m.load_state_dict(state)
+        m = m.cuda().train()
+        logits, loss = m(x.cuda(), y.cuda())
+        loss.backward()
+        g = torch.cat([p.grad.detach().flatten() for p in m.parameters()])
+        assert m.engine().fold == fold
+        return logits.detach().clone(), g.clone()
+
+    lg, gg = run(img, labels)
+    l0, g0 = run(img[:4], labels[:4])
+    l1, g1 = run(img[4:], labels[4:])
+    assert torch.equal(l0, lg[:4]) and torch.equal(l1, lg[4:])
+    # mean of the two shard gradients == global-batch gradient (up to the summation order of the reductions over the batch)
+    gs = 0.5 * (g0.double() + g1.double())
+    assert float((gs - gg.double()).norm() / gg.double().norm()) < 2e-3
