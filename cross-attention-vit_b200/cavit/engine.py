@@ -473,7 +473,12 @@ class Engine:
         fold = self.fold
         # K-EMBED: TMA-staged unfold fused with the embedding GEMM (csrc/embed.cu) wherever its brick geometry fits;
         # then neither the unfolded patch tensor nor the compacted token gradient exists
-        self.embed_fused = (self.kind in ("cross", "vit") and os.environ.get("CAVIT_EMBED_FUSED", "1") != "0" and
+        # ... and where it wins: the fused kernels stream the fp32 weight tile from L2 once per 128-token brick, which is
+        # cheap for a 384 x 256 projection (cfg2: step 30.32 -> 30.23 ms) and a wash at 512 x 512 (cfg5), but costs more than
+        # patchify + the paired bf16 GEMM once the weights are megabytes (cfg1, 1024 x 2048: 36.60 vs 36.31 ms; cfg3,
+        # 768 x 4096: 53.95 vs 52.99 ms, same box). CAVIT_EMBED_FUSED = 0 / 1 forces the choice.
+        want = os.environ.get("CAVIT_EMBED_FUSED", "auto")
+        self.embed_fused = (self.kind in ("cross", "vit") and want != "0" and (want == "1" or C * self.P <= 512 * 512) and
                             ops.embed_fused_supported((B, self.Mimg, 1) + tuple(self.cfg.img_size), self.cfg.patch_size, C))
         if not self.embed_fused:
             a["patches"] = e((self.Mimg * B * self.Np, self.P), BF16)
