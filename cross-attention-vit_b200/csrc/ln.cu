@@ -62,14 +62,6 @@ ln_fwd_kernel(const float* __restrict__ x, long long row_stride, long long gs, i
     const int g = (int)(row / rows_per_group);
     const long long r = row - (long long)g * rows_per_group;
     const float4* xr = reinterpret_cast<const float4*>(src_row(rm, x, g, r, row_stride, gs, C));
-    {   // L2 prefetch of this warp's next row (one 128-byte line per lane)
-      const long long nrow = row + (long long)gridDim.x * LN_WARPS;
-      if (nrow < total && lane < ((C + 31) >> 5)) {
-        const int ng = (int)(nrow / rows_per_group);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(
-                         src_row(rm, x, ng, nrow - (long long)ng * rows_per_group, row_stride, gs, C)) + lane * 128));
-      }
-    }
     float4 v[NV];
     float s = 0.f;
 #pragma unroll
@@ -168,21 +160,6 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
     long long doff;
     if (rm.fusion) doff = fusion_dst_offset(rm, g, r, row_stride, gs);  // scatter back into the donor stream
     else doff = (long long)g * dx_gs + r * dx_row_stride;
-    if (!rm.fusion) {
-      // L2 prefetch of this warp's NEXT row (x, dy, residual gradient: 128-byte lines, one lane each): the loop is one row per
-      // warp and 16 warps per SM, so without it every row pays the full HBM latency before its reductions can start
-      const long long rn = r + (long long)gridDim.x * LN_WARPS;
-      if (rn < rows_per_group) {
-        const int xl = (C + 31) >> 5, dl = DYF ? xl : (C + 63) >> 6;          // lines per row: fp32, incoming gradient
-        const char* pf = nullptr;
-        if (lane < xl) pf = reinterpret_cast<const char*>(x + (long long)g * gs + rn * row_stride) + lane * 128;
-        else if (lane < xl + dl)
-          pf = reinterpret_cast<const char*>(dy_) + ((long long)g * rows_per_group + rn) * C * (DYF ? 4 : 2) + (lane - xl) * 128;
-        if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-        if (dresid && lane < xl)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(dresid + (long long)g * dx_gs + rn * dx_row_stride) + lane * 128));
-      }
-    }
     // issue every load of the row up front (x, dy, residual gradient) before the reductions
     float4 xv[NV], dr[NV], d4[DYF ? NV : 1];
     uint2 d2[DYF ? 1 : NV];
