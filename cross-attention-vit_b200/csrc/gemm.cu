@@ -393,6 +393,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
     // HBM-bound. One 128-byte line per lane and instruction.
     // (measured: GELU' 0.385 -> 0.364 ms, out-proj 0.160 -> 0.156 ms; with a long mainloop between the prefetch and its use —
     // fc2 forward, K = 1536 — the kernel got 6 % SLOWER, also when only the current tile's slab was prefetched: hence the K limit)
+#ifndef CAVIT_NO_EPI_PREFETCH   // A/B switch (NVCC_EXTRA=-DCAVIT_NO_EPI_PREFETCH with CAVIT_BUILD_TAG)
     if ((EPI == CAVIT_EPI_GELU_BWD || (EPI == CAVIT_EPI_BIAS_RESID && p.K <= 512)) && work + num_units < total_tiles) {
       const int ntile = (work + num_units) / splits;
       const int ng = ntile / tiles_per_group;
@@ -411,6 +412,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, uint32_t tmem_ba
         if (nrow0 + rr < p.M && nn0 + ll * (128 / esz) < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + rr * pitch + ll * 128));
       }
     }
+#endif
     // the fast path needs the warp's whole 32-row slab inside M; the (last) partial slab of a group takes the generic path
     const bool fast_tile = fast_kind && ((long long)p.M - row0 >= 32);   // warp-uniform
     EpiPre<EPI> pre;

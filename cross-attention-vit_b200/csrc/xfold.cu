@@ -617,6 +617,9 @@ static XtLayout xt_layout(int N, int C) {
 template <int NV>
 __device__ __forceinline__ void xt_prefetch_rows(const float* xs, int r_next, int N, int lane) {
   constexpr int LINES = 4 * NV;                    // per row
+#ifdef CAVIT_NO_XF_PREFETCH
+  return;
+#endif
 #pragma unroll
   for (int q = lane; q < 4 * LINES; q += 32) {
     const int nn = r_next + XT_WARPS * (q / LINES);
@@ -1138,7 +1141,9 @@ xfold_tc_bwd_kernel(const XfoldParams p, const XbLayout L) {
         const float4* rcb = reinterpret_cast<const float4*>(s_c1) + n0;
         {   // L2 prefetch of the gradient rows this warp reads in its NEXT round: one 128-byte line per row, one lane each
           const int nn = n0 + 16 * (XT_WARPS / 4) * ((lane >> 4) + 1) + (lane & 15);   // lanes 0-15: next round, 16-31: the one after
+#ifndef CAVIT_NO_XF_PREFETCH
           if (nn < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(dxs + (long long)nn * C + (c - lane)));
+#endif
           // (the first two rounds of a channel tile are not prefetched: they overlap the previous tile's stores)
         }
         if (p.disjoint && n0 > 0 && n0 + 16 <= N) {
