@@ -16,10 +16,14 @@
 //     dp_n = w_h . xhat_n,  ds_n = p_n (dp_n - sum_j p_j dp_j),  dxhat_n = sum_h scale ds_hn a_h + p_hn w_h,
 //     dx_n = rstd_n (dxhat_n - mean(dxhat_n) - xhat_n mean(dxhat_n o xhat_n))     (both means follow from s_n, dp_n)
 //     da_h = scale sum_n ds_hn xhat_n  ->  dq'_h = da_h o gamma,  dgamma += da_h o q'_h + gz_h o zhat_h,  dbeta += gz_h.
-// Everything is fp32 (the token streams are fp32), so this path is also MORE accurate than the bf16 K/V route.
-//
-// One CTA per (fusion k, sample b), one thread per channel (C <= 1024). HBM-bound: 4*C bytes per token forward,
-// 12*C bytes per token backward (read x, read-modify-write the stream gradient).
+// Two implementations of this algebra live here:
+//   * xfold_fwd_kernel / xfold_bwd_kernel: everything fp32 on the CUDA cores (the token streams are fp32), MORE accurate than the
+//     bf16 K/V route; one CTA per (fusion k, sample b), one thread per channel pair (C <= 1024). Used by the fp32-tolerance
+//     mode and for shapes outside the tensor-core tile. Algorithmic traffic 4*C bytes per token forward, 12*C backward (read
+//     x, read-modify-write the stream gradient), but the kernels are bound by instruction issue (~55 thread instructions
+//     per token element), not by HBM;
+//   * xfold_tc_fwd_kernel / xfold_tc_bwd_kernel (further down): the contractions on tcgen05 from one bf16 xhat tile per
+//     sample — the bf16 mode's default where the shape fits.
 #include <stdlib.h>
 
 #include <atomic>
