@@ -105,6 +105,11 @@ class DataParallel:
 
     AUTO_OVERLAP_BYTES = 1 << 30     # mode="auto": overlapped slab all-reduces from this gradient volume on, else one post all-reduce
 
+    @classmethod
+    def auto_mode(cls, gradient_elems: int) -> str:
+        """What mode="auto" selects for a model with `gradient_elems` fp32 gradient elements."""
+        return "overlap" if gradient_elems * 4 >= cls.AUTO_OVERLAP_BYTES else "post"
+
     def __init__(self, model, group=None, min_slab_elems: int = 8 << 20, mode: str = "auto"):
         """mode = "overlap": every finished gradient slab (>= min_slab_elems, in backward-completion order) is
         all-reduced on a communication stream while the remaining backward kernels run. The slab all-reduces are
@@ -137,7 +142,7 @@ class DataParallel:
             # Overlap pays when the all-reduce is long: cfg3 (2.1 GB of fp32 gradients, 2 GPUs) 56.87 ms overlapped vs 58.29 ms
             # post. For a small model the collective is short and running it next to the backward kernels costs more (HBM / SM
             # contention) than exposing it: cfg2 (266 MB) on 4 GPUs 29.87 ms overlapped vs 29.56 ms post, same box.
-            mode = "overlap" if self.engine.layout.total * 4 >= self.AUTO_OVERLAP_BYTES else "post"
+            mode = self.auto_mode(self.engine.layout.total)
         if mode not in ("overlap", "post"):
             raise ValueError(f"mode must be 'auto', 'overlap' or 'post', got {mode!r}")
         self.mode = mode

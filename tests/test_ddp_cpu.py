@@ -131,3 +131,13 @@ def test_epoch_metrics_average_rank_means():
     for rank, vals in res:
         for k, v in enumerate(vals):
             assert abs(v - (k + 1) * (0.1 + 0.05) / 2) < 1e-12
+
+
+def test_auto_mode_switches_on_gradient_volume():
+    """mode="auto": one post-backward all-reduce for small models (cfg2: 66 M parameters), overlapped slabs from 1 GiB of fp32
+    gradients on (cfg3: 525 M parameters) — measured choice, DESIGN.md section 5."""
+    from cavit.ddp import DataParallel
+    assert DataParallel.auto_mode(66_408_640) == "post"
+    assert DataParallel.auto_mode(82_200_000) == "post"
+    assert DataParallel.auto_mode(524_600_000) == "overlap"
+    assert DataParallel.auto_mode((1 << 28)) == "overlap" and DataParallel.auto_mode((1 << 28) - 1) == "post"
