@@ -1185,12 +1185,16 @@ xfold_tc_bwd_kernel(const XfoldParams p, const XbLayout L) {
           }
         }
       }
-      tc_fence_before();
-      __syncthreads();                           // this dxhat buffer is free again
-      if (j + 2 < NV && warp == 0) {
-        tc_fence_after();
-        if (elect_one()) issue_dxhat(j + 2);
-        __syncwarp();
+      // Only a tile that is followed by another one in the same TMEM buffer (j + 2 < NV) needs the block to meet here; the
+      // other tiles run into the next one without a barrier (ncu: 3.7 barrier-stall cycles per issued instruction before)
+      if (j + 2 < NV) {
+        tc_fence_before();
+        __syncthreads();                         // this dxhat buffer is free again
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) issue_dxhat(j + 2);
+          __syncwarp();
+        }
       }
     }
     tc_fence_before();
